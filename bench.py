@@ -1,0 +1,424 @@
+#!/usr/bin/env python
+"""bench.py -- join throughput, (|R|+|S|) tuples/s, on N B200s of one node.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME]
+
+N = 1 (default): BASELINE.json config 2 -- PHJ, |R| = |S| = 2^27 unique 32-bit keys (S a
+permutation of R's key set), 32-bit payloads, materialised 3-column result.
+N > 1 (under torchrun, one rank per GPU): the CPRA path, weak scaling at 2^28 + 2^28 tuples
+per GPU, so that N = 8 is exactly config 4 (2^31 x 2^31): owner split -> NCCL all-to-all over
+NVLink -> local PHJ -> all-reduce of the checksums.
+
+A step = one whole join of one batch.  `value` has the inputs resident in HBM (the reference's
+timed region, npj.cpp:861-918); `e2e` goes through the host entry point with pinned host
+buffers (H2D of the inputs and D2H of the rows inside the timed region).  Every step's
+count / checksums are checked against the analytic expectation (count = |S|, checksums =
+column sums of S), a wrong step aborts the run.  One JSON line on stdout (rank 0).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "join throughput (R+S tuples/sec)"
+UNIT = "tuples/s"
+MASK64 = (1 << 64) - 1
+
+
+def measured_peak_gbs():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks + throttle reasons while the timed region runs (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        super().__init__(daemon=True)
+        self.gpu, self.samples, self._stop = gpu_index, [], threading.Event()
+
+    def run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                      "-i", str(self.gpu)], capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def stop(self):
+        self._stop.set()
+        self.join(timeout=6)
+        sm, mx, reasons = [], 0.0, set()
+        for s in self.samples:
+            try:
+                sm.append(float(s[1]))
+                mx = max(mx, float(s[2]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), s[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def physical_gpu_index(local):
+    vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+    if vis:
+        try:
+            return int(vis.split(",")[local])
+        except Exception:
+            return local
+    return local
+
+
+# ----------------------------------------------------------------------------- reference / CPU arm
+
+def host_threads():
+    try:
+        cpus = sorted(os.sched_getaffinity(0))
+    except Exception:
+        cpus = list(range(os.cpu_count() or 1))
+    return cpus
+
+
+def has_avx512():
+    try:
+        with open("/proc/cpuinfo") as f:
+            return "avx512f" in f.read()
+    except OSError:
+        return False
+
+
+def run_reference_program(prog, threads, rk, rv, sk, sv, timeout_s):
+    """Runs the UNMODIFIED reference program (oracle/_ref/<prog>, compiled from /root/reference by
+    oracle/Makefile) on the four relation files it expects in its CWD (npj.cpp:1013-1039) and
+    returns the seconds it prints (its own timer)."""
+    from hash_join_codes_knl_b200 import api
+    exe = os.path.join(ROOT, "oracle", "_ref", prog)
+    with tempfile.TemporaryDirectory(prefix="hjref_") as d:
+        api.relation_write(d, False, rk, rv)
+        api.relation_write(d, True, sk, sv)
+        args = [exe, str(threads), str(sk.size), str(rk.size)]
+        if prog != "cpra":
+            args.append("1")
+        out = subprocess.run(args, cwd=d, capture_output=True, text=True, timeout=timeout_s)
+        if out.returncode != 0:
+            raise RuntimeError(f"{prog} exited {out.returncode}: {out.stderr[-300:]}")
+        lines = [ln for ln in out.stdout.strip().splitlines() if ln and not ln.startswith("copy")]
+        return float(lines[-1].split()[0])
+
+
+def cpu_join_sample(log2_tuples, steps, warmup, workload):
+    """The reference's CPU implementation on a bounded sample of the workload, all usable host
+    threads.  Preferred: the reference's own program (kind "reference"); else the oracle port.
+    PHJ's shipped program performs no join (its join phase is commented out, phj.cpp:1869-1924),
+    so the partitioned path is timed with the reference's complete partitioned join, cpra."""
+    import numpy as np
+    from hash_join_codes_knl_b200 import datagen
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import _oracle
+    n = 1 << log2_tuples
+    if workload == "npj_cfg1":
+        nr, ns, kind = n >> 4, n, 1
+        prog, algo = "npj", "npj"
+    else:
+        nr, ns, kind = n, n, 0
+        prog, algo = "cpra", "cpra"
+    rk, rv = datagen.generate(0, nr, nr, 42, 1, datagen.INNER_FACTOR)
+    sk, sv = datagen.generate(kind, ns, nr, 42, 2, datagen.OUTER_FACTOR)
+    cpus = host_threads()
+    use_ref = (os.path.exists(os.path.join(ROOT, "oracle", "_ref", prog)) and has_avx512()
+               and cpus == list(range(len(cpus))))        # the reference pins thread t to CPU t (makefile -DSCATTER)
+    threads = min(len(cpus), 256)                          # repo_offset[256], cpra2.cpp:1861
+    secs, kind_used, note = [], None, ""
+    if use_ref:
+        try:
+            for i in range(warmup + steps):
+                s = run_reference_program(prog, threads, rk, rv, sk, sv, timeout_s=600)
+                if i >= warmup:
+                    secs.append(s)
+            kind_used = "reference"
+            note = f"oracle/_ref/{prog} (unmodified {('cpra2' if prog == 'cpra' else prog)}.cpp, g++ -O3 -march=skylake-avx512)"
+        except Exception as e:            # never let the baseline leg take the bench down
+            note = f"reference program failed ({type(e).__name__}: {e}); "
+            secs = []
+    if not secs:
+        _oracle.build_oracle()
+        threads = min(len(cpus), 64)
+        for i in range(warmup + steps):
+            r = _oracle.oracle_join(algo, rk, rv, sk, sv, threads=threads, materialize=False)
+            assert r.count == ns
+            if i >= warmup:
+                secs.append(r.seconds)
+        kind_used = "port"
+        note += "oracle/hj_oracle.c scalar restatement"
+    sec = sum(secs) / len(secs)
+    return {"value": (nr + ns) / sec, "unit": UNIT, "cores": threads, "kind": kind_used,
+            "sample": f"{algo.upper()} |R|=2^{nr.bit_length() - 1} x |S|=2^{ns.bit_length() - 1} ({note}), "
+                      f"mean of {len(secs)} run(s), {sec:.3f} s each", "seconds": sec}
+
+
+def reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    workload = args.workload if args.workload != "auto" else ("phj_cfg2" if args.gpus == 1 else "cpra_cfg4")
+    log2 = 25 if workload != "npj_cfg1" else 26
+    t0 = time.time()
+    base = cpu_join_sample(log2, max(1, args.steps), min(args.warmup, 1), "npj_cfg1" if workload == "npj_cfg1" else "phj_cfg2")
+    line = {"impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": base["seconds"] * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+            "config": {"workload": workload, "note": "CPU reference on a bounded sample of the workload; throughput in "
+                       "(R+S) tuples/s does not depend on the GPU count"},
+            "cpu_baseline": {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0, "wall_s": time.time() - t0}
+    print(json.dumps(line))
+    return 0
+
+
+# ----------------------------------------------------------------------------- our arm
+
+def expected_checks(eng, sk, sv, ns):
+    import torch
+    from hash_join_codes_knl_b200 import datagen
+    inner = (sk.to(torch.int64) & 0xFFFFFFFF) * datagen.INNER_FACTOR & 0xFFFFFFFF
+    return (ns, eng.column_sum(sk), eng.column_sum(sv), int(inner.sum().item()) & MASK64)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="auto", choices=["auto", "phj_cfg2", "npj_cfg1", "cpra_cfg4"])
+    ap.add_argument("--log2-per-gpu", type=int, default=0, help="override tuples per relation per GPU (2^k)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        return reference_arm(args)
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import hash_join_codes_knl_b200 as hj
+    from hash_join_codes_knl_b200 import cpra as cpra_mod, datagen
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("--gpus N > 1 must be launched with torch.distributed.run, one rank per GPU")
+        args.gpus = world
+    torch.cuda.set_device(local)
+    devname = f"cuda:{local}"
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device(devname))
+    workload = args.workload if args.workload != "auto" else ("phj_cfg2" if world == 1 else "cpra_cfg4")
+
+    eng = hj.Engine(local, use_torch_stream=True)
+    eng.set_profiling(True)
+
+    # ---- synthetic inputs, generated on the device (identical to datagen's numpy mirror)
+    if workload == "cpra_cfg4":
+        k = args.log2_per_gpu or 28
+        nr_g = ns_g = 1 << k
+        nr_tot, ns_tot = nr_g * world, ns_g * world
+        rk, rv = eng.generate(0, nr_g, nr_tot, 42, 1, datagen.INNER_FACTOR, first=rank * nr_g, total=nr_tot)
+        sk, sv = eng.generate(0, ns_g, nr_tot, 42, 2, datagen.OUTER_FACTOR, first=rank * ns_g, total=ns_tot)
+        algo = "cpra"
+    else:
+        nr_tot, ns_tot, kind = datagen.workload(workload)
+        if args.log2_per_gpu:
+            scale = (1 << args.log2_per_gpu) / ns_tot
+            nr_tot, ns_tot = max(1, int(nr_tot * scale)), 1 << args.log2_per_gpu
+        nr_g, ns_g = nr_tot, ns_tot
+        rk, rv = eng.generate(0, nr_tot, nr_tot, 42, 1, datagen.INNER_FACTOR)
+        sk, sv = eng.generate(kind, ns_tot, nr_tot, 42, 2, datagen.OUTER_FACTOR)
+        algo = "npj" if workload == "npj_cfg1" else "phj"
+    want_local = expected_checks(eng, sk, sv, ns_g)      # every probe tuple has exactly one partner
+    if world > 1:
+        want = cpra_mod.reduce_checks(*want_local, torch.device(devname))
+    else:
+        want = want_local
+
+    def step_device():
+        if algo == "cpra":
+            r = cpra_mod.cpra_join(eng, (rk, rv), (sk, sv))
+            got = (r["count"], r["sum_key"], r["sum_outer"], r["sum_inner"])
+            return got, r["local"].kernel_launches + (8 if world > 1 else 0), r
+        r = getattr(eng, algo)((rk, rv), (sk, sv))
+        return r.checks(), r.kernel_launches, r
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- warm-up (also sizes the workspace so the timed region never allocates)
+    for _ in range(args.warmup):
+        got, _, _ = step_device()
+        assert got == want, f"warm-up step produced a wrong result: {got} != {want}"
+    # ---- timed: device-resident
+    sampler = ClockSampler(physical_gpu_index(local)) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches = 0
+    ktimes = {}
+    phases = np.zeros(8)
+    extra = {"split_ms": 0.0, "exchange_ms": 0.0, "join_ms": 0.0}
+    barrier()
+    ev0.record()
+    for _ in range(args.steps):
+        got, nl, r = step_device()
+        launches += nl
+        if got != want:
+            raise SystemExit(f"timed step produced a wrong result: {got} != {want}")
+        for name, (ms, n) in eng.kernel_times().items():
+            a = ktimes.setdefault(name, [0.0, 0])
+            a[0] += ms
+            a[1] += n
+        if algo == "cpra":
+            for key in extra:
+                extra[key] += r[key]
+            phases += np.array(r["local"].phase_ms)
+        else:
+            phases += np.array(r.phase_ms)
+    ev1.record()
+    barrier()
+    ms_total = ev0.elapsed_time(ev1)
+    if world > 1:
+        t = torch.tensor([ms_total], device=devname)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+    clocks = sampler.stop() if sampler else None
+    ms_step = ms_total / args.steps
+    value = (nr_tot + ns_tot) / (ms_step * 1e-3)
+
+    # ---- timed: end to end through the host entry point, pinned host buffers
+    e2e = None
+    if not args.no_e2e:
+        pin = [torch.empty(t.numel(), dtype=torch.int32).pin_memory() for t in (rk, rv, sk, sv)]
+        for p, t in zip(pin, (rk, rv, sk, sv)):
+            p.copy_(t)
+        torch.cuda.synchronize()
+        hrk, hrv, hsk, hsv = (p.numpy() for p in pin)
+        e2e_steps = max(2, min(args.steps, 5))
+
+        def step_e2e():
+            if algo == "cpra":
+                drk, drv, dsk, dsv = (p.to(devname, non_blocking=True) for p in pin)
+                r = cpra_mod.cpra_join(eng, (drk, drv), (dsk, dsv))
+                rows = [c.to("cpu", non_blocking=True) for c in r["local"].rows_torch()]   # this rank's share of the rows
+                torch.cuda.synchronize()
+                return (r["count"], r["sum_key"], r["sum_outer"], r["sum_inner"]), r["local"].count, rows
+            r = getattr(eng, algo)((hrk, hrv), (hsk, hsv))
+            return r.checks(), r.count, None
+        got, _, _ = step_e2e()
+        assert got == want
+        barrier()
+        t0 = time.perf_counter()
+        rows_out = 0
+        for _ in range(e2e_steps):
+            got, cnt, _ = step_e2e()
+            rows_out = cnt
+            if got != want:
+                raise SystemExit("e2e step produced a wrong result")
+        barrier()
+        sec = (time.perf_counter() - t0) / e2e_steps
+        if world > 1:
+            t = torch.tensor([sec], device=devname, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            sec = float(t.item())
+        e2e = {"value": (nr_tot + ns_tot) / sec, "unit": UNIT, "h2d_bytes_per_step": 8 * (nr_g + ns_g) * world,
+               "d2h_bytes_per_step": 12 * (ns_tot if world > 1 else rows_out), "ms_per_step": sec * 1e3, "steps": e2e_steps,
+               "path": "Engine.%s(host columns) -> hjb_%s_host" % (algo, algo) if algo != "cpra" else
+                       "pinned host -> H2D -> cpra_join -> D2H of each rank's rows"}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    # ---- roofline of the dominant kernel, from the per-launch CUDA events of the timed steps
+    peak, peak_src = measured_peak_gbs()
+    alg_bytes_per_launch = {                       # algorithmic bytes per launch
+        "k_hist": lambda n: 4 * n, "k_scatter": lambda n: 16 * n,
+        "k_partition_join": lambda n: 8 * (nr_g + ns_g) + 12 * ns_g,
+        "k_npj_probe": lambda n: 8 * ns_g + 12 * ns_g + (0 if nr_g * 16 <= (64 << 20) else 8 * ns_g),
+        "k_npj_build": lambda n: 8 * nr_g + 16 * nr_g * 2,
+    }
+    dom = max(ktimes.items(), key=lambda kv: kv[1][0])[0] if ktimes else None
+    roof = None
+    if dom in alg_bytes_per_launch:
+        ms_k, n_k = ktimes[dom]
+        per_launch_ms = ms_k / max(1, n_k)
+        # scatter / hist launches alternate between R and S: average tuples per launch
+        n_avg = (nr_g + ns_g) / 2
+        achieved = alg_bytes_per_launch[dom](n_avg) / (per_launch_ms * 1e-3) / 1e9
+        roof = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "avg_launch_ms": per_launch_ms, "launches": n_k,
+                "share_of_step": ms_k / ms_total}
+    passes = 2 if (nr_g >> 11) > 256 else 1
+    step_bytes = (nr_g + ns_g) * (20 * passes + 8) + 12 * ns_g if algo != "npj" else None
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32",
+        "data": "synthetic",
+        "config": {"workload": {"phj_cfg2": "PHJ 2^27 x 2^27 unique keys (BASELINE config 2)",
+                                "npj_cfg1": "NPJ 2^24 x 2^28 foreign keys (BASELINE config 1)",
+                                "cpra_cfg4": f"CPRA {nr_g.bit_length() - 1}+{ns_g.bit_length() - 1} log2 tuples per GPU "
+                                             f"x {world} GPUs (N=8 is BASELINE config 4, 2^31 x 2^31)"}[workload],
+                   "inner_tuples": nr_tot, "outer_tuples": ns_tot, "materialize": True, "algorithm": algo,
+                   "l2_policy": "inputs (%.1f GiB) and every intermediate exceed the 126 MB L2; no flush needed"
+                                % (8 * (nr_g + ns_g) / 2**30),
+                   "result_check": "count and 3 checksums verified every step"},
+        "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roof,
+        "kernel_ms_per_step": {k: round(v[0] / args.steps, 4) for k, v in sorted(ktimes.items())},
+        "phase_ms_per_step": [round(float(x) / args.steps, 4) for x in phases],
+    }
+    if step_bytes:
+        line["step_roofline"] = {"algorithmic_bytes": step_bytes, "achieved_gbs": step_bytes / (ms_step * 1e-3) / 1e9 * (world if algo == "cpra" else 1) / (world if algo == "cpra" else 1),
+                                 "frac_of_hbm_peak": step_bytes / (ms_step * 1e-3) / 1e9 / peak}
+    if algo == "cpra":
+        line["cpra_ms_per_step"] = {k: round(v / args.steps, 4) for k, v in extra.items()}
+    if not args.no_cpu_baseline:
+        try:
+            base = cpu_join_sample(25 if workload != "npj_cfg1" else 26, 2, 1, "npj_cfg1" if workload == "npj_cfg1" else "phj_cfg2")
+            line["cpu_baseline"] = {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        except Exception as e:
+            line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": f"failed: {e}"}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,287 @@
+"""Host-side mirror of the reference's join interface over the C ABI (include/hjb200.h).
+
+Reference shape: main() loads four uint32 columns, fills one info_t_hj per thread (hj.h:1-72)
+and runs run()/run_hj() (npj.cpp:769, phj.cpp:1646, cpra2.cpp:1697); the result is the
+(join_keys, join_outer_vals, join_inner_vals) columns and join_tuples.  Here an Engine is one
+GPU; `inner` = R = build side, `outer` = S = probe side, as in the reference."""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import Gen, Opts, Rel, Result, Split
+
+
+class HjbError(RuntimeError):
+    pass
+
+
+class _CudaArray:
+    """Zero-copy view of library-owned device memory for torch.as_tensor (int32 bit pattern)."""
+
+    def __init__(self, ptr, n):
+        self.__cuda_array_interface__ = {"shape": (int(n),), "typestr": "<i4", "data": (int(ptr), False),
+                                         "version": 2, "strides": None}
+
+
+class JoinResult:
+    """count + the three uint64 checksums + the dense result columns."""
+
+    def __init__(self, res, engine):
+        self.count, self.sum_key = int(res.count), int(res.sum_key)
+        self.sum_outer, self.sum_inner = int(res.sum_outer), int(res.sum_inner)
+        self.seconds, self.seconds_e2e = float(res.seconds), float(res.seconds_e2e)
+        self.phase_ms = [float(x) for x in res.phase_ms]
+        self.kernel_launches, self.partitions = int(res.kernel_launches), int(res.partitions)
+        self.rows_on_device = bool(res.rows_on_device)
+        self._ptrs = (res.keys, res.outer_vals, res.inner_vals)
+        self._engine = engine
+
+    def checks(self):
+        return (self.count, self.sum_key, self.sum_outer, self.sum_inner)
+
+    @property
+    def materialized(self):
+        return self._ptrs[0] is not None or self.count == 0
+
+    def rows_numpy(self):
+        """(keys, outer_vals, inner_vals) as host uint32 arrays (copies)."""
+        n = self.count
+        if n == 0:
+            return tuple(np.empty(0, np.uint32) for _ in range(3))
+        if self._ptrs[0] is None:
+            raise HjbError("join ran with materialize=0")
+        if self.rows_on_device:
+            import torch
+            return tuple(torch.as_tensor(_CudaArray(p, n), device=f"cuda:{self._engine.device}").cpu().numpy()
+                         .view(np.uint32).copy() for p in self._ptrs)
+        return tuple(np.ctypeslib.as_array((C.c_uint32 * n).from_address(p)).copy() for p in self._ptrs)
+
+    def rows_torch(self):
+        """(keys, outer_vals, inner_vals) as int32 CUDA tensors aliasing the engine's buffers
+        (valid until the next join on the engine)."""
+        import torch
+        if not self.rows_on_device:
+            raise HjbError("rows are in host memory")
+        n = self.count
+        dev = f"cuda:{self._engine.device}"
+        if n == 0:
+            return tuple(torch.empty(0, dtype=torch.int32, device=dev) for _ in range(3))
+        return tuple(torch.as_tensor(_CudaArray(p, n), device=dev) for p in self._ptrs)
+
+
+def _is_torch(x):
+    return type(x).__module__.startswith("torch")
+
+
+def _col(x):
+    """-> (pointer, tuples, on_device, keepalive)"""
+    if _is_torch(x):
+        assert x.dim() == 1 and x.is_contiguous() and x.element_size() == 4, "columns are contiguous 1-D 32-bit"
+        return x.data_ptr(), x.numel(), x.is_cuda, x
+    a = np.ascontiguousarray(x)
+    assert a.ndim == 1 and a.dtype.itemsize == 4, "columns are 1-D 32-bit"
+    return a.ctypes.data, a.size, False, a
+
+
+class Engine:
+    """One GPU: wraps hjb_ctx.  Raises if libhjb200.so or a CUDA device is missing."""
+
+    def __init__(self, device=0, use_torch_stream=False):
+        self._lib = _lib.load()
+        self.device = int(device)
+        self._ctx = C.c_void_p()
+        rc = self._lib.hjb_create(self.device, C.byref(self._ctx))
+        if rc != 0:
+            msg = self._lib.hjb_last_error(None).decode()
+            self._ctx = None
+            raise HjbError(f"hjb_create({device}) failed ({rc}): {msg}")
+        if use_torch_stream:
+            import torch
+            self.set_stream(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def close(self):
+        if getattr(self, "_ctx", None):
+            self._lib.hjb_destroy(self._ctx)
+            self._ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def _check(self, rc, what):
+        if rc != 0:
+            raise HjbError(f"{what} failed ({rc}): {self._lib.hjb_last_error(self._ctx).decode()}")
+
+    def set_stream(self, cuda_stream):
+        self._check(self._lib.hjb_set_stream(self._ctx, C.c_void_p(int(cuda_stream))), "hjb_set_stream")
+
+    def synchronize(self):
+        self._check(self._lib.hjb_synchronize(self._ctx), "hjb_synchronize")
+
+    def set_profiling(self, on=True):
+        self._check(self._lib.hjb_set_profiling(self._ctx, int(on)), "hjb_set_profiling")
+
+    def kernel_times(self):
+        """{kernel name: (total ms, launches)} of the last whole join (needs set_profiling(True))."""
+        ms = (C.c_float * 16)()
+        n = (C.c_uint32 * 16)()
+        kinds = self._lib.hjb_kernel_times(self._ctx, ms, n, 16)
+        return {self._lib.hjb_kernel_name(k).decode(): (float(ms[k]), int(n[k])) for k in range(kinds)}
+
+    @staticmethod
+    def _opts(materialize=True, seed=0, npj_load=0.0, radix_bits=(), part_tuples=0, out_capacity=0):
+        o = Opts()
+        o.materialize, o.seed, o.npj_load = int(bool(materialize)), int(seed), float(npj_load)
+        for i, b in enumerate(radix_bits):
+            o.radix_bits[i] = int(b)
+        o.part_tuples, o.out_capacity = int(part_tuples), int(out_capacity)
+        return o
+
+    def _rels(self, inner, outer):
+        keep = []
+        rels = []
+        dev = None
+        for keys, vals in (inner, outer):
+            kp, kn, kd, ka = _col(keys)
+            vp, vn, vd, va = _col(vals)
+            if kn != vn:
+                raise HjbError("key and payload columns differ in length")
+            if kd != vd or (dev is not None and dev != kd):
+                raise HjbError("all four columns must live on the same side (host or device)")
+            dev = kd
+            keep += [ka, va]
+            rels.append(Rel(kp if kn else None, vp if kn else None, kn))
+        return rels[0], rels[1], dev, keep
+
+    def _join(self, algo, inner, outer, opts):
+        R, S, on_dev, keep = self._rels(inner, outer)
+        fn = getattr(self._lib, f"hjb_{algo}_{'device' if on_dev else 'host'}")
+        res = Result()
+        o = self._opts(**opts)
+        self._check(fn(self._ctx, C.byref(R), C.byref(S), C.byref(o), C.byref(res)), fn.__name__)
+        del keep
+        return JoinResult(res, self)
+
+    def npj(self, inner, outer, **opts):
+        """Non-partitioned join (npj.cpp).  inner / outer = (keys, vals), both numpy (host entry
+        point, copies in and out) or both CUDA tensors (device entry point)."""
+        return self._join("npj", inner, outer, opts)
+
+    def phj(self, inner, outer, **opts):
+        """Radix-partitioned join (phj.cpp)."""
+        return self._join("phj", inner, outer, opts)
+
+    # ---- CPRA pieces (cpra2.cpp:1697-1986); hash_join_codes_knl_b200.cpra strings them together
+    def cpra_split(self, inner_chunk, outer_chunk, ngpus, **opts):
+        R, S, on_dev, keep = self._rels(inner_chunk, outer_chunk)
+        if not on_dev:
+            raise HjbError("cpra_split takes device columns")
+        sp = Split()
+        o = self._opts(**opts)
+        self._check(self._lib.hjb_cpra_split(self._ctx, C.byref(R), C.byref(S), int(ngpus), C.byref(o), C.byref(sp)),
+                    "hjb_cpra_split")
+        import torch
+        dev = f"cuda:{self.device}"
+
+        def view(p, n):
+            return torch.as_tensor(_CudaArray(p, n), device=dev) if n else torch.empty(0, dtype=torch.int32, device=dev)
+        return {"r_keys": view(sp.r_keys, R.tuples), "r_vals": view(sp.r_vals, R.tuples),
+                "s_keys": view(sp.s_keys, S.tuples), "s_vals": view(sp.s_vals, S.tuples),
+                "r_offsets": [int(sp.r_offsets[g]) for g in range(ngpus + 1)],
+                "s_offsets": [int(sp.s_offsets[g]) for g in range(ngpus + 1)], "ms": float(sp.ms), "_keep": keep}
+
+    def cpra_join_local(self, inner_recv, outer_recv, gpu, ngpus, **opts):
+        R, S, on_dev, keep = self._rels(inner_recv, outer_recv)
+        if not on_dev:
+            raise HjbError("cpra_join_local takes device columns")
+        res = Result()
+        o = self._opts(**opts)
+        self._check(self._lib.hjb_cpra_join_local(self._ctx, C.byref(R), C.byref(S), int(gpu), int(ngpus), C.byref(o),
+                                                  C.byref(res)), "hjb_cpra_join_local")
+        return JoinResult(res, self)
+
+    # ---- single kernels, for comparing intermediate products with the oracle
+    def hash_factor(self, seed, which):
+        return int(self._lib.hjb_hash_factor(int(seed), int(which)))
+
+    def histogram(self, keys_dev, factor, shift, bits):
+        kp, n, on_dev, _ = _col(keys_dev)
+        assert on_dev
+        counts = np.zeros(1 << bits, np.uint32)
+        self._check(self._lib.hjb_histogram(self._ctx, kp, n, counts.ctypes.data_as(_lib.u32p), int(factor), shift, bits),
+                    "hjb_histogram")
+        return counts
+
+    def partition_pass(self, keys_dev, vals_dev, factor, shift, bits, parent_offsets=None):
+        import torch
+        kp, n, on_dev, _ = _col(keys_dev)
+        vp, _, _, _ = _col(vals_dev)
+        assert on_dev
+        ko, vo = torch.empty_like(keys_dev), torch.empty_like(vals_dev)
+        child = np.zeros((1 << (shift + bits)) + 1, np.uint32)
+        par = None
+        if parent_offsets is not None:
+            par = np.ascontiguousarray(parent_offsets, dtype=np.uint32)
+        self._check(self._lib.hjb_partition_pass(self._ctx, kp, vp, n,
+                                                 par.ctypes.data_as(_lib.u32p) if par is not None else None,
+                                                 ko.data_ptr(), vo.data_ptr(), child.ctypes.data_as(_lib.u32p),
+                                                 int(factor), shift, bits), "hjb_partition_pass")
+        return ko, vo, child
+
+    def npj_build(self, keys_dev, vals_dev, buckets, factor):
+        import torch
+        kp, n, on_dev, _ = _col(keys_dev)
+        vp, _, _, _ = _col(vals_dev)
+        assert on_dev
+        table = torch.empty(buckets * 4, dtype=torch.int64, device=keys_dev.device)
+        self._check(self._lib.hjb_npj_build(self._ctx, kp, vp, n, table.data_ptr(), int(buckets), int(factor)),
+                    "hjb_npj_build")
+        return table
+
+    def generate(self, kind, tuples, domain, seed, order_seed, payload_factor, first=0, total=None, theta=1.0,
+                 selectivity=1.0):
+        """Device generator (csrc/gen.cu).  Returns (keys, vals) int32 CUDA tensors."""
+        import torch
+        dev = f"cuda:{self.device}"
+        keys = torch.empty(tuples, dtype=torch.int32, device=dev)
+        vals = torch.empty(tuples, dtype=torch.int32, device=dev)
+        g = Gen(int(kind), int(tuples), int(domain), int(first), int(total if total is not None else tuples),
+                int(seed), int(order_seed), int(payload_factor), 0, float(theta), float(selectivity))
+        self._check(self._lib.hjb_generate(self._ctx, C.byref(g), keys.data_ptr(), vals.data_ptr()), "hjb_generate")
+        self.synchronize()
+        return keys, vals
+
+    def column_sum(self, col_dev):
+        p, n, on_dev, _ = _col(col_dev)
+        assert on_dev
+        s = C.c_uint64()
+        self._check(self._lib.hjb_column_sum(self._ctx, p, n, C.byref(s)), "hjb_column_sum")
+        return int(s.value)
+
+
+def relation_write(directory, outer, keys, vals):
+    """write.cpp:1824-1865 format: <dir>/{i|o}k_<n>.txt and {i|o}v_<n>.txt, raw uint32."""
+    k = np.ascontiguousarray(keys).view(np.uint32)
+    v = np.ascontiguousarray(vals).view(np.uint32)
+    rc = _lib.load().hjb_relation_write(str(directory).encode(), int(bool(outer)), k.size,
+                                        k.ctypes.data_as(_lib.u32p), v.ctypes.data_as(_lib.u32p))
+    if rc != 0:
+        raise HjbError(f"hjb_relation_write failed ({rc})")
+
+
+def relation_read(directory, outer, tuples):
+    k, v = np.empty(tuples, np.uint32), np.empty(tuples, np.uint32)
+    rc = _lib.load().hjb_relation_read(str(directory).encode(), int(bool(outer)), tuples,
+                                       k.ctypes.data_as(_lib.u32p), v.ctypes.data_as(_lib.u32p))
+    if rc != 0:
+        raise HjbError(f"hjb_relation_read failed ({rc}): missing file or size != 4*tuples")
+    return k, v

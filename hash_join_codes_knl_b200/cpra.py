@@ -1,0 +1,82 @@
+"""CPRA across GPUs: the reference's chunk-local partitioning + per-owner gather
+(cpra2.cpp:1783-1827 local passes, :1868-1906 / :1940-1959 the `memcpy` gather timed as
+"copy:") with threads replaced by GPUs -- one process per GPU, torch.distributed for the
+plumbing.
+
+  1. split     GPU g radix-partitions ITS chunk of R and S by owner = top log2(G) bits of
+               key*factor (Engine.cpra_split, kernels of csrc/radix.cu)
+  2. exchange  per-owner counts (all_to_all of G int64), then one variable-size all-to-all per
+               column over NVLink (NCCL); this replaces the reference's remote memcpy gather
+  3. join      every GPU joins what it received with the PHJ kernels below the owner bits
+               (Engine.cpra_join_local)
+  4. reduce    count and the three checksums are summed over ranks (all_reduce)
+
+`split_fn` / `join_fn` are injectable so the exchange logic can be exercised on CPU tensors
+with the gloo backend (tests/test_cpra_gloo.py); the product path always passes an Engine."""
+import torch
+import torch.distributed as dist
+
+
+def exchange_columns(columns, offsets, group=None):
+    """All-to-all of tuple columns grouped by owner.
+
+    columns: list of 1-D tensors of equal length, rows [offsets[g], offsets[g+1]) go to rank g.
+    Returns (received columns, recv_counts)."""
+    world = dist.get_world_size(group)
+    dev = columns[0].device
+    send_counts = torch.tensor([offsets[g + 1] - offsets[g] for g in range(world)], dtype=torch.int64, device=dev)
+    recv_counts = torch.empty(world, dtype=torch.int64, device=dev)
+    dist.all_to_all_single(recv_counts, send_counts, group=group)
+    send_list = [int(x) for x in send_counts.tolist()]
+    recv_list = [int(x) for x in recv_counts.tolist()]
+    total = sum(recv_list)
+    out = []
+    for col in columns:
+        recv = torch.empty(total, dtype=col.dtype, device=dev)
+        dist.all_to_all_single(recv, col, output_split_sizes=recv_list, input_split_sizes=send_list, group=group)
+        out.append(recv)
+    return out, recv_list
+
+
+def reduce_checks(count, sum_key, sum_outer, sum_inner, device, group=None):
+    """Sum (count, 3 checksums) over ranks with uint64 wrap-around (int64 adds have the same bits)."""
+    def to_i64(x):
+        x &= (1 << 64) - 1
+        return x - (1 << 64) if x >= (1 << 63) else x
+    t = torch.tensor([to_i64(count), to_i64(sum_key), to_i64(sum_outer), to_i64(sum_inner)], dtype=torch.int64,
+                     device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+    return tuple(int(x) & ((1 << 64) - 1) for x in t.tolist())
+
+
+def cpra_join(engine, inner_chunk, outer_chunk, group=None, split_fn=None, join_fn=None, **opts):
+    """Joins the union of all ranks' chunks.  Returns a dict with the GLOBAL count / checksums,
+    this rank's JoinResult (`local`: its share of the rows stays on its GPU, like the per-thread
+    output blocks of the reference) and per-step device times in ms."""
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    split_fn = split_fn or (lambda r, s, g: engine.cpra_split(r, s, g, **opts))
+    join_fn = join_fn or (lambda r, s, me, g: engine.cpra_join_local(r, s, me, g, **opts))
+    sp = split_fn(inner_chunk, outer_chunk, world)
+    dev = sp["r_keys"].device
+    use_events = dev.type == "cuda"
+    if use_events:
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+        ev[0].record()
+    if world == 1:
+        rk, rv, sk, sv = sp["r_keys"], sp["r_vals"], sp["s_keys"], sp["s_vals"]
+    else:
+        (rk, rv), _ = exchange_columns([sp["r_keys"], sp["r_vals"]], sp["r_offsets"], group)
+        (sk, sv), _ = exchange_columns([sp["s_keys"], sp["s_vals"]], sp["s_offsets"], group)
+    exchange_ms = 0.0
+    if use_events:
+        ev[1].record()
+        torch.cuda.current_stream(dev).synchronize()
+        exchange_ms = ev[0].elapsed_time(ev[1])
+    local = join_fn((rk, rv), (sk, sv), rank, world)
+    count, sum_key, sum_outer, sum_inner = reduce_checks(local.count, local.sum_key, local.sum_outer,
+                                                         local.sum_inner, dev, group)
+    return {"count": count, "sum_key": sum_key, "sum_outer": sum_outer, "sum_inner": sum_inner, "local": local,
+            "split_ms": float(sp.get("ms", 0.0)), "exchange_ms": exchange_ms,
+            "join_ms": float(getattr(local, "seconds", 0.0)) * 1e3,
+            "recv_tuples": (int(rk.numel()), int(sk.numel()))}

@@ -1,0 +1,877 @@
+// capi.cu -- the extern "C" boundary (include/hjb200.h): context, workspace, and the host-side
+// orchestration that replaces main() + run()/run_hj() of the reference (npj.cpp:769-1125,
+// phj.cpp:1646-2231, cpra2.cpp:1697-2231): plan, launch the kernels on one stream, read back
+// the count and checksums.  No CPU join path exists here.
+#include "hj_internal.h"
+#include <chrono>
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+using namespace hjb;
+
+struct hjb_ctx {
+	int device, sms;
+	cudaStream_t stream;
+	bool own_stream;
+	char err[512];
+	char *ws;                 // workspace arena (partition buffers, tables, scratch)
+	size_t ws_bytes;
+	uint32_t *out_cols;       // 3 result columns, out_cap rows each
+	uint64_t out_cap;
+	char *in_buf;             // device copies of host inputs (hjb_*_host)
+	size_t in_bytes;
+	uint32_t *h_rows;         // pinned host result rows (hjb_*_host)
+	uint64_t h_rows_cap;
+	char *split_buf;          // CPRA send buffers
+	size_t split_bytes;
+	unsigned long long *d_scalars, *h_scalars;   // 16 each; h_ pinned
+	uint32_t *h_small;        // pinned, 256 uint32
+	cudaEvent_t ev[12];
+	uint32_t launches;
+	KernelTimer timer;        // per-kernel times of the last join (hjb_set_profiling)
+};
+
+static char g_create_err[512];
+
+#define CK(call)                                                                                   \
+	do {                                                                                           \
+		cudaError_t e_ = (call);                                                                   \
+		if (e_ != cudaSuccess) {                                                                   \
+			snprintf(ctx->err, sizeof ctx->err, "%s:%d %s: %s", __FILE__, __LINE__, #call,         \
+			         cudaGetErrorString(e_));                                                      \
+			return e_ == cudaErrorMemoryAllocation ? HJB_E_NOMEM : HJB_E_CUDA;                     \
+		}                                                                                          \
+	} while (0)
+
+static int fail(hjb_ctx *ctx, int code, const char *msg)
+{
+	if (ctx) snprintf(ctx->err, sizeof ctx->err, "%s", msg);
+	return code;
+}
+
+static double wall_now()
+{
+	return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+extern "C" int hjb_version(void) { return HJB_VERSION; }
+
+extern "C" const char *hjb_last_error(const hjb_ctx *ctx) { return ctx ? ctx->err : g_create_err; }
+
+extern "C" int hjb_create(int device, hjb_ctx **out)
+{
+	if (!out) return HJB_E_INVALID;
+	*out = nullptr;
+	int ndev = 0;
+	cudaError_t e = cudaGetDeviceCount(&ndev);
+	if (e != cudaSuccess || ndev == 0) {
+		snprintf(g_create_err, sizeof g_create_err, "no CUDA device (%s): libhjb200 has no CPU fallback",
+		         e != cudaSuccess ? cudaGetErrorString(e) : "device count 0");
+		return HJB_E_NODEVICE;
+	}
+	if (device < 0 || device >= ndev) {
+		snprintf(g_create_err, sizeof g_create_err, "device %d out of range [0,%d)", device, ndev);
+		return HJB_E_INVALID;
+	}
+	hjb_ctx *ctx = (hjb_ctx *)calloc(1, sizeof(hjb_ctx));
+	if (!ctx) return HJB_E_NOMEM;
+	ctx->device = device;
+	cudaDeviceProp prop;
+	if (cudaSetDevice(device) != cudaSuccess || cudaGetDeviceProperties(&prop, device) != cudaSuccess) {
+		snprintf(g_create_err, sizeof g_create_err, "cannot open device %d", device);
+		free(ctx);
+		return HJB_E_CUDA;
+	}
+	if (prop.major < 10) {
+		snprintf(g_create_err, sizeof g_create_err, "device %d is sm_%d%d; libhjb200 is built for sm_100a only", device,
+		         prop.major, prop.minor);
+		free(ctx);
+		return HJB_E_NODEVICE;
+	}
+	ctx->sms = prop.multiProcessorCount;
+	bool ok = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) == cudaSuccess;
+	ctx->own_stream = true;
+	ok = ok && cudaMalloc(&ctx->d_scalars, 16 * 8) == cudaSuccess;
+	ok = ok && cudaHostAlloc(&ctx->h_scalars, 16 * 8, cudaHostAllocDefault) == cudaSuccess;
+	ok = ok && cudaHostAlloc(&ctx->h_small, 256 * 4, cudaHostAllocDefault) == cudaSuccess;
+	for (int i = 0; ok && i < 12; ++i) ok = cudaEventCreate(&ctx->ev[i]) == cudaSuccess;
+	for (int i = 0; ok && i < KernelTimer::kMaxLaunches; ++i)
+		ok = cudaEventCreate(&ctx->timer.beg[i]) == cudaSuccess && cudaEventCreate(&ctx->timer.end[i]) == cudaSuccess;
+	if (!ok) {
+		snprintf(g_create_err, sizeof g_create_err, "context setup failed: %s", cudaGetErrorString(cudaGetLastError()));
+		free(ctx);
+		return HJB_E_CUDA;
+	}
+	*out = ctx;
+	return HJB_OK;
+}
+
+extern "C" int hjb_destroy(hjb_ctx *ctx)
+{
+	if (!ctx) return HJB_E_INVALID;
+	cudaSetDevice(ctx->device);
+	cudaStreamSynchronize(ctx->stream);
+	cudaFree(ctx->ws);
+	cudaFree(ctx->out_cols);
+	cudaFree(ctx->in_buf);
+	cudaFree(ctx->split_buf);
+	cudaFree(ctx->d_scalars);
+	cudaFreeHost(ctx->h_scalars);
+	cudaFreeHost(ctx->h_small);
+	cudaFreeHost(ctx->h_rows);
+	for (int i = 0; i < 12; ++i) cudaEventDestroy(ctx->ev[i]);
+	for (int i = 0; i < KernelTimer::kMaxLaunches; ++i) {
+		cudaEventDestroy(ctx->timer.beg[i]);
+		cudaEventDestroy(ctx->timer.end[i]);
+	}
+	if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+	free(ctx);
+	return HJB_OK;
+}
+
+extern "C" int hjb_set_stream(hjb_ctx *ctx, void *cuda_stream)
+{
+	if (!ctx) return HJB_E_INVALID;
+	cudaSetDevice(ctx->device);
+	cudaStreamSynchronize(ctx->stream);
+	if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+	ctx->stream = (cudaStream_t)cuda_stream;
+	ctx->own_stream = false;
+	return HJB_OK;
+}
+
+extern "C" int hjb_synchronize(hjb_ctx *ctx)
+{
+	if (!ctx) return HJB_E_INVALID;
+	CK(cudaSetDevice(ctx->device));
+	CK(cudaStreamSynchronize(ctx->stream));
+	return HJB_OK;
+}
+
+// ------------------------------------------------------------------ buffers
+
+static int grow_device(hjb_ctx *ctx, char **buf, size_t *have, size_t need)
+{
+	if (need <= *have) return HJB_OK;
+	CK(cudaStreamSynchronize(ctx->stream));
+	if (*buf) CK(cudaFree(*buf));
+	*buf = nullptr;
+	*have = 0;
+	need = (need + ((size_t)1 << 21) - 1) & ~(((size_t)1 << 21) - 1);
+	CK(cudaMalloc(buf, need));
+	*have = need;
+	return HJB_OK;
+}
+
+static int grow_out(hjb_ctx *ctx, uint64_t rows)
+{
+	if (rows <= ctx->out_cap) return HJB_OK;
+	size_t have = (size_t)ctx->out_cap * 12;
+	char *p = (char *)ctx->out_cols;
+	rows = (rows + 1023) & ~1023ull;
+	int rc = grow_device(ctx, &p, &have, (size_t)rows * 12);
+	ctx->out_cols = (uint32_t *)p;
+	ctx->out_cap = rc == HJB_OK ? have / 12 : 0;
+	return rc;
+}
+
+struct Bump {
+	char *base;
+	size_t off;
+	template <typename T>
+	T *take(size_t count)
+	{
+		T *p = reinterpret_cast<T *>(base + off);
+		off += (count * sizeof(T) + 255) & ~(size_t)255;
+		return p;
+	}
+};
+static size_t pad256(size_t b) { return (b + 255) & ~(size_t)255; }
+
+static int check_rel(hjb_ctx *ctx, const hjb_rel *r, bool device_cols)
+{
+	if (!r) return fail(ctx, HJB_E_INVALID, "null relation");
+	if (r->tuples > 0xFFFFFFFFull) return fail(ctx, HJB_E_INVALID, "more than 2^32-1 tuples per relation per GPU");
+	if (r->tuples && (!r->keys || !r->vals)) return fail(ctx, HJB_E_INVALID, "null column");
+	if (device_cols && r->tuples && ((((uintptr_t)r->keys) | ((uintptr_t)r->vals)) & 15))
+		return fail(ctx, HJB_E_INVALID, "device columns must be 16-byte aligned");
+	return HJB_OK;
+}
+
+static const hjb_opts kDefaultOpts = {1, 0, 0.0, {0, 0, 0, 0}, 0, 0, {0}};
+
+extern "C" uint32_t hjb_hash_factor(uint32_t seed, int which)
+{
+	// odd multipliers; distinct per stage so that the table hash is independent of the radix digits
+	static const uint32_t base[4] = {0x9E3779B1u, 0x85EBCA6Bu, 0xC2B2AE35u, 0x27D4EB2Fu};
+	uint32_t x = base[which & 3];
+	if (seed) {
+		x ^= seed * 0x01000193u;
+		x ^= x >> 15;
+		x *= 0x2C1B3C6Du;
+		x ^= x >> 12;
+	}
+	return x | 1u;
+}
+
+static void zero_result(hjb_result *out)
+{
+	memset(out, 0, sizeof *out);
+}
+
+static void timer_reset(hjb_ctx *ctx)
+{
+	ctx->timer.n = 0;
+	memset(ctx->timer.ms, 0, sizeof ctx->timer.ms);
+	memset(ctx->timer.launches, 0, sizeof ctx->timer.launches);
+}
+
+// after a stream synchronize: fold the recorded event pairs into per-kernel totals
+static void timer_collect(hjb_ctx *ctx)
+{
+	KernelTimer &t = ctx->timer;
+	for (int i = 0; i < t.n; ++i) {
+		float ms = 0;
+		if (cudaEventElapsedTime(&ms, t.beg[i], t.end[i]) == cudaSuccess) {
+			t.ms[t.kind[i]] += ms;
+			t.launches[t.kind[i]] += 1;
+		}
+	}
+	t.n = 0;
+}
+
+extern "C" int hjb_set_profiling(hjb_ctx *ctx, int on)
+{
+	if (!ctx) return HJB_E_INVALID;
+	ctx->timer.enabled = on != 0;
+	timer_reset(ctx);
+	return HJB_OK;
+}
+
+extern "C" const char *hjb_kernel_name(int kind)
+{
+	static const char *names[KK_COUNT] = {"k_make_items", "k_hist", "k_scan", "k_scatter", "k_join_tasks",
+	                                      "k_partition_join", "k_npj_build", "k_npj_probe"};
+	return kind >= 0 && kind < KK_COUNT ? names[kind] : nullptr;
+}
+
+extern "C" int hjb_kernel_times(hjb_ctx *ctx, float *ms, uint32_t *launches, int max_kinds)
+{
+	if (!ctx || !ms || !launches) return HJB_E_INVALID;
+	for (int k = 0; k < max_kinds && k < KK_COUNT; ++k) {
+		ms[k] = ctx->timer.ms[k];
+		launches[k] = ctx->timer.launches[k];
+	}
+	return KK_COUNT;
+}
+
+static int read_scalars(hjb_ctx *ctx, hjb_result *out)
+{
+	CK(cudaMemcpyAsync(ctx->h_scalars, ctx->d_scalars, 16 * 8, cudaMemcpyDeviceToHost, ctx->stream));
+	CK(cudaStreamSynchronize(ctx->stream));
+	timer_collect(ctx);
+	out->count = ctx->h_scalars[1];
+	out->sum_key = ctx->h_scalars[2];
+	out->sum_outer = ctx->h_scalars[3];
+	out->sum_inner = ctx->h_scalars[4];
+	return HJB_OK;
+}
+
+static void set_rows(hjb_ctx *ctx, hjb_result *out, int materialize)
+{
+	if (materialize) {
+		out->keys = ctx->out_cols;
+		out->outer_vals = ctx->out_cols + ctx->out_cap;
+		out->inner_vals = ctx->out_cols + 2 * ctx->out_cap;
+		out->rows_on_device = 1;
+	}
+}
+
+// ------------------------------------------------------------------ NPJ
+
+static int npj_device(hjb_ctx *ctx, const hjb_rel *R, const hjb_rel *S, const hjb_opts *o, hjb_result *out)
+{
+	int rc;
+	if ((rc = check_rel(ctx, R, true)) || (rc = check_rel(ctx, S, true))) return rc;
+	zero_result(out);
+	CK(cudaSetDevice(ctx->device));
+	timer_reset(ctx);
+	if (R->tuples == 0 || S->tuples == 0) return HJB_OK;
+	const double load = o->npj_load > 0.0 ? o->npj_load : 0.5;
+	if (load > 0.95) return fail(ctx, HJB_E_INVALID, "npj_load must be <= 0.95");
+	uint64_t buckets = (uint64_t)ceil((double)R->tuples / load / 4.0) + 1;       // +1: at least one empty slot
+	if (buckets > 0xFFFFFFFFull) return fail(ctx, HJB_E_INVALID, "table too large");
+	if ((rc = grow_device(ctx, &ctx->ws, &ctx->ws_bytes, buckets * 32))) return rc;
+	uint64_t cap = 0;
+	if (o->materialize) {
+		cap = o->out_capacity ? o->out_capacity : (S->tuples > R->tuples ? S->tuples : R->tuples);
+		if ((rc = grow_out(ctx, cap))) return rc;
+	}
+	NpjArgs a;
+	a.rk = R->keys; a.rv = R->vals; a.sk = S->keys; a.sv = S->vals;
+	a.nr = R->tuples; a.ns = S->tuples;
+	a.table = (uint64_t *)ctx->ws;
+	a.buckets = buckets;
+	a.factor = hjb_hash_factor(o->seed, 1);
+	a.scalars = ctx->d_scalars;
+	a.materialize = o->materialize;
+	cudaStream_t s = ctx->stream;
+	uint32_t launches = 0;
+	for (int attempt = 0; attempt < 2; ++attempt) {
+		a.out_k = ctx->out_cols;
+		a.out_o = ctx->out_cols + ctx->out_cap;
+		a.out_i = ctx->out_cols + 2 * ctx->out_cap;
+		a.out_cap = o->materialize ? ctx->out_cap : 0;
+		CK(cudaEventRecord(ctx->ev[0], s));
+		CK(cudaMemsetAsync(ctx->d_scalars, 0, 16 * 8, s));
+		launches += launch_npj_build(a, s, ctx->sms, &ctx->timer);
+		CK(cudaEventRecord(ctx->ev[1], s));
+		launches += launch_npj_probe(a, s, ctx->sms, &ctx->timer);
+		CK(cudaEventRecord(ctx->ev[2], s));
+		CK(cudaGetLastError());
+		if ((rc = read_scalars(ctx, out))) return rc;
+		if (!o->materialize || out->count <= ctx->out_cap) break;
+		if (attempt == 1) return fail(ctx, HJB_E_CUDA, "result overflow after regrow");
+		if ((rc = grow_out(ctx, out->count))) return rc;       // duplicates: more rows than max(|R|,|S|)
+	}
+	float ms = 0;
+	CK(cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[2]));
+	out->seconds = ms * 1e-3;
+	CK(cudaEventElapsedTime(&out->phase_ms[1], ctx->ev[0], ctx->ev[1]));   // table init + build
+	CK(cudaEventElapsedTime(&out->phase_ms[2], ctx->ev[1], ctx->ev[2]));   // probe
+	out->kernel_launches = launches;
+	out->partitions = (uint32_t)buckets;
+	set_rows(ctx, out, o->materialize);
+	ctx->launches += launches;
+	return HJB_OK;
+}
+
+extern "C" int hjb_npj_device(hjb_ctx *ctx, const hjb_rel *R, const hjb_rel *S, const hjb_opts *opts, hjb_result *out)
+{
+	if (!ctx || !out) return HJB_E_INVALID;
+	return npj_device(ctx, R, S, opts ? opts : &kDefaultOpts, out);
+}
+
+// ------------------------------------------------------------------ PHJ / CPRA local join
+
+struct Plan {
+	int npass;
+	int bits[kMaxPasses];
+	int total_bits;
+};
+
+// Reference planner (phj.cpp:1791-1808): partitions = tuples / hash_table_limit, 1-4 passes of
+// equal fan-out.  Here: enough bits that a build partition averages part_tuples (a quarter of
+// the shared-memory table), passes of at most 8 bits (256-way scatter keeps per-digit runs long).
+static int make_plan(hjb_ctx *ctx, uint64_t nr, const hjb_opts *o, int consumed, Plan *p)
+{
+	memset(p, 0, sizeof *p);
+	int user = 0;
+	for (int i = 0; i < kMaxPasses; ++i) user += o->radix_bits[i] != 0;
+	if (user) {
+		for (int i = 0; i < kMaxPasses && o->radix_bits[i]; ++i) {
+			if (o->radix_bits[i] < 1 || o->radix_bits[i] > kMaxRadixBits)
+				return fail(ctx, HJB_E_INVALID, "radix_bits must be in [1,11]");
+			p->bits[p->npass++] = o->radix_bits[i];
+			p->total_bits += o->radix_bits[i];
+		}
+	} else {
+		const uint32_t target = o->part_tuples ? o->part_tuples : kDefaultPartTuples;
+		int tb = 0;
+		while (tb < 28 && (nr >> tb) > target) ++tb;
+		p->total_bits = tb;
+		p->npass = (tb + 7) / 8;
+		for (int i = 0; i < p->npass; ++i) p->bits[i] = tb / p->npass + (i < tb % p->npass ? 1 : 0);
+	}
+	if (consumed + p->total_bits > 32) return fail(ctx, HJB_E_INVALID, "more than 32 radix bits");
+	if (p->total_bits > 22) return fail(ctx, HJB_E_INVALID, "more than 2^22 partitions");
+	return HJB_OK;
+}
+
+static size_t phj_workspace(uint64_t nr, uint64_t ns, const Plan &p, size_t *radix_scratch)
+{
+	size_t total = 0;
+	const int nb = p.npass >= 2 ? 2 : p.npass;
+	total += (size_t)nb * 2 * (pad256(nr * 4) + pad256(ns * 4));
+	const uint32_t P = 1u << p.total_bits;
+	total += 4 * pad256(((size_t)P + 1) * 4);          // r_off / s_off, two generations each
+	total += pad256(((size_t)P + 1) * 4) + 256;        // task prefix + counter
+	size_t rs = 0;
+	uint32_t np = 1;
+	for (int i = 0; i < p.npass; ++i) {
+		uint32_t chunk, mi, tiles;
+		size_t a = radix_scratch_bytes(nr, np, p.bits[i], &chunk, &mi, &tiles);
+		size_t b = radix_scratch_bytes(ns, np, p.bits[i], &chunk, &mi, &tiles);
+		if (a > rs) rs = a;
+		if (b > rs) rs = b;
+		np <<= p.bits[i];
+	}
+	*radix_scratch = rs;
+	return total + rs + 4096;
+}
+
+struct Partitioned {
+	const uint32_t *k, *v;
+	const uint32_t *off;
+};
+
+// all passes over one relation; ping-pongs between two workspace buffers
+static int partition_relation(hjb_ctx *ctx, const hjb_rel *rel, const Plan &p, int consumed, uint32_t factor,
+                              uint32_t *bufk[2], uint32_t *bufv[2], uint32_t *off[2], char *scratch,
+                              Partitioned *res, uint32_t *launches)
+{
+	const uint32_t *ink = rel->keys, *inv = rel->vals;
+	const uint32_t *parent = nullptr;
+	uint32_t np = 1;
+	int used = consumed;
+	for (int i = 0; i < p.npass; ++i) {
+		RadixPassArgs a;
+		a.keys = ink; a.vals = inv;
+		a.keys_out = bufk[i & 1]; a.vals_out = bufv[i & 1];
+		a.n = rel->tuples;
+		a.np = np;
+		a.parent_off = parent;
+		a.child_off = off[i & 1];
+		a.factor = factor;
+		a.bits = p.bits[i];
+		a.rshift = 32 - used - p.bits[i];
+		uint32_t tiles;
+		radix_scratch_bytes(a.n, np, a.bits, &a.chunk, &a.max_items, &tiles);
+		Bump b = {scratch, 0};
+		a.item_prefix = b.take<uint32_t>(np + 1);
+		a.counts = b.take<uint32_t>((size_t)a.max_items << a.bits);
+		a.scan_status = b.take<uint64_t>(tiles);
+		a.scan_counter = b.take<uint32_t>(1);
+		*launches += launch_radix_pass(a, ctx->stream, ctx->sms, &ctx->timer);
+		ink = a.keys_out; inv = a.vals_out;
+		parent = a.child_off;
+		np <<= a.bits;
+		used += a.bits;
+	}
+	res->k = ink; res->v = inv; res->off = parent;
+	return HJB_OK;
+}
+
+static int phj_device(hjb_ctx *ctx, const hjb_rel *R, const hjb_rel *S, const hjb_opts *o, int consumed,
+                      hjb_result *out)
+{
+	int rc;
+	if ((rc = check_rel(ctx, R, true)) || (rc = check_rel(ctx, S, true))) return rc;
+	zero_result(out);
+	CK(cudaSetDevice(ctx->device));
+	timer_reset(ctx);
+	if (R->tuples == 0 || S->tuples == 0) return HJB_OK;
+	Plan plan;
+	if ((rc = make_plan(ctx, R->tuples, o, consumed, &plan))) return rc;
+	size_t rscratch;
+	const size_t need = phj_workspace(R->tuples, S->tuples, plan, &rscratch);
+	if ((rc = grow_device(ctx, &ctx->ws, &ctx->ws_bytes, need))) return rc;
+	uint64_t cap = 0;
+	if (o->materialize) {
+		cap = o->out_capacity ? o->out_capacity : (S->tuples > R->tuples ? S->tuples : R->tuples);
+		if ((rc = grow_out(ctx, cap))) return rc;
+	}
+	const uint32_t P = 1u << plan.total_bits;
+	Bump b = {ctx->ws, 0};
+	uint32_t *rbk[2] = {nullptr, nullptr}, *rbv[2] = {nullptr, nullptr}, *sbk[2] = {nullptr, nullptr}, *sbv[2] = {nullptr, nullptr};
+	const int nb = plan.npass >= 2 ? 2 : plan.npass;
+	for (int i = 0; i < nb; ++i) {
+		rbk[i] = b.take<uint32_t>(R->tuples); rbv[i] = b.take<uint32_t>(R->tuples);
+		sbk[i] = b.take<uint32_t>(S->tuples); sbv[i] = b.take<uint32_t>(S->tuples);
+	}
+	uint32_t *roff[2] = {b.take<uint32_t>(P + 1), b.take<uint32_t>(P + 1)};
+	uint32_t *soff[2] = {b.take<uint32_t>(P + 1), b.take<uint32_t>(P + 1)};
+	uint32_t *task_prefix = b.take<uint32_t>(P + 1);
+	uint32_t *task_counter = b.take<uint32_t>(1);
+	char *scratch = b.take<char>(rscratch);
+	cudaStream_t s = ctx->stream;
+	uint32_t launches = 0;
+	const uint32_t radix_factor = hjb_hash_factor(o->seed, 0);
+	CK(cudaEventRecord(ctx->ev[0], s));
+	CK(cudaMemsetAsync(ctx->d_scalars, 0, 16 * 8, s));
+	Partitioned pr, ps;
+	if (plan.npass == 0) {
+		// build side fits one table fill or two: single partition, no scatter
+		ctx->h_small[0] = 0; ctx->h_small[1] = (uint32_t)R->tuples;
+		ctx->h_small[2] = 0; ctx->h_small[3] = (uint32_t)S->tuples;
+		CK(cudaMemcpyAsync(roff[0], &ctx->h_small[0], 8, cudaMemcpyHostToDevice, s));
+		CK(cudaMemcpyAsync(soff[0], &ctx->h_small[2], 8, cudaMemcpyHostToDevice, s));
+		pr.k = R->keys; pr.v = R->vals; pr.off = roff[0];
+		ps.k = S->keys; ps.v = S->vals; ps.off = soff[0];
+	} else {
+		if ((rc = partition_relation(ctx, R, plan, consumed, radix_factor, rbk, rbv, roff, scratch, &pr, &launches))) return rc;
+		CK(cudaEventRecord(ctx->ev[1], s));
+		if ((rc = partition_relation(ctx, S, plan, consumed, radix_factor, sbk, sbv, soff, scratch, &ps, &launches))) return rc;
+	}
+	CK(cudaEventRecord(ctx->ev[2], s));
+	JoinArgs j;
+	j.rk = pr.k; j.rv = pr.v; j.sk = ps.k; j.sv = ps.v;
+	j.r_off = pr.off; j.s_off = ps.off;
+	j.P = P;
+	j.table_factor = hjb_hash_factor(o->seed, 1);
+	j.task_prefix = task_prefix;
+	j.task_counter = task_counter;
+	j.s_task = 16384;
+	j.scalars = ctx->d_scalars;
+	j.materialize = o->materialize;
+	for (int attempt = 0; attempt < 2; ++attempt) {
+		j.out_k = ctx->out_cols;
+		j.out_o = ctx->out_cols + ctx->out_cap;
+		j.out_i = ctx->out_cols + 2 * ctx->out_cap;
+		j.out_cap = o->materialize ? ctx->out_cap : 0;
+		launches += launch_partition_join(j, s, ctx->sms, &ctx->timer);
+		CK(cudaEventRecord(ctx->ev[3], s));
+		CK(cudaGetLastError());
+		if ((rc = read_scalars(ctx, out))) return rc;
+		if (!o->materialize || out->count <= ctx->out_cap) break;
+		if (attempt == 1) return fail(ctx, HJB_E_CUDA, "result overflow after regrow");
+		if ((rc = grow_out(ctx, out->count))) return rc;
+		CK(cudaMemsetAsync(ctx->d_scalars, 0, 16 * 8, s));         // rerun the join phase only
+	}
+	float ms = 0;
+	CK(cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[3]));
+	out->seconds = ms * 1e-3;
+	if (plan.npass) {
+		CK(cudaEventElapsedTime(&out->phase_ms[0], ctx->ev[0], ctx->ev[1]));   // all passes over R
+		CK(cudaEventElapsedTime(&out->phase_ms[1], ctx->ev[1], ctx->ev[2]));   // all passes over S
+	}
+	CK(cudaEventElapsedTime(&out->phase_ms[4], ctx->ev[2], ctx->ev[3]));       // join
+	out->kernel_launches = launches;
+	out->partitions = P;
+	set_rows(ctx, out, o->materialize);
+	ctx->launches += launches;
+	return HJB_OK;
+}
+
+extern "C" int hjb_phj_device(hjb_ctx *ctx, const hjb_rel *R, const hjb_rel *S, const hjb_opts *opts, hjb_result *out)
+{
+	if (!ctx || !out) return HJB_E_INVALID;
+	return phj_device(ctx, R, S, opts ? opts : &kDefaultOpts, 0, out);
+}
+
+// ------------------------------------------------------------------ host entry points
+
+typedef int (*device_join_fn)(hjb_ctx *, const hjb_rel *, const hjb_rel *, const hjb_opts *, hjb_result *);
+
+static int phj_device0(hjb_ctx *ctx, const hjb_rel *R, const hjb_rel *S, const hjb_opts *o, hjb_result *out)
+{
+	return phj_device(ctx, R, S, o, 0, out);
+}
+
+static int host_join(hjb_ctx *ctx, device_join_fn fn, const hjb_rel *R, const hjb_rel *S, const hjb_opts *o,
+                     hjb_result *out)
+{
+	int rc;
+	if ((rc = check_rel(ctx, R, false)) || (rc = check_rel(ctx, S, false))) return rc;
+	CK(cudaSetDevice(ctx->device));
+	const double t0 = wall_now();
+	const size_t rb = pad256(R->tuples * 4), sb = pad256(S->tuples * 4);
+	if ((rc = grow_device(ctx, &ctx->in_buf, &ctx->in_bytes, 2 * rb + 2 * sb + 256))) return rc;
+	cudaStream_t s = ctx->stream;
+	uint32_t *drk = (uint32_t *)ctx->in_buf, *drv = (uint32_t *)(ctx->in_buf + rb);
+	uint32_t *dsk = (uint32_t *)(ctx->in_buf + 2 * rb), *dsv = (uint32_t *)(ctx->in_buf + 2 * rb + sb);
+	CK(cudaEventRecord(ctx->ev[8], s));
+	if (R->tuples) {
+		CK(cudaMemcpyAsync(drk, R->keys, R->tuples * 4, cudaMemcpyHostToDevice, s));
+		CK(cudaMemcpyAsync(drv, R->vals, R->tuples * 4, cudaMemcpyHostToDevice, s));
+	}
+	if (S->tuples) {
+		CK(cudaMemcpyAsync(dsk, S->keys, S->tuples * 4, cudaMemcpyHostToDevice, s));
+		CK(cudaMemcpyAsync(dsv, S->vals, S->tuples * 4, cudaMemcpyHostToDevice, s));
+	}
+	CK(cudaEventRecord(ctx->ev[9], s));
+	hjb_rel dR = {drk, drv, R->tuples}, dS = {dsk, dsv, S->tuples};
+	if ((rc = fn(ctx, &dR, &dS, o, out))) return rc;
+	float h2d = 0, d2h = 0;
+	if (o->materialize && out->count) {
+		if (out->count > ctx->h_rows_cap) {
+			if (ctx->h_rows) CK(cudaFreeHost(ctx->h_rows));
+			ctx->h_rows = nullptr;
+			ctx->h_rows_cap = 0;
+			const uint64_t rows = (out->count + 4095) & ~4095ull;
+			CK(cudaHostAlloc(&ctx->h_rows, (size_t)rows * 12, cudaHostAllocDefault));
+			ctx->h_rows_cap = rows;
+		}
+		CK(cudaEventRecord(ctx->ev[10], s));
+		const uint32_t *cols[3] = {out->keys, out->outer_vals, out->inner_vals};
+		for (int c = 0; c < 3; ++c)
+			CK(cudaMemcpyAsync(ctx->h_rows + (size_t)c * ctx->h_rows_cap, cols[c], out->count * 4,
+			                   cudaMemcpyDeviceToHost, s));
+		CK(cudaEventRecord(ctx->ev[11], s));
+		CK(cudaStreamSynchronize(s));
+		CK(cudaEventElapsedTime(&d2h, ctx->ev[10], ctx->ev[11]));
+		out->keys = ctx->h_rows;
+		out->outer_vals = ctx->h_rows + ctx->h_rows_cap;
+		out->inner_vals = ctx->h_rows + 2 * ctx->h_rows_cap;
+	} else {
+		out->keys = out->outer_vals = out->inner_vals = nullptr;
+	}
+	out->rows_on_device = 0;
+	CK(cudaEventElapsedTime(&h2d, ctx->ev[8], ctx->ev[9]));
+	out->phase_ms[5] = h2d;
+	out->phase_ms[6] = d2h;
+	out->seconds_e2e = wall_now() - t0;
+	return HJB_OK;
+}
+
+extern "C" int hjb_npj_host(hjb_ctx *ctx, const hjb_rel *R, const hjb_rel *S, const hjb_opts *opts, hjb_result *out)
+{
+	if (!ctx || !out) return HJB_E_INVALID;
+	return host_join(ctx, npj_device, R, S, opts ? opts : &kDefaultOpts, out);
+}
+
+extern "C" int hjb_phj_host(hjb_ctx *ctx, const hjb_rel *R, const hjb_rel *S, const hjb_opts *opts, hjb_result *out)
+{
+	if (!ctx || !out) return HJB_E_INVALID;
+	return host_join(ctx, phj_device0, R, S, opts ? opts : &kDefaultOpts, out);
+}
+
+// ------------------------------------------------------------------ CPRA
+
+static int log2_exact(int x)
+{
+	int b = 0;
+	while ((1 << b) < x) ++b;
+	return (1 << b) == x ? b : -1;
+}
+
+extern "C" int hjb_cpra_split(hjb_ctx *ctx, const hjb_rel *R, const hjb_rel *S, int ngpus, const hjb_opts *opts,
+                              hjb_split *out)
+{
+	if (!ctx || !out) return HJB_E_INVALID;
+	const hjb_opts *o = opts ? opts : &kDefaultOpts;
+	int rc;
+	if ((rc = check_rel(ctx, R, true)) || (rc = check_rel(ctx, S, true))) return rc;
+	const int gbits = log2_exact(ngpus);
+	if (gbits < 0 || ngpus > 64) return fail(ctx, HJB_E_INVALID, "ngpus must be a power of two <= 64");
+	memset(out, 0, sizeof *out);
+	CK(cudaSetDevice(ctx->device));
+	if (ngpus == 1) {          // one owner: nothing to split (CPRA on one thread partitions only locally)
+		out->r_keys = R->keys; out->r_vals = R->vals; out->s_keys = S->keys; out->s_vals = S->vals;
+		out->r_offsets[1] = R->tuples; out->s_offsets[1] = S->tuples;
+		return HJB_OK;
+	}
+	const size_t rb = pad256(R->tuples * 4), sb = pad256(S->tuples * 4), ob = pad256((size_t)(ngpus + 1) * 4);
+	uint32_t chunk, mi, tiles;
+	size_t rs = radix_scratch_bytes(R->tuples, 1, gbits, &chunk, &mi, &tiles);
+	const size_t rs2 = radix_scratch_bytes(S->tuples, 1, gbits, &chunk, &mi, &tiles);
+	if (rs2 > rs) rs = rs2;
+	if ((rc = grow_device(ctx, &ctx->split_buf, &ctx->split_bytes, 2 * rb + 2 * sb + 2 * ob + 256))) return rc;
+	if ((rc = grow_device(ctx, &ctx->ws, &ctx->ws_bytes, rs + 4096))) return rc;
+	Bump b = {ctx->split_buf, 0};
+	uint32_t *ok[2] = {b.take<uint32_t>(R->tuples), b.take<uint32_t>(S->tuples)};
+	uint32_t *ov[2] = {b.take<uint32_t>(R->tuples), b.take<uint32_t>(S->tuples)};
+	uint32_t *off[2] = {b.take<uint32_t>(ngpus + 1), b.take<uint32_t>(ngpus + 1)};
+	cudaStream_t s = ctx->stream;
+	const hjb_rel *rel[2] = {R, S};
+	uint32_t launches = 0;
+	CK(cudaEventRecord(ctx->ev[4], s));
+	for (int r = 0; r < 2; ++r) {
+		if (rel[r]->tuples == 0) {
+			CK(cudaMemsetAsync(off[r], 0, (size_t)(ngpus + 1) * 4, s));
+			continue;
+		}
+		RadixPassArgs a;
+		a.keys = rel[r]->keys; a.vals = rel[r]->vals;
+		a.keys_out = ok[r]; a.vals_out = ov[r];
+		a.n = rel[r]->tuples;
+		a.np = 1;
+		a.parent_off = nullptr;
+		a.child_off = off[r];
+		a.factor = hjb_hash_factor(o->seed, 0);
+		a.bits = gbits;
+		a.rshift = 32 - gbits;
+		radix_scratch_bytes(a.n, 1, gbits, &a.chunk, &a.max_items, &tiles);
+		Bump w = {ctx->ws, 0};
+		a.item_prefix = w.take<uint32_t>(2);
+		a.counts = w.take<uint32_t>((size_t)a.max_items << gbits);
+		a.scan_status = w.take<uint64_t>(tiles);
+		a.scan_counter = w.take<uint32_t>(1);
+		launches += launch_radix_pass(a, s, ctx->sms);
+	}
+	CK(cudaEventRecord(ctx->ev[5], s));
+	CK(cudaMemcpyAsync(&ctx->h_small[0], off[0], (size_t)(ngpus + 1) * 4, cudaMemcpyDeviceToHost, s));
+	CK(cudaMemcpyAsync(&ctx->h_small[128], off[1], (size_t)(ngpus + 1) * 4, cudaMemcpyDeviceToHost, s));
+	CK(cudaStreamSynchronize(s));
+	CK(cudaGetLastError());
+	for (int g = 0; g <= ngpus; ++g) {
+		out->r_offsets[g] = ctx->h_small[g];
+		out->s_offsets[g] = ctx->h_small[128 + g];
+	}
+	out->r_keys = ok[0]; out->r_vals = ov[0]; out->s_keys = ok[1]; out->s_vals = ov[1];
+	CK(cudaEventElapsedTime(&out->ms, ctx->ev[4], ctx->ev[5]));
+	ctx->launches += launches;
+	return HJB_OK;
+}
+
+extern "C" int hjb_cpra_join_local(hjb_ctx *ctx, const hjb_rel *R, const hjb_rel *S, int gpu, int ngpus,
+                                   const hjb_opts *opts, hjb_result *out)
+{
+	if (!ctx || !out) return HJB_E_INVALID;
+	const int gbits = log2_exact(ngpus);
+	if (gbits < 0 || ngpus > 64 || gpu < 0 || gpu >= ngpus) return fail(ctx, HJB_E_INVALID, "bad gpu / ngpus");
+	return phj_device(ctx, R, S, opts ? opts : &kDefaultOpts, gbits, out);
+}
+
+// ------------------------------------------------------------------ kernel-level entry points
+
+extern "C" int hjb_histogram(hjb_ctx *ctx, const uint32_t *keys, uint64_t size, uint32_t *counts, uint32_t factor,
+                             int shift, int bits)
+{
+	if (!ctx || !counts || bits < 1 || bits > kMaxRadixBits || shift < 0 || shift + bits > 32)
+		return fail(ctx, HJB_E_INVALID, "bad histogram arguments");
+	if (size && (!keys || ((uintptr_t)keys & 15))) return fail(ctx, HJB_E_INVALID, "keys must be a 16-byte aligned device column");
+	CK(cudaSetDevice(ctx->device));
+	const uint32_t F = 1u << bits;
+	int rc;
+	if ((rc = grow_device(ctx, &ctx->ws, &ctx->ws_bytes, (size_t)F * 4 + 256))) return rc;
+	ctx->launches += launch_histogram_only(keys, size, (uint32_t *)ctx->ws, factor, 32 - shift - bits, bits, ctx->stream, ctx->sms);
+	CK(cudaMemcpyAsync(counts, ctx->ws, (size_t)F * 4, cudaMemcpyDeviceToHost, ctx->stream));
+	CK(cudaStreamSynchronize(ctx->stream));
+	CK(cudaGetLastError());
+	return HJB_OK;
+}
+
+extern "C" int hjb_partition_pass(hjb_ctx *ctx, const uint32_t *keys, const uint32_t *vals, uint64_t size,
+                                  const uint32_t *parent_offsets, uint32_t *keys_out, uint32_t *vals_out,
+                                  uint32_t *child_offsets, uint32_t factor, int shift, int bits)
+{
+	if (!ctx || !child_offsets || bits < 1 || bits > kMaxRadixBits || shift < 0 || shift + bits > 22)
+		return fail(ctx, HJB_E_INVALID, "bad partition arguments");
+	if (size > 0xFFFFFFFFull) return fail(ctx, HJB_E_INVALID, "more than 2^32-1 tuples");
+	if (size && (!keys || !vals || !keys_out || !vals_out)) return fail(ctx, HJB_E_INVALID, "null column");
+	if ((((uintptr_t)keys) | ((uintptr_t)vals)) & 15) return fail(ctx, HJB_E_INVALID, "columns must be 16-byte aligned");
+	if (shift > 0 && !parent_offsets) return fail(ctx, HJB_E_INVALID, "parent_offsets required when shift > 0");
+	CK(cudaSetDevice(ctx->device));
+	const uint32_t np = 1u << shift, nc = np << bits;
+	uint32_t chunk, mi, tiles;
+	const size_t rs = radix_scratch_bytes(size, np, bits, &chunk, &mi, &tiles);
+	int rc;
+	if ((rc = grow_device(ctx, &ctx->ws, &ctx->ws_bytes, rs + pad256(((size_t)np + 1) * 4) + pad256(((size_t)nc + 1) * 4) + 4096))) return rc;
+	Bump b = {ctx->ws, 0};
+	uint32_t *d_parent = b.take<uint32_t>(np + 1);
+	uint32_t *d_child = b.take<uint32_t>(nc + 1);
+	cudaStream_t s = ctx->stream;
+	if (size == 0) {
+		memset(child_offsets, 0, ((size_t)nc + 1) * 4);
+		return HJB_OK;
+	}
+	if (shift > 0) CK(cudaMemcpyAsync(d_parent, parent_offsets, ((size_t)np + 1) * 4, cudaMemcpyHostToDevice, s));
+	RadixPassArgs a;
+	a.keys = keys; a.vals = vals; a.keys_out = keys_out; a.vals_out = vals_out;
+	a.n = size;
+	a.np = np;
+	a.parent_off = shift > 0 ? d_parent : nullptr;
+	a.child_off = d_child;
+	a.factor = factor;
+	a.bits = bits;
+	a.rshift = 32 - shift - bits;
+	a.chunk = chunk;
+	a.max_items = mi;
+	a.item_prefix = b.take<uint32_t>(np + 1);
+	a.counts = b.take<uint32_t>((size_t)mi << bits);
+	a.scan_status = b.take<uint64_t>(tiles);
+	a.scan_counter = b.take<uint32_t>(1);
+	ctx->launches += launch_radix_pass(a, s, ctx->sms);
+	CK(cudaMemcpyAsync(child_offsets, d_child, ((size_t)nc + 1) * 4, cudaMemcpyDeviceToHost, s));
+	CK(cudaStreamSynchronize(s));
+	CK(cudaGetLastError());
+	return HJB_OK;
+}
+
+extern "C" int hjb_npj_build(hjb_ctx *ctx, const uint32_t *keys, const uint32_t *vals, uint64_t size, uint64_t *table,
+                             uint64_t buckets, uint32_t factor)
+{
+	if (!ctx || !table || buckets == 0 || buckets > 0xFFFFFFFFull || size >= buckets * 4)
+		return fail(ctx, HJB_E_INVALID, "bad build arguments (need size < 4*buckets)");
+	if (size && (!keys || !vals || ((((uintptr_t)keys) | ((uintptr_t)vals)) & 15)))
+		return fail(ctx, HJB_E_INVALID, "columns must be 16-byte aligned device memory");
+	CK(cudaSetDevice(ctx->device));
+	NpjArgs a;
+	memset(&a, 0, sizeof a);
+	a.rk = keys; a.rv = vals; a.nr = size;
+	a.table = table; a.buckets = buckets; a.factor = factor;
+	a.scalars = ctx->d_scalars;
+	CK(cudaMemsetAsync(ctx->d_scalars, 0, 16 * 8, ctx->stream));
+	ctx->launches += launch_npj_build(a, ctx->stream, ctx->sms);
+	CK(cudaStreamSynchronize(ctx->stream));
+	CK(cudaGetLastError());
+	return HJB_OK;
+}
+
+// ------------------------------------------------------------------ generator, checksums, files
+
+extern "C" int hjb_generate(hjb_ctx *ctx, const hjb_gen *g, uint32_t *keys_dev, uint32_t *vals_dev)
+{
+	if (!ctx || !g) return HJB_E_INVALID;
+	if (g->tuples && (!keys_dev || !vals_dev)) return fail(ctx, HJB_E_INVALID, "null column");
+	if (g->kind < 0 || g->kind > 2) return fail(ctx, HJB_E_INVALID, "kind must be 0, 1 or 2");
+	if (g->total == 0 || g->first + g->tuples > g->total) return fail(ctx, HJB_E_INVALID, "first + tuples exceeds total");
+	if (g->domain == 0 || g->domain > 0xFFFFFFFEull) return fail(ctx, HJB_E_INVALID, "domain must be in [1, 2^32-2]");
+	if (g->kind == 0 && g->total > 0xFFFFFFFEull) return fail(ctx, HJB_E_INVALID, "at most 2^32-2 unique keys");
+	if (g->kind == 2 && (g->selectivity < 0.0 || g->selectivity > 1.0 || g->theta < 0.0))
+		return fail(ctx, HJB_E_INVALID, "bad theta / selectivity");
+	CK(cudaSetDevice(ctx->device));
+	ctx->launches += launch_generate(*g, keys_dev, vals_dev, ctx->stream);
+	CK(cudaGetLastError());
+	return HJB_OK;
+}
+
+extern "C" int hjb_column_sum(hjb_ctx *ctx, const uint32_t *col_dev, uint64_t size, uint64_t *sum)
+{
+	if (!ctx || !sum || (size && !col_dev)) return HJB_E_INVALID;
+	CK(cudaSetDevice(ctx->device));
+	ctx->launches += launch_column_sum(col_dev, size, ctx->d_scalars + 8, ctx->stream, ctx->sms);
+	CK(cudaMemcpyAsync(ctx->h_scalars + 8, ctx->d_scalars + 8, 8, cudaMemcpyDeviceToHost, ctx->stream));
+	CK(cudaStreamSynchronize(ctx->stream));
+	CK(cudaGetLastError());
+	*sum = ctx->h_scalars[8];
+	return HJB_OK;
+}
+
+static int rel_path(char *buf, size_t cap, const char *dir, int outer, char col, uint64_t n)
+{
+	const int w = snprintf(buf, cap, "%s/%c%c_%llu.txt", dir && *dir ? dir : ".", outer ? 'o' : 'i', col,
+	                       (unsigned long long)n);
+	return w > 0 && (size_t)w < cap ? 0 : 1;
+}
+
+extern "C" int hjb_relation_write(const char *dir, int outer, uint64_t tuples, const uint32_t *keys, const uint32_t *vals)
+{
+	if (tuples && (!keys || !vals)) return HJB_E_INVALID;
+	char path[4096];
+	const uint32_t *cols[2] = {keys, vals};
+	const char names[2] = {'k', 'v'};
+	for (int c = 0; c < 2; ++c) {
+		if (rel_path(path, sizeof path, dir, outer, names[c], tuples)) return HJB_E_INVALID;
+		FILE *f = fopen(path, "wb");
+		if (!f) return HJB_E_IO;
+		const size_t w = fwrite(cols[c], 4, tuples, f);
+		if (fclose(f) != 0 || w != tuples) return HJB_E_IO;
+	}
+	return HJB_OK;
+}
+
+extern "C" int hjb_relation_read(const char *dir, int outer, uint64_t tuples, uint32_t *keys, uint32_t *vals)
+{
+	if (tuples && (!keys || !vals)) return HJB_E_INVALID;
+	char path[4096];
+	uint32_t *cols[2] = {keys, vals};
+	const char names[2] = {'k', 'v'};
+	for (int c = 0; c < 2; ++c) {
+		if (rel_path(path, sizeof path, dir, outer, names[c], tuples)) return HJB_E_INVALID;
+		FILE *f = fopen(path, "rb");
+		if (!f) return HJB_E_IO;
+		// the reference never checks fopen/fread (npj.cpp:1031-1039); a short or long file is an error here
+		fseek(f, 0, SEEK_END);
+		const long long bytes = ftell(f);
+		fseek(f, 0, SEEK_SET);
+		size_t r = 0;
+		if (bytes == (long long)(tuples * 4)) r = fread(cols[c], 4, tuples, f);
+		fclose(f);
+		if (bytes != (long long)(tuples * 4) || r != tuples) return HJB_E_IO;
+	}
+	return HJB_OK;
+}

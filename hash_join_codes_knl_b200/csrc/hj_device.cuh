@@ -1,0 +1,239 @@
+// hj_device.cuh -- device-side helpers shared by every kernel of libhjb200 (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace hjb {
+
+constexpr uint64_t kEmptySlot = 0xFFFFFFFFFFFFFFFFull;   // all-ones: cudaMemset(0xFF) initialises a table
+constexpr uint32_t kSentinelKey = 0xFFFFFFFFu;           // the one (key, payload) pair equal to kEmptySlot
+constexpr unsigned kFullMask = 0xFFFFFFFFu;
+
+// multiplicative hash of the reference: x = (uint32)(key * factor); h(key, f, N) = (x * N) >> 32
+// (npj.cpp:200-201, simd_hash npj.cpp:90-106).  Radix digits are bit fields of the same x, i.e.
+// h(key, f, 2^B) for B consumed bits.
+__device__ __forceinline__ uint32_t hash_mul(uint32_t key, uint32_t factor) { return key * factor; }
+__device__ __forceinline__ uint32_t hash_range(uint32_t key, uint32_t factor, uint32_t n)
+{
+	return __umulhi(key * factor, n);
+}
+// digit = bits [rshift, rshift + bits) of x; rshift = 32 - consumed - bits
+__device__ __forceinline__ uint32_t radix_digit(uint32_t x, int rshift, uint32_t mask)
+{
+	return (x >> rshift) & mask;
+}
+
+__device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31u; }
+__device__ __forceinline__ uint32_t lanemask_lt()
+{
+	uint32_t m;
+	asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
+	return m;
+}
+
+// streaming 128-bit load of read-once input columns (keeps L1 for tables / staging)
+__device__ __forceinline__ uint4 ldg_stream_u4(const uint4 *p)
+{
+	uint4 r;
+	asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
+	             : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+	return r;
+}
+__device__ __forceinline__ uint32_t ldg_stream_u32(const uint32_t *p)
+{
+	uint32_t r;
+	asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(r) : "l"(p));
+	return r;
+}
+// L2-coherent loads (bypass L1) for data other CTAs write during the same kernel
+__device__ __forceinline__ uint64_t ld_cg_u64(const uint64_t *p)
+{
+	uint64_t r;
+	asm volatile("ld.global.cg.u64 %0, [%1];" : "=l"(r) : "l"(p));
+	return r;
+}
+__device__ __forceinline__ uint64_t ld_volatile_u64(const uint64_t *p)
+{
+	uint64_t r;
+	asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(r) : "l"(p));
+	return r;
+}
+__device__ __forceinline__ void st_volatile_u64(uint64_t *p, uint64_t v)
+{
+	asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+__device__ __forceinline__ uint64_t warp_sum_u64(uint64_t v)
+{
+#pragma unroll
+	for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFullMask, v, o);
+	return v;
+}
+__device__ __forceinline__ uint32_t warp_inclusive_scan_u32(uint32_t v)
+{
+	const uint32_t lane = lane_id();
+#pragma unroll
+	for (int o = 1; o < 32; o <<= 1) {
+		uint32_t t = __shfl_up_sync(kFullMask, v, o);
+		if (lane >= (uint32_t)o) v += t;
+	}
+	return v;
+}
+
+// CTA-wide exclusive scan of one value per thread; `warp_totals` holds >= blockDim.x/32 + 1
+// uint32 of shared memory.  Returns the exclusive prefix; *total receives the CTA sum.
+// Ends with a __syncthreads(), so warp_totals may be reused right after.
+__device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t *warp_totals, uint32_t *total)
+{
+	const uint32_t lane = lane_id(), warp = threadIdx.x >> 5, nwarps = (blockDim.x + 31) >> 5;
+	uint32_t incl = warp_inclusive_scan_u32(v);
+	if (lane == 31) warp_totals[warp] = incl;
+	__syncthreads();
+	if (warp == 0) {
+		uint32_t w = lane < nwarps ? warp_totals[lane] : 0;
+		uint32_t wi = warp_inclusive_scan_u32(w);
+		if (lane < nwarps) warp_totals[lane] = wi - w;
+		if (lane == 31) warp_totals[nwarps] = wi;
+	}
+	__syncthreads();
+	uint32_t excl = warp_totals[warp] + incl - v;
+	*total = warp_totals[nwarps];
+	__syncthreads();
+	return excl;
+}
+
+// Per-thread running result statistics, folded into four global uint64 at kernel end.
+struct JoinSums {
+	uint64_t count, key, outer, inner;
+	__device__ __forceinline__ void zero() { count = key = outer = inner = 0; }
+	__device__ __forceinline__ void add(uint32_t k, uint32_t o, uint32_t i)
+	{
+		count += 1;
+		key += k;
+		outer += o;
+		inner += i;
+	}
+	// every thread of the CTA calls this; scratch: 4 * 32 uint64 of shared memory
+	__device__ __forceinline__ void reduce_to_global(unsigned long long *g /* [4] */, uint64_t *scratch)
+	{
+		const uint32_t lane = lane_id(), warp = threadIdx.x >> 5, nwarps = (blockDim.x + 31) >> 5;
+		uint64_t a = warp_sum_u64(count), b = warp_sum_u64(key), c = warp_sum_u64(outer), d = warp_sum_u64(inner);
+		__syncthreads();
+		if (lane == 0) {
+			scratch[warp * 4 + 0] = a;
+			scratch[warp * 4 + 1] = b;
+			scratch[warp * 4 + 2] = c;
+			scratch[warp * 4 + 3] = d;
+		}
+		__syncthreads();
+		if (threadIdx.x < 4) {
+			uint64_t s = 0;
+			for (uint32_t w = 0; w < nwarps; ++w) s += scratch[w * 4 + threadIdx.x];
+			if (s) atomicAdd(&g[threadIdx.x], (unsigned long long)s);
+		}
+	}
+};
+
+// Result rows staged in shared memory so that each CTA reserves output space with ONE
+// global atomic per flush and writes the three result columns coalesced (the reference's
+// 256-entry staging buffer + block allocator, npj.cpp:244-246,292-317).
+struct MatchStage {
+	uint32_t *k, *o, *i;     // shared memory, `cap` entries each
+	uint32_t *cnt;           // shared cursor (may run past cap: overflow)
+	uint32_t cap;
+
+	// warp-collective: all 32 lanes call it, converged.  Rows beyond cap are dropped (counted).
+	__device__ __forceinline__ void emit(bool hit, uint32_t key, uint32_t oval, uint32_t ival) const
+	{
+		const unsigned m = __ballot_sync(kFullMask, hit);
+		if (m == 0) return;
+		const int leader = __ffs(m) - 1;
+		uint32_t base = 0;
+		if ((int)lane_id() == leader) base = atomicAdd(cnt, (uint32_t)__popc(m));
+		base = __shfl_sync(kFullMask, base, leader);
+		if (hit) {
+			const uint32_t pos = base + __popc(m & lanemask_lt());
+			if (pos < cap) {
+				k[pos] = key;
+				o[pos] = oval;
+				i[pos] = ival;
+			}
+		}
+	}
+	// any single thread
+	__device__ __forceinline__ void emit_one(uint32_t key, uint32_t oval, uint32_t ival) const
+	{
+		const uint32_t pos = atomicAdd(cnt, 1u);
+		if (pos < cap) {
+			k[pos] = key;
+			o[pos] = oval;
+			i[pos] = ival;
+		}
+	}
+};
+
+struct OutCols {
+	uint32_t *k, *o, *i;          // global result columns
+	unsigned long long *cursor;   // global row cursor
+	uint64_t cap;                 // rows the columns can hold
+};
+
+// CTA-collective: copy the staged rows to the result columns.  Returns false (and writes
+// nothing) when the stage overflowed; the caller then re-probes in direct mode.  Leaves the
+// stage empty.  s_base: one uint64 of shared memory.
+__device__ __forceinline__ bool stage_flush(const MatchStage &st, const OutCols &out, unsigned long long *s_base)
+{
+	__syncthreads();
+	const uint32_t n = *st.cnt;
+	const bool ok = n <= st.cap;
+	if (ok && n) {
+		if (threadIdx.x == 0) *s_base = atomicAdd(out.cursor, (unsigned long long)n);
+		__syncthreads();
+		const uint64_t base = *s_base;
+		for (uint32_t j = threadIdx.x; j < n; j += blockDim.x) {
+			const uint64_t r = base + j;
+			if (r < out.cap) {
+				out.k[r] = st.k[j];
+				out.o[r] = st.o[j];
+				out.i[r] = st.i[j];
+			}
+		}
+	}
+	__syncthreads();
+	if (threadIdx.x == 0) *st.cnt = 0;
+	__syncthreads();
+	return ok;
+}
+
+// warp-collective direct emission (overflow path: duplicate-heavy build sides)
+__device__ __forceinline__ void emit_direct(const OutCols &out, bool hit, uint32_t key, uint32_t oval, uint32_t ival)
+{
+	const unsigned m = __ballot_sync(kFullMask, hit);
+	if (m == 0) return;
+	const int leader = __ffs(m) - 1;
+	unsigned long long base = 0;
+	if ((int)lane_id() == leader) base = atomicAdd(out.cursor, (unsigned long long)__popc(m));
+	base = __shfl_sync(kFullMask, base, leader);
+	if (hit) {
+		const uint64_t r = base + __popc(m & lanemask_lt());
+		if (r < out.cap) {
+			out.k[r] = key;
+			out.o[r] = oval;
+			out.i[r] = ival;
+		}
+	}
+}
+
+// largest q in [0, n) with a[q] <= x, for a non-decreasing a[0..n] with a[0] <= x < a[n]
+__device__ __forceinline__ uint32_t upper_parent(const uint32_t *a, uint32_t n, uint32_t x)
+{
+	uint32_t lo = 0, hi = n;
+	while (hi - lo > 1) {
+		const uint32_t mid = (lo + hi) >> 1;
+		if (a[mid] <= x) lo = mid;
+		else hi = mid;
+	}
+	return lo;
+}
+
+}  // namespace hjb

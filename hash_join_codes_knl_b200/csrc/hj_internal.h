@@ -1,0 +1,105 @@
+// hj_internal.h -- host-side declarations shared by the translation units of libhjb200.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stddef.h>
+#include "../../include/hjb200.h"
+
+namespace hjb {
+
+constexpr int kMaxPasses = 4;
+constexpr int kMaxRadixBits = 11;            // fan-out per pass <= 2048 (shared-memory counters)
+constexpr uint32_t kDefaultPartTuples = 2048; // planner: build tuples per final partition
+constexpr uint32_t kJoinSlots = 8192;         // shared-memory table slots per CTA (64 KB)
+constexpr uint32_t kJoinThreads = 256;
+constexpr uint32_t kJoinItems = 4;            // probe tuples per thread per sub-chunk
+constexpr uint32_t kStageCap = 2 * kJoinThreads * kJoinItems;
+constexpr uint32_t kScatterThreads = 512;
+constexpr uint32_t kScatterTile = kScatterThreads * 8;   // tuples staged per tile
+constexpr uint32_t kHistThreads = 512;
+constexpr uint32_t kScanThreads = 256;
+constexpr uint32_t kScanItems = 8;
+constexpr uint32_t kNpjThreads = 256;
+constexpr uint32_t kNpjItems = 4;
+
+// optional per-launch CUDA-event timing on the launching stream (bench.py's roofline line)
+enum KernelKind { KK_MAKE_ITEMS = 0, KK_HIST, KK_SCAN, KK_SCATTER, KK_JOIN_TASKS, KK_PART_JOIN, KK_NPJ_BUILD,
+                  KK_NPJ_PROBE, KK_COUNT };
+struct KernelTimer {
+	static constexpr int kMaxLaunches = 96;
+	cudaEvent_t beg[kMaxLaunches], end[kMaxLaunches];
+	int kind[kMaxLaunches];
+	int n;
+	bool enabled;
+	float ms[KK_COUNT];
+	uint32_t launches[KK_COUNT];
+	void start(int k, cudaStream_t s)
+	{
+		if (!enabled || n >= kMaxLaunches) return;
+		kind[n] = k;
+		cudaEventRecord(beg[n], s);
+	}
+	void stop(cudaStream_t s)
+	{
+		if (!enabled || n >= kMaxLaunches) return;
+		cudaEventRecord(end[n], s);
+		++n;
+	}
+};
+
+struct RadixPassArgs {
+	const uint32_t *keys, *vals;      // input columns (whole array, 16-byte aligned base)
+	uint32_t *keys_out, *vals_out;    // output columns
+	uint64_t n;                       // tuples in the array
+	uint32_t np;                      // parents
+	const uint32_t *parent_off;       // np + 1 entries, device; nullptr: one parent [0, n)
+	uint32_t *child_off;              // np * 2^bits + 1 entries, device
+	uint32_t factor;
+	int rshift, bits;                 // digit = (key*factor >> rshift) & (2^bits - 1)
+	uint32_t chunk;                   // tuples per work item
+	uint32_t max_items;               // upper bound n/chunk + np
+	// scratch (device)
+	uint32_t *item_prefix;            // np + 1
+	uint32_t *counts;                 // max_items * 2^bits  (histogram, then offsets in place)
+	uint64_t *scan_status;            // tiles
+	uint32_t *scan_counter;           // 1
+};
+size_t radix_scratch_bytes(uint64_t n, uint32_t np, int bits, uint32_t *chunk, uint32_t *max_items, uint32_t *tiles);
+// launches make_items + histogram + scan + scatter; returns kernels launched
+int launch_radix_pass(const RadixPassArgs &a, cudaStream_t s, int sms, KernelTimer *t = nullptr);
+int launch_histogram_only(const uint32_t *keys, uint64_t n, uint32_t *counts_dev, uint32_t factor,
+                          int rshift, int bits, cudaStream_t s, int sms);
+
+struct JoinArgs {
+	const uint32_t *rk, *rv, *sk, *sv;       // partitioned columns
+	const uint32_t *r_off, *s_off;           // P + 1 entries each
+	uint32_t P;
+	uint32_t table_factor;
+	uint32_t *task_prefix;                   // P + 1 scratch
+	uint32_t *task_counter;                  // 1, zeroed by the launcher
+	uint32_t s_task;                         // probe tuples per task
+	uint32_t *out_k, *out_o, *out_i;
+	uint64_t out_cap;
+	unsigned long long *scalars;             // [0] cursor, [1..4] count, sum_key, sum_outer, sum_inner
+	int materialize;
+};
+int launch_partition_join(const JoinArgs &a, cudaStream_t s, int sms, KernelTimer *t = nullptr);
+
+struct NpjArgs {
+	const uint32_t *rk, *rv, *sk, *sv;
+	uint64_t nr, ns;
+	uint64_t *table;
+	uint64_t buckets;                         // x 4 slots
+	uint32_t factor;
+	uint32_t *out_k, *out_o, *out_i;
+	uint64_t out_cap;
+	unsigned long long *scalars;              // [0] cursor, [1..4] sums, [5] sentinel build tuples
+	int materialize;
+};
+int launch_npj_build(const NpjArgs &a, cudaStream_t s, int sms, KernelTimer *t = nullptr);
+int launch_npj_probe(const NpjArgs &a, cudaStream_t s, int sms, KernelTimer *t = nullptr);
+
+int launch_generate(const hjb_gen &g, uint32_t *keys, uint32_t *vals, cudaStream_t s);
+int launch_column_sum(const uint32_t *col, uint64_t n, unsigned long long *out_dev, cudaStream_t s, int sms);
+
+}  // namespace hjb

@@ -1,0 +1,382 @@
+// radix.cu -- one radix-partitioning pass = four kernels on one stream:
+//   k_make_items : cut every parent partition into work items of <= chunk tuples
+//   k_hist       : per-item digit histogram in shared memory        (reference: histogram, cpra2.cpp:801-880)
+//   k_scan       : single-pass decoupled-look-back prefix sum over   (reference: interleave, phj.cpp:1263-1291)
+//                  the (parent, digit, item) ordered counts
+//   k_scatter    : tile-wise rank + shared-memory reorder + run-wise (reference: partition / partition_shared +
+//                  coalesced stores                                   flush, cpra2.cpp:882-1075, phj.cpp:877-1028)
+// The work item plays the role of the reference's thread: it owns a contiguous chunk of the
+// input, its counts row is the thread's counts[] and the scan hands it one start offset per
+// digit, so items never synchronise while scattering.
+#include "hj_device.cuh"
+#include "hj_internal.h"
+
+namespace hjb {
+
+// ------------------------------------------------------------------ work items
+
+__global__ void __launch_bounds__(1024)
+k_make_items(const uint32_t *__restrict__ parent_off, uint32_t np, uint64_t n, uint32_t chunk,
+             uint32_t *__restrict__ item_prefix, uint32_t *__restrict__ child_off, uint32_t child_total_idx)
+{
+	__shared__ uint32_t warp_totals[34];
+	const uint32_t per = (np + blockDim.x - 1) / blockDim.x;
+	const uint32_t q0 = threadIdx.x * per;
+	uint32_t local = 0;
+	for (uint32_t q = q0; q < q0 + per && q < np; ++q) {
+		const uint64_t size = parent_off ? (uint64_t)(parent_off[q + 1] - parent_off[q]) : n;
+		const uint32_t items = size ? (uint32_t)((size + chunk - 1) / chunk) : 1u;   // empty parents keep one (empty) item
+		local += items;
+	}
+	uint32_t total;
+	uint32_t run = block_exclusive_scan(local, warp_totals, &total);
+	for (uint32_t q = q0; q < q0 + per && q < np; ++q) {
+		const uint64_t size = parent_off ? (uint64_t)(parent_off[q + 1] - parent_off[q]) : n;
+		item_prefix[q] = run;
+		run += size ? (uint32_t)((size + chunk - 1) / chunk) : 1u;
+	}
+	if (threadIdx.x == 0) {
+		item_prefix[np] = total;
+		child_off[child_total_idx] = (uint32_t)n;       // end sentinel of the child offsets
+	}
+}
+
+struct ItemRange {
+	uint64_t beg, end;
+};
+
+__device__ __forceinline__ bool locate_item(const uint32_t *item_prefix, uint32_t np, const uint32_t *parent_off,
+                                            uint64_t n, uint32_t chunk, uint32_t item, ItemRange *r)
+{
+	if (item >= item_prefix[np]) return false;
+	const uint32_t q = upper_parent(item_prefix, np, item);
+	const uint32_t j = item - item_prefix[q];
+	const uint64_t pbeg = parent_off ? parent_off[q] : 0, pend = parent_off ? parent_off[q + 1] : n;
+	uint64_t beg = pbeg + (uint64_t)j * chunk;
+	if (beg > pend) beg = pend;
+	uint64_t end = beg + chunk;
+	if (end > pend) end = pend;
+	r->beg = beg;
+	r->end = end;
+	return true;
+}
+
+// Fetches the absolutely aligned group of four elements g (indices 4g .. 4g+3) of a column with
+// one 128-bit load, so that consecutive threads read consecutive 16-byte words whatever the
+// alignment of the range being processed; callers mask the ragged first / last group.
+// `n` is the column length: a vector load never crosses it.
+__device__ __forceinline__ void load_group4(const uint32_t *col, uint64_t g, uint64_t n, uint32_t (&out)[4])
+{
+	const uint64_t idx = g << 2;
+	if (idx + 3 < n) {
+		const uint4 w = ldg_stream_u4(reinterpret_cast<const uint4 *>(col) + g);
+		out[0] = w.x; out[1] = w.y; out[2] = w.z; out[3] = w.w;
+	} else {
+#pragma unroll
+		for (int e = 0; e < 4; ++e) out[e] = idx + e < n ? col[idx + e] : 0;
+	}
+}
+
+// ------------------------------------------------------------------ histogram
+
+__global__ void __launch_bounds__(kHistThreads)
+k_hist(const uint32_t *__restrict__ keys, uint64_t n, uint32_t np, const uint32_t *__restrict__ parent_off,
+       const uint32_t *__restrict__ item_prefix, uint32_t chunk, uint32_t factor, int rshift, int bits,
+       uint32_t *__restrict__ counts)
+{
+	extern __shared__ uint32_t s_hist[];
+	const uint32_t F = 1u << bits, mask = F - 1;
+	ItemRange r;
+	if (!locate_item(item_prefix, np, parent_off, n, chunk, blockIdx.x, &r)) return;
+	for (uint32_t p = threadIdx.x; p < F; p += blockDim.x) s_hist[p] = 0;
+	__syncthreads();
+	const uint64_t g_end = (r.end + 3) >> 2;
+	for (uint64_t g = (r.beg >> 2) + threadIdx.x; g < g_end; g += blockDim.x) {
+		uint32_t k[4];
+		load_group4(keys, g, n, k);
+#pragma unroll
+		for (int e = 0; e < 4; ++e) {
+			const uint64_t idx = (g << 2) + e;
+			if (idx >= r.beg && idx < r.end) atomicAdd(&s_hist[radix_digit(hash_mul(k[e], factor), rshift, mask)], 1u);
+		}
+	}
+	__syncthreads();
+	uint32_t *row = counts + (size_t)blockIdx.x * F;
+	for (uint32_t p = threadIdx.x; p < F; p += blockDim.x) row[p] = s_hist[p];
+}
+
+// whole-column histogram into one global counts[F] (public hjb_histogram)
+__global__ void __launch_bounds__(kHistThreads)
+k_hist_global(const uint32_t *__restrict__ keys, uint64_t n, uint32_t factor, int rshift, int bits,
+              uint32_t *__restrict__ counts)
+{
+	extern __shared__ uint32_t s_hist[];
+	const uint32_t F = 1u << bits, mask = F - 1;
+	for (uint32_t p = threadIdx.x; p < F; p += blockDim.x) s_hist[p] = 0;
+	__syncthreads();
+	const uint64_t groups = (n + 3) >> 2;
+	for (uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; g < groups; g += (uint64_t)gridDim.x * blockDim.x) {
+		uint32_t k[4];
+		load_group4(keys, g, n, k);
+#pragma unroll
+		for (int e = 0; e < 4; ++e)
+			if ((g << 2) + e < n) atomicAdd(&s_hist[radix_digit(hash_mul(k[e], factor), rshift, mask)], 1u);
+	}
+	__syncthreads();
+	for (uint32_t p = threadIdx.x; p < F; p += blockDim.x)
+		if (s_hist[p]) atomicAdd(&counts[p], s_hist[p]);
+}
+
+// ------------------------------------------------------------------ scan (decoupled look-back)
+
+constexpr uint64_t kFlagAggregate = 1ull << 62, kFlagInclusive = 2ull << 62, kFlagMask = 3ull << 62;
+
+// Exclusive prefix sum over the counts taken in (parent, digit, item) order: the value that
+// lands in counts[item][digit] is the absolute output position of that item's first tuple with
+// that digit.  One pass: each tile publishes its aggregate, then looks back over its
+// predecessors' status words until it meets an inclusive prefix (Merrill & Garland).
+__global__ void __launch_bounds__(kScanThreads)
+k_scan(const uint32_t *__restrict__ item_prefix, uint32_t np, int bits, uint32_t *__restrict__ counts,
+       uint32_t *__restrict__ child_off, uint64_t *__restrict__ status, uint32_t *__restrict__ tile_counter)
+{
+	__shared__ uint32_t warp_totals[34];
+	__shared__ uint32_t s_tile;
+	__shared__ uint32_t s_excl;
+	const uint32_t F = 1u << bits;
+	if (threadIdx.x == 0) s_tile = atomicAdd(tile_counter, 1u);   // tiles start in look-back order
+	__syncthreads();
+	const uint32_t tile = s_tile;
+	const uint64_t E = (uint64_t)item_prefix[np] * F;
+	const uint64_t tile_base = (uint64_t)tile * (kScanThreads * kScanItems);
+	if (tile_base >= E) return;
+
+	uint32_t addr[kScanItems], child[kScanItems], v[kScanItems];
+	uint64_t i = tile_base + (uint64_t)threadIdx.x * kScanItems;
+	uint32_t q = 0, nq = 1, p2 = 0, j = 0;
+	if (i < E) {
+		q = upper_parent(item_prefix, np, (uint32_t)(i >> bits));
+		nq = item_prefix[q + 1] - item_prefix[q];
+		const uint32_t local = (uint32_t)(i - (uint64_t)item_prefix[q] * F);
+		p2 = local / nq;
+		j = local - p2 * nq;
+	}
+	uint32_t sum = 0;
+#pragma unroll
+	for (uint32_t k = 0; k < kScanItems; ++k) {
+		v[k] = 0;
+		addr[k] = 0xFFFFFFFFu;
+		child[k] = 0xFFFFFFFFu;
+		if (i + k < E) {
+			addr[k] = (item_prefix[q] + j) * F + p2;
+			v[k] = counts[addr[k]];
+			if (j == 0) child[k] = q * F + p2;
+			sum += v[k];
+			if (++j == nq) {
+				j = 0;
+				if (++p2 == F) {
+					p2 = 0;
+					++q;
+					if (q < np) nq = item_prefix[q + 1] - item_prefix[q];
+				}
+			}
+		}
+	}
+	uint32_t block_total;
+	const uint32_t thread_excl = block_exclusive_scan(sum, warp_totals, &block_total);
+
+	if (threadIdx.x < 32) {
+		const uint32_t lane = threadIdx.x;
+		if (tile == 0) {
+			if (lane == 0) {
+				st_volatile_u64(&status[0], kFlagInclusive | block_total);
+				s_excl = 0;
+			}
+		} else {
+			if (lane == 0) st_volatile_u64(&status[tile], kFlagAggregate | block_total);
+			uint64_t excl = 0;
+			int look = (int)tile - 1;
+			while (true) {
+				const int idx = look - (int)lane;
+				uint64_t w = idx >= 0 ? ld_volatile_u64(&status[idx]) : kFlagInclusive;
+				while (__any_sync(kFullMask, (w & kFlagMask) == 0)) {
+					if ((w & kFlagMask) == 0) w = ld_volatile_u64(&status[idx]);
+				}
+				const unsigned incl = __ballot_sync(kFullMask, (w & kFlagMask) == kFlagInclusive);
+				uint64_t contrib = w & ~kFlagMask;
+				if (incl) {
+					const int first = __ffs(incl) - 1;     // nearest predecessor holding an inclusive prefix
+					if ((int)lane > first) contrib = 0;
+					excl += warp_sum_u64(contrib);
+					break;
+				}
+				excl += warp_sum_u64(contrib);
+				look -= 32;
+			}
+			if (lane == 0) {
+				st_volatile_u64(&status[tile], kFlagInclusive | (excl + block_total));
+				s_excl = (uint32_t)excl;
+			}
+		}
+	}
+	__syncthreads();
+	uint32_t run = s_excl + thread_excl;
+#pragma unroll
+	for (uint32_t k = 0; k < kScanItems; ++k) {
+		if (addr[k] != 0xFFFFFFFFu) {
+			counts[addr[k]] = run;
+			if (child[k] != 0xFFFFFFFFu) child_off[child[k]] = run;
+			run += v[k];
+		}
+	}
+}
+
+// ------------------------------------------------------------------ scatter
+
+// dynamic shared memory: cnt[F] base[F] delta[F] gpos[F] | buf[kScatterTile] (uint2)
+__global__ void __launch_bounds__(kScatterThreads)
+k_scatter(const uint32_t *__restrict__ keys, const uint32_t *__restrict__ vals, uint64_t n, uint32_t np,
+          const uint32_t *__restrict__ parent_off, const uint32_t *__restrict__ item_prefix, uint32_t chunk,
+          uint32_t factor, int rshift, int bits, const uint32_t *__restrict__ offsets,
+          uint32_t *__restrict__ keys_out, uint32_t *__restrict__ vals_out)
+{
+	extern __shared__ __align__(16) uint32_t s_mem[];
+	__shared__ uint32_t warp_totals[34];
+	const uint32_t F = 1u << bits, mask = F - 1;
+	uint32_t *cnt = s_mem, *base = cnt + F, *delta = base + F, *gpos = delta + F;
+	uint2 *buf = reinterpret_cast<uint2 *>(gpos + F);
+	ItemRange r;
+	if (!locate_item(item_prefix, np, parent_off, n, chunk, blockIdx.x, &r)) return;
+	const uint32_t *row = offsets + (size_t)blockIdx.x * F;
+	for (uint32_t p = threadIdx.x; p < F; p += blockDim.x) gpos[p] = row[p];
+	const uint32_t ept = (F + kScatterThreads - 1) / kScatterThreads;   // digits per thread in the tile scan
+	constexpr uint32_t kGroupsPerTile = kScatterTile / 4, kGroupsPerThread = kGroupsPerTile / kScatterThreads;
+	const uint64_t g_end = (r.end + 3) >> 2;
+	for (uint64_t g0 = r.beg >> 2; g0 < g_end; g0 += kGroupsPerTile) {
+		for (uint32_t p = threadIdx.x; p < F; p += blockDim.x) cnt[p] = 0;
+		__syncthreads();
+		uint32_t key[4 * kGroupsPerThread], val[4 * kGroupsPerThread], rank[4 * kGroupsPerThread];
+		bool ok[4 * kGroupsPerThread];
+#pragma unroll
+		for (uint32_t t = 0; t < kGroupsPerThread; ++t) {
+			const uint64_t g = g0 + threadIdx.x + (uint64_t)t * kScatterThreads;
+			uint32_t k4[4] = {0, 0, 0, 0}, v4[4] = {0, 0, 0, 0};
+			if (g < g_end) {
+				load_group4(keys, g, n, k4);
+				load_group4(vals, g, n, v4);
+			}
+#pragma unroll
+			for (int e = 0; e < 4; ++e) {
+				const uint64_t idx = (g << 2) + e;
+				key[4 * t + e] = k4[e];
+				val[4 * t + e] = v4[e];
+				ok[4 * t + e] = g < g_end && idx >= r.beg && idx < r.end;
+			}
+		}
+#pragma unroll
+		for (uint32_t t = 0; t < 4 * kGroupsPerThread; ++t)
+			if (ok[t]) rank[t] = atomicAdd(&cnt[radix_digit(hash_mul(key[t], factor), rshift, mask)], 1u);
+		__syncthreads();
+		// exclusive scan of cnt -> base; delta = global cursor - base; advance the cursor
+		uint32_t local = 0;
+		const uint32_t p0 = threadIdx.x * ept;
+		for (uint32_t p = p0; p < p0 + ept && p < F; ++p) local += cnt[p];
+		uint32_t tile_n;
+		uint32_t run = block_exclusive_scan(local, warp_totals, &tile_n);
+		for (uint32_t p = p0; p < p0 + ept && p < F; ++p) {
+			const uint32_t c = cnt[p];
+			base[p] = run;
+			delta[p] = gpos[p] - run;
+			gpos[p] += c;
+			run += c;
+		}
+		__syncthreads();
+#pragma unroll
+		for (uint32_t t = 0; t < 4 * kGroupsPerThread; ++t)
+			if (ok[t]) {
+				const uint32_t d = radix_digit(hash_mul(key[t], factor), rshift, mask);
+				buf[base[d] + rank[t]] = make_uint2(key[t], val[t]);
+			}
+		__syncthreads();
+		// the tile is now grouped by digit: neighbouring threads write neighbouring addresses of a run
+		for (uint32_t i = threadIdx.x; i < tile_n; i += kScatterThreads) {
+			const uint2 kv = buf[i];
+			const uint32_t dst = delta[radix_digit(hash_mul(kv.x, factor), rshift, mask)] + i;
+			keys_out[dst] = kv.x;
+			vals_out[dst] = kv.y;
+		}
+		__syncthreads();
+	}
+}
+
+// ------------------------------------------------------------------ host launchers
+
+size_t radix_scratch_bytes(uint64_t n, uint32_t np, int bits, uint32_t *chunk, uint32_t *max_items, uint32_t *tiles)
+{
+	// ~2K-4K items: enough to balance 148 SMs x several resident CTAs, few enough that the
+	// counts matrix stays small; chunk is a multiple of the scatter tile
+	uint64_t c = (n + 2047) / 2048;
+	c = (c + kScatterTile - 1) / kScatterTile * kScatterTile;
+	if (c < 2 * kScatterTile) c = 2 * kScatterTile;
+	if (c > (1u << 24)) c = 1u << 24;
+	*chunk = (uint32_t)c;
+	const uint64_t mi = n / c + np + 1;
+	*max_items = (uint32_t)mi;
+	const uint64_t E = mi << bits;
+	*tiles = (uint32_t)((E + kScanThreads * kScanItems - 1) / (kScanThreads * kScanItems));
+	size_t bytes = 0;
+	bytes += ((size_t)(np + 1) * 4 + 255) / 256 * 256;           // item_prefix
+	bytes += ((size_t)E * 4 + 255) / 256 * 256;                   // counts / offsets
+	bytes += ((size_t)*tiles * 8 + 255) / 256 * 256 + 256;        // scan status + counter
+	return bytes + 1024;                                            // per-array 256-byte padding of the bump allocator
+}
+
+int launch_radix_pass(const RadixPassArgs &a, cudaStream_t s, int /*sms*/, KernelTimer *t)
+{
+	KernelTimer off;
+	off.enabled = false;
+	off.n = 0;
+	if (!t) t = &off;
+	const uint32_t F = 1u << a.bits;
+	const uint32_t tiles = (uint32_t)((((uint64_t)a.max_items << a.bits) + kScanThreads * kScanItems - 1) /
+	                                  (kScanThreads * kScanItems));
+	cudaMemsetAsync(a.scan_status, 0, (size_t)tiles * 8, s);
+	cudaMemsetAsync(a.scan_counter, 0, 4, s);
+	t->start(KK_MAKE_ITEMS, s);
+	k_make_items<<<1, 1024, 0, s>>>(a.parent_off, a.np, a.n, a.chunk, a.item_prefix, a.child_off, a.np << a.bits);
+	t->stop(s);
+	t->start(KK_HIST, s);
+	k_hist<<<a.max_items, kHistThreads, F * 4, s>>>(a.keys, a.n, a.np, a.parent_off, a.item_prefix, a.chunk,
+	                                                a.factor, a.rshift, a.bits, a.counts);
+	t->stop(s);
+	t->start(KK_SCAN, s);
+	k_scan<<<tiles, kScanThreads, 0, s>>>(a.item_prefix, a.np, a.bits, a.counts, a.child_off, a.scan_status,
+	                                      a.scan_counter);
+	t->stop(s);
+	const size_t smem = (size_t)F * 16 + (size_t)kScatterTile * 8;
+	static bool attr_set = false;
+	if (!attr_set) {
+		cudaFuncSetAttribute(k_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, 2048 * 16 + kScatterTile * 8);
+		attr_set = true;
+	}
+	t->start(KK_SCATTER, s);
+	k_scatter<<<a.max_items, kScatterThreads, smem, s>>>(a.keys, a.vals, a.n, a.np, a.parent_off, a.item_prefix,
+	                                                     a.chunk, a.factor, a.rshift, a.bits, a.counts,
+	                                                     a.keys_out, a.vals_out);
+	t->stop(s);
+	return 4;
+}
+
+int launch_histogram_only(const uint32_t *keys, uint64_t n, uint32_t *counts_dev, uint32_t factor, int rshift,
+                          int bits, cudaStream_t s, int sms)
+{
+	const uint32_t F = 1u << bits;
+	cudaMemsetAsync(counts_dev, 0, (size_t)F * 4, s);
+	uint64_t groups = (n + 3) / 4;
+	uint32_t grid = (uint32_t)((groups + kHistThreads - 1) / kHistThreads);
+	if (grid > (uint32_t)sms * 4) grid = (uint32_t)sms * 4;
+	if (grid == 0) grid = 1;
+	k_hist_global<<<grid, kHistThreads, F * 4, s>>>(keys, n, factor, rshift, bits, counts_dev);
+	return 1;
+}
+
+}  // namespace hjb

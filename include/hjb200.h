@@ -1,0 +1,180 @@
+/* hjb200.h -- C ABI of the B200-native hash-join engine (libhjb200.so).
+ *
+ * Drop-in boundary for the hot path of xtcyclist/hash_join_codes_KNL: the three join
+ * programs NPJ (npj.cpp), PHJ (phj.cpp), CPRA (cpra2.cpp) and the kernels they are made of.
+ * The reference has no FFI; its interface is (1) the CLI `./npj|./phj|./cpra [#threads]
+ * [outer] [inner]` over four raw uint32 files and (2) C-linkage-style free functions over SoA
+ * uint32 columns (hj.h:73-83 and the definitions cited below).  Every entry point here names
+ * the reference interface it replaces.  Plain pointers and sizes only; no C++/torch types.
+ *
+ * Conventions (as in the reference): R = inner = build side, S = outer = probe side
+ * (npj.cpp:933-934); a tuple is a 32-bit key + 32-bit payload held in two separate columns;
+ * a result row is (key, outer/S payload, inner/R payload) in three columns (npj.cpp:998-1000);
+ * every (r, s) pair with equal keys is emitted (no _UNIQUE, npj.cpp:288-290).
+ * Unlike the reference no key value is reserved: key 0 is legal (the reference uses it as
+ * the empty sentinel, npj.cpp:205,583).
+ *
+ * All functions return 0 (HJB_OK) or a negative error code; hjb_last_error(ctx) gives text.
+ * Nothing here ever runs the join on the CPU: without a CUDA device hjb_create fails.
+ */
+#ifndef HJB200_H
+#define HJB200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HJB_VERSION 100
+
+enum {
+	HJB_OK = 0,
+	HJB_E_INVALID = -1,   /* bad argument (null pointer, misaligned device column, size > 2^32-1) */
+	HJB_E_CUDA = -2,      /* CUDA runtime error, see hjb_last_error */
+	HJB_E_NOMEM = -3,     /* device or host allocation failed */
+	HJB_E_IO = -4,        /* relation file missing or of the wrong size */
+	HJB_E_NODEVICE = -5   /* no CUDA device: there is no CPU fallback */
+};
+
+typedef struct hjb_ctx hjb_ctx;        /* one per GPU: device, stream, workspace, output buffers */
+
+/* One relation: two columns of `tuples` uint32 each.  Host or device pointers depending on
+ * the entry point.  Device columns must be 16-byte aligned.  Replaces the inner_keys /
+ * inner_vals / outer_keys / outer_vals members of info_t_hj (hj.h:15-18). */
+typedef struct hjb_rel {
+	const uint32_t *keys;
+	const uint32_t *vals;
+	uint64_t tuples;                   /* <= 2^32 - 1 per GPU (the reference: uint32 counts, phj.cpp:1722-1727) */
+} hjb_rel;
+
+/* Tunables the reference hard-codes in main() (npj.cpp:944-945, phj.cpp:1976-1979,
+ * cpra2.cpp:2023,2031-2034).  Zero / 0.0 selects the default. */
+typedef struct hjb_opts {
+	int materialize;       /* 1 (reference behaviour): write the dense 3-column result; 0: count + checksums only */
+	uint32_t seed;         /* hash factors are drawn from it (npj.cpp:975-977); 0 -> fixed default */
+	double npj_load;       /* NPJ table load factor (reference 0.90); default 0.50 */
+	int radix_bits[4];     /* PHJ/CPRA fan-out bits per pass (reference: planner phj.cpp:1791-1808); all 0 -> planner */
+	uint32_t part_tuples;  /* planner target for build tuples per final partition (reference hash_table_limit 6400) */
+	uint64_t out_capacity; /* rows the result buffers may hold; 0 -> max(|S|, |R|); grown and retried on overflow */
+	int reserved[8];
+} hjb_opts;
+
+/* Result of one join.  Replaces join_keys / join_outer_vals / join_inner_vals and
+ * join_tuples of info_t_hj (hj.h:11,19-21) and the value close_gaps returns (npj.cpp:905).
+ * The rows are dense ([0, count)), in no particular order.  The buffers belong to the
+ * context and stay valid until the next join on it or hjb_destroy. */
+typedef struct hjb_result {
+	uint64_t count;        /* number of matching pairs */
+	uint64_t sum_key;      /* sum of key over the rows, uint64 wrap */
+	uint64_t sum_outer;    /* sum of S payloads */
+	uint64_t sum_inner;    /* sum of R payloads */
+	const uint32_t *keys;        /* NULL when !materialize */
+	const uint32_t *outer_vals;
+	const uint32_t *inner_vals;
+	int rows_on_device;    /* 1: the three pointers are device memory; 0: (pinned) host memory */
+	double seconds;        /* device-timed region: the reference's definition (npj.cpp:861-918): table
+	                          init + every partition pass + join + materialisation, inputs resident */
+	double seconds_e2e;    /* host entry points: wall time including H2D of the inputs and D2H of the rows */
+	float phase_ms[8];     /* [0] table init / pass-1 R, [1] build / pass-1 S, [2] probe / pass-2 R, [3] pass-2 S,
+	                          [4] per-partition join, [5] H2D, [6] D2H, [7] spare */
+	uint32_t kernel_launches;  /* kernels of this library launched by the call */
+	uint32_t partitions;   /* final partition count (PHJ / CPRA), NPJ: buckets */
+} hjb_result;
+
+/* ---- context ---------------------------------------------------------------------- */
+int hjb_version(void);
+int hjb_create(int device, hjb_ctx **ctx);
+int hjb_destroy(hjb_ctx *ctx);
+const char *hjb_last_error(const hjb_ctx *ctx);    /* ctx may be NULL: error of the last failed hjb_create */
+/* run on a caller-owned CUDA stream (cudaStream_t as void*), e.g. torch's current stream */
+int hjb_set_stream(hjb_ctx *ctx, void *cuda_stream);
+int hjb_synchronize(hjb_ctx *ctx);
+/* Per-kernel device times of the LAST whole join, from CUDA events recorded around every launch on
+ * the launching stream (replaces the reference's per-phase times[] / -DTIMELOG, npj.cpp:878-915,
+ * hj.h:69-70).  hjb_kernel_times fills ms[k] / launches[k] for kernel kind k and returns the number
+ * of kinds; hjb_kernel_name(k) names kind k. */
+int hjb_set_profiling(hjb_ctx *ctx, int on);
+int hjb_kernel_times(hjb_ctx *ctx, float *ms, uint32_t *launches, int max_kinds);
+const char *hjb_kernel_name(int kind);
+
+/* ---- whole joins: replace run() / run_hj() + main()'s allocation ------------------- */
+/* NPJ, npj.cpp:769-927.  Columns in device memory. */
+int hjb_npj_device(hjb_ctx *ctx, const hjb_rel *R, const hjb_rel *S, const hjb_opts *opts, hjb_result *out);
+/* PHJ, phj.cpp:1646-1949 (with the join phase of phj.cpp:1869-1924). */
+int hjb_phj_device(hjb_ctx *ctx, const hjb_rel *R, const hjb_rel *S, const hjb_opts *opts, hjb_result *out);
+/* Same, columns in host memory (what the reference's main() holds after fread,
+ * npj.cpp:1036-1039): copies them in, joins, copies the rows out to pinned host memory. */
+int hjb_npj_host(hjb_ctx *ctx, const hjb_rel *R, const hjb_rel *S, const hjb_opts *opts, hjb_result *out);
+int hjb_phj_host(hjb_ctx *ctx, const hjb_rel *R, const hjb_rel *S, const hjb_opts *opts, hjb_result *out);
+
+/* ---- CPRA, cpra2.cpp:1697-1986, one context (= one GPU = one of the reference's "threads")
+ * per process.  The reference partitions each thread's chunk locally, then thread t gathers
+ * the pieces of the partitions it owns (cpra2.cpp:1868-1906).  Here: GPU g owns the hash
+ * range [g/G, (g+1)/G); hjb_cpra_split radix-partitions this GPU's chunk by owner (the
+ * GPU-assign pass) into ctx-owned send buffers, the caller exchanges them (NCCL all-to-all or
+ * peer copies -- plumbing, not part of this library), and hjb_cpra_join_local joins what
+ * arrived exactly like PHJ. */
+typedef struct hjb_split {
+	const uint32_t *r_keys, *r_vals;   /* device, grouped by owner GPU */
+	const uint32_t *s_keys, *s_vals;
+	uint64_t r_offsets[65];            /* owner g holds [r_offsets[g], r_offsets[g+1]) ; ngpus <= 64 */
+	uint64_t s_offsets[65];
+	float ms;
+} hjb_split;
+int hjb_cpra_split(hjb_ctx *ctx, const hjb_rel *R_chunk, const hjb_rel *S_chunk, int ngpus,
+                   const hjb_opts *opts, hjb_split *out);
+/* hash range restriction for the local join: the tuples all hash into owner `gpu` of `ngpus` */
+int hjb_cpra_join_local(hjb_ctx *ctx, const hjb_rel *R_recv, const hjb_rel *S_recv, int gpu, int ngpus,
+                        const hjb_opts *opts, hjb_result *out);
+
+/* ---- the kernels, one call each, device pointers: mirror the reference's free functions
+ * so intermediate products can be compared with the oracle -------------------------- */
+/* hash h(key,f,N) = ((uint32)(key*f) * N) >> 32, npj.cpp:200-201 / simd_hash npj.cpp:90-106;
+ * the factor the library derives from `seed` for stage `which` (0: radix, 1: table) */
+uint32_t hjb_hash_factor(uint32_t seed, int which);
+/* histogram(), cpra2.cpp:801-802: counts[p] = #keys with radix digit p.  The digit is bits
+ * [32-shift-bits, 32-shift) of key*factor, i.e. h(key,f,2^(shift+bits)) mod 2^bits. */
+int hjb_histogram(hjb_ctx *ctx, const uint32_t *keys, uint64_t size, uint32_t *counts,
+                  uint32_t factor, int shift, int bits);
+/* histogram + interleave + partition, cpra2.cpp:801-1075, phj.cpp:1263-1291: one radix pass
+ * of `bits` bits below `shift` already-partitioned bits.  parent_offsets has 2^shift + 1
+ * entries (NULL when shift == 0); child_offsets receives 2^(shift+bits) + 1. */
+int hjb_partition_pass(hjb_ctx *ctx, const uint32_t *keys, const uint32_t *vals, uint64_t size,
+                       const uint32_t *parent_offsets, uint32_t *keys_out, uint32_t *vals_out,
+                       uint32_t *child_offsets, uint32_t factor, int shift, int bits);
+/* set + build, npj.cpp:366-380,190-212: table of `buckets` x 4 slots of (payload<<32 | key),
+ * all-ones = empty.  table must hold buckets*4 uint64. */
+int hjb_npj_build(hjb_ctx *ctx, const uint32_t *keys, const uint32_t *vals, uint64_t size,
+                  uint64_t *table, uint64_t buckets, uint32_t factor);
+
+/* ---- relation files, write.cpp:1824-1865 / npj.cpp:1013-1039: headerless little-endian
+ * uint32[n]; <dir>/ik_<n>.txt iv_<n>.txt (inner) and ok_<n>.txt ov_<n>.txt (outer) ------ */
+int hjb_relation_write(const char *dir, int outer, uint64_t tuples, const uint32_t *keys, const uint32_t *vals);
+int hjb_relation_read(const char *dir, int outer, uint64_t tuples, uint32_t *keys, uint32_t *vals);
+
+/* ---- deterministic generator on the device (replaces write.cpp / generate_data_for_join,
+ * cpra2.cpp:1578-1696; seeded, real Zipf -- SURVEY.md §2 note on W).  kind: 0 = unique keys
+ * (R, or S as a permutation of R's key set), 1 = foreign keys into a build side of
+ * `domain` keys (every key at least once when tuples >= domain, the rest uniform),
+ * 2 = Zipf(theta) ranks over `domain` keys of which a `selectivity` fraction of TUPLES hit. */
+typedef struct hjb_gen {
+	int kind;
+	uint64_t tuples;       /* size of this column pair */
+	uint64_t domain;       /* |R| the keys refer to */
+	uint64_t first;        /* global index of element 0 (for sharded generation) */
+	uint64_t total;        /* global size of the relation (permutation domain) */
+	uint32_t seed;         /* selects the key SET: rank r -> key is a function of (seed, r) only */
+	uint32_t order_seed;   /* selects the order / the uniform picks, so R and S share keys but not order */
+	uint32_t payload_factor;   /* payload = key * factor (cpra2.cpp:1663-1674) */
+	uint32_t pad_;
+	double theta, selectivity;
+} hjb_gen;
+int hjb_generate(hjb_ctx *ctx, const hjb_gen *g, uint32_t *keys_dev, uint32_t *vals_dev);
+/* sum of a device column as uint64 (input checksums, cpra2.cpp:1628,1650) */
+int hjb_column_sum(hjb_ctx *ctx, const uint32_t *col_dev, uint64_t size, uint64_t *sum);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,313 @@
+"""Parity tests proper: the CUDA path, called through the C ABI, against the oracle
+(oracle/hj_oracle.c, pinned to the reference by tests/test_oracle_golden.py), the committed
+golden rows of the reference itself, and an independent numpy join -- bit-exact: count, the
+three uint64 checksums, and the sorted materialised rows."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import hash_join_codes_knl_b200 as hj
+from hash_join_codes_knl_b200 import datagen
+from _oracle import lib as olib, _p, numpy_join, oracle_generate, oracle_join, sort_rows
+
+pytestmark = pytest.mark.gpu
+G = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_vectors.npz"))
+
+
+@pytest.fixture(scope="module")
+def eng():
+    e = hj.Engine(0)
+    yield e
+    e.close()
+
+
+def dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a).view(np.int32)).cuda()
+
+
+def run(eng, algo, rk, rv, sk, sv, where="device", **opts):
+    if where == "device":
+        return getattr(eng, algo)((dev(rk), dev(rv)), (dev(sk), dev(sv)), **opts)
+    return getattr(eng, algo)((rk, rv), (sk, sv), **opts)
+
+
+def assert_same(got, want, rows=True):
+    assert got.checks() == want.checks()
+    if rows:
+        assert (sort_rows(*got.rows_numpy()) == want.sorted_rows()).all()
+
+
+ALGOS = ["npj", "phj"]
+
+
+@pytest.mark.parametrize("algo", ALGOS)
+@pytest.mark.parametrize("nr,ns,seed", [(1000, 1000, 1), (3000, 10000, 2), (1 << 16, 1 << 18, 3),
+                                        (100003, 70001, 4), (1 << 20, 1 << 20, 5), (1 << 18, 1 << 22, 6)])
+def test_join_matches_oracle(eng, algo, nr, ns, seed):
+    rk, rv, sk, sv, _, _ = oracle_generate(nr, ns, threads=3, seed=seed)
+    want = oracle_join(algo, rk, rv, sk, sv, threads=4)
+    assert_same(run(eng, algo, rk, rv, sk, sv), want)
+
+
+@pytest.mark.parametrize("algo", ALGOS)
+@pytest.mark.parametrize("rkey,rows", [("in_small_rk", "ref_small_npj_rows"), ("in_small_rk", "ref_small_phj_rows"),
+                                       ("in_small_rk_nodup", "ref_small_cpra_rows")])
+def test_join_matches_reference_golden_rows(eng, algo, rkey, rows):
+    """rows produced by the reference's own build/probe/run_hj (tests/golden/make_golden.py)"""
+    got = run(eng, algo, G[rkey], G[rkey.replace("rk", "rv")], G["in_small_sk"], G["in_small_sv"])
+    assert got.count == G[rows].shape[0]
+    assert (sort_rows(*got.rows_numpy()) == G[rows]).all()
+
+
+@pytest.mark.parametrize("algo", ALGOS)
+@pytest.mark.parametrize("row", range(2))
+def test_join_matches_reference_golden_checksums(eng, algo, row):
+    nr, ns, seed, T, cnt, s_key, s_outer, s_inner = (int(x) for x in G["ref_medium"][row])
+    rk, rv, sk, sv, _, _ = oracle_generate(nr, ns, threads=T, seed=seed)
+    assert run(eng, algo, rk, rv, sk, sv).checks() == (cnt, s_key, s_outer, s_inner)
+
+
+@pytest.mark.parametrize("algo", ALGOS)
+@pytest.mark.parametrize("nr,ns", [(0, 0), (0, 100), (100, 0), (1, 1), (5, 3), (31, 33), (17, 1025), (4097, 15)])
+def test_tiny_and_ragged_sizes(eng, algo, nr, ns):
+    rng = np.random.default_rng(nr * 1000 + ns)
+    rk = rng.integers(1, 50, nr, dtype=np.uint32)          # many duplicates on both sides
+    sk = rng.integers(1, 50, ns, dtype=np.uint32)
+    rv, sv = rk * np.uint32(3) + np.uint32(1), sk * np.uint32(5) + np.uint32(2)
+    want = numpy_join(rk, rv, sk, sv)
+    for where in ("device", "host"):
+        assert_same(run(eng, algo, rk, rv, sk, sv, where=where), want)
+
+
+@pytest.mark.parametrize("algo", ALGOS)
+def test_special_key_values(eng, algo):
+    """key 0 (the reference's empty sentinel, npj.cpp:205), 0xFFFFFFFF, and the one pair
+    (0xFFFFFFFF, 0xFFFFFFFF) that looks like an empty slot of this engine's tables"""
+    rk = np.array([0, 0, 1, 0xFFFFFFFF, 0xFFFFFFFF, 0xFFFFFFFF, 0xFFFFFFFE, 0x80000000, 7, 7], np.uint32)
+    rv = np.array([0, 9, 1, 0xFFFFFFFF, 0xFFFFFFFF, 5, 0xFFFFFFFF, 3, 0, 0xFFFFFFFF], np.uint32)
+    sk = np.array([0, 0xFFFFFFFF, 7, 2, 0x80000000, 0xFFFFFFFF, 0xFFFFFFFE, 0], np.uint32)
+    sv = np.array([11, 0xFFFFFFFF, 13, 14, 15, 16, 0xFFFFFFFF, 0], np.uint32)
+    want = numpy_join(rk, rv, sk, sv)
+    assert want.count == 2 * 3 + 2 * 3 + 2 + 1 + 1
+    assert_same(run(eng, algo, rk, rv, sk, sv), want)
+    # and at scale: many sentinel pairs on the build side
+    rng = np.random.default_rng(5)
+    rk = np.concatenate([np.full(300, 0xFFFFFFFF, np.uint32), rng.integers(0, 1 << 32, 5000, dtype=np.uint32)])
+    rv = np.concatenate([np.full(300, 0xFFFFFFFF, np.uint32), rng.integers(0, 1 << 32, 5000, dtype=np.uint32)])
+    sk = np.concatenate([np.full(40, 0xFFFFFFFF, np.uint32), rk[300:2000], rng.integers(0, 1 << 32, 3000, dtype=np.uint32)])
+    sv = np.arange(sk.size, dtype=np.uint32)
+    assert_same(run(eng, algo, rk, rv, sk, sv), numpy_join(rk, rv, sk, sv))
+
+
+@pytest.mark.parametrize("algo", ALGOS)
+def test_duplicate_heavy_build_side_overflows_stage_and_capacity(eng, algo):
+    """every pair is emitted (no _UNIQUE, npj.cpp:288-290): 3000 x 2000 equal keys -> 6M rows from
+    5000 input tuples, which overflows the shared-memory stage and the default result capacity"""
+    rk = np.full(3000, 77, np.uint32)
+    rv = np.arange(3000, dtype=np.uint32)
+    sk = np.concatenate([np.full(2000, 77, np.uint32), np.arange(100, 600, dtype=np.uint32)])
+    sv = np.arange(sk.size, dtype=np.uint32) * np.uint32(7)
+    want = numpy_join(rk, rv, sk, sv)
+    assert want.count == 6_000_000
+    assert_same(run(eng, algo, rk, rv, sk, sv), want)
+
+
+@pytest.mark.parametrize("algo", ALGOS)
+@pytest.mark.parametrize("sel", [0.0, 0.5, 1.0])
+def test_selectivity(eng, algo, sel):
+    rk, rv, sk, sv, _, _ = oracle_generate(1 << 15, 1 << 15, selectivity=sel, threads=2, seed=8)
+    want = oracle_join(algo, rk, rv, sk, sv, threads=2)
+    assert want.count == int((1 << 15) * sel)
+    assert_same(run(eng, algo, rk, rv, sk, sv), want)
+
+
+@pytest.mark.parametrize("algo", ALGOS)
+def test_heavy_hitter_probe_keys(eng, algo):
+    """one probe key holds half of S: its partition is cut into many tasks (csrc/part_join.cu)"""
+    rk, rv, sk, sv, _, _ = oracle_generate(1 << 14, 1 << 20, threads=2, seed=9)
+    sk[::2] = rk[5]
+    sv[::2] = np.arange(sk.size // 2, dtype=np.uint32)
+    want = numpy_join(rk, rv, sk, sv, materialize=False)
+    got = run(eng, algo, rk, rv, sk, sv)
+    assert got.checks() == want.checks()
+    got2 = run(eng, algo, rk, rv, sk, sv, materialize=False)
+    assert got2.checks() == want.checks() and not got2.materialized
+
+
+@pytest.mark.parametrize("algo", ALGOS)
+def test_host_entry_equals_device_entry(eng, algo):
+    rk, rv, sk, sv, _, _ = oracle_generate(50000, 200000, threads=2, seed=10)
+    a = run(eng, algo, rk, rv, sk, sv, where="device")
+    b = run(eng, algo, rk, rv, sk, sv, where="host")
+    assert a.checks() == b.checks() and b.seconds_e2e > 0 and not b.rows_on_device
+    assert (sort_rows(*a.rows_numpy()) == sort_rows(*b.rows_numpy())).all()
+
+
+def test_phj_plans_and_hash_seeds_do_not_change_the_result(eng):
+    rk, rv, sk, sv, _, _ = oracle_generate(1 << 17, 1 << 18, threads=2, seed=11)
+    want = oracle_join("phj", rk, rv, sk, sv, threads=2)
+    for opts in ({"radix_bits": (4,)}, {"radix_bits": (8, 8)}, {"radix_bits": (3, 4, 2)}, {"radix_bits": (11, 5)},
+                 {"radix_bits": (2, 2, 2, 2)}, {"part_tuples": 100}, {"part_tuples": 1 << 20}, {"seed": 12345},
+                 {"npj_load": 0.9}):
+        assert_same(run(eng, "phj", rk, rv, sk, sv, **opts), want)
+        assert_same(run(eng, "npj", rk, rv, sk, sv, **opts), want, rows=False)
+
+
+def test_misaligned_device_columns_are_rejected(eng):
+    k = dev(np.arange(1, 200, dtype=np.uint32))
+    with pytest.raises(hj.HjbError):
+        eng.npj((k[1:101], k[1:101]), (k[:100], k[:100]))
+
+
+# ---------------------------------------------------------------- single kernels vs oracle
+
+@pytest.mark.parametrize("bits", [1, 6, 8, 11])
+def test_histogram_kernel_matches_oracle(eng, bits):
+    rk, rv, sk, sv, _, _ = oracle_generate(1000, 300001, threads=2, seed=13)
+    f = eng.hash_factor(0, 0)
+    want = np.zeros(1 << bits, np.uint32)
+    olib().hjo_histogram(_p(sk), sk.size, _p(want), f, 1 << bits)     # h(key, f, 2^bits), cpra2.cpp:730-741
+    assert (eng.histogram(dev(sk), f, 0, bits) == want).all()
+
+
+@pytest.mark.parametrize("bits1,bits2", [(6, 6), (8, 8), (3, 11), (11, 0), (1, 1)])
+def test_partition_pass_kernels_match_oracle(eng, bits1, bits2):
+    rk, rv, sk, sv, _, _ = oracle_generate(1000, 500003, threads=2, seed=14)
+    f = eng.hash_factor(0, 0)
+    P1 = 1 << bits1
+    c1 = np.zeros(P1, np.uint32)
+    olib().hjo_histogram(_p(sk), sk.size, _p(c1), f, P1)
+    wk, wv = np.empty_like(sk), np.empty_like(sv)
+    olib().hjo_partition(_p(sk), _p(sv), sk.size, _p(c1), _p(wk), _p(wv), f, P1)
+    k1, v1, off1 = eng.partition_pass(dev(sk), dev(sv), f, 0, bits1)
+    assert (off1 == np.concatenate([[0], np.cumsum(c1)])).all()
+
+    def canon(k, v, off):                # order inside a partition is not part of the contract
+        k, v = k.copy(), v.copy()
+        for p in range(off.size - 1):
+            s = slice(int(off[p]), int(off[p + 1]))
+            o = np.lexsort((v[s], k[s]))
+            k[s], v[s] = k[s][o], v[s][o]
+        return k, v
+    gk, gv = canon(k1.cpu().numpy().view(np.uint32), v1.cpu().numpy().view(np.uint32), off1)
+    ok, ov = canon(wk, wv, off1)
+    assert (gk == ok).all() and (gv == ov).all()
+    if bits2:
+        P = 1 << (bits1 + bits2)
+        c2 = np.zeros(P, np.uint32)
+        olib().hjo_histogram(_p(sk), sk.size, _p(c2), f, P)           # two passes == one pass of bits1+bits2
+        k2, v2, off2 = eng.partition_pass(k1, v1, f, bits1, bits2, parent_offsets=off1)
+        assert (off2 == np.concatenate([[0], np.cumsum(c2)])).all()
+        wk2, wv2 = np.empty_like(sk), np.empty_like(sv)
+        olib().hjo_partition(_p(sk), _p(sv), sk.size, _p(c2), _p(wk2), _p(wv2), f, P)
+        gk, gv = canon(k2.cpu().numpy().view(np.uint32), v2.cpu().numpy().view(np.uint32), off2)
+        ok, ov = canon(wk2, wv2, off2)
+        assert (gk == ok).all() and (gv == ov).all()
+
+
+def test_npj_build_kernel_holds_exactly_the_build_side(eng):
+    rk, rv, sk, sv, _, _ = oracle_generate(100000, 100000, threads=2, seed=15)
+    rk[:500] = rk[500:1000]
+    buckets = 60000
+    f = eng.hash_factor(0, 1)
+    tab = eng.npj_build(dev(rk), dev(rv), buckets, f).cpu().numpy().view(np.uint64)
+    used = tab[tab != np.uint64(0xFFFFFFFFFFFFFFFF)]
+    pairs = (rv.astype(np.uint64) << np.uint64(32)) | rk.astype(np.uint64)
+    assert (np.sort(used) == np.sort(pairs)).all()
+    # chain invariant the probe relies on: between a key's home bucket and its slot every bucket is full
+    slot_bucket = np.nonzero(tab != np.uint64(0xFFFFFFFFFFFFFFFF))[0] // 4
+    keys = (tab[tab != np.uint64(0xFFFFFFFFFFFFFFFF)] & np.uint64(0xFFFFFFFF)).astype(np.uint32)
+    home = ((keys * np.uint32(f)).astype(np.uint64) * np.uint64(buckets)) >> np.uint64(32)
+    full = (tab.reshape(-1, 4) != np.uint64(0xFFFFFFFFFFFFFFFF)).all(axis=1)
+    for h, b in zip(home[home != slot_bucket][:2000], slot_bucket[home != slot_bucket][:2000]):
+        h, b = int(h), int(b)
+        rng = range(h, b) if b >= h else list(range(h, buckets)) + list(range(0, b))
+        assert all(full[x] for x in rng)
+
+
+# ---------------------------------------------------------------- generator
+
+def test_device_generator_equals_numpy_mirror(eng):
+    for kind, n, domain in ((0, 100003, 100003), (1, 300000, 5000), (0, 1 << 16, 1 << 16)):
+        k, v = eng.generate(kind, n, domain, 42, 3, datagen.OUTER_FACTOR)
+        hk, hv = datagen.generate(kind, n, domain, 42, 3, datagen.OUTER_FACTOR)
+        assert (k.cpu().numpy().view(np.uint32) == hk).all() and (v.cpu().numpy().view(np.uint32) == hv).all()
+        assert eng.column_sum(k) == int(hk.astype(np.uint64).sum())
+    k, _ = eng.generate(0, 1000, 5000, 42, 3, datagen.OUTER_FACTOR, first=2000, total=5000)
+    hk, _ = datagen.generate(0, 5000, 5000, 42, 3, datagen.OUTER_FACTOR)
+    assert (k.cpu().numpy().view(np.uint32) == hk[2000:3000]).all()
+
+
+def test_skewed_generator_and_join(eng):
+    nr, ns = 1 << 16, 1 << 21
+    rk, rv = eng.generate(0, nr, nr, 21, 1, datagen.INNER_FACTOR)
+    sk, sv = eng.generate(2, ns, nr, 21, 2, datagen.OUTER_FACTOR, theta=1.0, selectivity=0.5)
+    hrk, hsk = rk.cpu().numpy().view(np.uint32), sk.cpu().numpy().view(np.uint32)
+    hits = np.isin(hsk, hrk)
+    assert abs(hits.mean() - 0.5) < 0.01                          # 50 % of TUPLES match
+    top = np.unique(hsk[hits], return_counts=True)[1].max() / hits.sum()
+    assert 0.03 < top < 0.12                                      # rank-1 key of a theta=1 law over 2^16 keys
+    want = numpy_join(hrk, rv.cpu().numpy().view(np.uint32), hsk, sv.cpu().numpy().view(np.uint32), materialize=False)
+    assert want.count == int(hits.sum())
+    for algo in ALGOS:
+        assert getattr(eng, algo)((rk, rv), (sk, sv)).checks() == want.checks()
+
+
+# ---------------------------------------------------------------- CPRA on one GPU (G virtual owners)
+
+@pytest.mark.parametrize("G_", [1, 2, 4, 8])
+def test_cpra_split_exchange_join_single_process(eng, G_):
+    """the multi-GPU data path with the G ranks played one after the other on one device:
+    split every chunk by owner, hand each owner its pieces (what the all-to-all does), join
+    locally below the owner bits, add up -- must equal the oracle's CPRA on the whole input"""
+    nr, ns = 200000, 600000
+    rk, rv, sk, sv, _, _ = oracle_generate(nr, ns, threads=2, seed=16)
+    want = oracle_join("cpra", rk, rv, sk, sv, threads=4)
+    pieces = {g: {"rk": [], "rv": [], "sk": [], "sv": []} for g in range(G_)}
+    for c in range(G_):
+        cr, cs = slice(c * nr // G_, (c + 1) * nr // G_), slice(c * ns // G_, (c + 1) * ns // G_)
+        sp = eng.cpra_split((dev(rk[cr]), dev(rv[cr])), (dev(sk[cs]), dev(sv[cs])), G_)
+        assert sp["r_offsets"][-1] == cr.stop - cr.start and sp["s_offsets"][-1] == cs.stop - cs.start
+        for g in range(G_):
+            for name, col, off in (("rk", "r_keys", "r_offsets"), ("rv", "r_vals", "r_offsets"),
+                                   ("sk", "s_keys", "s_offsets"), ("sv", "s_vals", "s_offsets")):
+                pieces[g][name].append(sp[col][sp[off][g]:sp[off][g + 1]].clone())
+    total = [0, 0, 0, 0]
+    rows = []
+    for g in range(G_):
+        cols = {n: torch.cat(v) for n, v in pieces[g].items()}
+        res = eng.cpra_join_local((cols["rk"], cols["rv"]), (cols["sk"], cols["sv"]), g, G_)
+        for i, x in enumerate(res.checks()):
+            total[i] = (total[i] + x) & ((1 << 64) - 1)
+        rows.append(res.rows_numpy())
+    assert tuple(total) == want.checks()
+    got_rows = sort_rows(*(np.concatenate([r[i] for r in rows]) for i in range(3)))
+    assert (got_rows == want.sorted_rows()).all()
+
+
+# ---------------------------------------------------------------- BASELINE sizes: size-independent properties
+
+@pytest.mark.parametrize("algo,name", [("phj", "phj_cfg2"), ("npj", "npj_cfg1"), ("npj", "phj_cfg2")])
+def test_full_size_configs_by_properties(eng, algo, name):
+    """BASELINE.json configs 1 and 2 at full size, inputs generated on the device.  Every probe
+    key has exactly one build partner, so count = |S| and the checksums are plain column sums of
+    S: sum_key = sum(S.key), sum_outer = sum(S.val), sum_inner = sum(S.key * f_R mod 2^32)."""
+    nr, ns, kind = datagen.workload(name)
+    rk, rv = eng.generate(0, nr, nr, 42, 1, datagen.INNER_FACTOR)
+    sk, sv = eng.generate(kind, ns, nr, 42, 2, datagen.OUTER_FACTOR)
+    res = getattr(eng, algo)((rk, rv), (sk, sv))
+    assert res.count == ns
+    assert res.sum_key == eng.column_sum(sk) and res.sum_outer == eng.column_sum(sv)
+    inner = (sk.to(torch.int64) & 0xFFFFFFFF) * datagen.INNER_FACTOR & 0xFFFFFFFF
+    assert res.sum_inner == int(inner.sum().item()) & ((1 << 64) - 1)
+    k, o, i = res.rows_torch()
+    # the rows are a permutation of S extended by the build payload: same multiset of keys ...
+    assert eng.column_sum(k) == res.sum_key and eng.column_sum(o) == res.sum_outer and eng.column_sum(i) == res.sum_inner
+    # ... every row is internally consistent (payloads are functions of the key)
+    kk = k.to(torch.int64) & 0xFFFFFFFF
+    assert bool(((kk * datagen.OUTER_FACTOR & 0xFFFFFFFF) == (o.to(torch.int64) & 0xFFFFFFFF)).all())
+    assert bool(((kk * datagen.INNER_FACTOR & 0xFFFFFFFF) == (i.to(torch.int64) & 0xFFFFFFFF)).all())
+    # ... and idempotence: a second run gives the same checks
+    assert getattr(eng, algo)((rk, rv), (sk, sv), materialize=False).checks() == res.checks()
