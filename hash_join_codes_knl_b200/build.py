@@ -52,7 +52,7 @@ def build_programs(force=False, verbose=False):
             continue
         exe = os.path.join(BIN, name)
         if force or _stale(exe, [src] + common):
-            cmd = [_nvcc(), "-O2", "-std=c++17", "-I", os.path.join(os.path.dirname(HERE), "include"), src,
+            cmd = [_nvcc(), "-O2", "-std=c++17", "-Wno-deprecated-gpu-targets", "-I", os.path.join(os.path.dirname(HERE), "include"), src,
                    "-o", exe, "-L", HERE, "-lhjb200", "-Xlinker", "-rpath", "-Xlinker", "$ORIGIN/..", "-lpthread"]
             if verbose:
                 print(" ".join(cmd))

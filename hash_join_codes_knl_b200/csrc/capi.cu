@@ -607,6 +607,7 @@ static int host_join(hjb_ctx *ctx, device_join_fn fn, const hjb_rel *R, const hj
 		out->inner_vals = ctx->h_rows + 2 * ctx->h_rows_cap;
 	} else {
 		out->keys = out->outer_vals = out->inner_vals = nullptr;
+		CK(cudaStreamSynchronize(s));          // empty inputs return before any synchronisation
 	}
 	out->rows_on_device = 0;
 	CK(cudaEventElapsedTime(&h2d, ctx->ev[8], ctx->ev[9]));
