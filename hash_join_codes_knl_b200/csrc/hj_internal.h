@@ -10,17 +10,16 @@ namespace hjb {
 constexpr int kMaxPasses = 4;
 constexpr int kMaxRadixBits = 11;            // fan-out per pass <= 2048 (shared-memory counters)
 constexpr uint32_t kDefaultPartTuples = 2048; // planner: build tuples per final partition
-constexpr uint32_t kJoinSlots = 8192;         // shared-memory table slots per CTA (64 KB)
-constexpr uint32_t kJoinThreads = 256;
-constexpr uint32_t kJoinItems = 4;            // probe tuples per thread per sub-chunk
-constexpr uint32_t kStageCap = 2 * kJoinThreads * kJoinItems;
+constexpr int kJoinLog2Slots = 12;            // shared-memory table slots per CTA (4096 x 8 B = 32 KB)
+constexpr int kJoinThreads = 256;
+constexpr int kJoinItems = 8;                 // probe tuples per thread per round
 constexpr uint32_t kScatterThreads = 512;
 constexpr uint32_t kScatterTile = kScatterThreads * 8;   // tuples staged per tile
 constexpr uint32_t kHistThreads = 512;
 constexpr uint32_t kScanThreads = 256;
 constexpr uint32_t kScanItems = 8;
-constexpr uint32_t kNpjThreads = 256;
-constexpr uint32_t kNpjItems = 4;
+constexpr int kNpjThreads = 256;
+constexpr int kNpjItems = 4;                  // probe tuples per thread per round (their home buckets are in flight together)
 
 // optional per-launch CUDA-event timing on the launching stream (bench.py's roofline line)
 enum KernelKind { KK_MAKE_ITEMS = 0, KK_HIST, KK_SCAN, KK_SCATTER, KK_JOIN_TASKS, KK_PART_JOIN, KK_NPJ_BUILD,
@@ -93,7 +92,7 @@ struct NpjArgs {
 	uint32_t factor;
 	uint32_t *out_k, *out_o, *out_i;
 	uint64_t out_cap;
-	unsigned long long *scalars;              // [0] cursor, [1..4] sums, [5] sentinel build tuples
+	unsigned long long *scalars;              // [0] cursor, [1..4] sums, [5] sentinel build tuples, [6] duplicate build keys seen
 	int materialize;
 };
 int launch_npj_build(const NpjArgs &a, cudaStream_t s, int sms, KernelTimer *t = nullptr);

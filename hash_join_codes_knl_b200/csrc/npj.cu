@@ -14,7 +14,7 @@ namespace hjb {
 __global__ void __launch_bounds__(kNpjThreads)
 k_npj_build(const uint32_t *__restrict__ keys, const uint32_t *__restrict__ vals, uint64_t n,
             uint64_t *__restrict__ table, uint32_t buckets, uint32_t factor,
-            unsigned long long *__restrict__ sentinel_count)
+            unsigned long long *__restrict__ flags /* [0] sentinel pairs, [1] duplicate build keys seen */)
 {
 	const uint64_t groups = (n + 3) >> 2;
 	for (uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; g < groups; g += (uint64_t)gridDim.x * blockDim.x) {
@@ -37,7 +37,7 @@ k_npj_build(const uint32_t *__restrict__ keys, const uint32_t *__restrict__ vals
 			if (idx + e >= n) continue;
 			const uint64_t pair = ((uint64_t)v[e] << 32) | k[e];
 			if (pair == kEmptySlot) {
-				atomicAdd(sentinel_count, 1ull);
+				atomicAdd(&flags[0], 1ull);
 				continue;
 			}
 			uint32_t b = hash_range(k[e], factor, buckets);
@@ -46,8 +46,11 @@ k_npj_build(const uint32_t *__restrict__ keys, const uint32_t *__restrict__ vals
 				uint64_t *slots = table + (uint64_t)b * 4;
 				int free_slot = -1;
 #pragma unroll
-				for (int z = 3; z >= 0; --z)
-					if (ld_cg_u64(&slots[z]) == kEmptySlot) free_slot = z;      // lowest free slot
+				for (int z = 3; z >= 0; --z) {
+					const uint64_t cur = ld_cg_u64(&slots[z]);
+					if (cur == kEmptySlot) free_slot = z;                       // lowest free slot
+					else if ((uint32_t)cur == k[e]) flags[1] = 1;               // equal build keys: probes walk whole chains
+				}
 				if (free_slot < 0) {
 					b = b + 1 == buckets ? 0 : b + 1;
 					continue;
@@ -60,106 +63,137 @@ k_npj_build(const uint32_t *__restrict__ keys, const uint32_t *__restrict__ vals
 	}
 }
 
-// dynamic shared memory: stage k,o,i [kStageCap] | scratch 4*32 uint64
+// one row, reservation aggregated over whichever lanes of the warp are here together
+__device__ __forceinline__ void npj_emit_row(const OutCols &out, uint32_t key, uint32_t oval, uint32_t ival)
+{
+	const unsigned m = __activemask();
+	const int leader = __ffs(m) - 1;
+	unsigned long long base = 0;
+	if ((int)lane_id() == leader) base = atomicAdd(out.cursor, (unsigned long long)__popc(m));
+	base = __shfl_sync(m, base, leader);
+	const uint64_t r = base + __popc(m & lanemask_lt());
+	if (r < out.cap) {
+		out.k[r] = key;
+		out.o[r] = oval;
+		out.i[r] = ival;
+	}
+}
+
+// Probe.  Each thread takes kNpjItems probe tuples per round (a warp owns 32*kNpjItems consecutive
+// tuples, item t of lane l = tuple 32*t + l, so every load and every result store is a coalesced
+// 128-byte run) and fetches the home buckets of all of them before looking at any: the probe is
+// bound by the latency of random 32-byte sector reads, so loads in flight are what counts.
+// Unique build keys (flags[1] == 0, detected by the build): a lane stops at its first match, the
+// warp reserves rows with one atomicAdd per round and stores them ballot-ranked from registers.
+// Otherwise every match is emitted as it is met.
 template <bool MATERIALIZE>
-__global__ void __launch_bounds__(kNpjThreads)
+__global__ void __launch_bounds__(kNpjThreads, 4)
 k_npj_probe(const uint32_t *__restrict__ keys, const uint32_t *__restrict__ vals, uint64_t n,
             const uint64_t *__restrict__ table, uint32_t buckets, uint32_t factor, OutCols out,
-            unsigned long long *__restrict__ sums, const unsigned long long *__restrict__ sentinel_count)
+            unsigned long long *__restrict__ sums, const unsigned long long *__restrict__ flags)
 {
-	extern __shared__ __align__(16) unsigned char s_raw[];
-	uint32_t *stage_mem = reinterpret_cast<uint32_t *>(s_raw);
-	uint64_t *scratch = reinterpret_cast<uint64_t *>(stage_mem + 3 * kStageCap);
-	__shared__ uint32_t s_cnt;
-	__shared__ unsigned long long s_base;
-	MatchStage st;
-	st.k = stage_mem;
-	st.o = stage_mem + kStageCap;
-	st.i = stage_mem + 2 * kStageCap;
-	st.cnt = &s_cnt;
-	st.cap = kStageCap;
-	if (threadIdx.x == 0) s_cnt = 0;
-	__syncthreads();
+	__shared__ uint64_t scratch[4 * 32];
 	JoinSums acc;
 	acc.zero();
-	const uint32_t sentinels = (uint32_t)*sentinel_count;
-	const uint64_t groups = (n + 3) >> 2;
-	// one round = one absolutely aligned group of four probe tuples per thread
-	for (uint64_t g0 = (uint64_t)blockIdx.x * kNpjThreads; g0 < groups; g0 += (uint64_t)gridDim.x * kNpjThreads) {
-		const uint64_t g = g0 + threadIdx.x, idx = g << 2;
-		uint32_t k[4] = {0, 0, 0, 0}, v[4] = {0, 0, 0, 0};
-		if (g < groups) {
-			if (idx + 3 < n) {
-				const uint4 kk = ldg_stream_u4(reinterpret_cast<const uint4 *>(keys) + g);
-				const uint4 vv = ldg_stream_u4(reinterpret_cast<const uint4 *>(vals) + g);
-				k[0] = kk.x; k[1] = kk.y; k[2] = kk.z; k[3] = kk.w;
-				v[0] = vv.x; v[1] = vv.y; v[2] = vv.z; v[3] = vv.w;
-			} else {
+	const uint32_t sentinels = (uint32_t)flags[0];
+	const bool slow = flags[1] != 0 || sentinels != 0;
+	constexpr uint32_t kRound = kNpjThreads * kNpjItems;
+	const uint64_t rounds = (n + kRound - 1) / kRound;
+	for (uint64_t rd = blockIdx.x; rd < rounds; rd += gridDim.x) {
+		const uint64_t wbase = rd * kRound + (threadIdx.x & ~31u) * kNpjItems + lane_id();
+		uint32_t k[kNpjItems], v[kNpjItems], ival[kNpjItems], b[kNpjItems];
+		bool found[kNpjItems];
+		ulonglong2 lo[kNpjItems], hi[kNpjItems];
 #pragma unroll
-				for (int e = 0; e < 4; ++e) {
-					k[e] = idx + e < n ? keys[idx + e] : 0;
-					v[e] = idx + e < n ? vals[idx + e] : 0;
-				}
-			}
+		for (int t = 0; t < kNpjItems; ++t) {
+			const uint64_t i = wbase + (uint64_t)t * 32;
+			found[t] = i < n;                               // "valid" until probed
+			k[t] = found[t] ? ldg_stream_u32(&keys[i]) : 0;
+			v[t] = found[t] ? ldg_stream_u32(&vals[i]) : 0;
 		}
-		// first bucket of all four tuples in flight together: the probe is latency bound
-		uint32_t b[4];
-		ulonglong2 lo[4], hi[4];
 #pragma unroll
-		for (int e = 0; e < 4; ++e) {
-			b[e] = hash_range(k[e], factor, buckets);
-			const ulonglong2 *bp = reinterpret_cast<const ulonglong2 *>(table + (uint64_t)b[e] * 4);
-			lo[e] = __ldg(bp);
-			hi[e] = __ldg(bp + 1);
+		for (int t = 0; t < kNpjItems; ++t) {
+			b[t] = hash_range(k[t], factor, buckets);
+			const ulonglong2 *bp = reinterpret_cast<const ulonglong2 *>(table + (uint64_t)b[t] * 4);
+			lo[t] = __ldg(bp);
+			hi[t] = __ldg(bp + 1);
 		}
-		for (int mode = 0; mode < 2; ++mode) {         // 0: staged; 1: direct, only after a stage overflow
+		if (!slow) {
 #pragma unroll
-			for (int e = 0; e < 4; ++e) {
-				bool active = g < groups && idx + e < n;
-				uint32_t bb = b[e];
-				uint64_t s0 = lo[e].x, s1 = lo[e].y, s2 = hi[e].x, s3 = hi[e].y;
-				while (__any_sync(kFullMask, active)) {
-					const uint64_t slot[4] = {s0, s1, s2, s3};
-					bool full = true;
-#pragma unroll
-					for (int z = 0; z < 4; ++z) {
-						const bool used = slot[z] != kEmptySlot;
-						full = full && used;
-						const bool hit = active && used && (uint32_t)slot[z] == k[e];
-						const uint32_t ival = (uint32_t)(slot[z] >> 32);
-						if (mode == 0) {
-							if (hit) acc.add(k[e], v[e], ival);
-							if (MATERIALIZE) st.emit(hit, k[e], v[e], ival);
-						} else {
-							emit_direct(out, hit, k[e], v[e], ival);
-						}
-					}
-					active = active && full;               // an empty slot ends the chain
-					if (active) {
+			for (int t = 0; t < kNpjItems; ++t) {
+				bool hit = false;
+				if (found[t]) {
+					uint32_t bb = b[t];
+					uint64_t s0 = lo[t].x, s1 = lo[t].y, s2 = hi[t].x, s3 = hi[t].y;
+					while (true) {
+						if ((uint32_t)s0 == k[t] && s0 != kEmptySlot) { ival[t] = (uint32_t)(s0 >> 32); hit = true; break; }
+						if ((uint32_t)s1 == k[t] && s1 != kEmptySlot) { ival[t] = (uint32_t)(s1 >> 32); hit = true; break; }
+						if ((uint32_t)s2 == k[t] && s2 != kEmptySlot) { ival[t] = (uint32_t)(s2 >> 32); hit = true; break; }
+						if ((uint32_t)s3 == k[t] && s3 != kEmptySlot) { ival[t] = (uint32_t)(s3 >> 32); hit = true; break; }
+						if (s3 == kEmptySlot) break;               // slots fill lowest-first: a free last slot ends the chain
 						bb = bb + 1 == buckets ? 0 : bb + 1;
 						const ulonglong2 *bp = reinterpret_cast<const ulonglong2 *>(table + (uint64_t)bb * 4);
 						const ulonglong2 a = __ldg(bp), c = __ldg(bp + 1);
 						s0 = a.x; s1 = a.y; s2 = c.x; s3 = c.y;
 					}
 				}
-				if (sentinels && g < groups && idx + e < n && k[e] == kSentinelKey) {
-					for (uint32_t c = 0; c < sentinels; ++c) {
-						if (mode == 0) {
-							acc.add(k[e], v[e], kSentinelKey);
-							if (MATERIALIZE) st.emit_one(k[e], v[e], kSentinelKey);
-						} else {
-							const unsigned long long r = atomicAdd(out.cursor, 1ull);
-							if (r < out.cap) {
-								out.k[r] = k[e];
-								out.o[r] = v[e];
-								out.i[r] = kSentinelKey;
-							}
+				found[t] = hit;
+				if (hit) acc.add(k[t], v[t], ival[t]);
+			}
+			if (MATERIALIZE) {
+				unsigned m[kNpjItems];
+				uint32_t total = 0;
+#pragma unroll
+				for (int t = 0; t < kNpjItems; ++t) {
+					m[t] = __ballot_sync(kFullMask, found[t]);
+					total += __popc(m[t]);
+				}
+				if (total) {
+					unsigned long long base = 0;
+					if (lane_id() == 0) base = atomicAdd(out.cursor, (unsigned long long)total);
+					base = __shfl_sync(kFullMask, base, 0);
+					const unsigned lt = lanemask_lt();
+#pragma unroll
+					for (int t = 0; t < kNpjItems; ++t) {
+						const uint64_t r = base + __popc(m[t] & lt);
+						if (found[t] && r < out.cap) {
+							out.k[r] = k[t];
+							out.o[r] = v[t];
+							out.i[r] = ival[t];
 						}
+						base += __popc(m[t]);
 					}
 				}
 			}
-			if (!MATERIALIZE || mode == 1) break;
-			if (stage_flush(st, out, &s_base)) break;
+		} else {
+#pragma unroll
+			for (int t = 0; t < kNpjItems; ++t) {
+				if (!found[t]) continue;
+				uint32_t bb = b[t];
+				uint64_t slot[4] = {lo[t].x, lo[t].y, hi[t].x, hi[t].y};
+				while (true) {
+					bool full = true;
+#pragma unroll
+					for (int z = 0; z < 4; ++z) {
+						if (slot[z] == kEmptySlot) {
+							full = false;
+						} else if ((uint32_t)slot[z] == k[t]) {
+							acc.add(k[t], v[t], (uint32_t)(slot[z] >> 32));
+							if (MATERIALIZE) npj_emit_row(out, k[t], v[t], (uint32_t)(slot[z] >> 32));
+						}
+					}
+					if (!full) break;                              // an empty slot ends the chain
+					bb = bb + 1 == buckets ? 0 : bb + 1;
+					const ulonglong2 *bp = reinterpret_cast<const ulonglong2 *>(table + (uint64_t)bb * 4);
+					const ulonglong2 a = __ldg(bp), c = __ldg(bp + 1);
+					slot[0] = a.x; slot[1] = a.y; slot[2] = c.x; slot[3] = c.y;
+				}
+				if (k[t] == kSentinelKey)
+					for (uint32_t c = 0; c < sentinels; ++c) {
+						acc.add(k[t], v[t], kSentinelKey);
+						if (MATERIALIZE) npj_emit_row(out, k[t], v[t], kSentinelKey);
+					}
+			}
 		}
 	}
 	acc.reduce_to_global(sums, scratch);
@@ -189,19 +223,12 @@ int launch_npj_probe(const NpjArgs &a, cudaStream_t s, int sms, KernelTimer *t)
 	off.enabled = false;
 	off.n = 0;
 	if (!t) t = &off;
-	const size_t smem = (size_t)3 * kStageCap * 4 + 4 * 32 * 8;
-	static bool attr_set = false;
-	if (!attr_set) {
-		cudaFuncSetAttribute(k_npj_probe<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-		cudaFuncSetAttribute(k_npj_probe<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-		attr_set = true;
-	}
 	int per_sm = 0;
-	if (a.materialize) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_npj_probe<true>, kNpjThreads, smem);
-	else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_npj_probe<false>, kNpjThreads, smem);
+	if (a.materialize) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_npj_probe<true>, kNpjThreads, 0);
+	else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_npj_probe<false>, kNpjThreads, 0);
 	if (per_sm < 1) per_sm = 1;
-	const uint64_t groups = (a.ns + 3) / 4;
-	uint64_t grid = (groups + kNpjThreads - 1) / kNpjThreads;
+	const uint64_t rounds = (a.ns + kNpjThreads * kNpjItems - 1) / (kNpjThreads * kNpjItems);
+	uint64_t grid = rounds;
 	if (grid > (uint64_t)sms * per_sm) grid = (uint64_t)sms * per_sm;
 	if (grid == 0) grid = 1;
 	OutCols out;
@@ -212,11 +239,11 @@ int launch_npj_probe(const NpjArgs &a, cudaStream_t s, int sms, KernelTimer *t)
 	out.cap = a.materialize ? a.out_cap : 0;
 	t->start(KK_NPJ_PROBE, s);
 	if (a.materialize)
-		k_npj_probe<true><<<(uint32_t)grid, kNpjThreads, smem, s>>>(a.sk, a.sv, a.ns, a.table, (uint32_t)a.buckets,
-		                                                            a.factor, out, a.scalars + 1, a.scalars + 5);
+		k_npj_probe<true><<<(uint32_t)grid, kNpjThreads, 0, s>>>(a.sk, a.sv, a.ns, a.table, (uint32_t)a.buckets,
+		                                                         a.factor, out, a.scalars + 1, a.scalars + 5);
 	else
-		k_npj_probe<false><<<(uint32_t)grid, kNpjThreads, smem, s>>>(a.sk, a.sv, a.ns, a.table, (uint32_t)a.buckets,
-		                                                             a.factor, out, a.scalars + 1, a.scalars + 5);
+		k_npj_probe<false><<<(uint32_t)grid, kNpjThreads, 0, s>>>(a.sk, a.sv, a.ns, a.table, (uint32_t)a.buckets,
+		                                                          a.factor, out, a.scalars + 1, a.scalars + 5);
 	t->stop(s);
 	return 1;
 }

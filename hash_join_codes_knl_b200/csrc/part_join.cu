@@ -5,151 +5,244 @@
 // Persistent CTAs pull tasks from an atomic counter.  A task = (partition p, one slice of at
 // most s_task probe tuples of p): uniform inputs give one task per partition, a skewed probe
 // side (Zipf) is cut into many tasks that each rebuild p's small table, so no CTA is stuck
-// with a hot partition.  A build partition larger than the table is joined in several fills
-// (block nested loop), so any input is handled -- duplicates included.
+// with a hot partition.  A build partition larger than half the table is joined in several
+// fills (block nested loop), so any input is handled -- duplicates included.
+//
+// Hot path (a fill without duplicate build keys, the common case): every lane walks its own
+// probe chain and stops at the first equal key; the warp then reserves result rows with ONE
+// global atomicAdd per round of 32 x kItems probe tuples and writes the three result columns
+// straight from registers, one coalesced 128-byte run per item (ballot-ranked).  No CTA
+// barrier between the end of the build and the end of the probe.
+// Slow path (a fill that saw an equal build key twice, or the all-ones sentinel pair): every
+// match is emitted as it is met, with opportunistic warp aggregation of the row reservation.
 #include "hj_device.cuh"
 #include "hj_internal.h"
 
 namespace hjb {
 
-// tasks per partition -> exclusive prefix; P <= 2^22, one CTA
+// tasks per partition -> exclusive prefix; P <= 2^22, one CTA of 32 warps.  Each warp owns a
+// contiguous chunk of partitions and walks it 32 at a time (coalesced offset reads): first to
+// total its chunk, then -- after a scan of the 32 chunk totals -- to write the prefixes.
 __global__ void __launch_bounds__(1024)
 k_join_tasks(const uint32_t *__restrict__ r_off, const uint32_t *__restrict__ s_off, uint32_t P, uint32_t s_task,
              uint32_t *__restrict__ task_prefix)
 {
-	__shared__ uint32_t warp_totals[34];
-	const uint32_t per = (P + blockDim.x - 1) / blockDim.x;
-	const uint32_t p0 = threadIdx.x * per;
+	__shared__ uint32_t chunk_base[33];
+	const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
+	const uint32_t chunk = ((P + 31) / 32 + 31) & ~31u;          // partitions per warp, multiple of 32
+	const uint32_t beg = warp * chunk, end = min(P, beg + chunk);
 	auto tasks_of = [&](uint32_t p) -> uint32_t {
+		if (p >= end) return 0u;
 		const uint32_t rc = r_off[p + 1] - r_off[p], sc = s_off[p + 1] - s_off[p];
 		return (rc && sc) ? (sc + s_task - 1) / s_task : 0u;     // an empty side cannot match
 	};
 	uint32_t local = 0;
-	for (uint32_t p = p0; p < p0 + per && p < P; ++p) local += tasks_of(p);
-	uint32_t total;
-	uint32_t run = block_exclusive_scan(local, warp_totals, &total);
-	for (uint32_t p = p0; p < p0 + per && p < P; ++p) {
-		task_prefix[p] = run;
-		run += tasks_of(p);
+	for (uint32_t p = beg + lane; p < end; p += 32) local += tasks_of(p);
+	local = (uint32_t)warp_sum_u64(local);
+	if (lane == 0) chunk_base[warp] = local;
+	__syncthreads();
+	if (warp == 0) {
+		const uint32_t v = chunk_base[lane];
+		const uint32_t incl = warp_inclusive_scan_u32(v);
+		chunk_base[lane] = incl - v;
+		if (lane == 31) chunk_base[32] = incl;
 	}
-	if (threadIdx.x == 0) task_prefix[P] = total;
+	__syncthreads();
+	uint32_t run = chunk_base[warp];
+	for (uint32_t p0 = beg; p0 < end; p0 += 32) {
+		const uint32_t v = tasks_of(p0 + lane);
+		const uint32_t incl = warp_inclusive_scan_u32(v);
+		if (p0 + lane < end) task_prefix[p0 + lane] = run + incl - v;
+		run += __shfl_sync(kFullMask, incl, 31);
+	}
+	if (threadIdx.x == 0) task_prefix[P] = chunk_base[32];
 }
 
-// dynamic shared memory: table[kJoinSlots] (uint64) | stage k,o,i [kStageCap] | scratch
-template <bool MATERIALIZE>
-__global__ void __launch_bounds__(kJoinThreads)
+// one row, reservation aggregated over whichever lanes of the warp are here together
+__device__ __forceinline__ void emit_row_opportunistic(const OutCols &out, uint32_t key, uint32_t oval, uint32_t ival)
+{
+	const unsigned m = __activemask();
+	const int leader = __ffs(m) - 1;
+	unsigned long long base = 0;
+	if ((int)lane_id() == leader) base = atomicAdd(out.cursor, (unsigned long long)__popc(m));
+	base = __shfl_sync(m, base, leader);
+	const uint64_t r = base + __popc(m & lanemask_lt());
+	if (r < out.cap) {
+		out.k[r] = key;
+		out.o[r] = oval;
+		out.i[r] = ival;
+	}
+}
+
+template <int LOG2_SLOTS, int THREADS, int ITEMS, bool MATERIALIZE>
+__global__ void __launch_bounds__(THREADS, 1024 / THREADS)
 k_partition_join(const uint32_t *__restrict__ rk, const uint32_t *__restrict__ rv,
                  const uint32_t *__restrict__ sk, const uint32_t *__restrict__ sv,
                  const uint32_t *__restrict__ r_off, const uint32_t *__restrict__ s_off, uint32_t P,
                  const uint32_t *__restrict__ task_prefix, uint32_t *__restrict__ task_counter, uint32_t s_task,
                  uint32_t table_factor, OutCols out, unsigned long long *__restrict__ sums)
 {
-	extern __shared__ __align__(16) unsigned char s_raw[];
-	uint64_t *table = reinterpret_cast<uint64_t *>(s_raw);
-	uint32_t *stage_mem = reinterpret_cast<uint32_t *>(table + kJoinSlots);
-	uint64_t *scratch = reinterpret_cast<uint64_t *>(stage_mem + 3 * kStageCap);   // 4 * 32 uint64
-	__shared__ uint32_t s_task_id, s_cnt, s_sentinels;
-	__shared__ unsigned long long s_base;
-	MatchStage st;
-	st.k = stage_mem;
-	st.o = stage_mem + kStageCap;
-	st.i = stage_mem + 2 * kStageCap;
-	st.cnt = &s_cnt;
-	st.cap = kStageCap;
-	constexpr uint32_t kMask = kJoinSlots - 1, kFill = kJoinSlots / 2;   // build tuples per table fill
-	constexpr int kTableShift = 32 - 13;
-	static_assert(kJoinSlots == 1u << 13, "table hash takes the top 13 bits");
+	constexpr uint32_t kSlots = 1u << LOG2_SLOTS, kMask = kSlots - 1;
+	constexpr uint32_t kFill = kSlots / 4 * 3;       // build tuples per table fill: load <= 0.75, 0.5 on average
+	constexpr int kShift = 32 - LOG2_SLOTS;
+	extern __shared__ __align__(16) uint64_t table[];   // kSlots slots of payload<<32 | key
+	__shared__ uint64_t scratch[4 * 32];
+	__shared__ uint32_t s_task_id[2], s_dups, s_sentinels;
 	JoinSums acc;
 	acc.zero();
-	if (threadIdx.x == 0) s_cnt = 0;
 	const uint32_t total_tasks = task_prefix[P];
-
-	while (true) {
-		__syncthreads();
-		if (threadIdx.x == 0) s_task_id = atomicAdd(task_counter, 1u);
-		__syncthreads();
-		const uint32_t task = s_task_id;
+	if (threadIdx.x == 0) s_task_id[0] = atomicAdd(task_counter, 1u);
+	__syncthreads();
+	for (uint32_t it = 0;; ++it) {
+		const uint32_t task = s_task_id[it & 1];
 		if (task >= total_tasks) break;
+		if (threadIdx.x == 0) s_task_id[(it + 1) & 1] = atomicAdd(task_counter, 1u);   // read after this task's barriers
 		const uint32_t p = upper_parent(task_prefix, P, task);
 		const uint32_t slice = task - task_prefix[p];
 		const uint32_t r_beg = r_off[p], r_end = r_off[p + 1];
-		uint32_t s_beg = s_off[p] + slice * s_task, s_end = s_off[p + 1];
-		if (s_end - s_beg > s_task) s_end = s_beg + s_task;
+		const uint32_t s_beg = s_off[p] + slice * s_task;
+		const uint32_t s_end = min(s_off[p + 1], s_beg + s_task);
 
 		for (uint32_t fb = r_beg; fb < r_end; fb += kFill) {
 			const uint32_t fe = min(fb + kFill, r_end);
-			// ---- build (reference build(): double hashing into a prime table; here linear probing
-			// into a power-of-two table indexed by the top bits of key * table_factor)
-			for (uint32_t h = threadIdx.x; h < kJoinSlots; h += kJoinThreads) table[h] = kEmptySlot;
-			if (threadIdx.x == 0) s_sentinels = 0;
+			// ---- clear + build (reference build(): double hashing into a prime table; here linear
+			// probing into a power-of-two table indexed by the top bits of key * table_factor)
+			{
+				ulonglong2 *t2 = reinterpret_cast<ulonglong2 *>(table);
+				for (uint32_t h = threadIdx.x; h < kSlots / 2; h += THREADS) t2[h] = make_ulonglong2(kEmptySlot, kEmptySlot);
+			}
+			if (threadIdx.x == 0) {
+				s_dups = 0;
+				s_sentinels = 0;
+			}
 			__syncthreads();
-			for (uint32_t i = fb + threadIdx.x; i < fe; i += kJoinThreads) {
+			for (uint32_t i = fb + threadIdx.x; i < fe; i += THREADS) {
 				const uint32_t key = rk[i];
 				const uint64_t pair = ((uint64_t)rv[i] << 32) | key;
 				if (pair == kEmptySlot) {                  // the one pair that looks like an empty slot
 					atomicAdd(&s_sentinels, 1u);
 					continue;
 				}
-				uint32_t h = hash_mul(key, table_factor) >> kTableShift;
-				while (atomicCAS(reinterpret_cast<unsigned long long *>(&table[h]), (unsigned long long)kEmptySlot,
-				                 (unsigned long long)pair) != kEmptySlot)
+				uint32_t h = hash_mul(key, table_factor) >> kShift;
+				while (true) {
+					const uint64_t old = atomicCAS(reinterpret_cast<unsigned long long *>(&table[h]),
+					                               (unsigned long long)kEmptySlot, (unsigned long long)pair);
+					if (old == kEmptySlot) break;
+					if ((uint32_t)old == key) s_dups = 1;   // equal build keys: probes must walk to the chain's end
 					h = (h + 1) & kMask;
+				}
 			}
 			__syncthreads();
+			const bool slow = s_dups != 0 || s_sentinels != 0;
 			const uint32_t sentinels = s_sentinels;
-			// ---- probe, kJoinThreads * kJoinItems tuples per round
-			for (uint32_t sb = s_beg; sb < s_end; sb += kJoinThreads * kJoinItems) {
-				uint32_t key[kJoinItems], val[kJoinItems];
-				bool valid[kJoinItems];
+			// ---- probe, THREADS * ITEMS tuples per round
+			for (uint32_t sb = s_beg; sb < s_end; sb += THREADS * ITEMS) {
+				uint32_t key[ITEMS], val[ITEMS], ival[ITEMS];
+				bool found[ITEMS];
+				const uint32_t wbase = sb + (threadIdx.x & ~31u) * ITEMS + lane_id();   // a warp owns 32*ITEMS consecutive tuples
 #pragma unroll
-				for (uint32_t t = 0; t < kJoinItems; ++t) {
-					const uint32_t i = sb + t * kJoinThreads + threadIdx.x;
-					valid[t] = i < s_end;
-					key[t] = valid[t] ? ldg_stream_u32(&sk[i]) : 0;
-					val[t] = valid[t] ? ldg_stream_u32(&sv[i]) : 0;
+				for (int t = 0; t < ITEMS; ++t) {
+					const uint32_t i = wbase + t * 32;
+					found[t] = i < s_end;                   // "valid" until probed
+					key[t] = found[t] ? ldg_stream_u32(&sk[i]) : 0;
+					val[t] = found[t] ? ldg_stream_u32(&sv[i]) : 0;
 				}
-				for (int mode = 0; mode < 2; ++mode) {     // 0: staged; 1: direct, only after a stage overflow
+				if (!slow) {
 #pragma unroll
-					for (uint32_t t = 0; t < kJoinItems; ++t) {
-						bool active = valid[t];
-						uint32_t h = hash_mul(key[t], table_factor) >> kTableShift;
-						while (__any_sync(kFullMask, active)) {
-							const uint64_t slot = active ? table[h] : kEmptySlot;
-							active = active && slot != kEmptySlot;
-							const bool hit = active && (uint32_t)slot == key[t];
-							const uint32_t ival = (uint32_t)(slot >> 32);
-							if (mode == 0) {
-								if (hit) acc.add(key[t], val[t], ival);
-								if (MATERIALIZE) st.emit(hit, key[t], val[t], ival);
-							} else {
-								emit_direct(out, hit, key[t], val[t], ival);
-							}
-							h = (h + 1) & kMask;
-						}
-						if (sentinels && valid[t] && key[t] == kSentinelKey) {
-							for (uint32_t c = 0; c < sentinels; ++c) {
-								if (mode == 0) {
-									acc.add(key[t], val[t], kSentinelKey);
-									if (MATERIALIZE) st.emit_one(key[t], val[t], kSentinelKey);
-								} else {
-									const unsigned long long r = atomicAdd(out.cursor, 1ull);
-									if (r < out.cap) {
-										out.k[r] = key[t];
-										out.o[r] = val[t];
-										out.i[r] = kSentinelKey;
-									}
+					for (int t = 0; t < ITEMS; ++t) {
+						bool hit = false;
+						if (found[t]) {
+							uint32_t h = hash_mul(key[t], table_factor) >> kShift;
+							while (true) {
+								const uint64_t slot = table[h];
+								if (slot == kEmptySlot) break;
+								if ((uint32_t)slot == key[t]) {
+									ival[t] = (uint32_t)(slot >> 32);
+									hit = true;
+									break;
 								}
+								h = (h + 1) & kMask;
+							}
+						}
+						found[t] = hit;
+						if (hit) acc.add(key[t], val[t], ival[t]);
+					}
+					if (MATERIALIZE) {
+						unsigned m[ITEMS];
+						uint32_t total = 0;
+#pragma unroll
+						for (int t = 0; t < ITEMS; ++t) {
+							m[t] = __ballot_sync(kFullMask, found[t]);
+							total += __popc(m[t]);
+						}
+						if (total) {
+							unsigned long long base = 0;
+							if (lane_id() == 0) base = atomicAdd(out.cursor, (unsigned long long)total);
+							base = __shfl_sync(kFullMask, base, 0);
+							const unsigned lt = lanemask_lt();
+#pragma unroll
+							for (int t = 0; t < ITEMS; ++t) {
+								const uint64_t r = base + __popc(m[t] & lt);
+								if (found[t] && r < out.cap) {
+									out.k[r] = key[t];
+									out.o[r] = val[t];
+									out.i[r] = ival[t];
+								}
+								base += __popc(m[t]);
 							}
 						}
 					}
-					if (!MATERIALIZE || mode == 1) break;
-					if (stage_flush(st, out, &s_base)) break;      // common case: rows copied out, done
+				} else {
+#pragma unroll
+					for (int t = 0; t < ITEMS; ++t) {
+						if (!found[t]) continue;
+						uint32_t h = hash_mul(key[t], table_factor) >> kShift;
+						while (true) {
+							const uint64_t slot = table[h];
+							if (slot == kEmptySlot) break;
+							if ((uint32_t)slot == key[t]) {
+								acc.add(key[t], val[t], (uint32_t)(slot >> 32));
+								if (MATERIALIZE) emit_row_opportunistic(out, key[t], val[t], (uint32_t)(slot >> 32));
+							}
+							h = (h + 1) & kMask;
+						}
+						if (key[t] == kSentinelKey)
+							for (uint32_t c = 0; c < sentinels; ++c) {
+								acc.add(key[t], val[t], kSentinelKey);
+								if (MATERIALIZE) emit_row_opportunistic(out, key[t], val[t], kSentinelKey);
+							}
+					}
 				}
 			}
-			__syncthreads();
+			__syncthreads();          // the table is cleared next; also publishes the prefetched task id
 		}
 	}
 	acc.reduce_to_global(sums, scratch);
+}
+
+template <int LOG2_SLOTS, int THREADS, int ITEMS>
+static void launch_join_variant(const JoinArgs &a, cudaStream_t s, int sms, const OutCols &out)
+{
+	auto kt = k_partition_join<LOG2_SLOTS, THREADS, ITEMS, true>;
+	auto kf = k_partition_join<LOG2_SLOTS, THREADS, ITEMS, false>;
+	constexpr size_t smem = (size_t)8 << LOG2_SLOTS;
+	static bool attr_set = false;
+	if (!attr_set) {
+		cudaFuncSetAttribute(kt, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+		cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+		attr_set = true;
+	}
+	int per_sm = 0;
+	if (a.materialize) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kt, THREADS, smem);
+	else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kf, THREADS, smem);
+	if (per_sm < 1) per_sm = 1;
+	const uint32_t grid = (uint32_t)(sms * per_sm);
+	if (a.materialize)
+		kt<<<grid, THREADS, smem, s>>>(a.rk, a.rv, a.sk, a.sv, a.r_off, a.s_off, a.P, a.task_prefix, a.task_counter,
+		                            a.s_task, a.table_factor, out, a.scalars + 1);
+	else
+		kf<<<grid, THREADS, smem, s>>>(a.rk, a.rv, a.sk, a.sv, a.r_off, a.s_off, a.P, a.task_prefix, a.task_counter,
+		                            a.s_task, a.table_factor, out, a.scalars + 1);
 }
 
 int launch_partition_join(const JoinArgs &a, cudaStream_t s, int sms, KernelTimer *t)
@@ -158,24 +251,10 @@ int launch_partition_join(const JoinArgs &a, cudaStream_t s, int sms, KernelTime
 	off.enabled = false;
 	off.n = 0;
 	if (!t) t = &off;
-	const size_t smem = (size_t)kJoinSlots * 8 + (size_t)3 * kStageCap * 4 + 4 * 32 * 8;
-	static bool attr_set = false;
-	if (!attr_set) {
-		cudaFuncSetAttribute(k_partition_join<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-		cudaFuncSetAttribute(k_partition_join<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-		attr_set = true;
-	}
 	cudaMemsetAsync(a.task_counter, 0, 4, s);
 	t->start(KK_JOIN_TASKS, s);
 	k_join_tasks<<<1, 1024, 0, s>>>(a.r_off, a.s_off, a.P, a.s_task, a.task_prefix);
 	t->stop(s);
-	int per_sm = 0;
-	if (a.materialize)
-		cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_partition_join<true>, kJoinThreads, smem);
-	else
-		cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_partition_join<false>, kJoinThreads, smem);
-	if (per_sm < 1) per_sm = 1;
-	const uint32_t grid = (uint32_t)(sms * per_sm);
 	OutCols out;
 	out.k = a.out_k;
 	out.o = a.out_o;
@@ -183,14 +262,7 @@ int launch_partition_join(const JoinArgs &a, cudaStream_t s, int sms, KernelTime
 	out.cursor = a.scalars;
 	out.cap = a.materialize ? a.out_cap : 0;
 	t->start(KK_PART_JOIN, s);
-	if (a.materialize)
-		k_partition_join<true><<<grid, kJoinThreads, smem, s>>>(a.rk, a.rv, a.sk, a.sv, a.r_off, a.s_off, a.P,
-		                                                        a.task_prefix, a.task_counter, a.s_task,
-		                                                        a.table_factor, out, a.scalars + 1);
-	else
-		k_partition_join<false><<<grid, kJoinThreads, smem, s>>>(a.rk, a.rv, a.sk, a.sv, a.r_off, a.s_off, a.P,
-		                                                         a.task_prefix, a.task_counter, a.s_task,
-		                                                         a.table_factor, out, a.scalars + 1);
+	launch_join_variant<kJoinLog2Slots, kJoinThreads, kJoinItems>(a, s, sms, out);
 	t->stop(s);
 	return 2;
 }

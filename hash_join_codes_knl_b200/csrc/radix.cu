@@ -233,7 +233,7 @@ k_scan(const uint32_t *__restrict__ item_prefix, uint32_t np, int bits, uint32_t
 // ------------------------------------------------------------------ scatter
 
 // dynamic shared memory: cnt[F] base[F] delta[F] gpos[F] | buf[kScatterTile] (uint2)
-__global__ void __launch_bounds__(kScatterThreads)
+__global__ void __launch_bounds__(kScatterThreads, 3)
 k_scatter(const uint32_t *__restrict__ keys, const uint32_t *__restrict__ vals, uint64_t n, uint32_t np,
           const uint32_t *__restrict__ parent_off, const uint32_t *__restrict__ item_prefix, uint32_t chunk,
           uint32_t factor, int rshift, int bits, const uint32_t *__restrict__ offsets,
