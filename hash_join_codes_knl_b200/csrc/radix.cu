@@ -232,33 +232,28 @@ k_scan(const uint32_t *__restrict__ item_prefix, uint32_t np, int bits, uint32_t
 
 // ------------------------------------------------------------------ scatter
 
-// dynamic shared memory: cnt[F] base[F] delta[F] gpos[F] | buf[kScatterTile] (uint2)
-__global__ void __launch_bounds__(kScatterThreads, 3)
-k_scatter(const uint32_t *__restrict__ keys, const uint32_t *__restrict__ vals, uint64_t n, uint32_t np,
-          const uint32_t *__restrict__ parent_off, const uint32_t *__restrict__ item_prefix, uint32_t chunk,
-          uint32_t factor, int rshift, int bits, const uint32_t *__restrict__ offsets,
-          uint32_t *__restrict__ keys_out, uint32_t *__restrict__ vals_out)
+// One tile = kScatterTile tuples = kScatterTile/4 absolutely aligned groups; thread t owns
+// groups t and t + kScatterThreads of the tile (coalesced 128-bit loads).
+struct TileRegs {
+	uint32_t key[8], val[8];
+	uint32_t ok;          // bit e: element e lies inside the item's range
+};
+
+template <bool FULL>
+__device__ __forceinline__ void load_tile(TileRegs &t, const uint32_t *keys, const uint32_t *vals, uint64_t g0,
+                                          uint64_t g_end, uint64_t beg, uint64_t end, uint64_t n)
 {
-	extern __shared__ __align__(16) uint32_t s_mem[];
-	__shared__ uint32_t warp_totals[34];
-	const uint32_t F = 1u << bits, mask = F - 1;
-	uint32_t *cnt = s_mem, *base = cnt + F, *delta = base + F, *gpos = delta + F;
-	uint2 *buf = reinterpret_cast<uint2 *>(gpos + F);
-	ItemRange r;
-	if (!locate_item(item_prefix, np, parent_off, n, chunk, blockIdx.x, &r)) return;
-	const uint32_t *row = offsets + (size_t)blockIdx.x * F;
-	for (uint32_t p = threadIdx.x; p < F; p += blockDim.x) gpos[p] = row[p];
-	const uint32_t ept = (F + kScatterThreads - 1) / kScatterThreads;   // digits per thread in the tile scan
-	constexpr uint32_t kGroupsPerTile = kScatterTile / 4, kGroupsPerThread = kGroupsPerTile / kScatterThreads;
-	const uint64_t g_end = (r.end + 3) >> 2;
-	for (uint64_t g0 = r.beg >> 2; g0 < g_end; g0 += kGroupsPerTile) {
-		for (uint32_t p = threadIdx.x; p < F; p += blockDim.x) cnt[p] = 0;
-		__syncthreads();
-		uint32_t key[4 * kGroupsPerThread], val[4 * kGroupsPerThread], rank[4 * kGroupsPerThread];
-		bool ok[4 * kGroupsPerThread];
+	t.ok = 0;
 #pragma unroll
-		for (uint32_t t = 0; t < kGroupsPerThread; ++t) {
-			const uint64_t g = g0 + threadIdx.x + (uint64_t)t * kScatterThreads;
+	for (int h = 0; h < 2; ++h) {
+		const uint64_t g = g0 + threadIdx.x + (uint64_t)h * kScatterThreads;
+		if (FULL) {
+			const uint4 kk = ldg_stream_u4(reinterpret_cast<const uint4 *>(keys) + g);
+			const uint4 vv = ldg_stream_u4(reinterpret_cast<const uint4 *>(vals) + g);
+			t.key[4 * h + 0] = kk.x; t.key[4 * h + 1] = kk.y; t.key[4 * h + 2] = kk.z; t.key[4 * h + 3] = kk.w;
+			t.val[4 * h + 0] = vv.x; t.val[4 * h + 1] = vv.y; t.val[4 * h + 2] = vv.z; t.val[4 * h + 3] = vv.w;
+			t.ok |= 0xFu << (4 * h);
+		} else {
 			uint32_t k4[4] = {0, 0, 0, 0}, v4[4] = {0, 0, 0, 0};
 			if (g < g_end) {
 				load_group4(keys, g, n, k4);
@@ -267,44 +262,161 @@ k_scatter(const uint32_t *__restrict__ keys, const uint32_t *__restrict__ vals, 
 #pragma unroll
 			for (int e = 0; e < 4; ++e) {
 				const uint64_t idx = (g << 2) + e;
-				key[4 * t + e] = k4[e];
-				val[4 * t + e] = v4[e];
-				ok[4 * t + e] = g < g_end && idx >= r.beg && idx < r.end;
+				t.key[4 * h + e] = k4[e];
+				t.val[4 * h + e] = v4[e];
+				if (g < g_end && idx >= beg && idx < end) t.ok |= 1u << (4 * h + e);
 			}
 		}
+	}
+}
+
+// Per tile: (1) every tuple takes a rank inside its digit with a shared-memory atomicAdd,
+// (2) warp 0 turns the digit counts into tile offsets and decides, per digit, how far the
+// item's output may be flushed, (3) tuples are placed into shared memory grouped by digit,
+// (4) the tile is streamed out, neighbouring threads writing neighbouring addresses of one
+// partition's run.  The loads of the NEXT tile are issued before (1) and stay in flight
+// through all four steps.
+//
+// Software write-combining (the reference's per-partition staging buffers, cpra2.cpp:976-1008,
+// flush cpra2.cpp:711-729): a digit's run is only written up to the last 32-byte sector boundary
+// of its output position; the < 8 tuples beyond it wait in a per-digit carry buffer and lead
+// the digit's run of the next tile.  Every store but an item's first and last per digit then
+// covers whole sectors, so L2 never has to fetch the rest of a half-written sector from HBM.
+// (WC is on for fan-outs <= 256, where the carry buffers fit; wider passes write runs as is.)
+// dynamic shared memory: cnt base fpos oldp wpos pend [F] | golim[F] (uint2) | buf[kScatterTile] (uint2) | carry[F*8] (uint2)
+constexpr uint32_t kCarry = 8;         // tuples per 32-byte sector of a 4-byte column
+
+__global__ void __launch_bounds__(kScatterThreads, 2)
+k_scatter(const uint32_t *__restrict__ keys, const uint32_t *__restrict__ vals, uint64_t n, uint32_t np,
+          const uint32_t *__restrict__ parent_off, const uint32_t *__restrict__ item_prefix, uint32_t chunk,
+          uint32_t factor, int rshift, int bits, const uint32_t *__restrict__ offsets,
+          uint32_t *__restrict__ keys_out, uint32_t *__restrict__ vals_out)
+{
+	extern __shared__ __align__(16) uint32_t s_mem[];
+	__shared__ uint32_t warp_totals[34];
+	__shared__ uint32_t s_tile_n;
+	const uint32_t F = 1u << bits, mask = F - 1;
+	const bool wc = F <= 256;
+	uint32_t *cnt = s_mem, *base = cnt + F, *fpos = base + F, *oldp = fpos + F, *wpos = oldp + F, *pend = wpos + F;
+	uint2 *golim = reinterpret_cast<uint2 *>(pend + F);                 // x: global offset of tile index 0, y: flush limit
+	uint2 *buf = golim + F;
+	uint2 *carry = buf + kScatterTile;
+	ItemRange r;
+	if (!locate_item(item_prefix, np, parent_off, n, chunk, blockIdx.x, &r)) return;
+	const uint32_t *row = offsets + (size_t)blockIdx.x * F;
+	for (uint32_t p = threadIdx.x; p < F; p += blockDim.x) {
+		wpos[p] = row[p];
+		pend[p] = 0;
+		cnt[p] = 0;
+	}
+	constexpr uint32_t kGroupsPerTile = kScatterTile / 4;
+	const uint64_t g_beg = r.beg >> 2, g_end = (r.end + 3) >> 2;
+	auto tile_is_full = [&](uint64_t g0) {
+		return (g0 << 2) >= r.beg && ((g0 + kGroupsPerTile) << 2) <= r.end;    // r.end <= n: vector loads stay inside
+	};
+	TileRegs cur, nxt;
+	if (g_beg < g_end) {
+		if (tile_is_full(g_beg)) load_tile<true>(nxt, keys, vals, g_beg, g_end, r.beg, r.end, n);
+		else load_tile<false>(nxt, keys, vals, g_beg, g_end, r.beg, r.end, n);
+	}
+	__syncthreads();
+	for (uint64_t g0 = g_beg; g0 < g_end; g0 += kGroupsPerTile) {
+		cur = nxt;
+		const uint64_t g1 = g0 + kGroupsPerTile;
+		const bool last = g1 >= g_end;
+		if (!last) {
+			if (tile_is_full(g1)) load_tile<true>(nxt, keys, vals, g1, g_end, r.beg, r.end, n);
+			else load_tile<false>(nxt, keys, vals, g1, g_end, r.beg, r.end, n);
+		}
+		// (1) rank: digit << 16 | rank-in-digit (rank < kScatterTile <= 2^16, digit < 2^11)
+		uint32_t dr[8];
 #pragma unroll
-		for (uint32_t t = 0; t < 4 * kGroupsPerThread; ++t)
-			if (ok[t]) rank[t] = atomicAdd(&cnt[radix_digit(hash_mul(key[t], factor), rshift, mask)], 1u);
+		for (int e = 0; e < 8; ++e) {
+			const uint32_t d = radix_digit(hash_mul(cur.key[e], factor), rshift, mask);
+			dr[e] = (cur.ok >> e) & 1u ? (d << 16) | atomicAdd(&cnt[d], 1u) : 0xFFFFFFFFu;
+		}
 		__syncthreads();
-		// exclusive scan of cnt -> base; delta = global cursor - base; advance the cursor
-		uint32_t local = 0;
-		const uint32_t p0 = threadIdx.x * ept;
-		for (uint32_t p = p0; p < p0 + ept && p < F; ++p) local += cnt[p];
-		uint32_t tile_n;
-		uint32_t run = block_exclusive_scan(local, warp_totals, &tile_n);
-		for (uint32_t p = p0; p < p0 + ept && p < F; ++p) {
-			const uint32_t c = cnt[p];
+		// (2) per digit: tile offset, global offset, flush limit, what stays pending
+		auto plan_digit = [&](uint32_t p, uint32_t c, uint32_t run) {
+			const uint32_t w = wpos[p], pe = pend[p], endpos = w + pe + c;
+			uint32_t lim = (last || !wc) ? endpos : (endpos & ~(kCarry - 1));
+			const bool flush = lim > w;
+			if (!flush) lim = w;
 			base[p] = run;
-			delta[p] = gpos[p] - run;
-			gpos[p] += c;
-			run += c;
-		}
-		__syncthreads();
+			golim[p] = make_uint2(w + pe - run, lim);
+			fpos[p] = w;
+			oldp[p] = flush ? pe : 0;
+			wpos[p] = lim;
+			pend[p] = endpos - lim;
+			cnt[p] = 0;
+		};
+		if (F <= 256) {
+			if (threadIdx.x < 32) {
+				const uint32_t per = F >> 5 ? F >> 5 : 1;          // digits per lane (F >= 32), else one
+				const uint32_t p0 = threadIdx.x * per;
+				uint32_t c[8], local = 0;
 #pragma unroll
-		for (uint32_t t = 0; t < 4 * kGroupsPerThread; ++t)
-			if (ok[t]) {
-				const uint32_t d = radix_digit(hash_mul(key[t], factor), rshift, mask);
-				buf[base[d] + rank[t]] = make_uint2(key[t], val[t]);
+				for (uint32_t j = 0; j < 8; ++j) {
+					c[j] = (j < per && p0 + j < F) ? cnt[p0 + j] : 0;
+					local += c[j];
+				}
+				const uint32_t incl = warp_inclusive_scan_u32(local);
+				uint32_t run = incl - local;
+#pragma unroll
+				for (uint32_t j = 0; j < 8; ++j)
+					if (j < per && p0 + j < F) {
+						plan_digit(p0 + j, c[j], run);
+						run += c[j];
+					}
+				if (threadIdx.x == 31) s_tile_n = incl;
+			}
+			__syncthreads();
+		} else {
+			const uint32_t ept = (F + kScatterThreads - 1) / kScatterThreads;
+			const uint32_t p0 = threadIdx.x * ept;
+			uint32_t local = 0;
+			for (uint32_t p = p0; p < p0 + ept && p < F; ++p) local += cnt[p];
+			uint32_t tile_total;
+			uint32_t run = block_exclusive_scan(local, warp_totals, &tile_total);
+			for (uint32_t p = p0; p < p0 + ept && p < F; ++p) {
+				const uint32_t c = cnt[p];
+				plan_digit(p, c, run);
+				run += c;
+			}
+			if (threadIdx.x == 0) s_tile_n = tile_total;
+			__syncthreads();
+		}
+		// (3) place the tile's tuples; flush the carried tuples of every digit that reached a boundary
+#pragma unroll
+		for (int e = 0; e < 8; ++e)
+			if (dr[e] != 0xFFFFFFFFu) buf[base[dr[e] >> 16] + (dr[e] & 0xFFFFu)] = make_uint2(cur.key[e], cur.val[e]);
+		if (wc)
+			for (uint32_t i = threadIdx.x; i < F * kCarry; i += kScatterThreads) {
+				const uint32_t d = i / kCarry, j = i % kCarry;
+				if (j < oldp[d]) {
+					const uint2 kv = carry[i];
+					const uint32_t dst = fpos[d] + j;
+					keys_out[dst] = kv.x;
+					vals_out[dst] = kv.y;
+				}
 			}
 		__syncthreads();
-		// the tile is now grouped by digit: neighbouring threads write neighbouring addresses of a run
+		// (4) stream the digit-grouped tile: below the digit's limit to global memory, beyond it into
+		// the carry buffer.  The next tile's step (1) barrier orders this loop before step (2) rewrites
+		// golim and before step (3) reads carry.
+		const uint32_t tile_n = s_tile_n;
 		for (uint32_t i = threadIdx.x; i < tile_n; i += kScatterThreads) {
 			const uint2 kv = buf[i];
-			const uint32_t dst = delta[radix_digit(hash_mul(kv.x, factor), rshift, mask)] + i;
-			keys_out[dst] = kv.x;
-			vals_out[dst] = kv.y;
+			const uint32_t d = radix_digit(hash_mul(kv.x, factor), rshift, mask);
+			const uint2 gl = golim[d];
+			const uint32_t pos = gl.x + i;
+			if (pos < gl.y) {
+				keys_out[pos] = kv.x;
+				vals_out[pos] = kv.y;
+			} else {
+				carry[d * kCarry + (pos - gl.y)] = kv;
+			}
 		}
-		__syncthreads();
 	}
 }
 
@@ -352,10 +464,10 @@ int launch_radix_pass(const RadixPassArgs &a, cudaStream_t s, int /*sms*/, Kerne
 	k_scan<<<tiles, kScanThreads, 0, s>>>(a.item_prefix, a.np, a.bits, a.counts, a.child_off, a.scan_status,
 	                                      a.scan_counter);
 	t->stop(s);
-	const size_t smem = (size_t)F * 16 + (size_t)kScatterTile * 8;
+	const size_t smem = (size_t)F * 32 + (size_t)kScatterTile * 8 + (F <= 256 ? (size_t)F * kCarry * 8 : 0);
 	static bool attr_set = false;
 	if (!attr_set) {
-		cudaFuncSetAttribute(k_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, 2048 * 16 + kScatterTile * 8);
+		cudaFuncSetAttribute(k_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, 2048 * 32 + kScatterTile * 8);
 		attr_set = true;
 	}
 	t->start(KK_SCATTER, s);
