@@ -365,7 +365,7 @@ struct Plan {
 // Reference planner (phj.cpp:1791-1808): partitions = tuples / hash_table_limit, 1-4 passes of
 // equal fan-out.  Here: enough bits that a build partition averages part_tuples (a quarter of
 // the shared-memory table), passes of at most 8 bits (256-way scatter keeps per-digit runs long).
-static int make_plan(hjb_ctx *ctx, uint64_t nr, const hjb_opts *o, int consumed, Plan *p)
+static int make_plan(hjb_ctx *ctx, uint64_t nr, uint64_t ns, const hjb_opts *o, int consumed, Plan *p)
 {
 	memset(p, 0, sizeof *p);
 	int user = 0;
@@ -381,6 +381,9 @@ static int make_plan(hjb_ctx *ctx, uint64_t nr, const hjb_opts *o, int consumed,
 		const uint32_t target = o->part_tuples ? o->part_tuples : kDefaultPartTuples;
 		int tb = 0;
 		while (tb < 28 && (nr >> tb) > target) ++tb;
+		// with <= 16 hash bits left below the partition id the join kernel addresses payloads directly
+		// (csrc/part_join.cu); worth two full passes as soon as the input is not tiny
+		if (!o->part_tuples && nr + ns >= (1u << 22) && consumed + tb < 16) tb = 16 - consumed;
 		p->total_bits = tb;
 		p->npass = (tb + 7) / 8;
 		for (int i = 0; i < p->npass; ++i) p->bits[i] = tb / p->npass + (i < tb % p->npass ? 1 : 0);
@@ -464,7 +467,7 @@ static int phj_device(hjb_ctx *ctx, const hjb_rel *R, const hjb_rel *S, const hj
 	timer_reset(ctx);
 	if (R->tuples == 0 || S->tuples == 0) return HJB_OK;
 	Plan plan;
-	if ((rc = make_plan(ctx, R->tuples, o, consumed, &plan))) return rc;
+	if ((rc = make_plan(ctx, R->tuples, S->tuples, o, consumed, &plan))) return rc;
 	size_t rscratch;
 	const size_t need = phj_workspace(R->tuples, S->tuples, plan, &rscratch);
 	if ((rc = grow_device(ctx, &ctx->ws, &ctx->ws_bytes, need))) return rc;
@@ -510,6 +513,8 @@ static int phj_device(hjb_ctx *ctx, const hjb_rel *R, const hjb_rel *S, const hj
 	j.rk = pr.k; j.rv = pr.v; j.sk = ps.k; j.sv = ps.v;
 	j.r_off = pr.off; j.s_off = ps.off;
 	j.P = P;
+	j.radix_factor = radix_factor;
+	j.rem_bits = 32 - consumed - plan.total_bits;
 	j.table_factor = hjb_hash_factor(o->seed, 1);
 	j.task_prefix = task_prefix;
 	j.task_counter = task_counter;

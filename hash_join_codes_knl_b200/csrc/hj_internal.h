@@ -73,6 +73,8 @@ struct JoinArgs {
 	const uint32_t *rk, *rv, *sk, *sv;       // partitioned columns
 	const uint32_t *r_off, *s_off;           // P + 1 entries each
 	uint32_t P;
+	uint32_t radix_factor;                   // the partitions are radix digits of key * radix_factor
+	int rem_bits;                            // hash bits of key * radix_factor below the partition id
 	uint32_t table_factor;
 	uint32_t *task_prefix;                   // P + 1 scratch
 	uint32_t *task_counter;                  // 1, zeroed by the launcher

@@ -1,20 +1,29 @@
-// part_join.cu -- per-partition build + probe with the partition's hash table resident in
-// shared memory (reference: the cache-resident join loop, phj.cpp:1880-1923 / cpra2.cpp:1907-1969,
+// part_join.cu -- per-partition build + probe with the partition's table resident in shared
+// memory (reference: the cache-resident join loop, phj.cpp:1880-1923 / cpra2.cpp:1907-1969,
 // build phj.cpp:307-397, probe phj.cpp:399-571).
 //
 // Persistent CTAs pull tasks from an atomic counter.  A task = (partition p, one slice of at
 // most s_task probe tuples of p): uniform inputs give one task per partition, a skewed probe
 // side (Zipf) is cut into many tasks that each rebuild p's small table, so no CTA is stuck
-// with a hot partition.  A build partition larger than half the table is joined in several
+// with a hot partition.  A build partition larger than one table fill is joined in several
 // fills (block nested loop), so any input is handled -- duplicates included.
 //
-// Hot path (a fill without duplicate build keys, the common case): every lane walks its own
-// probe chain and stops at the first equal key; the warp then reserves result rows with ONE
-// global atomicAdd per round of 32 x kItems probe tuples and writes the three result columns
-// straight from registers, one coalesced 128-byte run per item (ballot-ranked).  No CTA
-// barrier between the end of the build and the end of the probe.
-// Slow path (a fill that saw an equal build key twice, or the all-ones sentinel pair): every
-// match is emitted as it is met, with opportunistic warp aggregation of the row reservation.
+// Two table forms, chosen per fill:
+//  * DIRECT (needs <= 16 hash bits left below the radix bits).  x = key * factor is a
+//    bijection on 32-bit keys (factor is odd), and all tuples of a partition share x's top
+//    bits, so the remaining low bits of x identify the key: a 2^16-bit bitmap says whether
+//    a key is present, and the rank of its bit (popcount prefix) addresses its payload in a
+//    dense array.  No key comparison, no collision chain, no divergent loop: build is an
+//    atomicOr + one store, probe is two loads + a popcount.  A fill in which two build
+//    tuples have the SAME key (atomicOr finds the bit already set) falls back to:
+//  * HASH: open addressing with linear probing over 64-bit slots (payload<<32 | key),
+//    atomicCAS insert as in the reference's build (npj.cpp:206); fills without equal build
+//    keys stop a probe at its first match, the others walk each chain to its end and emit
+//    every match (no _UNIQUE, npj.cpp:288-290).
+//
+// Result rows: every lane keeps its matches in registers; the warp reserves rows with ONE
+// global atomicAdd per round of 32 x kJoinItems probe tuples and stores the three result
+// columns straight from registers, one coalesced 128-byte run per item (ballot-ranked).
 #include "hj_device.cuh"
 #include "hj_internal.h"
 
@@ -74,20 +83,78 @@ __device__ __forceinline__ void emit_row_opportunistic(const OutCols &out, uint3
 	}
 }
 
-template <int LOG2_SLOTS, int THREADS, int ITEMS, bool MATERIALIZE>
+// warp-collective: at most one match per item and lane, rows of item t of all lanes contiguous
+template <int ITEMS>
+__device__ __forceinline__ void emit_round(const OutCols &out, const bool (&found)[ITEMS], const uint32_t (&key)[ITEMS],
+                                           const uint32_t (&val)[ITEMS], const uint32_t (&ival)[ITEMS])
+{
+	unsigned m[ITEMS];
+	uint32_t total = 0;
+#pragma unroll
+	for (int t = 0; t < ITEMS; ++t) {
+		m[t] = __ballot_sync(kFullMask, found[t]);
+		total += __popc(m[t]);
+	}
+	if (total == 0) return;
+	unsigned long long base = 0;
+	if (lane_id() == 0) base = atomicAdd(out.cursor, (unsigned long long)total);
+	base = __shfl_sync(kFullMask, base, 0);
+	const unsigned lt = lanemask_lt();
+	if (base + total <= out.cap) {                 // common case: no per-row capacity test
+#pragma unroll
+		for (int t = 0; t < ITEMS; ++t) {
+			const uint64_t r = base + __popc(m[t] & lt);
+			if (found[t]) {
+				out.k[r] = key[t];
+				out.o[r] = val[t];
+				out.i[r] = ival[t];
+			}
+			base += __popc(m[t]);
+		}
+	} else {
+#pragma unroll
+		for (int t = 0; t < ITEMS; ++t) {
+			const uint64_t r = base + __popc(m[t] & lt);
+			if (found[t] && r < out.cap) {
+				out.k[r] = key[t];
+				out.o[r] = val[t];
+				out.i[r] = ival[t];
+			}
+			base += __popc(m[t]);
+		}
+	}
+}
+
+constexpr uint32_t kDirectWords = 2048;                  // 2^16-bit presence bitmap
+constexpr uint32_t kDirectFill = 3072;                   // build tuples per DIRECT fill (payload array)
+constexpr uint32_t kHashSlots = 1u << kJoinLog2Slots;    // HASH table slots
+constexpr uint32_t kHashFill = kHashSlots / 4 * 3;       // load <= 0.75
+constexpr size_t kDirectBytes = (size_t)kDirectWords * 8 + (size_t)kDirectFill * 4;
+constexpr size_t kJoinSmemBytes = (size_t)kHashSlots * 8 > kDirectBytes ? (size_t)kHashSlots * 8 : kDirectBytes;
+
+template <int THREADS, int ITEMS, bool MATERIALIZE>
 __global__ void __launch_bounds__(THREADS, 1024 / THREADS)
 k_partition_join(const uint32_t *__restrict__ rk, const uint32_t *__restrict__ rv,
                  const uint32_t *__restrict__ sk, const uint32_t *__restrict__ sv,
                  const uint32_t *__restrict__ r_off, const uint32_t *__restrict__ s_off, uint32_t P,
                  const uint32_t *__restrict__ task_prefix, uint32_t *__restrict__ task_counter, uint32_t s_task,
-                 uint32_t table_factor, OutCols out, unsigned long long *__restrict__ sums)
+                 uint32_t radix_factor, uint32_t table_factor, int rem_bits, OutCols out,
+                 unsigned long long *__restrict__ sums)
 {
-	constexpr uint32_t kSlots = 1u << LOG2_SLOTS, kMask = kSlots - 1;
-	constexpr uint32_t kFill = kSlots / 4 * 3;       // build tuples per table fill: load <= 0.75, 0.5 on average
-	constexpr int kShift = 32 - LOG2_SLOTS;
-	extern __shared__ __align__(16) uint64_t table[];   // kSlots slots of payload<<32 | key
+	extern __shared__ __align__(16) unsigned char s_raw[];
+	// DIRECT view
+	uint32_t *bitmap = reinterpret_cast<uint32_t *>(s_raw);            // kDirectWords
+	uint32_t *prefix = bitmap + kDirectWords;                          // kDirectWords
+	uint32_t *dvals = prefix + kDirectWords;                           // kDirectFill
+	// HASH view
+	uint64_t *table = reinterpret_cast<uint64_t *>(s_raw);             // kHashSlots
 	__shared__ uint64_t scratch[4 * 32];
-	__shared__ uint32_t s_task_id[2], s_dups, s_sentinels;
+	__shared__ uint32_t warp_totals[34];
+	__shared__ uint32_t s_task_id[2], s_dups, s_hdups, s_sentinels, s_range[4];
+	constexpr uint32_t kMask = kHashSlots - 1;
+	constexpr int kShift = 32 - kJoinLog2Slots;
+	const bool direct_ok = rem_bits <= 16;
+	const uint32_t rem_mask = rem_bits >= 32 ? 0xFFFFFFFFu : (1u << rem_bits) - 1;
 	JoinSums acc;
 	acc.zero();
 	const uint32_t total_tasks = task_prefix[P];
@@ -96,23 +163,98 @@ k_partition_join(const uint32_t *__restrict__ rk, const uint32_t *__restrict__ r
 	for (uint32_t it = 0;; ++it) {
 		const uint32_t task = s_task_id[it & 1];
 		if (task >= total_tasks) break;
-		if (threadIdx.x == 0) s_task_id[(it + 1) & 1] = atomicAdd(task_counter, 1u);   // read after this task's barriers
-		const uint32_t p = upper_parent(task_prefix, P, task);
-		const uint32_t slice = task - task_prefix[p];
-		const uint32_t r_beg = r_off[p], r_end = r_off[p + 1];
-		const uint32_t s_beg = s_off[p] + slice * s_task;
-		const uint32_t s_end = min(s_off[p + 1], s_beg + s_task);
+		if (threadIdx.x == 0) {
+			s_task_id[(it + 1) & 1] = atomicAdd(task_counter, 1u);    // read after this task's barriers
+			const uint32_t p = upper_parent(task_prefix, P, task);
+			const uint32_t slice = task - task_prefix[p];
+			const uint32_t sb = s_off[p] + slice * s_task;
+			s_range[0] = r_off[p];
+			s_range[1] = r_off[p + 1];
+			s_range[2] = sb;
+			s_range[3] = min(s_off[p + 1], sb + s_task);
+		}
+		__syncthreads();
+		const uint32_t r_beg = s_range[0], r_end = s_range[1], s_beg = s_range[2], s_end = s_range[3];
 
-		for (uint32_t fb = r_beg; fb < r_end; fb += kFill) {
-			const uint32_t fe = min(fb + kFill, r_end);
-			// ---- clear + build (reference build(): double hashing into a prime table; here linear
+		uint32_t fb = r_beg;
+		while (fb < r_end) {
+			bool use_hash = !direct_ok;
+			uint32_t fe = min(fb + (use_hash ? kHashFill : kDirectFill), r_end);
+			if (!use_hash) {
+				// ---- DIRECT build, step 1: presence bits; equal keys show up as an already-set bit
+				for (uint32_t w = threadIdx.x; w < kDirectWords / 4; w += THREADS)
+					reinterpret_cast<uint4 *>(bitmap)[w] = make_uint4(0, 0, 0, 0);
+				if (threadIdx.x == 0) s_dups = 0;
+				__syncthreads();
+				for (uint32_t i = fb + threadIdx.x; i < fe; i += THREADS) {
+					const uint32_t lo = hash_mul(rk[i], radix_factor) & rem_mask;
+					const uint32_t bit = 1u << (lo & 31);
+					if (atomicOr(&bitmap[lo >> 5], bit) & bit) s_dups = 1;
+				}
+				__syncthreads();
+				use_hash = s_dups != 0;
+				if (!use_hash) {
+					// step 2: rank structure -- prefix[w] = set bits before word w
+					constexpr uint32_t kPer = kDirectWords / THREADS;
+					uint32_t c[kPer], local = 0;
+#pragma unroll
+					for (uint32_t j = 0; j < kPer; ++j) {
+						c[j] = __popc(bitmap[threadIdx.x * kPer + j]);
+						local += c[j];
+					}
+					uint32_t tot;
+					uint32_t run = block_exclusive_scan(local, warp_totals, &tot);
+#pragma unroll
+					for (uint32_t j = 0; j < kPer; ++j) {
+						prefix[threadIdx.x * kPer + j] = run;
+						run += c[j];
+					}
+					__syncthreads();
+					// step 3: payloads in rank order
+					for (uint32_t i = fb + threadIdx.x; i < fe; i += THREADS) {
+						const uint32_t lo = hash_mul(rk[i], radix_factor) & rem_mask;
+						const uint32_t w = lo >> 5;
+						dvals[prefix[w] + __popc(bitmap[w] & ((1u << (lo & 31)) - 1))] = rv[i];
+					}
+					__syncthreads();
+					// ---- DIRECT probe
+					for (uint32_t sb = s_beg; sb < s_end; sb += THREADS * ITEMS) {
+						uint32_t key[ITEMS], val[ITEMS], ival[ITEMS];
+						bool found[ITEMS];
+						const uint32_t wbase = sb + (threadIdx.x & ~31u) * ITEMS + lane_id();   // a warp owns 32*ITEMS consecutive tuples
+#pragma unroll
+						for (int t = 0; t < ITEMS; ++t) {
+							const uint32_t i = wbase + t * 32;
+							found[t] = i < s_end;
+							key[t] = found[t] ? ldg_stream_u32(&sk[i]) : 0;
+							val[t] = found[t] ? ldg_stream_u32(&sv[i]) : 0;
+						}
+#pragma unroll
+						for (int t = 0; t < ITEMS; ++t) {
+							const uint32_t lo = hash_mul(key[t], radix_factor) & rem_mask;
+							const uint32_t w = lo >> 5, word = bitmap[w];
+							found[t] = found[t] && ((word >> (lo & 31)) & 1u);
+							// rank < fill size whenever the bit is set; a miss may compute fill size itself: clamp
+							const uint32_t pos = min(prefix[w] + (uint32_t)__popc(word & ((1u << (lo & 31)) - 1)), kDirectFill - 1);
+							ival[t] = dvals[pos];
+							if (found[t]) acc.add(key[t], val[t], ival[t]);
+						}
+						if (MATERIALIZE) emit_round<ITEMS>(out, found, key, val, ival);
+					}
+					__syncthreads();            // the bitmap is cleared next; also publishes the prefetched task id
+					fb = fe;
+					continue;
+				}
+				fe = min(fb + kHashFill, r_end);       // equal build keys in this fill: redo it with the hash table
+			}
+			// ---- HASH build (reference build(): double hashing into a prime table; here linear
 			// probing into a power-of-two table indexed by the top bits of key * table_factor)
 			{
 				ulonglong2 *t2 = reinterpret_cast<ulonglong2 *>(table);
-				for (uint32_t h = threadIdx.x; h < kSlots / 2; h += THREADS) t2[h] = make_ulonglong2(kEmptySlot, kEmptySlot);
+				for (uint32_t h = threadIdx.x; h < kHashSlots / 2; h += THREADS) t2[h] = make_ulonglong2(kEmptySlot, kEmptySlot);
 			}
 			if (threadIdx.x == 0) {
-				s_dups = 0;
+				s_hdups = 0;                               // not s_dups: slow threads may still be reading it
 				s_sentinels = 0;
 			}
 			__syncthreads();
@@ -128,24 +270,24 @@ k_partition_join(const uint32_t *__restrict__ rk, const uint32_t *__restrict__ r
 					const uint64_t old = atomicCAS(reinterpret_cast<unsigned long long *>(&table[h]),
 					                               (unsigned long long)kEmptySlot, (unsigned long long)pair);
 					if (old == kEmptySlot) break;
-					if ((uint32_t)old == key) s_dups = 1;   // equal build keys: probes must walk to the chain's end
+					if ((uint32_t)old == key) s_hdups = 1;  // equal build keys: probes must walk to the chain's end
 					h = (h + 1) & kMask;
 				}
 			}
 			__syncthreads();
-			const bool slow = s_dups != 0 || s_sentinels != 0;
+			const bool slow = s_hdups != 0 || s_sentinels != 0;
 			const uint32_t sentinels = s_sentinels;
-			// ---- probe, THREADS * ITEMS tuples per round
 			for (uint32_t sb = s_beg; sb < s_end; sb += THREADS * ITEMS) {
 				uint32_t key[ITEMS], val[ITEMS], ival[ITEMS];
 				bool found[ITEMS];
-				const uint32_t wbase = sb + (threadIdx.x & ~31u) * ITEMS + lane_id();   // a warp owns 32*ITEMS consecutive tuples
+				const uint32_t wbase = sb + (threadIdx.x & ~31u) * ITEMS + lane_id();
 #pragma unroll
 				for (int t = 0; t < ITEMS; ++t) {
 					const uint32_t i = wbase + t * 32;
 					found[t] = i < s_end;                   // "valid" until probed
 					key[t] = found[t] ? ldg_stream_u32(&sk[i]) : 0;
 					val[t] = found[t] ? ldg_stream_u32(&sv[i]) : 0;
+					ival[t] = 0;
 				}
 				if (!slow) {
 #pragma unroll
@@ -167,31 +309,7 @@ k_partition_join(const uint32_t *__restrict__ rk, const uint32_t *__restrict__ r
 						found[t] = hit;
 						if (hit) acc.add(key[t], val[t], ival[t]);
 					}
-					if (MATERIALIZE) {
-						unsigned m[ITEMS];
-						uint32_t total = 0;
-#pragma unroll
-						for (int t = 0; t < ITEMS; ++t) {
-							m[t] = __ballot_sync(kFullMask, found[t]);
-							total += __popc(m[t]);
-						}
-						if (total) {
-							unsigned long long base = 0;
-							if (lane_id() == 0) base = atomicAdd(out.cursor, (unsigned long long)total);
-							base = __shfl_sync(kFullMask, base, 0);
-							const unsigned lt = lanemask_lt();
-#pragma unroll
-							for (int t = 0; t < ITEMS; ++t) {
-								const uint64_t r = base + __popc(m[t] & lt);
-								if (found[t] && r < out.cap) {
-									out.k[r] = key[t];
-									out.o[r] = val[t];
-									out.i[r] = ival[t];
-								}
-								base += __popc(m[t]);
-							}
-						}
-					}
+					if (MATERIALIZE) emit_round<ITEMS>(out, found, key, val, ival);
 				} else {
 #pragma unroll
 					for (int t = 0; t < ITEMS; ++t) {
@@ -215,34 +333,10 @@ k_partition_join(const uint32_t *__restrict__ rk, const uint32_t *__restrict__ r
 				}
 			}
 			__syncthreads();          // the table is cleared next; also publishes the prefetched task id
+			fb = fe;
 		}
 	}
 	acc.reduce_to_global(sums, scratch);
-}
-
-template <int LOG2_SLOTS, int THREADS, int ITEMS>
-static void launch_join_variant(const JoinArgs &a, cudaStream_t s, int sms, const OutCols &out)
-{
-	auto kt = k_partition_join<LOG2_SLOTS, THREADS, ITEMS, true>;
-	auto kf = k_partition_join<LOG2_SLOTS, THREADS, ITEMS, false>;
-	constexpr size_t smem = (size_t)8 << LOG2_SLOTS;
-	static bool attr_set = false;
-	if (!attr_set) {
-		cudaFuncSetAttribute(kt, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-		cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-		attr_set = true;
-	}
-	int per_sm = 0;
-	if (a.materialize) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kt, THREADS, smem);
-	else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kf, THREADS, smem);
-	if (per_sm < 1) per_sm = 1;
-	const uint32_t grid = (uint32_t)(sms * per_sm);
-	if (a.materialize)
-		kt<<<grid, THREADS, smem, s>>>(a.rk, a.rv, a.sk, a.sv, a.r_off, a.s_off, a.P, a.task_prefix, a.task_counter,
-		                            a.s_task, a.table_factor, out, a.scalars + 1);
-	else
-		kf<<<grid, THREADS, smem, s>>>(a.rk, a.rv, a.sk, a.sv, a.r_off, a.s_off, a.P, a.task_prefix, a.task_counter,
-		                            a.s_task, a.table_factor, out, a.scalars + 1);
 }
 
 int launch_partition_join(const JoinArgs &a, cudaStream_t s, int sms, KernelTimer *t)
@@ -261,8 +355,28 @@ int launch_partition_join(const JoinArgs &a, cudaStream_t s, int sms, KernelTime
 	out.i = a.out_i;
 	out.cursor = a.scalars;
 	out.cap = a.materialize ? a.out_cap : 0;
+	auto kt = k_partition_join<kJoinThreads, kJoinItems, true>;
+	auto kf = k_partition_join<kJoinThreads, kJoinItems, false>;
+	static bool attr_set = false;
+	if (!attr_set) {
+		cudaFuncSetAttribute(kt, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kJoinSmemBytes);
+		cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kJoinSmemBytes);
+		attr_set = true;
+	}
+	int per_sm = 0;
+	if (a.materialize) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kt, kJoinThreads, kJoinSmemBytes);
+	else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kf, kJoinThreads, kJoinSmemBytes);
+	if (per_sm < 1) per_sm = 1;
+	const uint32_t grid = (uint32_t)(sms * per_sm);
 	t->start(KK_PART_JOIN, s);
-	launch_join_variant<kJoinLog2Slots, kJoinThreads, kJoinItems>(a, s, sms, out);
+	if (a.materialize)
+		kt<<<grid, kJoinThreads, kJoinSmemBytes, s>>>(a.rk, a.rv, a.sk, a.sv, a.r_off, a.s_off, a.P, a.task_prefix,
+		                                              a.task_counter, a.s_task, a.radix_factor, a.table_factor,
+		                                              a.rem_bits, out, a.scalars + 1);
+	else
+		kf<<<grid, kJoinThreads, kJoinSmemBytes, s>>>(a.rk, a.rv, a.sk, a.sv, a.r_off, a.s_off, a.P, a.task_prefix,
+		                                              a.task_counter, a.s_task, a.radix_factor, a.table_factor,
+		                                              a.rem_bits, out, a.scalars + 1);
 	t->stop(s);
 	return 2;
 }

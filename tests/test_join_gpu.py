@@ -81,8 +81,14 @@ def test_tiny_and_ragged_sizes(eng, algo, nr, ns):
         assert_same(run(eng, algo, rk, rv, sk, sv, where=where), want)
 
 
+# {} lets the planner choose (small inputs: HASH tables); 16 radix bits leave 16 hash bits, which
+# selects the DIRECT (bitmap + rank) tables of csrc/part_join.cu
+PLANS = [{}, {"radix_bits": (8, 8)}, {"radix_bits": (6, 5, 5)}]
+
+
+@pytest.mark.parametrize("plan", PLANS)
 @pytest.mark.parametrize("algo", ALGOS)
-def test_special_key_values(eng, algo):
+def test_special_key_values(eng, algo, plan):
     """key 0 (the reference's empty sentinel, npj.cpp:205), 0xFFFFFFFF, and the one pair
     (0xFFFFFFFF, 0xFFFFFFFF) that looks like an empty slot of this engine's tables"""
     rk = np.array([0, 0, 1, 0xFFFFFFFF, 0xFFFFFFFF, 0xFFFFFFFF, 0xFFFFFFFE, 0x80000000, 7, 7], np.uint32)
@@ -91,18 +97,19 @@ def test_special_key_values(eng, algo):
     sv = np.array([11, 0xFFFFFFFF, 13, 14, 15, 16, 0xFFFFFFFF, 0], np.uint32)
     want = numpy_join(rk, rv, sk, sv)
     assert want.count == 2 * 2 + 3 * 2 + 2 + 1 + 1      # keys 0, 0xFFFFFFFF, 7, 0x80000000, 0xFFFFFFFE
-    assert_same(run(eng, algo, rk, rv, sk, sv), want)
+    assert_same(run(eng, algo, rk, rv, sk, sv, **plan), want)
     # and at scale: many sentinel pairs on the build side
     rng = np.random.default_rng(5)
     rk = np.concatenate([np.full(300, 0xFFFFFFFF, np.uint32), rng.integers(0, 1 << 32, 5000, dtype=np.uint32)])
     rv = np.concatenate([np.full(300, 0xFFFFFFFF, np.uint32), rng.integers(0, 1 << 32, 5000, dtype=np.uint32)])
     sk = np.concatenate([np.full(40, 0xFFFFFFFF, np.uint32), rk[300:2000], rng.integers(0, 1 << 32, 3000, dtype=np.uint32)])
     sv = np.arange(sk.size, dtype=np.uint32)
-    assert_same(run(eng, algo, rk, rv, sk, sv), numpy_join(rk, rv, sk, sv))
+    assert_same(run(eng, algo, rk, rv, sk, sv, **plan), numpy_join(rk, rv, sk, sv))
 
 
+@pytest.mark.parametrize("plan", PLANS)
 @pytest.mark.parametrize("algo", ALGOS)
-def test_duplicate_heavy_build_side_overflows_stage_and_capacity(eng, algo):
+def test_duplicate_heavy_build_side_overflows_capacity(eng, algo, plan):
     """every pair is emitted (no _UNIQUE, npj.cpp:288-290): 3000 x 2000 equal keys -> 6M rows from
     5000 input tuples, which overflows the shared-memory stage and the default result capacity"""
     rk = np.full(3000, 77, np.uint32)
@@ -111,7 +118,20 @@ def test_duplicate_heavy_build_side_overflows_stage_and_capacity(eng, algo):
     sv = np.arange(sk.size, dtype=np.uint32) * np.uint32(7)
     want = numpy_join(rk, rv, sk, sv)
     assert want.count == 6_000_000
-    assert_same(run(eng, algo, rk, rv, sk, sv), want)
+    assert_same(run(eng, algo, rk, rv, sk, sv, **plan), want)
+
+
+@pytest.mark.parametrize("plan", PLANS)
+def test_some_partitions_with_equal_build_keys(eng, plan):
+    """a large build side in which a few keys repeat: most partition fills take the DIRECT tables,
+    the fills holding an equal pair fall back to HASH tables inside the same kernel"""
+    rk, rv, sk, sv, _, _ = oracle_generate(1 << 19, 1 << 20, threads=2, seed=17)
+    rk[1000:1400] = rk[5000:5400]                     # 400 keys now appear twice
+    rk[2000:2010] = rk[7000]                          # one key eleven times
+    rv = np.arange(rk.size, dtype=np.uint32)          # payloads no longer a function of the key
+    want = numpy_join(rk, rv, sk, sv)
+    assert_same(run(eng, "phj", rk, rv, sk, sv, **plan), want)
+    assert_same(run(eng, "npj", rk, rv, sk, sv), want)
 
 
 @pytest.mark.parametrize("algo", ALGOS)
