@@ -10,6 +10,7 @@
 // digit, so items never synchronise while scattering.
 #include "hj_device.cuh"
 #include "hj_internal.h"
+#include <stdlib.h>
 
 namespace hjb {
 
@@ -232,39 +233,28 @@ k_scan(const uint32_t *__restrict__ item_prefix, uint32_t np, int bits, uint32_t
 
 // ------------------------------------------------------------------ scatter
 
-// One tile = kScatterTile tuples = kScatterTile/4 absolutely aligned groups; thread t owns
-// groups t and t + kScatterThreads of the tile (coalesced 128-bit loads).
-struct TileRegs {
-	uint32_t key[8], val[8];
-	uint32_t ok;          // bit e: element e lies inside the item's range
-};
-
-template <bool FULL>
-__device__ __forceinline__ void load_tile(TileRegs &t, const uint32_t *keys, const uint32_t *vals, uint64_t g0,
-                                          uint64_t g_end, uint64_t beg, uint64_t end, uint64_t n)
+// One tile = THREADS * 8 tuples = THREADS * 2 absolutely aligned groups; thread t owns groups t
+// and t + THREADS of the tile (coalesced 128-bit loads).
+template <int THREADS, bool FULL>
+__device__ __forceinline__ void load_col8(uint32_t (&x)[8], uint32_t &ok, const uint32_t *col, uint64_t g0, uint64_t g_end,
+                                          uint64_t beg, uint64_t end, uint64_t n)
 {
-	t.ok = 0;
+	ok = 0;
 #pragma unroll
 	for (int h = 0; h < 2; ++h) {
-		const uint64_t g = g0 + threadIdx.x + (uint64_t)h * kScatterThreads;
+		const uint64_t g = g0 + threadIdx.x + (uint64_t)h * THREADS;
 		if (FULL) {
-			const uint4 kk = ldg_stream_u4(reinterpret_cast<const uint4 *>(keys) + g);
-			const uint4 vv = ldg_stream_u4(reinterpret_cast<const uint4 *>(vals) + g);
-			t.key[4 * h + 0] = kk.x; t.key[4 * h + 1] = kk.y; t.key[4 * h + 2] = kk.z; t.key[4 * h + 3] = kk.w;
-			t.val[4 * h + 0] = vv.x; t.val[4 * h + 1] = vv.y; t.val[4 * h + 2] = vv.z; t.val[4 * h + 3] = vv.w;
-			t.ok |= 0xFu << (4 * h);
+			const uint4 w = ldg_stream_u4(reinterpret_cast<const uint4 *>(col) + g);
+			x[4 * h + 0] = w.x; x[4 * h + 1] = w.y; x[4 * h + 2] = w.z; x[4 * h + 3] = w.w;
+			ok |= 0xFu << (4 * h);
 		} else {
-			uint32_t k4[4] = {0, 0, 0, 0}, v4[4] = {0, 0, 0, 0};
-			if (g < g_end) {
-				load_group4(keys, g, n, k4);
-				load_group4(vals, g, n, v4);
-			}
+			uint32_t k4[4] = {0, 0, 0, 0};
+			if (g < g_end) load_group4(col, g, n, k4);
 #pragma unroll
 			for (int e = 0; e < 4; ++e) {
 				const uint64_t idx = (g << 2) + e;
-				t.key[4 * h + e] = k4[e];
-				t.val[4 * h + e] = v4[e];
-				if (g < g_end && idx >= beg && idx < end) t.ok |= 1u << (4 * h + e);
+				x[4 * h + e] = k4[e];
+				if (g < g_end && idx >= beg && idx < end) ok |= 1u << (4 * h + e);
 			}
 		}
 	}
@@ -274,24 +264,27 @@ __device__ __forceinline__ void load_tile(TileRegs &t, const uint32_t *keys, con
 // (2) warp 0 turns the digit counts into tile offsets and decides, per digit, how far the
 // item's output may be flushed, (3) tuples are placed into shared memory grouped by digit,
 // (4) the tile is streamed out, neighbouring threads writing neighbouring addresses of one
-// partition's run.  The loads of the NEXT tile are issued before (1) and stay in flight
-// through all four steps.
+// partition's run.  The key loads of the NEXT tile are issued before (1) and stay in flight
+// through all four steps; the payload loads of this tile are issued before (1) and first
+// needed in (3).
 //
 // Software write-combining (the reference's per-partition staging buffers, cpra2.cpp:976-1008,
 // flush cpra2.cpp:711-729): a digit's run is only written up to the last 32-byte sector boundary
 // of its output position; the < 8 tuples beyond it wait in a per-digit carry buffer and lead
 // the digit's run of the next tile.  Every store but an item's first and last per digit then
-// covers whole sectors, so L2 never has to fetch the rest of a half-written sector from HBM.
+// ends on a sector boundary, so L2 rarely has to fetch the rest of a half-written sector from HBM.
 // (WC is on for fan-outs <= 256, where the carry buffers fit; wider passes write runs as is.)
-// dynamic shared memory: cnt base fpos oldp wpos pend [F] | golim[F] (uint2) | buf[kScatterTile] (uint2) | carry[F*8] (uint2)
+// dynamic shared memory: cnt base fpos oldp wpos pend [F] | golim[F] (uint2) | buf[TILE] (uint2) | carry[F*8] (uint2)
 constexpr uint32_t kCarry = 8;         // tuples per 32-byte sector of a 4-byte column
 
-__global__ void __launch_bounds__(kScatterThreads, 2)
+template <int THREADS, int MINB, bool PREFETCH>
+__global__ void __launch_bounds__(THREADS, MINB)
 k_scatter(const uint32_t *__restrict__ keys, const uint32_t *__restrict__ vals, uint64_t n, uint32_t np,
           const uint32_t *__restrict__ parent_off, const uint32_t *__restrict__ item_prefix, uint32_t chunk,
           uint32_t factor, int rshift, int bits, const uint32_t *__restrict__ offsets,
           uint32_t *__restrict__ keys_out, uint32_t *__restrict__ vals_out)
 {
+	constexpr uint32_t TILE = THREADS * 8, kGroupsPerTile = TILE / 4;
 	extern __shared__ __align__(16) uint32_t s_mem[];
 	__shared__ uint32_t warp_totals[34];
 	__shared__ uint32_t s_tile_n;
@@ -300,40 +293,49 @@ k_scatter(const uint32_t *__restrict__ keys, const uint32_t *__restrict__ vals, 
 	uint32_t *cnt = s_mem, *base = cnt + F, *fpos = base + F, *oldp = fpos + F, *wpos = oldp + F, *pend = wpos + F;
 	uint2 *golim = reinterpret_cast<uint2 *>(pend + F);                 // x: global offset of tile index 0, y: flush limit
 	uint2 *buf = golim + F;
-	uint2 *carry = buf + kScatterTile;
+	uint2 *carry = buf + TILE;
 	ItemRange r;
 	if (!locate_item(item_prefix, np, parent_off, n, chunk, blockIdx.x, &r)) return;
 	const uint32_t *row = offsets + (size_t)blockIdx.x * F;
-	for (uint32_t p = threadIdx.x; p < F; p += blockDim.x) {
+	for (uint32_t p = threadIdx.x; p < F; p += THREADS) {
 		wpos[p] = row[p];
 		pend[p] = 0;
 		cnt[p] = 0;
 	}
-	constexpr uint32_t kGroupsPerTile = kScatterTile / 4;
 	const uint64_t g_beg = r.beg >> 2, g_end = (r.end + 3) >> 2;
 	auto tile_is_full = [&](uint64_t g0) {
 		return (g0 << 2) >= r.beg && ((g0 + kGroupsPerTile) << 2) <= r.end;    // r.end <= n: vector loads stay inside
 	};
-	TileRegs cur, nxt;
-	if (g_beg < g_end) {
-		if (tile_is_full(g_beg)) load_tile<true>(nxt, keys, vals, g_beg, g_end, r.beg, r.end, n);
-		else load_tile<false>(nxt, keys, vals, g_beg, g_end, r.beg, r.end, n);
+	uint32_t key[8], nkey[8], val[8], ok = 0, nok = 0;
+	if (PREFETCH && g_beg < g_end) {
+		if (tile_is_full(g_beg)) load_col8<THREADS, true>(nkey, nok, keys, g_beg, g_end, r.beg, r.end, n);
+		else load_col8<THREADS, false>(nkey, nok, keys, g_beg, g_end, r.beg, r.end, n);
 	}
 	__syncthreads();
 	for (uint64_t g0 = g_beg; g0 < g_end; g0 += kGroupsPerTile) {
-		cur = nxt;
 		const uint64_t g1 = g0 + kGroupsPerTile;
 		const bool last = g1 >= g_end;
-		if (!last) {
-			if (tile_is_full(g1)) load_tile<true>(nxt, keys, vals, g1, g_end, r.beg, r.end, n);
-			else load_tile<false>(nxt, keys, vals, g1, g_end, r.beg, r.end, n);
+		if (PREFETCH) {
+#pragma unroll
+			for (int e = 0; e < 8; ++e) key[e] = nkey[e];
+			ok = nok;
+		} else {
+			if (tile_is_full(g0)) load_col8<THREADS, true>(key, ok, keys, g0, g_end, r.beg, r.end, n);
+			else load_col8<THREADS, false>(key, ok, keys, g0, g_end, r.beg, r.end, n);
 		}
-		// (1) rank: digit << 16 | rank-in-digit (rank < kScatterTile <= 2^16, digit < 2^11)
+		uint32_t vok;
+		if (tile_is_full(g0)) load_col8<THREADS, true>(val, vok, vals, g0, g_end, r.beg, r.end, n);
+		else load_col8<THREADS, false>(val, vok, vals, g0, g_end, r.beg, r.end, n);
+		if (PREFETCH && !last) {
+			if (tile_is_full(g1)) load_col8<THREADS, true>(nkey, nok, keys, g1, g_end, r.beg, r.end, n);
+			else load_col8<THREADS, false>(nkey, nok, keys, g1, g_end, r.beg, r.end, n);
+		}
+		// (1) rank: digit << 16 | rank-in-digit (rank < TILE <= 2^16, digit < 2^11)
 		uint32_t dr[8];
 #pragma unroll
 		for (int e = 0; e < 8; ++e) {
-			const uint32_t d = radix_digit(hash_mul(cur.key[e], factor), rshift, mask);
-			dr[e] = (cur.ok >> e) & 1u ? (d << 16) | atomicAdd(&cnt[d], 1u) : 0xFFFFFFFFu;
+			const uint32_t d = radix_digit(hash_mul(key[e], factor), rshift, mask);
+			dr[e] = (ok >> e) & 1u ? (d << 16) | atomicAdd(&cnt[d], 1u) : 0xFFFFFFFFu;
 		}
 		__syncthreads();
 		// (2) per digit: tile offset, global offset, flush limit, what stays pending
@@ -350,29 +352,25 @@ k_scatter(const uint32_t *__restrict__ keys, const uint32_t *__restrict__ vals, 
 			pend[p] = endpos - lim;
 			cnt[p] = 0;
 		};
-		if (F <= 256) {
-			if (threadIdx.x < 32) {
-				const uint32_t per = F >> 5 ? F >> 5 : 1;          // digits per lane (F >= 32), else one
-				const uint32_t p0 = threadIdx.x * per;
-				uint32_t c[8], local = 0;
+		if (F <= THREADS) {
+			// one digit per thread: warp scans, then the warp totals through shared memory
+			const uint32_t p = threadIdx.x;
+			const uint32_t c = p < F ? cnt[p] : 0;
+			const uint32_t incl = warp_inclusive_scan_u32(c);
+			if (lane_id() == 31) warp_totals[p >> 5] = incl;
+			__syncthreads();
+			uint32_t before = 0, tile_total = 0;
 #pragma unroll
-				for (uint32_t j = 0; j < 8; ++j) {
-					c[j] = (j < per && p0 + j < F) ? cnt[p0 + j] : 0;
-					local += c[j];
-				}
-				const uint32_t incl = warp_inclusive_scan_u32(local);
-				uint32_t run = incl - local;
-#pragma unroll
-				for (uint32_t j = 0; j < 8; ++j)
-					if (j < per && p0 + j < F) {
-						plan_digit(p0 + j, c[j], run);
-						run += c[j];
-					}
-				if (threadIdx.x == 31) s_tile_n = incl;
+			for (uint32_t w = 0; w < THREADS / 32; ++w) {
+				const uint32_t t = warp_totals[w];
+				before += w < (p >> 5) ? t : 0;
+				tile_total += t;
 			}
+			if (p < F) plan_digit(p, c, before + incl - c);
+			if (p == 0) s_tile_n = tile_total;
 			__syncthreads();
 		} else {
-			const uint32_t ept = (F + kScatterThreads - 1) / kScatterThreads;
+			const uint32_t ept = (F + THREADS - 1) / THREADS;
 			const uint32_t p0 = threadIdx.x * ept;
 			uint32_t local = 0;
 			for (uint32_t p = p0; p < p0 + ept && p < F; ++p) local += cnt[p];
@@ -389,9 +387,9 @@ k_scatter(const uint32_t *__restrict__ keys, const uint32_t *__restrict__ vals, 
 		// (3) place the tile's tuples; flush the carried tuples of every digit that reached a boundary
 #pragma unroll
 		for (int e = 0; e < 8; ++e)
-			if (dr[e] != 0xFFFFFFFFu) buf[base[dr[e] >> 16] + (dr[e] & 0xFFFFu)] = make_uint2(cur.key[e], cur.val[e]);
+			if (dr[e] != 0xFFFFFFFFu) buf[base[dr[e] >> 16] + (dr[e] & 0xFFFFu)] = make_uint2(key[e], val[e]);
 		if (wc)
-			for (uint32_t i = threadIdx.x; i < F * kCarry; i += kScatterThreads) {
+			for (uint32_t i = threadIdx.x; i < F * kCarry; i += THREADS) {
 				const uint32_t d = i / kCarry, j = i % kCarry;
 				if (j < oldp[d]) {
 					const uint2 kv = carry[i];
@@ -405,7 +403,7 @@ k_scatter(const uint32_t *__restrict__ keys, const uint32_t *__restrict__ vals, 
 		// the carry buffer.  The next tile's step (1) barrier orders this loop before step (2) rewrites
 		// golim and before step (3) reads carry.
 		const uint32_t tile_n = s_tile_n;
-		for (uint32_t i = threadIdx.x; i < tile_n; i += kScatterThreads) {
+		for (uint32_t i = threadIdx.x; i < tile_n; i += THREADS) {
 			const uint2 kv = buf[i];
 			const uint32_t d = radix_digit(hash_mul(kv.x, factor), rshift, mask);
 			const uint2 gl = golim[d];
@@ -427,8 +425,8 @@ size_t radix_scratch_bytes(uint64_t n, uint32_t np, int bits, uint32_t *chunk, u
 	// ~2K-4K items: enough to balance 148 SMs x several resident CTAs, few enough that the
 	// counts matrix stays small; chunk is a multiple of the scatter tile
 	uint64_t c = (n + 2047) / 2048;
-	c = (c + kScatterTile - 1) / kScatterTile * kScatterTile;
-	if (c < 2 * kScatterTile) c = 2 * kScatterTile;
+	c = (c + 8191) / 8192 * 8192;
+	if (c < 16384) c = 16384;
 	if (c > (1u << 24)) c = 1u << 24;
 	*chunk = (uint32_t)c;
 	const uint64_t mi = n / c + np + 1;
@@ -464,16 +462,33 @@ int launch_radix_pass(const RadixPassArgs &a, cudaStream_t s, int /*sms*/, Kerne
 	k_scan<<<tiles, kScanThreads, 0, s>>>(a.item_prefix, a.np, a.bits, a.counts, a.child_off, a.scan_status,
 	                                      a.scan_counter);
 	t->stop(s);
-	const size_t smem = (size_t)F * 32 + (size_t)kScatterTile * 8 + (F <= 256 ? (size_t)F * kCarry * 8 : 0);
-	static bool attr_set = false;
-	if (!attr_set) {
-		cudaFuncSetAttribute(k_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, 2048 * 32 + kScatterTile * 8);
-		attr_set = true;
+	// CTA shape and register budget; HJB_SCATTER_VARIANT picks alternatives for experiments
+	static int variant = -1;
+	if (variant < 0) {
+		const char *e = getenv("HJB_SCATTER_VARIANT");
+		variant = e ? atoi(e) : 3;       // measured best on B200: one 1024-thread CTA per SM, 8192-tuple tiles
+		if (variant < 0 || variant > 4) variant = 3;
+		const int big = 2048 * 32 + 1024 * 8 * 8;
+		cudaFuncSetAttribute(k_scatter<512, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+		cudaFuncSetAttribute(k_scatter<512, 3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+		cudaFuncSetAttribute(k_scatter<512, 3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+		cudaFuncSetAttribute(k_scatter<1024, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+		cudaFuncSetAttribute(k_scatter<1024, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
 	}
+	const int threads = variant >= 3 ? 1024 : 512;
+	const size_t smem = (size_t)F * 32 + (size_t)threads * 8 * 8 + (F <= 256 ? (size_t)F * kCarry * 8 : 0);
 	t->start(KK_SCATTER, s);
-	k_scatter<<<a.max_items, kScatterThreads, smem, s>>>(a.keys, a.vals, a.n, a.np, a.parent_off, a.item_prefix,
-	                                                     a.chunk, a.factor, a.rshift, a.bits, a.counts,
-	                                                     a.keys_out, a.vals_out);
+#define HJB_LAUNCH_SCATTER(T, M, P)                                                                                  \
+	k_scatter<T, M, P><<<a.max_items, T, smem, s>>>(a.keys, a.vals, a.n, a.np, a.parent_off, a.item_prefix, a.chunk, \
+	                                                a.factor, a.rshift, a.bits, a.counts, a.keys_out, a.vals_out)
+	switch (variant) {
+	case 1: HJB_LAUNCH_SCATTER(512, 3, true); break;
+	case 2: HJB_LAUNCH_SCATTER(512, 3, false); break;
+	case 4: HJB_LAUNCH_SCATTER(1024, 2, false); break;
+	case 0: HJB_LAUNCH_SCATTER(512, 2, true); break;
+	default: HJB_LAUNCH_SCATTER(1024, 1, true); break;
+	}
+#undef HJB_LAUNCH_SCATTER
 	t->stop(s);
 	return 4;
 }
