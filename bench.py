@@ -213,6 +213,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="auto", choices=["auto", "phj_cfg2", "npj_cfg1", "cpra_cfg4"])
     ap.add_argument("--log2-per-gpu", type=int, default=0, help="override tuples per relation per GPU (2^k)")
+    ap.add_argument("--exchange", default="fused", choices=["fused", "nccl"],
+                    help="N>1: GPU-assign pass storing straight into the owners' buffers over NVLink, or split + NCCL all-to-all")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -242,6 +244,12 @@ def main():
 
     eng = hj.Engine(local, use_torch_stream=True)
     eng.set_profiling(True)
+    fused = cpra_mod.FusedExchange(eng) if (world > 1 and args.exchange == "fused") else None
+
+    def cpra_step(inner, outer):
+        if fused is not None:
+            return cpra_mod.cpra_join_fused(eng, inner, outer, fused)
+        return cpra_mod.cpra_join(eng, inner, outer)
 
     # ---- synthetic inputs, generated on the device (identical to datagen's numpy mirror)
     if workload == "cpra_cfg4":
@@ -268,7 +276,7 @@ def main():
 
     def step_device():
         if algo == "cpra":
-            r = cpra_mod.cpra_join(eng, (rk, rv), (sk, sv))
+            r = cpra_step((rk, rv), (sk, sv))
             got = (r["count"], r["sum_key"], r["sum_outer"], r["sum_inner"])
             return got, r["local"].kernel_launches + (8 if world > 1 else 0), r
         r = getattr(eng, algo)((rk, rv), (sk, sv))
@@ -333,7 +341,7 @@ def main():
         def step_e2e():
             if algo == "cpra":
                 drk, drv, dsk, dsv = (p.to(devname, non_blocking=True) for p in pin)
-                r = cpra_mod.cpra_join(eng, (drk, drv), (dsk, dsv))
+                r = cpra_step((drk, drv), (dsk, dsv))
                 rows = [c.to("cpu", non_blocking=True) for c in r["local"].rows_torch()]   # this rank's share of the rows
                 torch.cuda.synchronize()
                 return (r["count"], r["sum_key"], r["sum_outer"], r["sum_inner"]), r["local"].count, rows

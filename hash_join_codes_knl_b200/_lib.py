@@ -33,6 +33,11 @@ class Split(C.Structure):
                 ("r_offsets", C.c_uint64 * 65), ("s_offsets", C.c_uint64 * 65), ("ms", C.c_float)]
 
 
+class Recv(C.Structure):
+    _fields_ = [("r_keys", C.c_void_p), ("r_vals", C.c_void_p), ("s_keys", C.c_void_p), ("s_vals", C.c_void_p),
+                ("r_capacity", C.c_uint64), ("s_capacity", C.c_uint64), ("ipc", (C.c_ubyte * 64) * 4)]
+
+
 class Gen(C.Structure):
     _fields_ = [("kind", C.c_int), ("tuples", C.c_uint64), ("domain", C.c_uint64), ("first", C.c_uint64),
                 ("total", C.c_uint64), ("seed", C.c_uint32), ("order_seed", C.c_uint32), ("payload_factor", C.c_uint32), ("pad_", C.c_uint32),
@@ -56,6 +61,12 @@ SYMBOLS = {
     "hjb_phj_host": (C.c_int, [C.c_void_p, C.POINTER(Rel), C.POINTER(Rel), C.POINTER(Opts), C.POINTER(Result)]),
     "hjb_cpra_split": (C.c_int, [C.c_void_p, C.POINTER(Rel), C.POINTER(Rel), C.c_int, C.POINTER(Opts), C.POINTER(Split)]),
     "hjb_cpra_join_local": (C.c_int, [C.c_void_p, C.POINTER(Rel), C.POINTER(Rel), C.c_int, C.c_int, C.POINTER(Opts), C.POINTER(Result)]),
+    "hjb_cpra_recv_alloc": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64, C.POINTER(Recv)]),
+    "hjb_ipc_open": (C.c_int, [C.c_void_p, C.POINTER(C.c_ubyte), C.POINTER(C.c_void_p)]),
+    "hjb_ipc_close": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "hjb_cpra_count": (C.c_int, [C.c_void_p, C.POINTER(Rel), C.POINTER(Rel), C.c_int, C.POINTER(Opts), u64p, u64p]),
+    "hjb_cpra_scatter_peer": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
+                                        C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), u64p, u64p, C.POINTER(C.c_float)]),
     "hjb_hash_factor": (C.c_uint32, [C.c_uint32, C.c_int]),
     "hjb_histogram": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, u32p, C.c_uint32, C.c_int, C.c_int]),
     "hjb_partition_pass": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, u32p, C.c_void_p, C.c_void_p, u32p, C.c_uint32, C.c_int, C.c_int]),

@@ -9,7 +9,7 @@ import ctypes as C
 import numpy as np
 
 from . import _lib
-from ._lib import Gen, Opts, Rel, Result, Split
+from ._lib import Gen, Opts, Recv, Rel, Result, Split
 
 
 class HjbError(RuntimeError):
@@ -208,6 +208,52 @@ class Engine:
         self._check(self._lib.hjb_cpra_join_local(self._ctx, C.byref(R), C.byref(S), int(gpu), int(ngpus), C.byref(o),
                                                   C.byref(res)), "hjb_cpra_join_local")
         return JoinResult(res, self)
+
+    # ---- CPRA with the exchange fused into the GPU-assign pass (peer stores over NVLink)
+    def cpra_recv_alloc(self, r_capacity, s_capacity):
+        """(Re)allocates this GPU's receive buffers; returns {"ptrs": 4 device pointers, "ipc": 4 x 64-byte handles}."""
+        rv = Recv()
+        self._check(self._lib.hjb_cpra_recv_alloc(self._ctx, int(r_capacity), int(s_capacity), C.byref(rv)),
+                    "hjb_cpra_recv_alloc")
+        return {"ptrs": [rv.r_keys, rv.r_vals, rv.s_keys, rv.s_vals], "ipc": [bytes(rv.ipc[i]) for i in range(4)],
+                "r_capacity": int(rv.r_capacity), "s_capacity": int(rv.s_capacity)}
+
+    def ipc_open(self, handle):
+        buf = (C.c_ubyte * 64).from_buffer_copy(handle)
+        p = C.c_void_p()
+        self._check(self._lib.hjb_ipc_open(self._ctx, buf, C.byref(p)), "hjb_ipc_open")
+        return p.value
+
+    def ipc_close(self, ptr):
+        self._check(self._lib.hjb_ipc_close(self._ctx, C.c_void_p(ptr)), "hjb_ipc_close")
+
+    def cpra_count(self, inner_chunk, outer_chunk, ngpus, **opts):
+        R, S, on_dev, keep = self._rels(inner_chunk, outer_chunk)
+        if not on_dev:
+            raise HjbError("cpra_count takes device columns")
+        rc, sc = (C.c_uint64 * 64)(), (C.c_uint64 * 64)()
+        o = self._opts(**opts)
+        self._check(self._lib.hjb_cpra_count(self._ctx, C.byref(R), C.byref(S), int(ngpus), C.byref(o), rc, sc),
+                    "hjb_cpra_count")
+        self._pending_keep = keep          # the chunks must outlive cpra_scatter_peer
+        return [int(rc[g]) for g in range(ngpus)], [int(sc[g]) for g in range(ngpus)]
+
+    def cpra_scatter_peer(self, ngpus, peer_ptrs, r_base, s_base):
+        """peer_ptrs[c][g]: column c (r_keys, r_vals, s_keys, s_vals) of owner g as mapped into this process."""
+        cols = [(C.c_void_p * ngpus)(*[C.c_void_p(p) for p in peer_ptrs[c]]) for c in range(4)]
+        rb = (C.c_uint64 * ngpus)(*[int(x) for x in r_base])
+        sb = (C.c_uint64 * ngpus)(*[int(x) for x in s_base])
+        ms = C.c_float()
+        self._check(self._lib.hjb_cpra_scatter_peer(self._ctx, int(ngpus), cols[0], cols[1], cols[2], cols[3], rb, sb,
+                                                    C.byref(ms)), "hjb_cpra_scatter_peer")
+        self._pending_keep = None
+        return float(ms.value)
+
+    def device_view(self, ptr, n):
+        """int32 CUDA tensor aliasing n elements of library-owned device memory."""
+        import torch
+        dev = f"cuda:{self.device}"
+        return torch.as_tensor(_CudaArray(ptr, n), device=dev) if n else torch.empty(0, dtype=torch.int32, device=dev)
 
     # ---- single kernels, for comparing intermediate products with the oracle
     def hash_factor(self, seed, which):

@@ -80,3 +80,73 @@ def cpra_join(engine, inner_chunk, outer_chunk, group=None, split_fn=None, join_
             "split_ms": float(sp.get("ms", 0.0)), "exchange_ms": exchange_ms,
             "join_ms": float(getattr(local, "seconds", 0.0)) * 1e3,
             "recv_tuples": (int(rk.numel()), int(sk.numel()))}
+
+
+class FusedExchange:
+    """State of the fused GPU-assign + exchange pass for one Engine / process group: this GPU's
+    receive buffers and the peers' buffers mapped through CUDA IPC.  (Re)built collectively
+    whenever some rank would receive more rows than the current capacity."""
+
+    def __init__(self, engine, group=None):
+        self.engine, self.group = engine, group
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        self.r_cap = self.s_cap = 0
+        self.own = None
+        self.peers = None          # [column][owner] device pointers valid in this process
+        self._opened = []
+
+    def ensure(self, r_need, s_need):
+        """r_need / s_need: the largest row count any rank receives (identical on every rank)."""
+        if r_need <= self.r_cap and s_need <= self.s_cap:
+            return
+        for p in self._opened:
+            self.engine.ipc_close(p)
+        self._opened = []
+        if self.own is not None:
+            dist.barrier(group=self.group)       # nobody still maps the buffers about to be freed
+        self.r_cap = max(self.r_cap, int(r_need * 1.05) + 1024)
+        self.s_cap = max(self.s_cap, int(s_need * 1.05) + 1024)
+        self.own = self.engine.cpra_recv_alloc(self.r_cap, self.s_cap)
+        handles = [None] * self.world
+        dist.all_gather_object(handles, self.own["ipc"], group=self.group)
+        self.peers = [[None] * self.world for _ in range(4)]
+        for g in range(self.world):
+            for c in range(4):
+                if g == self.rank:
+                    self.peers[c][g] = self.own["ptrs"][c]
+                else:
+                    self.peers[c][g] = self.engine.ipc_open(handles[g][c])
+                    self._opened.append(self.peers[c][g])
+
+
+def cpra_join_fused(engine, inner_chunk, outer_chunk, state, group=None, **opts):
+    """CPRA with the all-to-all fused into the GPU-assign pass: counts -> all-gather of the
+    count matrix -> every sender scatters straight into the owners' receive buffers over NVLink
+    -> barrier -> local join.  Same result dict as cpra_join."""
+    world, rank = state.world, state.rank
+    dev = torch.device(f"cuda:{engine.device}")
+    r_cnt, s_cnt = engine.cpra_count(inner_chunk, outer_chunk, world, **opts)
+    mine = torch.tensor(r_cnt + s_cnt, dtype=torch.int64, device=dev)
+    allc = torch.empty(world * 2 * world, dtype=torch.int64, device=dev)
+    dist.all_gather_into_tensor(allc, mine, group=group)
+    C = allc.view(world, 2 * world).cpu().tolist()          # C[src][dst] (R), C[src][world + dst] (S)
+    r_recv = [sum(C[s][g] for s in range(world)) for g in range(world)]
+    s_recv = [sum(C[s][world + g] for s in range(world)) for g in range(world)]
+    state.ensure(max(r_recv), max(s_recv))
+    r_base = [sum(C[s][g] for s in range(rank)) for g in range(world)]
+    s_base = [sum(C[s][world + g] for s in range(rank)) for g in range(world)]
+    scatter_ms = engine.cpra_scatter_peer(world, state.peers, r_base, s_base)
+    t0 = torch.cuda.Event(enable_timing=True)
+    t1 = torch.cuda.Event(enable_timing=True)
+    t0.record()
+    dist.barrier(group=group)                                # every sender's stores have landed
+    t1.record()
+    own = state.own["ptrs"]
+    rk, rv = engine.device_view(own[0], r_recv[rank]), engine.device_view(own[1], r_recv[rank])
+    sk, sv = engine.device_view(own[2], s_recv[rank]), engine.device_view(own[3], s_recv[rank])
+    local = engine.cpra_join_local((rk, rv), (sk, sv), rank, world, **opts)
+    count, sum_key, sum_outer, sum_inner = reduce_checks(local.count, local.sum_key, local.sum_outer,
+                                                         local.sum_inner, dev, group)
+    return {"count": count, "sum_key": sum_key, "sum_outer": sum_outer, "sum_inner": sum_inner, "local": local,
+            "split_ms": scatter_ms, "exchange_ms": t0.elapsed_time(t1), "join_ms": float(local.seconds) * 1e3,
+            "recv_tuples": (r_recv[rank], s_recv[rank])}

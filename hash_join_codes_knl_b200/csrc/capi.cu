@@ -31,6 +31,11 @@ struct hjb_ctx {
 	cudaEvent_t ev[12];
 	uint32_t launches;
 	KernelTimer timer;        // per-kernel times of the last join (hjb_set_profiling)
+	char *recv_buf[4];        // CPRA fused exchange: receive columns r_keys r_vals s_keys s_vals
+	uint64_t recv_cap[2];
+	RadixPassArgs pending[2]; // hjb_cpra_count -> hjb_cpra_scatter_peer
+	uint32_t pending_off[2][65];
+	int pending_gpus;
 };
 
 static char g_create_err[512];
@@ -117,6 +122,7 @@ extern "C" int hjb_destroy(hjb_ctx *ctx)
 	cudaFree(ctx->out_cols);
 	cudaFree(ctx->in_buf);
 	cudaFree(ctx->split_buf);
+	for (int i = 0; i < 4; ++i) cudaFree(ctx->recv_buf[i]);
 	cudaFree(ctx->d_scalars);
 	cudaFreeHost(ctx->h_scalars);
 	cudaFreeHost(ctx->h_small);
@@ -708,6 +714,147 @@ extern "C" int hjb_cpra_split(hjb_ctx *ctx, const hjb_rel *R, const hjb_rel *S, 
 	}
 	out->r_keys = ok[0]; out->r_vals = ov[0]; out->s_keys = ok[1]; out->s_vals = ov[1];
 	CK(cudaEventElapsedTime(&out->ms, ctx->ev[4], ctx->ev[5]));
+	ctx->launches += launches;
+	return HJB_OK;
+}
+
+// ---- fused exchange ----------------------------------------------------------------
+
+extern "C" int hjb_cpra_recv_alloc(hjb_ctx *ctx, uint64_t r_capacity, uint64_t s_capacity, hjb_recv *out)
+{
+	if (!ctx || !out) return HJB_E_INVALID;
+	CK(cudaSetDevice(ctx->device));
+	CK(cudaStreamSynchronize(ctx->stream));
+	const uint64_t cap[2] = {r_capacity ? r_capacity : 1, s_capacity ? s_capacity : 1};
+	for (int i = 0; i < 4; ++i) {
+		if (ctx->recv_buf[i]) CK(cudaFree(ctx->recv_buf[i]));
+		ctx->recv_buf[i] = nullptr;
+		CK(cudaMalloc(&ctx->recv_buf[i], cap[i / 2] * 4 + 256));
+		cudaIpcMemHandle_t h;
+		CK(cudaIpcGetMemHandle(&h, ctx->recv_buf[i]));
+		static_assert(sizeof(h) == 64, "cudaIpcMemHandle_t is 64 bytes");
+		memcpy(out->ipc[i], &h, 64);
+	}
+	ctx->recv_cap[0] = cap[0];
+	ctx->recv_cap[1] = cap[1];
+	out->r_keys = (uint32_t *)ctx->recv_buf[0];
+	out->r_vals = (uint32_t *)ctx->recv_buf[1];
+	out->s_keys = (uint32_t *)ctx->recv_buf[2];
+	out->s_vals = (uint32_t *)ctx->recv_buf[3];
+	out->r_capacity = cap[0];
+	out->s_capacity = cap[1];
+	return HJB_OK;
+}
+
+extern "C" int hjb_ipc_open(hjb_ctx *ctx, const unsigned char *handle64, void **dev_ptr)
+{
+	if (!ctx || !handle64 || !dev_ptr) return HJB_E_INVALID;
+	CK(cudaSetDevice(ctx->device));
+	cudaIpcMemHandle_t h;
+	memcpy(&h, handle64, 64);
+	CK(cudaIpcOpenMemHandle(dev_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+	return HJB_OK;
+}
+
+extern "C" int hjb_ipc_close(hjb_ctx *ctx, void *dev_ptr)
+{
+	if (!ctx || !dev_ptr) return HJB_E_INVALID;
+	CK(cudaSetDevice(ctx->device));
+	CK(cudaIpcCloseMemHandle(dev_ptr));
+	return HJB_OK;
+}
+
+extern "C" int hjb_cpra_count(hjb_ctx *ctx, const hjb_rel *R, const hjb_rel *S, int ngpus, const hjb_opts *opts,
+                              uint64_t *r_counts, uint64_t *s_counts)
+{
+	if (!ctx || !r_counts || !s_counts) return HJB_E_INVALID;
+	const hjb_opts *o = opts ? opts : &kDefaultOpts;
+	int rc;
+	if ((rc = check_rel(ctx, R, true)) || (rc = check_rel(ctx, S, true))) return rc;
+	const int gbits = log2_exact(ngpus);
+	if (gbits < 1 || ngpus > 64) return fail(ctx, HJB_E_INVALID, "ngpus must be a power of two in [2, 64]");
+	CK(cudaSetDevice(ctx->device));
+	const hjb_rel *rel[2] = {R, S};
+	size_t scratch[2], total = 0;
+	for (int r = 0; r < 2; ++r) {
+		uint32_t chunk, mi, tiles;
+		scratch[r] = radix_scratch_bytes(rel[r]->tuples, 1, gbits, &chunk, &mi, &tiles) + pad256((size_t)(ngpus + 1) * 4);
+		total += scratch[r];
+	}
+	if ((rc = grow_device(ctx, &ctx->split_buf, &ctx->split_bytes, total + 4096))) return rc;
+	cudaStream_t s = ctx->stream;
+	Bump w = {ctx->split_buf, 0};
+	uint32_t launches = 0;
+	uint32_t *off_dev[2];
+	for (int r = 0; r < 2; ++r) {
+		RadixPassArgs &a = ctx->pending[r];
+		memset(&a, 0, sizeof a);
+		a.keys = rel[r]->keys; a.vals = rel[r]->vals;
+		a.n = rel[r]->tuples;
+		a.np = 1;
+		a.factor = hjb_hash_factor(o->seed, 0);
+		a.bits = gbits;
+		a.rshift = 32 - gbits;
+		uint32_t tiles;
+		radix_scratch_bytes(a.n, 1, gbits, &a.chunk, &a.max_items, &tiles);
+		off_dev[r] = a.child_off = w.take<uint32_t>(ngpus + 1);
+		a.item_prefix = w.take<uint32_t>(2);
+		a.counts = w.take<uint32_t>((size_t)a.max_items << gbits);
+		a.scan_status = w.take<uint64_t>(tiles);
+		a.scan_counter = w.take<uint32_t>(1);
+		if (a.n == 0) {
+			CK(cudaMemsetAsync(a.child_off, 0, (size_t)(ngpus + 1) * 4, s));
+			continue;
+		}
+		launches += launch_radix_count(a, s, &ctx->timer);
+	}
+	CK(cudaMemcpyAsync(&ctx->h_small[0], off_dev[0], (size_t)(ngpus + 1) * 4, cudaMemcpyDeviceToHost, s));
+	CK(cudaMemcpyAsync(&ctx->h_small[128], off_dev[1], (size_t)(ngpus + 1) * 4, cudaMemcpyDeviceToHost, s));
+	CK(cudaStreamSynchronize(s));
+	CK(cudaGetLastError());
+	for (int g = 0; g <= ngpus; ++g) {
+		ctx->pending_off[0][g] = ctx->h_small[g];
+		ctx->pending_off[1][g] = ctx->h_small[128 + g];
+	}
+	for (int g = 0; g < ngpus; ++g) {
+		r_counts[g] = ctx->pending_off[0][g + 1] - ctx->pending_off[0][g];
+		s_counts[g] = ctx->pending_off[1][g + 1] - ctx->pending_off[1][g];
+	}
+	ctx->pending_gpus = ngpus;
+	ctx->launches += launches;
+	return HJB_OK;
+}
+
+extern "C" int hjb_cpra_scatter_peer(hjb_ctx *ctx, int ngpus, void *const *peer_r_keys, void *const *peer_r_vals,
+                                     void *const *peer_s_keys, void *const *peer_s_vals, const uint64_t *r_base,
+                                     const uint64_t *s_base, float *ms)
+{
+	if (!ctx || !peer_r_keys || !peer_r_vals || !peer_s_keys || !peer_s_vals || !r_base || !s_base) return HJB_E_INVALID;
+	if (ngpus != ctx->pending_gpus || ngpus < 2) return fail(ctx, HJB_E_INVALID, "hjb_cpra_count must precede with the same ngpus");
+	CK(cudaSetDevice(ctx->device));
+	cudaStream_t s = ctx->stream;
+	void *const *pk[2] = {peer_r_keys, peer_s_keys}, *const *pv[2] = {peer_r_vals, peer_s_vals};
+	const uint64_t *base[2] = {r_base, s_base};
+	uint32_t launches = 0;
+	CK(cudaEventRecord(ctx->ev[6], s));
+	for (int r = 0; r < 2; ++r) {
+		RadixPassArgs &a = ctx->pending[r];
+		if (a.n == 0) continue;
+		PeerTable t;
+		memset(&t, 0, sizeof t);
+		for (int g = 0; g < ngpus; ++g) {
+			// the scan's positions start at pending_off[g] for owner g: shift the column so that they land at base[g]
+			const int64_t shift = (int64_t)base[r][g] - (int64_t)ctx->pending_off[r][g];
+			t.k[g] = (uint32_t *)pk[r][g] + shift;
+			t.v[g] = (uint32_t *)pv[r][g] + shift;
+		}
+		launches += launch_radix_scatter(a, s, &ctx->timer, &t);
+	}
+	CK(cudaEventRecord(ctx->ev[7], s));
+	CK(cudaStreamSynchronize(s));            // the owners may read once every sender has passed this point
+	CK(cudaGetLastError());
+	if (ms) CK(cudaEventElapsedTime(ms, ctx->ev[6], ctx->ev[7]));
+	ctx->pending_gpus = 0;
 	ctx->launches += launches;
 	return HJB_OK;
 }

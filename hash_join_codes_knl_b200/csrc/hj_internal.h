@@ -61,9 +61,16 @@ struct RadixPassArgs {
 	uint64_t *scan_status;            // tiles
 	uint32_t *scan_counter;           // 1
 };
+// per-owner output columns of the fused GPU-assign pass (CPRA): pointers into the owners' receive buffers
+struct PeerTable {
+	uint32_t *k[64];
+	uint32_t *v[64];
+};
 size_t radix_scratch_bytes(uint64_t n, uint32_t np, int bits, uint32_t *chunk, uint32_t *max_items, uint32_t *tiles);
 // launches make_items + histogram + scan + scatter; returns kernels launched
 int launch_radix_pass(const RadixPassArgs &a, cudaStream_t s, int sms, KernelTimer *t = nullptr);
+int launch_radix_count(const RadixPassArgs &a, cudaStream_t s, KernelTimer *t = nullptr);
+int launch_radix_scatter(const RadixPassArgs &a, cudaStream_t s, KernelTimer *t = nullptr, const PeerTable *peers = nullptr);
 int launch_histogram_only(const uint32_t *keys, uint64_t n, uint32_t *counts_dev, uint32_t factor,
                           int rshift, int bits, cudaStream_t s, int sms);
 

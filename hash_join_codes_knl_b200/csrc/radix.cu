@@ -277,12 +277,16 @@ __device__ __forceinline__ void load_col8(uint32_t (&x)[8], uint32_t &ok, const 
 // dynamic shared memory: cnt base fpos oldp wpos pend [F] | golim[F] (uint2) | buf[TILE] (uint2) | carry[F*8] (uint2)
 constexpr uint32_t kCarry = 8;         // tuples per 32-byte sector of a 4-byte column
 
-template <int THREADS, int MINB, bool PREFETCH>
+// PEER: digit d's run does not go to keys_out / vals_out but to peers.k[d] / peers.v[d] -- the
+// receive buffers of GPU d, mapped into this process (CUDA IPC) and pre-offset so that the
+// position the scan produced indexes them directly.  The stores then travel over NVLink: the
+// GPU-assign pass of CPRA and its all-to-all are one kernel.
+template <int THREADS, int MINB, bool PREFETCH, bool PEER>
 __global__ void __launch_bounds__(THREADS, MINB)
 k_scatter(const uint32_t *__restrict__ keys, const uint32_t *__restrict__ vals, uint64_t n, uint32_t np,
           const uint32_t *__restrict__ parent_off, const uint32_t *__restrict__ item_prefix, uint32_t chunk,
           uint32_t factor, int rshift, int bits, const uint32_t *__restrict__ offsets,
-          uint32_t *__restrict__ keys_out, uint32_t *__restrict__ vals_out)
+          uint32_t *__restrict__ keys_out, uint32_t *__restrict__ vals_out, const PeerTable peers)
 {
 	constexpr uint32_t TILE = THREADS * 8, kGroupsPerTile = TILE / 4;
 	extern __shared__ __align__(16) uint32_t s_mem[];
@@ -394,8 +398,8 @@ k_scatter(const uint32_t *__restrict__ keys, const uint32_t *__restrict__ vals, 
 				if (j < oldp[d]) {
 					const uint2 kv = carry[i];
 					const uint32_t dst = fpos[d] + j;
-					keys_out[dst] = kv.x;
-					vals_out[dst] = kv.y;
+					(PEER ? peers.k[d] : keys_out)[dst] = kv.x;
+					(PEER ? peers.v[d] : vals_out)[dst] = kv.y;
 				}
 			}
 		__syncthreads();
@@ -409,8 +413,8 @@ k_scatter(const uint32_t *__restrict__ keys, const uint32_t *__restrict__ vals, 
 			const uint2 gl = golim[d];
 			const uint32_t pos = gl.x + i;
 			if (pos < gl.y) {
-				keys_out[pos] = kv.x;
-				vals_out[pos] = kv.y;
+				(PEER ? peers.k[d] : keys_out)[pos] = kv.x;
+				(PEER ? peers.v[d] : vals_out)[pos] = kv.y;
 			} else {
 				carry[d * kCarry + (pos - gl.y)] = kv;
 			}
@@ -440,7 +444,23 @@ size_t radix_scratch_bytes(uint64_t n, uint32_t np, int bits, uint32_t *chunk, u
 	return bytes + 1024;                                            // per-array 256-byte padding of the bump allocator
 }
 
-int launch_radix_pass(const RadixPassArgs &a, cudaStream_t s, int /*sms*/, KernelTimer *t)
+static void scatter_attrs()
+{
+	static bool done = false;
+	if (done) return;
+	done = true;
+	const int big = 2048 * 32 + 1024 * 8 * 8;
+	cudaFuncSetAttribute(k_scatter<512, 2, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+	cudaFuncSetAttribute(k_scatter<512, 3, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+	cudaFuncSetAttribute(k_scatter<512, 3, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+	cudaFuncSetAttribute(k_scatter<1024, 1, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+	cudaFuncSetAttribute(k_scatter<1024, 2, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+	cudaFuncSetAttribute(k_scatter<1024, 1, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+}
+
+// make_items + histogram + scan: after this a.counts holds every item's start offset per digit
+// and a.child_off the partition offsets
+int launch_radix_count(const RadixPassArgs &a, cudaStream_t s, KernelTimer *t)
 {
 	KernelTimer off;
 	off.enabled = false;
@@ -462,35 +482,50 @@ int launch_radix_pass(const RadixPassArgs &a, cudaStream_t s, int /*sms*/, Kerne
 	k_scan<<<tiles, kScanThreads, 0, s>>>(a.item_prefix, a.np, a.bits, a.counts, a.child_off, a.scan_status,
 	                                      a.scan_counter);
 	t->stop(s);
+	return 3;
+}
+
+int launch_radix_scatter(const RadixPassArgs &a, cudaStream_t s, KernelTimer *t, const PeerTable *peers)
+{
+	KernelTimer off;
+	off.enabled = false;
+	off.n = 0;
+	if (!t) t = &off;
+	const uint32_t F = 1u << a.bits;
+	scatter_attrs();
 	// CTA shape and register budget; HJB_SCATTER_VARIANT picks alternatives for experiments
 	static int variant = -1;
 	if (variant < 0) {
 		const char *e = getenv("HJB_SCATTER_VARIANT");
 		variant = e ? atoi(e) : 3;       // measured best on B200: one 1024-thread CTA per SM, 8192-tuple tiles
 		if (variant < 0 || variant > 4) variant = 3;
-		const int big = 2048 * 32 + 1024 * 8 * 8;
-		cudaFuncSetAttribute(k_scatter<512, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
-		cudaFuncSetAttribute(k_scatter<512, 3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
-		cudaFuncSetAttribute(k_scatter<512, 3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
-		cudaFuncSetAttribute(k_scatter<1024, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
-		cudaFuncSetAttribute(k_scatter<1024, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
 	}
-	const int threads = variant >= 3 ? 1024 : 512;
+	const int threads = (variant >= 3 || peers) ? 1024 : 512;
 	const size_t smem = (size_t)F * 32 + (size_t)threads * 8 * 8 + (F <= 256 ? (size_t)F * kCarry * 8 : 0);
+	static const PeerTable no_peers = {};
 	t->start(KK_SCATTER, s);
-#define HJB_LAUNCH_SCATTER(T, M, P)                                                                                  \
-	k_scatter<T, M, P><<<a.max_items, T, smem, s>>>(a.keys, a.vals, a.n, a.np, a.parent_off, a.item_prefix, a.chunk, \
-	                                                a.factor, a.rshift, a.bits, a.counts, a.keys_out, a.vals_out)
-	switch (variant) {
-	case 1: HJB_LAUNCH_SCATTER(512, 3, true); break;
-	case 2: HJB_LAUNCH_SCATTER(512, 3, false); break;
-	case 4: HJB_LAUNCH_SCATTER(1024, 2, false); break;
-	case 0: HJB_LAUNCH_SCATTER(512, 2, true); break;
-	default: HJB_LAUNCH_SCATTER(1024, 1, true); break;
+#define HJB_LAUNCH_SCATTER(T, M, P, PEER, TABLE)                                                                            \
+	k_scatter<T, M, P, PEER><<<a.max_items, T, smem, s>>>(a.keys, a.vals, a.n, a.np, a.parent_off, a.item_prefix, a.chunk,  \
+	                                                      a.factor, a.rshift, a.bits, a.counts, a.keys_out, a.vals_out, TABLE)
+	if (peers) {
+		HJB_LAUNCH_SCATTER(1024, 1, true, true, *peers);
+	} else {
+		switch (variant) {
+		case 0: HJB_LAUNCH_SCATTER(512, 2, true, false, no_peers); break;
+		case 1: HJB_LAUNCH_SCATTER(512, 3, true, false, no_peers); break;
+		case 2: HJB_LAUNCH_SCATTER(512, 3, false, false, no_peers); break;
+		case 4: HJB_LAUNCH_SCATTER(1024, 2, false, false, no_peers); break;
+		default: HJB_LAUNCH_SCATTER(1024, 1, true, false, no_peers); break;
+		}
 	}
 #undef HJB_LAUNCH_SCATTER
 	t->stop(s);
-	return 4;
+	return 1;
+}
+
+int launch_radix_pass(const RadixPassArgs &a, cudaStream_t s, int /*sms*/, KernelTimer *t)
+{
+	return launch_radix_count(a, s, t) + launch_radix_scatter(a, s, t, nullptr);
 }
 
 int launch_histogram_only(const uint32_t *keys, uint64_t n, uint32_t *counts_dev, uint32_t factor, int rshift,

@@ -128,6 +128,32 @@ int hjb_cpra_split(hjb_ctx *ctx, const hjb_rel *R_chunk, const hjb_rel *S_chunk,
 int hjb_cpra_join_local(hjb_ctx *ctx, const hjb_rel *R_recv, const hjb_rel *S_recv, int gpu, int ngpus,
                         const hjb_opts *opts, hjb_result *out);
 
+/* ---- CPRA with the exchange FUSED into the GPU-assign pass: instead of split -> all-to-all,
+ * the scatter kernel stores every tuple straight into its owner's receive buffer over NVLink
+ * (the owners' buffers are mapped into this process through CUDA IPC).  Per join:
+ *   hjb_cpra_count         histogram + scan of this GPU's chunk by owner; counts to the host
+ *   (caller)               all-gather the counts; sender s gets rows [base, base + count) of owner g's buffers
+ *   hjb_cpra_scatter_peer  the scatter, one coalesced sector-aligned NVLink store stream per owner
+ *   (caller)               barrier, then hjb_cpra_join_local on the own receive buffers
+ * This replaces the reference's per-partition memcpy gather (cpra2.cpp:1896-1904, :1951-1958). */
+typedef struct hjb_recv {
+	uint32_t *r_keys, *r_vals, *s_keys, *s_vals;   /* this GPU's receive buffers (device, owned by ctx) */
+	uint64_t r_capacity, s_capacity;               /* rows */
+	unsigned char ipc[4][64];                      /* cudaIpcMemHandle_t of the four buffers, in that order */
+} hjb_recv;
+int hjb_cpra_recv_alloc(hjb_ctx *ctx, uint64_t r_capacity, uint64_t s_capacity, hjb_recv *out);
+int hjb_ipc_open(hjb_ctx *ctx, const unsigned char *handle64, void **dev_ptr);
+int hjb_ipc_close(hjb_ctx *ctx, void *dev_ptr);
+/* r_counts / s_counts: ngpus entries each.  Keeps the chunk pointers and the scan state in ctx
+ * until hjb_cpra_scatter_peer; the chunks must stay untouched in between. */
+int hjb_cpra_count(hjb_ctx *ctx, const hjb_rel *R_chunk, const hjb_rel *S_chunk, int ngpus, const hjb_opts *opts,
+                   uint64_t *r_counts, uint64_t *s_counts);
+/* peer_*[g]: owner g's receive column as seen from this process (own pointer for g == this GPU,
+ * hjb_ipc_open'ed otherwise); r_base[g] / s_base[g]: first row of owner g reserved for this sender */
+int hjb_cpra_scatter_peer(hjb_ctx *ctx, int ngpus, void *const *peer_r_keys, void *const *peer_r_vals,
+                          void *const *peer_s_keys, void *const *peer_s_vals, const uint64_t *r_base,
+                          const uint64_t *s_base, float *ms);
+
 /* ---- the kernels, one call each, device pointers: mirror the reference's free functions
  * so intermediate products can be compared with the oracle -------------------------- */
 /* hash h(key,f,N) = ((uint32)(key*f) * N) >> 32, npj.cpp:200-201 / simd_hash npj.cpp:90-106;

@@ -24,6 +24,7 @@ def main():
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
     eng = hj.Engine(local, use_torch_stream=True)
+    fused = cpra.FusedExchange(eng)
     ok = True
     for nr, ns, seed in ((200000, 600000, 16), (1 << 20, 1 << 22, 17), (100003, 70001, 18)):
         rk, rv, sk, sv, _, _ = oracle_generate(nr, ns, threads=2, seed=seed)
@@ -31,17 +32,21 @@ def main():
         cr = slice(rank * nr // world, (rank + 1) * nr // world)
         cs = slice(rank * ns // world, (rank + 1) * ns // world)
         dev = lambda a: torch.from_numpy(np.ascontiguousarray(a).view(np.int32)).cuda()
-        res = cpra.cpra_join(eng, (dev(rk[cr]), dev(rv[cr])), (dev(sk[cs]), dev(sv[cs])))
-        got = (res["count"], res["sum_key"], res["sum_outer"], res["sum_inner"])
-        rows = [torch.from_numpy(c) for c in res["local"].rows_numpy()]
-        gathered = [None] * world
-        dist.all_gather_object(gathered, rows)
-        if rank == 0:
-            allrows = sort_rows(*(np.concatenate([g[i].numpy() for g in gathered]) for i in range(3)))
-            good = got == want.checks() and (allrows == want.sorted_rows()).all()
-            print(f"cpra world={world} |R|={nr} |S|={ns}: {'OK' if good else 'MISMATCH'} {got} want {want.checks()} "
-                  f"split {res['split_ms']:.3f} ms exchange {res['exchange_ms']:.3f} ms join {res['join_ms']:.3f} ms", flush=True)
-            ok = ok and good
+        for mode in ("nccl", "fused"):
+            if mode == "nccl":
+                res = cpra.cpra_join(eng, (dev(rk[cr]), dev(rv[cr])), (dev(sk[cs]), dev(sv[cs])))
+            else:
+                res = cpra.cpra_join_fused(eng, (dev(rk[cr]), dev(rv[cr])), (dev(sk[cs]), dev(sv[cs])), fused)
+            got = (res["count"], res["sum_key"], res["sum_outer"], res["sum_inner"])
+            rows = list(res["local"].rows_numpy())
+            gathered = [None] * world
+            dist.all_gather_object(gathered, rows)
+            if rank == 0:
+                allrows = sort_rows(*(np.concatenate([g[i] for g in gathered]) for i in range(3)))
+                good = got == want.checks() and (allrows == want.sorted_rows()).all()
+                print(f"cpra {mode} world={world} |R|={nr} |S|={ns}: {'OK' if good else 'MISMATCH'} {got} want {want.checks()} "
+                      f"split {res['split_ms']:.3f} ms exchange {res['exchange_ms']:.3f} ms join {res['join_ms']:.3f} ms", flush=True)
+                ok = ok and good
     dist.destroy_process_group()
     if rank == 0:
         print("CPRA_NCCL_OK" if ok else "CPRA_NCCL_FAIL", flush=True)
