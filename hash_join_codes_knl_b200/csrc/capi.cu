@@ -384,12 +384,14 @@ static int make_plan(hjb_ctx *ctx, uint64_t nr, uint64_t ns, const hjb_opts *o, 
 			p->total_bits += o->radix_bits[i];
 		}
 	} else {
-		const uint32_t target = o->part_tuples ? o->part_tuples : kDefaultPartTuples;
+		// with <= 16 hash bits left below the partition id the join kernel addresses payloads directly
+		// (csrc/part_join.cu: one fill holds 6144 build tuples, so partitions may average 4096); worth
+		// two full passes as soon as the input is not tiny.  Otherwise hash tables, 2048 per partition.
+		const bool big = !o->part_tuples && nr + ns >= (1u << 22);
+		const uint32_t target = o->part_tuples ? o->part_tuples : (big ? 4096u : kDefaultPartTuples);
 		int tb = 0;
 		while (tb < 28 && (nr >> tb) > target) ++tb;
-		// with <= 16 hash bits left below the partition id the join kernel addresses payloads directly
-		// (csrc/part_join.cu); worth two full passes as soon as the input is not tiny
-		if (!o->part_tuples && nr + ns >= (1u << 22) && consumed + tb < 16) tb = 16 - consumed;
+		if (big && consumed + tb < 16) tb = 16 - consumed;
 		p->total_bits = tb;
 		p->npass = (tb + 7) / 8;
 		for (int i = 0; i < p->npass; ++i) p->bits[i] = tb / p->npass + (i < tb % p->npass ? 1 : 0);

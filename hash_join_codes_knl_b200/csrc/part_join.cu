@@ -126,7 +126,7 @@ __device__ __forceinline__ void emit_round(const OutCols &out, const bool (&foun
 }
 
 constexpr uint32_t kDirectWords = 2048;                  // 2^16-bit presence bitmap
-constexpr uint32_t kDirectFill = 3072;                   // build tuples per DIRECT fill (payload array)
+constexpr uint32_t kDirectFill = 6144;                   // build tuples per DIRECT fill (payload array, 24 KB)
 constexpr uint32_t kHashSlots = 1u << kJoinLog2Slots;    // HASH table slots
 constexpr uint32_t kHashFill = kHashSlots / 4 * 3;       // load <= 0.75
 constexpr size_t kDirectBytes = (size_t)kDirectWords * 8 + (size_t)kDirectFill * 4;
