@@ -292,6 +292,7 @@ k_scatter(const uint32_t *__restrict__ keys, const uint32_t *__restrict__ vals, 
 	extern __shared__ __align__(16) uint32_t s_mem[];
 	__shared__ uint32_t warp_totals[34];
 	__shared__ uint32_t s_tile_n;
+	__shared__ uint32_t *s_pk[PEER ? 64 : 1], *s_pv[PEER ? 64 : 1];
 	const uint32_t F = 1u << bits, mask = F - 1;
 	const bool wc = F <= 256;
 	uint32_t *cnt = s_mem, *base = cnt + F, *fpos = base + F, *oldp = fpos + F, *wpos = oldp + F, *pend = wpos + F;
@@ -306,6 +307,10 @@ k_scatter(const uint32_t *__restrict__ keys, const uint32_t *__restrict__ vals, 
 		pend[p] = 0;
 		cnt[p] = 0;
 	}
+	if (PEER && threadIdx.x < 64) {
+		s_pk[threadIdx.x] = peers.k[threadIdx.x];
+		s_pv[threadIdx.x] = peers.v[threadIdx.x];
+	}
 	const uint64_t g_beg = r.beg >> 2, g_end = (r.end + 3) >> 2;
 	auto tile_is_full = [&](uint64_t g0) {
 		return (g0 << 2) >= r.beg && ((g0 + kGroupsPerTile) << 2) <= r.end;    // r.end <= n: vector loads stay inside
@@ -319,27 +324,37 @@ k_scatter(const uint32_t *__restrict__ keys, const uint32_t *__restrict__ vals, 
 	for (uint64_t g0 = g_beg; g0 < g_end; g0 += kGroupsPerTile) {
 		const uint64_t g1 = g0 + kGroupsPerTile;
 		const bool last = g1 >= g_end;
+		const bool full = tile_is_full(g0);
 		if (PREFETCH) {
 #pragma unroll
 			for (int e = 0; e < 8; ++e) key[e] = nkey[e];
 			ok = nok;
 		} else {
-			if (tile_is_full(g0)) load_col8<THREADS, true>(key, ok, keys, g0, g_end, r.beg, r.end, n);
+			if (full) load_col8<THREADS, true>(key, ok, keys, g0, g_end, r.beg, r.end, n);
 			else load_col8<THREADS, false>(key, ok, keys, g0, g_end, r.beg, r.end, n);
 		}
 		uint32_t vok;
-		if (tile_is_full(g0)) load_col8<THREADS, true>(val, vok, vals, g0, g_end, r.beg, r.end, n);
+		if (full) load_col8<THREADS, true>(val, vok, vals, g0, g_end, r.beg, r.end, n);
 		else load_col8<THREADS, false>(val, vok, vals, g0, g_end, r.beg, r.end, n);
 		if (PREFETCH && !last) {
 			if (tile_is_full(g1)) load_col8<THREADS, true>(nkey, nok, keys, g1, g_end, r.beg, r.end, n);
 			else load_col8<THREADS, false>(nkey, nok, keys, g1, g_end, r.beg, r.end, n);
 		}
-		// (1) rank: digit << 16 | rank-in-digit (rank < TILE <= 2^16, digit < 2^11)
+		// (1) rank: digit << 16 | rank-in-digit (rank < TILE <= 2^16, digit < 2^11).  Interior tiles
+		// (all but an item's first and last) have every element valid: no per-element predicate.
 		uint32_t dr[8];
+		if (full) {
 #pragma unroll
-		for (int e = 0; e < 8; ++e) {
-			const uint32_t d = radix_digit(hash_mul(key[e], factor), rshift, mask);
-			dr[e] = (ok >> e) & 1u ? (d << 16) | atomicAdd(&cnt[d], 1u) : 0xFFFFFFFFu;
+			for (int e = 0; e < 8; ++e) {
+				const uint32_t d = radix_digit(hash_mul(key[e], factor), rshift, mask);
+				dr[e] = (d << 16) | atomicAdd(&cnt[d], 1u);
+			}
+		} else {
+#pragma unroll
+			for (int e = 0; e < 8; ++e) {
+				const uint32_t d = radix_digit(hash_mul(key[e], factor), rshift, mask);
+				dr[e] = (ok >> e) & 1u ? (d << 16) | atomicAdd(&cnt[d], 1u) : 0xFFFFFFFFu;
+			}
 		}
 		__syncthreads();
 		// (2) per digit: tile offset, global offset, flush limit, what stays pending
@@ -357,21 +372,24 @@ k_scatter(const uint32_t *__restrict__ keys, const uint32_t *__restrict__ vals, 
 			cnt[p] = 0;
 		};
 		if (F <= THREADS) {
-			// one digit per thread: warp scans, then the warp totals through shared memory
+			// one digit per thread (threads >= F idle): warp scans, then the warp totals through shared memory
 			const uint32_t p = threadIdx.x;
-			const uint32_t c = p < F ? cnt[p] : 0;
-			const uint32_t incl = warp_inclusive_scan_u32(c);
-			if (lane_id() == 31) warp_totals[p >> 5] = incl;
-			__syncthreads();
-			uint32_t before = 0, tile_total = 0;
-#pragma unroll
-			for (uint32_t w = 0; w < THREADS / 32; ++w) {
-				const uint32_t t = warp_totals[w];
-				before += w < (p >> 5) ? t : 0;
-				tile_total += t;
+			const uint32_t nw = (F + 31) >> 5;                 // warps that own digits
+			uint32_t c = 0, incl = 0;
+			if (p < nw * 32) {
+				c = p < F ? cnt[p] : 0;
+				incl = warp_inclusive_scan_u32(c);
+				if (lane_id() == 31) warp_totals[p >> 5] = incl;
 			}
-			if (p < F) plan_digit(p, c, before + incl - c);
-			if (p == 0) s_tile_n = tile_total;
+			__syncthreads();
+			if (p < nw * 32) {
+				const uint32_t t = lane_id() < nw ? warp_totals[lane_id()] : 0;
+				const uint32_t tincl = warp_inclusive_scan_u32(t);
+				const uint32_t before = __shfl_sync(kFullMask, tincl - t, p >> 5);
+				if (p < F) plan_digit(p, c, before + incl - c);
+				const uint32_t tile_total = __shfl_sync(kFullMask, tincl, 31);
+				if (p == 0) s_tile_n = tile_total;
+			}
 			__syncthreads();
 		} else {
 			const uint32_t ept = (F + THREADS - 1) / THREADS;
@@ -389,17 +407,22 @@ k_scatter(const uint32_t *__restrict__ keys, const uint32_t *__restrict__ vals, 
 			__syncthreads();
 		}
 		// (3) place the tile's tuples; flush the carried tuples of every digit that reached a boundary
+		if (full) {
 #pragma unroll
-		for (int e = 0; e < 8; ++e)
-			if (dr[e] != 0xFFFFFFFFu) buf[base[dr[e] >> 16] + (dr[e] & 0xFFFFu)] = make_uint2(key[e], val[e]);
+			for (int e = 0; e < 8; ++e) buf[base[dr[e] >> 16] + (dr[e] & 0xFFFFu)] = make_uint2(key[e], val[e]);
+		} else {
+#pragma unroll
+			for (int e = 0; e < 8; ++e)
+				if (dr[e] != 0xFFFFFFFFu) buf[base[dr[e] >> 16] + (dr[e] & 0xFFFFu)] = make_uint2(key[e], val[e]);
+		}
 		if (wc)
 			for (uint32_t i = threadIdx.x; i < F * kCarry; i += THREADS) {
 				const uint32_t d = i / kCarry, j = i % kCarry;
 				if (j < oldp[d]) {
 					const uint2 kv = carry[i];
 					const uint32_t dst = fpos[d] + j;
-					(PEER ? peers.k[d] : keys_out)[dst] = kv.x;
-					(PEER ? peers.v[d] : vals_out)[dst] = kv.y;
+					(PEER ? s_pk[d] : keys_out)[dst] = kv.x;
+					(PEER ? s_pv[d] : vals_out)[dst] = kv.y;
 				}
 			}
 		__syncthreads();
@@ -407,14 +430,16 @@ k_scatter(const uint32_t *__restrict__ keys, const uint32_t *__restrict__ vals, 
 		// the carry buffer.  The next tile's step (1) barrier orders this loop before step (2) rewrites
 		// golim and before step (3) reads carry.
 		const uint32_t tile_n = s_tile_n;
+		uint32_t *const ko = keys_out, *const vo = vals_out;
+#pragma unroll 4
 		for (uint32_t i = threadIdx.x; i < tile_n; i += THREADS) {
 			const uint2 kv = buf[i];
 			const uint32_t d = radix_digit(hash_mul(kv.x, factor), rshift, mask);
 			const uint2 gl = golim[d];
 			const uint32_t pos = gl.x + i;
 			if (pos < gl.y) {
-				(PEER ? peers.k[d] : keys_out)[pos] = kv.x;
-				(PEER ? peers.v[d] : vals_out)[pos] = kv.y;
+				(PEER ? s_pk[d] : ko)[pos] = kv.x;
+				(PEER ? s_pv[d] : vo)[pos] = kv.y;
 			} else {
 				carry[d * kCarry + (pos - gl.y)] = kv;
 			}
