@@ -305,7 +305,7 @@ static int npj_device(hjb_ctx *ctx, const hjb_rel *R, const hjb_rel *S, const hj
 	CK(cudaSetDevice(ctx->device));
 	timer_reset(ctx);
 	if (R->tuples == 0 || S->tuples == 0) return HJB_OK;
-	const double load = o->npj_load > 0.0 ? o->npj_load : 0.5;
+	const double load = o->npj_load > 0.0 ? o->npj_load : 0.75;   // measured best on B200 (smaller table: more L2 hits)
 	if (load > 0.95) return fail(ctx, HJB_E_INVALID, "npj_load must be <= 0.95");
 	uint64_t buckets = (uint64_t)ceil((double)R->tuples / load / 4.0) + 1;       // +1: at least one empty slot
 	if (buckets > 0xFFFFFFFFull) return fail(ctx, HJB_E_INVALID, "table too large");

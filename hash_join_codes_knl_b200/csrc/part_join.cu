@@ -186,10 +186,19 @@ k_partition_join(const uint32_t *__restrict__ rk, const uint32_t *__restrict__ r
 					reinterpret_cast<uint4 *>(bitmap)[w] = make_uint4(0, 0, 0, 0);
 				if (threadIdx.x == 0) s_dups = 0;
 				__syncthreads();
-				for (uint32_t i = fb + threadIdx.x; i < fe; i += THREADS) {
-					const uint32_t lo = hash_mul(rk[i], radix_factor) & rem_mask;
-					const uint32_t bit = 1u << (lo & 31);
-					if (atomicOr(&bitmap[lo >> 5], bit) & bit) s_dups = 1;
+				// build tuples are fetched kBatch at a time so that their loads are in flight together
+				constexpr int kBatch = 8;
+				for (uint32_t i0 = fb + threadIdx.x; i0 < fe; i0 += THREADS * kBatch) {
+					uint32_t bk[kBatch];
+#pragma unroll
+					for (int t = 0; t < kBatch; ++t) bk[t] = i0 + t * THREADS < fe ? rk[i0 + t * THREADS] : 0;
+#pragma unroll
+					for (int t = 0; t < kBatch; ++t)
+						if (i0 + t * THREADS < fe) {
+							const uint32_t lo = hash_mul(bk[t], radix_factor) & rem_mask;
+							const uint32_t bit = 1u << (lo & 31);
+							if (atomicOr(&bitmap[lo >> 5], bit) & bit) s_dups = 1;
+						}
 				}
 				__syncthreads();
 				use_hash = s_dups != 0;
@@ -211,10 +220,21 @@ k_partition_join(const uint32_t *__restrict__ rk, const uint32_t *__restrict__ r
 					}
 					__syncthreads();
 					// step 3: payloads in rank order
-					for (uint32_t i = fb + threadIdx.x; i < fe; i += THREADS) {
-						const uint32_t lo = hash_mul(rk[i], radix_factor) & rem_mask;
-						const uint32_t w = lo >> 5;
-						dvals[prefix[w] + __popc(bitmap[w] & ((1u << (lo & 31)) - 1))] = rv[i];
+					for (uint32_t i0 = fb + threadIdx.x; i0 < fe; i0 += THREADS * kBatch) {
+						uint32_t bk[kBatch], bv[kBatch];
+#pragma unroll
+						for (int t = 0; t < kBatch; ++t) {
+							const bool in = i0 + t * THREADS < fe;
+							bk[t] = in ? rk[i0 + t * THREADS] : 0;
+							bv[t] = in ? rv[i0 + t * THREADS] : 0;
+						}
+#pragma unroll
+						for (int t = 0; t < kBatch; ++t)
+							if (i0 + t * THREADS < fe) {
+								const uint32_t lo = hash_mul(bk[t], radix_factor) & rem_mask;
+								const uint32_t w = lo >> 5;
+								dvals[prefix[w] + __popc(bitmap[w] & ((1u << (lo & 31)) - 1))] = bv[t];
+							}
 					}
 					__syncthreads();
 					// ---- DIRECT probe

@@ -53,7 +53,7 @@ typedef struct hjb_rel {
 typedef struct hjb_opts {
 	int materialize;       /* 1 (reference behaviour): write the dense 3-column result; 0: count + checksums only */
 	uint32_t seed;         /* hash factors are drawn from it (npj.cpp:975-977); 0 -> fixed default */
-	double npj_load;       /* NPJ table load factor (reference 0.90); default 0.50 */
+	double npj_load;       /* NPJ table load factor (reference 0.90); default 0.75 */
 	int radix_bits[4];     /* PHJ/CPRA fan-out bits per pass (reference: planner phj.cpp:1791-1808); all 0 -> planner */
 	uint32_t part_tuples;  /* planner target for build tuples per final partition (reference hash_table_limit 6400) */
 	uint64_t out_capacity; /* rows the result buffers may hold; 0 -> max(|S|, |R|); grown and retried on overflow */
