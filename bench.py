@@ -278,7 +278,7 @@ def main():
         if algo == "cpra":
             r = cpra_step((rk, rv), (sk, sv))
             got = (r["count"], r["sum_key"], r["sum_outer"], r["sum_inner"])
-            return got, r["local"].kernel_launches + (8 if world > 1 else 0), r
+            return got, sum(v[1] for v in eng.kernel_times().values()), r
         r = getattr(eng, algo)((rk, rv), (sk, sv))
         return r.checks(), r.kernel_launches, r
 
@@ -375,47 +375,68 @@ def main():
 
     # ---- roofline of the dominant kernel, from the per-launch CUDA events of the timed steps
     peak, peak_src = measured_peak_gbs()
-    alg_bytes_per_launch = {                       # algorithmic bytes per launch
-        "k_hist": lambda n: 4 * n, "k_scatter": lambda n: 16 * n,
-        "k_partition_join": lambda n: 8 * (nr_g + ns_g) + 12 * ns_g,
-        "k_npj_probe": lambda n: 8 * ns_g + 12 * ns_g + (0 if nr_g * 16 <= (64 << 20) else 8 * ns_g),
-        "k_npj_build": lambda n: 8 * nr_g + 16 * nr_g * 2,
+    n_in = nr_g + ns_g                              # tuples this GPU partitions per pass / joins
+    # algorithmic bytes per step summed over a kernel's launches
+    alg_bytes_per_step = {
+        "k_hist": lambda L: 4 * n_in * (L / 2),                 # 4 B/tuple; R and S launches alternate
+        "k_scatter": lambda L: 16 * n_in * (L / 2),             # 8 B read + 8 B written per tuple
+        "k_partition_join": lambda L: 8 * n_in + 12 * ns_g,     # read both partitioned relations, write 12 B/match
+        "k_npj_probe": lambda L: 8 * ns_g + 12 * ns_g + (0 if nr_g * 16 <= (64 << 20) else 8 * ns_g),
+        "k_npj_build": lambda L: 8 * nr_g + 8 * (4 * nr_g / 3) + 8 * nr_g,   # read R, init the table (load 0.75), write slots
     }
-    dom = max(ktimes.items(), key=lambda kv: kv[1][0])[0] if ktimes else None
+    per_step = {k: (v[0] / args.steps, v[1] / args.steps) for k, v in ktimes.items() if v[1]}
+    dom = max(per_step.items(), key=lambda kv: kv[1][0])[0] if per_step else None
+    ncu_traffic = {}
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            ncu_traffic = json.load(f)
+    except Exception:
+        pass
     roof = None
-    if dom in alg_bytes_per_launch:
-        ms_k, n_k = ktimes[dom]
-        per_launch_ms = ms_k / max(1, n_k)
-        # scatter / hist launches alternate between R and S: average tuples per launch
-        n_avg = (nr_g + ns_g) / 2
-        achieved = alg_bytes_per_launch[dom](n_avg) / (per_launch_ms * 1e-3) / 1e9
+    if dom in alg_bytes_per_step:
+        ms_k, launches_k = per_step[dom]
+        per_launch_bytes = alg_bytes_per_step[dom](launches_k) / launches_k
+        per_launch_ms = ms_k / launches_k
+        achieved = per_launch_bytes / (per_launch_ms * 1e-3) / 1e9
+        tr = ncu_traffic.get(workload, {}).get(dom)
         roof = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
-                "avg_launch_ms": per_launch_ms, "launches": n_k,
-                "share_of_step": ms_k / ms_total}
-    passes = 2 if (nr_g >> 11) > 256 else 1
-    step_bytes = (nr_g + ns_g) * (20 * passes + 8) + 12 * ns_g if algo != "npj" else None
+                "frac": achieved / peak, "traffic": tr, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": per_launch_bytes, "avg_launch_ms": per_launch_ms,
+                "launches_per_step": launches_k, "share_of_step": ms_k / ms_step,
+                "traffic_source": "profiles/ncu_traffic.json (dram__bytes_read.sum + dram__bytes_write.sum per launch, "
+                                  "ncu --set full)" if tr else None}
+    if algo == "npj":
+        step_bytes = sum(alg_bytes_per_step[k](1) for k in ("k_npj_build", "k_npj_probe"))
+    else:
+        passes = sum(1 for _ in range(int(per_step.get("k_scatter", (0, 0))[1] // 2))) or 2
+        step_bytes = n_in * (20 * passes + 8) + 12 * ns_g
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32",
         "data": "synthetic",
         "config": {"workload": {"phj_cfg2": "PHJ 2^27 x 2^27 unique keys (BASELINE config 2)",
                                 "npj_cfg1": "NPJ 2^24 x 2^28 foreign keys (BASELINE config 1)",
-                                "cpra_cfg4": f"CPRA {nr_g.bit_length() - 1}+{ns_g.bit_length() - 1} log2 tuples per GPU "
+                                "cpra_cfg4": f"CPRA 2^{nr_g.bit_length() - 1} + 2^{ns_g.bit_length() - 1} tuples per GPU "
                                              f"x {world} GPUs (N=8 is BASELINE config 4, 2^31 x 2^31)"}[workload],
                    "inner_tuples": nr_tot, "outer_tuples": ns_tot, "materialize": True, "algorithm": algo,
-                   "l2_policy": "inputs (%.1f GiB) and every intermediate exceed the 126 MB L2; no flush needed"
+                   "exchange": (args.exchange if world > 1 else None),
+                   "l2_policy": "inputs (%.1f GiB per GPU) and every intermediate exceed the 126 MB L2; no flush needed"
                                 % (8 * (nr_g + ns_g) / 2**30),
                    "result_check": "count and 3 checksums verified every step"},
         "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roof,
-        "kernel_ms_per_step": {k: round(v[0] / args.steps, 4) for k, v in sorted(ktimes.items())},
+        "kernel_ms_per_step": {k: round(v[0], 4) for k, v in sorted(per_step.items())},
         "phase_ms_per_step": [round(float(x) / args.steps, 4) for x in phases],
+        "step_roofline": {"algorithmic_bytes_per_gpu": step_bytes, "achieved_gbs_per_gpu": step_bytes / (ms_step * 1e-3) / 1e9,
+                          "frac_of_hbm_peak": step_bytes / (ms_step * 1e-3) / 1e9 / peak},
     }
-    if step_bytes:
-        line["step_roofline"] = {"algorithmic_bytes": step_bytes, "achieved_gbs": step_bytes / (ms_step * 1e-3) / 1e9 * (world if algo == "cpra" else 1) / (world if algo == "cpra" else 1),
-                                 "frac_of_hbm_peak": step_bytes / (ms_step * 1e-3) / 1e9 / peak}
     if algo == "cpra":
         line["cpra_ms_per_step"] = {k: round(v / args.steps, 4) for k, v in extra.items()}
+        if world > 1:
+            sent = 8 * n_in * (world - 1) / world                # bytes each GPU stores into its peers per step
+            line["nvlink"] = {"bytes_out_per_gpu": sent, "scatter_ms": line["cpra_ms_per_step"]["split_ms"],
+                              "achieved_gbs_per_direction": sent / (line["cpra_ms_per_step"]["split_ms"] * 1e-3) / 1e9
+                              if args.exchange == "fused" else sent / (line["cpra_ms_per_step"]["exchange_ms"] * 1e-3) / 1e9,
+                              "reference_gbs": 770.0, "note": "measured peer-copy bandwidth per direction (B200_PROFILING.md); nominal 900"}
     if not args.no_cpu_baseline:
         try:
             base = cpu_join_sample(25 if workload != "npj_cfg1" else 26, 2, 1, "npj_cfg1" if workload == "npj_cfg1" else "phj_cfg2")

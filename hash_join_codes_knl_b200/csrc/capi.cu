@@ -472,7 +472,7 @@ static int phj_device(hjb_ctx *ctx, const hjb_rel *R, const hjb_rel *S, const hj
 	if ((rc = check_rel(ctx, R, true)) || (rc = check_rel(ctx, S, true))) return rc;
 	zero_result(out);
 	CK(cudaSetDevice(ctx->device));
-	timer_reset(ctx);
+	if (consumed == 0) timer_reset(ctx);       // a CPRA join keeps the times of its count / scatter steps
 	if (R->tuples == 0 || S->tuples == 0) return HJB_OK;
 	Plan plan;
 	if ((rc = make_plan(ctx, R->tuples, S->tuples, o, consumed, &plan))) return rc;
@@ -662,6 +662,7 @@ extern "C" int hjb_cpra_split(hjb_ctx *ctx, const hjb_rel *R, const hjb_rel *S, 
 	if (gbits < 0 || ngpus > 64) return fail(ctx, HJB_E_INVALID, "ngpus must be a power of two <= 64");
 	memset(out, 0, sizeof *out);
 	CK(cudaSetDevice(ctx->device));
+	timer_reset(ctx);
 	if (ngpus == 1) {          // one owner: nothing to split (CPRA on one thread partitions only locally)
 		out->r_keys = R->keys; out->r_vals = R->vals; out->s_keys = S->keys; out->s_vals = S->vals;
 		out->r_offsets[1] = R->tuples; out->s_offsets[1] = S->tuples;
@@ -703,13 +704,14 @@ extern "C" int hjb_cpra_split(hjb_ctx *ctx, const hjb_rel *R, const hjb_rel *S, 
 		a.counts = w.take<uint32_t>((size_t)a.max_items << gbits);
 		a.scan_status = w.take<uint64_t>(tiles);
 		a.scan_counter = w.take<uint32_t>(1);
-		launches += launch_radix_pass(a, s, ctx->sms);
+		launches += launch_radix_pass(a, s, ctx->sms, &ctx->timer);
 	}
 	CK(cudaEventRecord(ctx->ev[5], s));
 	CK(cudaMemcpyAsync(&ctx->h_small[0], off[0], (size_t)(ngpus + 1) * 4, cudaMemcpyDeviceToHost, s));
 	CK(cudaMemcpyAsync(&ctx->h_small[128], off[1], (size_t)(ngpus + 1) * 4, cudaMemcpyDeviceToHost, s));
 	CK(cudaStreamSynchronize(s));
 	CK(cudaGetLastError());
+	timer_collect(ctx);
 	for (int g = 0; g <= ngpus; ++g) {
 		out->r_offsets[g] = ctx->h_small[g];
 		out->s_offsets[g] = ctx->h_small[128 + g];
@@ -776,6 +778,7 @@ extern "C" int hjb_cpra_count(hjb_ctx *ctx, const hjb_rel *R, const hjb_rel *S, 
 	const int gbits = log2_exact(ngpus);
 	if (gbits < 1 || ngpus > 64) return fail(ctx, HJB_E_INVALID, "ngpus must be a power of two in [2, 64]");
 	CK(cudaSetDevice(ctx->device));
+	timer_reset(ctx);
 	const hjb_rel *rel[2] = {R, S};
 	size_t scratch[2], total = 0;
 	for (int r = 0; r < 2; ++r) {
@@ -814,6 +817,7 @@ extern "C" int hjb_cpra_count(hjb_ctx *ctx, const hjb_rel *R, const hjb_rel *S, 
 	CK(cudaMemcpyAsync(&ctx->h_small[128], off_dev[1], (size_t)(ngpus + 1) * 4, cudaMemcpyDeviceToHost, s));
 	CK(cudaStreamSynchronize(s));
 	CK(cudaGetLastError());
+	timer_collect(ctx);
 	for (int g = 0; g <= ngpus; ++g) {
 		ctx->pending_off[0][g] = ctx->h_small[g];
 		ctx->pending_off[1][g] = ctx->h_small[128 + g];
@@ -855,6 +859,7 @@ extern "C" int hjb_cpra_scatter_peer(hjb_ctx *ctx, int ngpus, void *const *peer_
 	CK(cudaEventRecord(ctx->ev[7], s));
 	CK(cudaStreamSynchronize(s));            // the owners may read once every sender has passed this point
 	CK(cudaGetLastError());
+	timer_collect(ctx);
 	if (ms) CK(cudaEventElapsedTime(ms, ctx->ev[6], ctx->ev[7]));
 	ctx->pending_gpus = 0;
 	ctx->launches += launches;
