@@ -408,7 +408,7 @@ def main():
     if algo == "npj":
         step_bytes = sum(alg_bytes_per_step[k](1) for k in ("k_npj_build", "k_npj_probe"))
     else:
-        passes = sum(1 for _ in range(int(per_step.get("k_scatter", (0, 0))[1] // 2))) or 2
+        passes = max(1, round(per_step.get("k_scatter", (0, 4))[1] / 2))     # scatter launches come in (R, S) pairs
         step_bytes = n_in * (20 * passes + 8) + 12 * ns_g
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
