@@ -55,6 +55,7 @@ SYMBOLS = {
     "hjb_set_profiling": (C.c_int, [C.c_void_p, C.c_int]),
     "hjb_kernel_times": (C.c_int, [C.c_void_p, C.POINTER(C.c_float), u32p, C.c_int]),
     "hjb_kernel_name": (C.c_char_p, [C.c_int]),
+    "hjb_debug_counters": (C.c_int, [C.c_void_p, u64p]),
     "hjb_npj_device": (C.c_int, [C.c_void_p, C.POINTER(Rel), C.POINTER(Rel), C.POINTER(Opts), C.POINTER(Result)]),
     "hjb_phj_device": (C.c_int, [C.c_void_p, C.POINTER(Rel), C.POINTER(Rel), C.POINTER(Opts), C.POINTER(Result)]),
     "hjb_npj_host": (C.c_int, [C.c_void_p, C.POINTER(Rel), C.POINTER(Rel), C.POINTER(Opts), C.POINTER(Result)]),

@@ -248,6 +248,14 @@ static void timer_collect(hjb_ctx *ctx)
 	t.n = 0;
 }
 
+// debug: the 8 phase-cycle counters the join kernel fills when HJB_PHASE_CLOCKS is set (d_scalars[8..15])
+extern "C" int hjb_debug_counters(hjb_ctx *ctx, uint64_t *out8)
+{
+	if (!ctx || !out8) return HJB_E_INVALID;
+	for (int k = 0; k < 8; ++k) out8[k] = ctx->h_scalars[8 + k];
+	return HJB_OK;
+}
+
 extern "C" int hjb_set_profiling(hjb_ctx *ctx, int on)
 {
 	if (!ctx) return HJB_E_INVALID;

@@ -113,6 +113,14 @@ struct JoinSums {
 		outer += o;
 		inner += i;
 	}
+	// branch-free form: hit is 0 or 1; one 32x32+64 multiply-add per sum (IMAD.WIDE.U32)
+	__device__ __forceinline__ void add_if(uint32_t hit, uint32_t k, uint32_t o, uint32_t i)
+	{
+		asm("mad.wide.u32 %0, %1, %2, %0;" : "+l"(count) : "r"(hit), "r"(1u));
+		asm("mad.wide.u32 %0, %1, %2, %0;" : "+l"(key) : "r"(k), "r"(hit));
+		asm("mad.wide.u32 %0, %1, %2, %0;" : "+l"(outer) : "r"(o), "r"(hit));
+		asm("mad.wide.u32 %0, %1, %2, %0;" : "+l"(inner) : "r"(i), "r"(hit));
+	}
 	// every thread of the CTA calls this; scratch: 4 * 32 uint64 of shared memory
 	__device__ __forceinline__ void reduce_to_global(unsigned long long *g /* [4] */, uint64_t *scratch)
 	{

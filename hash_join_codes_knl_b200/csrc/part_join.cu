@@ -26,6 +26,7 @@
 // columns straight from registers, one coalesced 128-byte run per item (ballot-ranked).
 #include "hj_device.cuh"
 #include "hj_internal.h"
+#include <stdlib.h>
 
 namespace hjb {
 
@@ -100,16 +101,18 @@ __device__ __forceinline__ void emit_round(const OutCols &out, const bool (&foun
 	if (lane_id() == 0) base = atomicAdd(out.cursor, (unsigned long long)total);
 	base = __shfl_sync(kFullMask, base, 0);
 	const unsigned lt = lanemask_lt();
-	if (base + total <= out.cap) {                 // common case: no per-row capacity test
+	if (base + total <= out.cap) {                 // common case: no per-row capacity test, 32-bit offsets
+		uint32_t *const ck = out.k + base, *const co = out.o + base, *const ci = out.i + base;
+		uint32_t off = 0;
 #pragma unroll
 		for (int t = 0; t < ITEMS; ++t) {
-			const uint64_t r = base + __popc(m[t] & lt);
+			const uint32_t r = off + __popc(m[t] & lt);
 			if (found[t]) {
-				out.k[r] = key[t];
-				out.o[r] = val[t];
-				out.i[r] = ival[t];
+				ck[r] = key[t];
+				co[r] = val[t];
+				ci[r] = ival[t];
 			}
-			base += __popc(m[t]);
+			off += __popc(m[t]);
 		}
 	} else {
 #pragma unroll
@@ -132,15 +135,25 @@ constexpr uint32_t kHashFill = kHashSlots / 4 * 3;       // load <= 0.75
 constexpr size_t kDirectBytes = (size_t)kDirectWords * 8 + (size_t)kDirectFill * 4;
 constexpr size_t kJoinSmemBytes = (size_t)kHashSlots * 8 > kDirectBytes ? (size_t)kHashSlots * 8 : kDirectBytes;
 
-template <int THREADS, int ITEMS, bool MATERIALIZE>
-__global__ void __launch_bounds__(THREADS, 1024 / THREADS)
+template <int THREADS, int ITEMS, int MINB, bool MATERIALIZE>
+__global__ void __launch_bounds__(THREADS, MINB)
 k_partition_join(const uint32_t *__restrict__ rk, const uint32_t *__restrict__ rv,
                  const uint32_t *__restrict__ sk, const uint32_t *__restrict__ sv,
                  const uint32_t *__restrict__ r_off, const uint32_t *__restrict__ s_off, uint32_t P,
                  const uint32_t *__restrict__ task_prefix, uint32_t *__restrict__ task_counter, uint32_t s_task,
                  uint32_t radix_factor, uint32_t table_factor, int rem_bits, OutCols out,
-                 unsigned long long *__restrict__ sums)
+                 unsigned long long *__restrict__ sums, unsigned long long *__restrict__ phase_clk)
 {
+	// optional phase clocks (HJB_PHASE_CLOCKS=1): thread 0 of every CTA adds the cycles it spent per phase
+	long long clk_t = 0;
+	unsigned long long clk_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#define PHASE_MARK(k)                                              \
+	if (phase_clk && threadIdx.x == 0) {                            \
+		const long long now_ = clock64();                           \
+		clk_acc[k] += (unsigned long long)(now_ - clk_t);           \
+		clk_t = now_;                                               \
+	}
+	if (phase_clk && threadIdx.x == 0) clk_t = clock64();
 	extern __shared__ __align__(16) unsigned char s_raw[];
 	// DIRECT view
 	uint32_t *bitmap = reinterpret_cast<uint32_t *>(s_raw);            // kDirectWords
@@ -150,7 +163,7 @@ k_partition_join(const uint32_t *__restrict__ rk, const uint32_t *__restrict__ r
 	uint64_t *table = reinterpret_cast<uint64_t *>(s_raw);             // kHashSlots
 	__shared__ uint64_t scratch[4 * 32];
 	__shared__ uint32_t warp_totals[34];
-	__shared__ uint32_t s_task_id[2], s_dups, s_hdups, s_sentinels, s_range[4];
+	__shared__ uint32_t s_task_id[2], s_dups, s_hdups, s_sentinels;
 	constexpr uint32_t kMask = kHashSlots - 1;
 	constexpr int kShift = 32 - kJoinLog2Slots;
 	const bool direct_ok = rem_bits <= 16;
@@ -158,23 +171,45 @@ k_partition_join(const uint32_t *__restrict__ rk, const uint32_t *__restrict__ r
 	JoinSums acc;
 	acc.zero();
 	const uint32_t total_tasks = task_prefix[P];
+	// Every thread resolves a task's ranges itself from uniform (broadcast) loads -- no barrier, no
+	// serial search by one thread.  With one task per partition (no skew) task == partition.
+	auto resolve = [&](uint32_t task, uint32_t &rb, uint32_t &re, uint32_t &sb, uint32_t &se) {
+		uint32_t p = task < P ? task : P - 1;
+		if (!(task_prefix[p] <= task && task < task_prefix[p + 1])) p = upper_parent(task_prefix, P, task);
+		rb = r_off[p];
+		re = r_off[p + 1];
+		sb = s_off[p] + (task - task_prefix[p]) * s_task;
+		se = min(s_off[p + 1], sb + s_task);
+	};
+	// pull the 128-byte lines of [beg, end) of a column towards L2 (one line per thread and round)
+	auto prefetch_col = [&](const uint32_t *col, uint32_t beg, uint32_t end) {
+		const char *lo = reinterpret_cast<const char *>(col + beg), *hi = reinterpret_cast<const char *>(col + end);
+		for (const char *q = lo + (size_t)threadIdx.x * 128; q < hi; q += (size_t)THREADS * 128)
+			asm volatile("prefetch.global.L2 [%0];" ::"l"(q));
+	};
 	if (threadIdx.x == 0) s_task_id[0] = atomicAdd(task_counter, 1u);
 	__syncthreads();
+	uint32_t r_beg = 0, r_end = 0, s_beg = 0, s_end = 0;
+	if (s_task_id[0] < total_tasks) resolve(s_task_id[0], r_beg, r_end, s_beg, s_end);
 	for (uint32_t it = 0;; ++it) {
 		const uint32_t task = s_task_id[it & 1];
 		if (task >= total_tasks) break;
-		if (threadIdx.x == 0) {
-			s_task_id[(it + 1) & 1] = atomicAdd(task_counter, 1u);    // read after this task's barriers
-			const uint32_t p = upper_parent(task_prefix, P, task);
-			const uint32_t slice = task - task_prefix[p];
-			const uint32_t sb = s_off[p] + slice * s_task;
-			s_range[0] = r_off[p];
-			s_range[1] = r_off[p + 1];
-			s_range[2] = sb;
-			s_range[3] = min(s_off[p + 1], sb + s_task);
-		}
-		__syncthreads();
-		const uint32_t r_beg = s_range[0], r_end = s_range[1], s_beg = s_range[2], s_end = s_range[3];
+		if (threadIdx.x == 0) s_task_id[(it + 1) & 1] = atomicAdd(task_counter, 1u);    // visible after this task's first barrier
+		uint32_t nr_beg = 0, nr_end = 0, ns_beg = 0, ns_end = 0;
+		bool next_pending = true;
+		// after the task's first barrier: resolve the NEXT task and start its tuples on their way from HBM
+		auto look_ahead = [&]() {
+			if (!next_pending) return;
+			next_pending = false;
+			const uint32_t ntask = s_task_id[(it + 1) & 1];
+			if (ntask >= total_tasks) return;
+			resolve(ntask, nr_beg, nr_end, ns_beg, ns_end);
+			prefetch_col(rk, nr_beg, min(nr_end, nr_beg + kDirectFill));
+			prefetch_col(rv, nr_beg, min(nr_end, nr_beg + kDirectFill));
+			prefetch_col(sk, ns_beg, ns_end);
+			prefetch_col(sv, ns_beg, ns_end);
+		};
+		PHASE_MARK(0)      // task bookkeeping
 
 		uint32_t fb = r_beg;
 		while (fb < r_end) {
@@ -186,9 +221,26 @@ k_partition_join(const uint32_t *__restrict__ rk, const uint32_t *__restrict__ r
 					reinterpret_cast<uint4 *>(bitmap)[w] = make_uint4(0, 0, 0, 0);
 				if (threadIdx.x == 0) s_dups = 0;
 				__syncthreads();
-				// build tuples are fetched kBatch at a time so that their loads are in flight together
+				PHASE_MARK(1)      // bitmap clear
+				look_ahead();
+				// build tuples are fetched kBatch at a time so that their loads are in flight together; the
+				// first batch (all of a typical partition) stays in registers for step 3
 				constexpr int kBatch = 8;
-				for (uint32_t i0 = fb + threadIdx.x; i0 < fe; i0 += THREADS * kBatch) {
+				uint32_t k0[kBatch], v0[kBatch];
+#pragma unroll
+				for (int t = 0; t < kBatch; ++t) {
+					const uint32_t i = fb + threadIdx.x + t * THREADS;
+					k0[t] = i < fe ? rk[i] : 0;
+					v0[t] = i < fe ? rv[i] : 0;
+				}
+#pragma unroll
+				for (int t = 0; t < kBatch; ++t)
+					if (fb + threadIdx.x + t * THREADS < fe) {
+						const uint32_t lo = hash_mul(k0[t], radix_factor) & rem_mask;
+						const uint32_t bit = 1u << (lo & 31);
+						if (atomicOr(&bitmap[lo >> 5], bit) & bit) s_dups = 1;
+					}
+				for (uint32_t i0 = fb + threadIdx.x + THREADS * kBatch; i0 < fe; i0 += THREADS * kBatch) {
 					uint32_t bk[kBatch];
 #pragma unroll
 					for (int t = 0; t < kBatch; ++t) bk[t] = i0 + t * THREADS < fe ? rk[i0 + t * THREADS] : 0;
@@ -201,6 +253,7 @@ k_partition_join(const uint32_t *__restrict__ rk, const uint32_t *__restrict__ r
 						}
 				}
 				__syncthreads();
+				PHASE_MARK(2)      // build step 1: key loads + atomicOr
 				use_hash = s_dups != 0;
 				if (!use_hash) {
 					// step 2: rank structure -- prefix[w] = set bits before word w
@@ -219,8 +272,16 @@ k_partition_join(const uint32_t *__restrict__ rk, const uint32_t *__restrict__ r
 						run += c[j];
 					}
 					__syncthreads();
+					PHASE_MARK(3)      // rank scan
 					// step 3: payloads in rank order
-					for (uint32_t i0 = fb + threadIdx.x; i0 < fe; i0 += THREADS * kBatch) {
+#pragma unroll
+					for (int t = 0; t < kBatch; ++t)
+						if (fb + threadIdx.x + t * THREADS < fe) {
+							const uint32_t lo = hash_mul(k0[t], radix_factor) & rem_mask;
+							const uint32_t w = lo >> 5;
+							dvals[prefix[w] + __popc(bitmap[w] & ((1u << (lo & 31)) - 1))] = v0[t];
+						}
+					for (uint32_t i0 = fb + threadIdx.x + THREADS * kBatch; i0 < fe; i0 += THREADS * kBatch) {
 						uint32_t bk[kBatch], bv[kBatch];
 #pragma unroll
 						for (int t = 0; t < kBatch; ++t) {
@@ -237,6 +298,7 @@ k_partition_join(const uint32_t *__restrict__ rk, const uint32_t *__restrict__ r
 							}
 					}
 					__syncthreads();
+					PHASE_MARK(4)      // build step 3: key + payload loads, placement
 					// ---- DIRECT probe
 					for (uint32_t sb = s_beg; sb < s_end; sb += THREADS * ITEMS) {
 						uint32_t key[ITEMS], val[ITEMS], ival[ITEMS];
@@ -253,15 +315,17 @@ k_partition_join(const uint32_t *__restrict__ rk, const uint32_t *__restrict__ r
 						for (int t = 0; t < ITEMS; ++t) {
 							const uint32_t lo = hash_mul(key[t], radix_factor) & rem_mask;
 							const uint32_t w = lo >> 5, word = bitmap[w];
-							found[t] = found[t] && ((word >> (lo & 31)) & 1u);
+							const uint32_t hit = found[t] ? (word >> (lo & 31)) & 1u : 0u;
 							// rank < fill size whenever the bit is set; a miss may compute fill size itself: clamp
 							const uint32_t pos = min(prefix[w] + (uint32_t)__popc(word & ((1u << (lo & 31)) - 1)), kDirectFill - 1);
 							ival[t] = dvals[pos];
-							if (found[t]) acc.add(key[t], val[t], ival[t]);
+							found[t] = hit != 0;
+							acc.add_if(hit, key[t], val[t], ival[t]);
 						}
 						if (MATERIALIZE) emit_round<ITEMS>(out, found, key, val, ival);
 					}
 					__syncthreads();            // the bitmap is cleared next; also publishes the prefetched task id
+					PHASE_MARK(5)      // probe + emit
 					fb = fe;
 					continue;
 				}
@@ -278,6 +342,7 @@ k_partition_join(const uint32_t *__restrict__ rk, const uint32_t *__restrict__ r
 				s_sentinels = 0;
 			}
 			__syncthreads();
+			look_ahead();
 			for (uint32_t i = fb + threadIdx.x; i < fe; i += THREADS) {
 				const uint32_t key = rk[i];
 				const uint64_t pair = ((uint64_t)rv[i] << 32) | key;
@@ -355,8 +420,16 @@ k_partition_join(const uint32_t *__restrict__ rk, const uint32_t *__restrict__ r
 			__syncthreads();          // the table is cleared next; also publishes the prefetched task id
 			fb = fe;
 		}
+		r_beg = nr_beg;
+		r_end = nr_end;
+		s_beg = ns_beg;
+		s_end = ns_end;
 	}
 	acc.reduce_to_global(sums, scratch);
+	if (phase_clk && threadIdx.x == 0)
+		for (int k = 0; k < 8; ++k)
+			if (clk_acc[k]) atomicAdd(&phase_clk[k], clk_acc[k]);
+#undef PHASE_MARK
 }
 
 int launch_partition_join(const JoinArgs &a, cudaStream_t s, int sms, KernelTimer *t)
@@ -375,28 +448,45 @@ int launch_partition_join(const JoinArgs &a, cudaStream_t s, int sms, KernelTime
 	out.i = a.out_i;
 	out.cursor = a.scalars;
 	out.cap = a.materialize ? a.out_cap : 0;
-	auto kt = k_partition_join<kJoinThreads, kJoinItems, true>;
-	auto kf = k_partition_join<kJoinThreads, kJoinItems, false>;
-	static bool attr_set = false;
-	if (!attr_set) {
-		cudaFuncSetAttribute(kt, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kJoinSmemBytes);
-		cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kJoinSmemBytes);
-		attr_set = true;
+	// CTA shape; HJB_JOIN_VARIANT picks alternatives for experiments
+	static int variant = -1;
+	if (variant < 0) {
+		const char *e = getenv("HJB_JOIN_VARIANT");
+		variant = e ? atoi(e) : 0;
+		if (variant < 0 || variant > 4) variant = 0;
 	}
-	int per_sm = 0;
-	if (a.materialize) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kt, kJoinThreads, kJoinSmemBytes);
-	else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kf, kJoinThreads, kJoinSmemBytes);
-	if (per_sm < 1) per_sm = 1;
-	const uint32_t grid = (uint32_t)(sms * per_sm);
+	static int clocks = -1;
+	if (clocks < 0) clocks = getenv("HJB_PHASE_CLOCKS") ? 1 : 0;
+	unsigned long long *clk = clocks ? a.scalars + 8 : nullptr;
 	t->start(KK_PART_JOIN, s);
-	if (a.materialize)
-		kt<<<grid, kJoinThreads, kJoinSmemBytes, s>>>(a.rk, a.rv, a.sk, a.sv, a.r_off, a.s_off, a.P, a.task_prefix,
-		                                              a.task_counter, a.s_task, a.radix_factor, a.table_factor,
-		                                              a.rem_bits, out, a.scalars + 1);
-	else
-		kf<<<grid, kJoinThreads, kJoinSmemBytes, s>>>(a.rk, a.rv, a.sk, a.sv, a.r_off, a.s_off, a.P, a.task_prefix,
-		                                              a.task_counter, a.s_task, a.radix_factor, a.table_factor,
-		                                              a.rem_bits, out, a.scalars + 1);
+#define HJB_LAUNCH_JOIN(T, I, MB)                                                                                            \
+	do {                                                                                                                   \
+		auto kt = k_partition_join<T, I, MB, true>;                                                                          \
+		auto kf = k_partition_join<T, I, MB, false>;                                                                          \
+		cudaFuncSetAttribute(kt, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kJoinSmemBytes);                       \
+		cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kJoinSmemBytes);                       \
+		int per_sm = 0;                                                                                                    \
+		if (a.materialize) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kt, T, kJoinSmemBytes);                  \
+		else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kf, T, kJoinSmemBytes);                                \
+		if (per_sm < 1) per_sm = 1;                                                                                        \
+		const uint32_t grid = (uint32_t)(sms * per_sm);                                                                    \
+		if (a.materialize)                                                                                                 \
+			kt<<<grid, T, kJoinSmemBytes, s>>>(a.rk, a.rv, a.sk, a.sv, a.r_off, a.s_off, a.P, a.task_prefix,               \
+			                                   a.task_counter, a.s_task, a.radix_factor, a.table_factor, a.rem_bits, out,  \
+			                                   a.scalars + 1, clk);                                                             \
+		else                                                                                                               \
+			kf<<<grid, T, kJoinSmemBytes, s>>>(a.rk, a.rv, a.sk, a.sv, a.r_off, a.s_off, a.P, a.task_prefix,               \
+			                                   a.task_counter, a.s_task, a.radix_factor, a.table_factor, a.rem_bits, out,  \
+			                                   a.scalars + 1, clk);                                                             \
+	} while (0)
+	switch (variant) {
+	case 1: HJB_LAUNCH_JOIN(256, 8, 3); break;
+	case 2: HJB_LAUNCH_JOIN(256, 4, 4); break;
+	case 3: HJB_LAUNCH_JOIN(256, 4, 5); break;
+	case 4: HJB_LAUNCH_JOIN(128, 8, 8); break;
+	default: HJB_LAUNCH_JOIN(kJoinThreads, kJoinItems, 4); break;
+	}
+#undef HJB_LAUNCH_JOIN
 	t->stop(s);
 	return 2;
 }

@@ -97,6 +97,9 @@ int hjb_synchronize(hjb_ctx *ctx);
 int hjb_set_profiling(hjb_ctx *ctx, int on);
 int hjb_kernel_times(hjb_ctx *ctx, float *ms, uint32_t *launches, int max_kinds);
 const char *hjb_kernel_name(int kind);
+/* debug aid: per-phase SM cycle counters of the last partition join (filled when the environment
+ * variable HJB_PHASE_CLOCKS is set; summed over CTAs) */
+int hjb_debug_counters(hjb_ctx *ctx, uint64_t *out8);
 
 /* ---- whole joins: replace run() / run_hj() + main()'s allocation ------------------- */
 /* NPJ, npj.cpp:769-927.  Columns in device memory. */
