@@ -313,7 +313,9 @@ static int npj_device(hjb_ctx *ctx, const hjb_rel *R, const hjb_rel *S, const hj
 	CK(cudaSetDevice(ctx->device));
 	timer_reset(ctx);
 	if (R->tuples == 0 || S->tuples == 0) return HJB_OK;
-	const double load = o->npj_load > 0.0 ? o->npj_load : 0.75;   // measured best on B200 (smaller table: more L2 hits)
+	// measured on B200: a table that overflows L2 probes fastest at 0.75 (fewer DRAM sectors), a
+	// cache-resident one at 0.5 (shorter bucket chains)
+	const double load = o->npj_load > 0.0 ? o->npj_load : (R->tuples * 16 <= (32u << 20) ? 0.5 : 0.75);
 	if (load > 0.95) return fail(ctx, HJB_E_INVALID, "npj_load must be <= 0.95");
 	uint64_t buckets = (uint64_t)ceil((double)R->tuples / load / 4.0) + 1;       // +1: at least one empty slot
 	if (buckets > 0xFFFFFFFFull) return fail(ctx, HJB_E_INVALID, "table too large");
@@ -395,7 +397,7 @@ static int make_plan(hjb_ctx *ctx, uint64_t nr, uint64_t ns, const hjb_opts *o, 
 		// with <= 16 hash bits left below the partition id the join kernel addresses payloads directly
 		// (csrc/part_join.cu: one fill holds 6144 build tuples, so partitions may average 4096); worth
 		// two full passes as soon as the input is not tiny.  Otherwise hash tables, 2048 per partition.
-		const bool big = !o->part_tuples && nr + ns >= (1u << 22);
+		const bool big = !o->part_tuples && nr + ns >= (1u << 22) && nr >= (1u << 20);   // a small build side: one pass, hash tables
 		const uint32_t target = o->part_tuples ? o->part_tuples : (big ? 4096u : kDefaultPartTuples);
 		int tb = 0;
 		while (tb < 28 && (nr >> tb) > target) ++tb;
@@ -474,7 +476,7 @@ static int partition_relation(hjb_ctx *ctx, const hjb_rel *rel, const Plan &p, i
 }
 
 static int phj_device(hjb_ctx *ctx, const hjb_rel *R, const hjb_rel *S, const hjb_opts *o, int consumed,
-                      hjb_result *out)
+                      hjb_result *out, uint32_t owner = 0)
 {
 	int rc;
 	if ((rc = check_rel(ctx, R, true)) || (rc = check_rel(ctx, S, true))) return rc;
@@ -531,6 +533,8 @@ static int phj_device(hjb_ctx *ctx, const hjb_rel *R, const hjb_rel *S, const hj
 	j.P = P;
 	j.radix_factor = radix_factor;
 	j.rem_bits = 32 - consumed - plan.total_bits;
+	j.owner = owner;
+	j.owner_bits = consumed;
 	j.table_factor = hjb_hash_factor(o->seed, 1);
 	j.task_prefix = task_prefix;
 	j.task_counter = task_counter;
@@ -546,6 +550,7 @@ static int phj_device(hjb_ctx *ctx, const hjb_rel *R, const hjb_rel *S, const hj
 		CK(cudaEventRecord(ctx->ev[3], s));
 		CK(cudaGetLastError());
 		if ((rc = read_scalars(ctx, out))) return rc;
+		if (ctx->h_scalars[7]) return fail(ctx, HJB_E_INVALID, "hjb_cpra_join_local: a tuple does not hash into this owner's range");
 		if (!o->materialize || out->count <= ctx->out_cap) break;
 		if (attempt == 1) return fail(ctx, HJB_E_CUDA, "result overflow after regrow");
 		if ((rc = grow_out(ctx, out->count))) return rc;
@@ -880,7 +885,7 @@ extern "C" int hjb_cpra_join_local(hjb_ctx *ctx, const hjb_rel *R, const hjb_rel
 	if (!ctx || !out) return HJB_E_INVALID;
 	const int gbits = log2_exact(ngpus);
 	if (gbits < 0 || ngpus > 64 || gpu < 0 || gpu >= ngpus) return fail(ctx, HJB_E_INVALID, "bad gpu / ngpus");
-	return phj_device(ctx, R, S, opts ? opts : &kDefaultOpts, gbits, out);
+	return phj_device(ctx, R, S, opts ? opts : &kDefaultOpts, gbits, out, (uint32_t)gpu);
 }
 
 // ------------------------------------------------------------------ kernel-level entry points

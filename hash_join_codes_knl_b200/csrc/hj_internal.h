@@ -81,6 +81,8 @@ struct JoinArgs {
 	uint32_t radix_factor;                   // the partitions are radix digits of key * radix_factor
 	int rem_bits;                            // hash bits of key * radix_factor below the partition id
 	uint32_t table_factor;
+	uint32_t owner;                          // CPRA local join: this GPU's owner id and the bits that encode it
+	int owner_bits;
 	uint32_t *task_prefix;                   // P + 1 scratch
 	uint32_t *task_counter;                  // 1, zeroed by the launcher
 	uint32_t s_task;                         // probe tuples per task

@@ -141,8 +141,8 @@ k_partition_join(const uint32_t *__restrict__ rk, const uint32_t *__restrict__ r
                  const uint32_t *__restrict__ sk, const uint32_t *__restrict__ sv,
                  const uint32_t *__restrict__ r_off, const uint32_t *__restrict__ s_off, uint32_t P,
                  const uint32_t *__restrict__ task_prefix, uint32_t *__restrict__ task_counter, uint32_t s_task,
-                 uint32_t radix_factor, uint32_t table_factor, int rem_bits, OutCols out,
-                 unsigned long long *__restrict__ sums, unsigned long long *__restrict__ phase_clk)
+                 uint32_t radix_factor, uint32_t table_factor, int rem_bits, uint32_t owner, int owner_bits,
+                 OutCols out, unsigned long long *__restrict__ sums, unsigned long long *__restrict__ phase_clk)
 {
 	// optional phase clocks (HJB_PHASE_CLOCKS=1): thread 0 of every CTA adds the cycles it spent per phase
 	long long clk_t = 0;
@@ -170,6 +170,10 @@ k_partition_join(const uint32_t *__restrict__ rk, const uint32_t *__restrict__ r
 	const uint32_t rem_mask = rem_bits >= 32 ? 0xFFFFFFFFu : (1u << rem_bits) - 1;
 	JoinSums acc;
 	acc.zero();
+	// CPRA local join: every tuple must hash into this GPU's owner range (top owner_bits bits of
+	// key * radix_factor), else the DIRECT tables would confuse keys; violations are reported, not joined
+	const int owner_shift = owner_bits ? 32 - owner_bits : 0;
+	uint32_t foreign = 0;
 	const uint32_t total_tasks = task_prefix[P];
 	// Every thread resolves a task's ranges itself from uniform (broadcast) loads -- no barrier, no
 	// serial search by one thread.  With one task per partition (no skew) task == partition.
@@ -236,8 +240,9 @@ k_partition_join(const uint32_t *__restrict__ rk, const uint32_t *__restrict__ r
 #pragma unroll
 				for (int t = 0; t < kBatch; ++t)
 					if (fb + threadIdx.x + t * THREADS < fe) {
-						const uint32_t lo = hash_mul(k0[t], radix_factor) & rem_mask;
+						const uint32_t x = hash_mul(k0[t], radix_factor), lo = x & rem_mask;
 						const uint32_t bit = 1u << (lo & 31);
+						if (owner_bits) foreign |= (x >> owner_shift) ^ owner;
 						if (atomicOr(&bitmap[lo >> 5], bit) & bit) s_dups = 1;
 					}
 				for (uint32_t i0 = fb + threadIdx.x + THREADS * kBatch; i0 < fe; i0 += THREADS * kBatch) {
@@ -247,8 +252,9 @@ k_partition_join(const uint32_t *__restrict__ rk, const uint32_t *__restrict__ r
 #pragma unroll
 					for (int t = 0; t < kBatch; ++t)
 						if (i0 + t * THREADS < fe) {
-							const uint32_t lo = hash_mul(bk[t], radix_factor) & rem_mask;
+							const uint32_t x = hash_mul(bk[t], radix_factor), lo = x & rem_mask;
 							const uint32_t bit = 1u << (lo & 31);
+							if (owner_bits) foreign |= (x >> owner_shift) ^ owner;
 							if (atomicOr(&bitmap[lo >> 5], bit) & bit) s_dups = 1;
 						}
 				}
@@ -313,7 +319,8 @@ k_partition_join(const uint32_t *__restrict__ rk, const uint32_t *__restrict__ r
 						}
 #pragma unroll
 						for (int t = 0; t < ITEMS; ++t) {
-							const uint32_t lo = hash_mul(key[t], radix_factor) & rem_mask;
+							const uint32_t x = hash_mul(key[t], radix_factor), lo = x & rem_mask;
+							if (owner_bits && found[t]) foreign |= (x >> owner_shift) ^ owner;
 							const uint32_t w = lo >> 5, word = bitmap[w];
 							const uint32_t hit = found[t] ? (word >> (lo & 31)) & 1u : 0u;
 							// rank < fill size whenever the bit is set; a miss may compute fill size itself: clamp
@@ -426,6 +433,7 @@ k_partition_join(const uint32_t *__restrict__ rk, const uint32_t *__restrict__ r
 		s_end = ns_end;
 	}
 	acc.reduce_to_global(sums, scratch);
+	if (foreign) sums[6] = 1;                    // scalars[7]: foreign tuple seen
 	if (phase_clk && threadIdx.x == 0)
 		for (int k = 0; k < 8; ++k)
 			if (clk_acc[k]) atomicAdd(&phase_clk[k], clk_acc[k]);
@@ -472,12 +480,12 @@ int launch_partition_join(const JoinArgs &a, cudaStream_t s, int sms, KernelTime
 		const uint32_t grid = (uint32_t)(sms * per_sm);                                                                    \
 		if (a.materialize)                                                                                                 \
 			kt<<<grid, T, kJoinSmemBytes, s>>>(a.rk, a.rv, a.sk, a.sv, a.r_off, a.s_off, a.P, a.task_prefix,               \
-			                                   a.task_counter, a.s_task, a.radix_factor, a.table_factor, a.rem_bits, out,  \
-			                                   a.scalars + 1, clk);                                                             \
+			                                   a.task_counter, a.s_task, a.radix_factor, a.table_factor, a.rem_bits,       \
+			                                   a.owner, a.owner_bits, out, a.scalars + 1, clk);                                                             \
 		else                                                                                                               \
 			kf<<<grid, T, kJoinSmemBytes, s>>>(a.rk, a.rv, a.sk, a.sv, a.r_off, a.s_off, a.P, a.task_prefix,               \
-			                                   a.task_counter, a.s_task, a.radix_factor, a.table_factor, a.rem_bits, out,  \
-			                                   a.scalars + 1, clk);                                                             \
+			                                   a.task_counter, a.s_task, a.radix_factor, a.table_factor, a.rem_bits,       \
+			                                   a.owner, a.owner_bits, out, a.scalars + 1, clk);                                                             \
 	} while (0)
 	switch (variant) {
 	case 1: HJB_LAUNCH_JOIN(256, 8, 3); break;

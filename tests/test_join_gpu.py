@@ -331,3 +331,48 @@ def test_full_size_configs_by_properties(eng, algo, name):
     assert bool(((kk * datagen.INNER_FACTOR & 0xFFFFFFFF) == (i.to(torch.int64) & 0xFFFFFFFF)).all())
     # ... and idempotence: a second run gives the same checks
     assert getattr(eng, algo)((rk, rv), (sk, sv), materialize=False).checks() == res.checks()
+
+
+def test_cpra_join_local_rejects_foreign_tuples(eng):
+    """the local join trusts that every tuple hashes into its owner's range (the DIRECT tables rely
+    on it); a caller that hands it somebody else's tuples gets an error, not a wrong result"""
+    nr, ns = 1 << 21, 1 << 21
+    rk, rv = eng.generate(0, nr, nr, 5, 1, datagen.INNER_FACTOR)
+    sk, sv = eng.generate(0, ns, nr, 5, 2, datagen.OUTER_FACTOR)
+    with pytest.raises(hj.HjbError):
+        eng.cpra_join_local((rk, rv), (sk, sv), 1, 4)           # all owners' tuples, claimed to be owner 1's
+
+
+# ---------------------------------------------------------------- the reference's command line
+
+def test_cli_programs_keep_the_reference_interface(tmp_path):
+    """./write then ./npj | ./phj | ./cpra [#threads] [outer] [inner] on the four raw uint32 files
+    (write.cpp:1824-1865, npj.cpp:929-1039): first stdout line is the reference's seconds line, the
+    JSON line after it must carry the oracle's count and checksums for the files written."""
+    import json
+    import subprocess
+    from hash_join_codes_knl_b200 import api, build
+    build.build_programs()
+    bin_dir = os.path.join(os.path.dirname(os.path.abspath(hj.__file__)), "bin")
+    nr, ns = 50000, 200000
+    subprocess.check_call([os.path.join(bin_dir, "write"), "4", str(ns), str(nr)], cwd=tmp_path)
+    assert sorted(os.listdir(tmp_path)) == [f"ik_{nr}.txt", f"iv_{nr}.txt", f"ok_{ns}.txt", f"ov_{ns}.txt"]
+    rk, rv = api.relation_read(tmp_path, False, nr)
+    sk, sv = api.relation_read(tmp_path, True, ns)
+    assert np.unique(rk).size == nr and (rk != 0).all() and np.isin(sk, rk).all()
+    want = oracle_join("npj", rk, rv, sk, sv, threads=2, materialize=False)
+    for prog in ("npj", "phj", "cpra"):
+        out = subprocess.run([os.path.join(bin_dir, prog), "4", str(ns), str(nr), "1"], cwd=tmp_path,
+                             capture_output=True, text=True, check=True).stdout.strip().splitlines()
+        first = out[1] if prog == "cpra" else out[0]
+        assert out[0].startswith("copy:") if prog == "cpra" else True
+        float(first.split()[0])                                   # the reference's "%.4f" / "%lf" seconds line
+        js = json.loads(out[-1])
+        assert (js["join_tuples"], js["sum_key"], js["sum_outer"], js["sum_inner"]) == want.checks(), prog
+    # selectivity / skew knobs of ./write (write.cpp:1685-1686), which the reference accepts but does not honour
+    subprocess.check_call([os.path.join(bin_dir, "write"), "4", str(ns), str(nr), "0.5", "1.0"], cwd=tmp_path)
+    sk2, _ = api.relation_read(tmp_path, True, ns)
+    assert abs(np.isin(sk2, rk).mean() - 0.5) < 0.02
+    with pytest.raises(subprocess.CalledProcessError):
+        subprocess.run([os.path.join(bin_dir, "npj"), "4", "12345", str(nr)], cwd=tmp_path, check=True,
+                       capture_output=True)                        # no such file: an error, not garbage
