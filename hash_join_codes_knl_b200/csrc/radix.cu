@@ -235,13 +235,13 @@ k_scan(const uint32_t *__restrict__ item_prefix, uint32_t np, int bits, uint32_t
 
 // One tile = THREADS * 8 tuples = THREADS * 2 absolutely aligned groups; thread t owns groups t
 // and t + THREADS of the tile (coalesced 128-bit loads).
-template <int THREADS, bool FULL>
-__device__ __forceinline__ void load_col8(uint32_t (&x)[8], uint32_t &ok, const uint32_t *col, uint64_t g0, uint64_t g_end,
+template <int THREADS, int G, bool FULL>
+__device__ __forceinline__ void load_col8(uint32_t (&x)[4 * G], uint32_t &ok, const uint32_t *col, uint64_t g0, uint64_t g_end,
                                           uint64_t beg, uint64_t end, uint64_t n)
 {
 	ok = 0;
 #pragma unroll
-	for (int h = 0; h < 2; ++h) {
+	for (int h = 0; h < G; ++h) {
 		const uint64_t g = g0 + threadIdx.x + (uint64_t)h * THREADS;
 		if (FULL) {
 			const uint4 w = ldg_stream_u4(reinterpret_cast<const uint4 *>(col) + g);
@@ -281,14 +281,15 @@ constexpr uint32_t kCarry = 8;         // tuples per 32-byte sector of a 4-byte 
 // receive buffers of GPU d, mapped into this process (CUDA IPC) and pre-offset so that the
 // position the scan produced indexes them directly.  The stores then travel over NVLink: the
 // GPU-assign pass of CPRA and its all-to-all are one kernel.
-template <int THREADS, int MINB, bool PREFETCH, bool PEER>
+template <int THREADS, int MINB, bool PREFETCH, bool PEER, int G = 2>
 __global__ void __launch_bounds__(THREADS, MINB)
 k_scatter(const uint32_t *__restrict__ keys, const uint32_t *__restrict__ vals, uint64_t n, uint32_t np,
           const uint32_t *__restrict__ parent_off, const uint32_t *__restrict__ item_prefix, uint32_t chunk,
           uint32_t factor, int rshift, int bits, const uint32_t *__restrict__ offsets,
           uint32_t *__restrict__ keys_out, uint32_t *__restrict__ vals_out, const PeerTable peers)
 {
-	constexpr uint32_t TILE = THREADS * 8, kGroupsPerTile = TILE / 4;
+	constexpr int IT = 4 * G;                                   // tuples per thread and tile
+	constexpr uint32_t TILE = THREADS * IT, kGroupsPerTile = TILE / 4;
 	extern __shared__ __align__(16) uint32_t s_mem[];
 	__shared__ uint32_t warp_totals[34];
 	__shared__ uint32_t s_tile_n;
@@ -315,10 +316,10 @@ k_scatter(const uint32_t *__restrict__ keys, const uint32_t *__restrict__ vals, 
 	auto tile_is_full = [&](uint64_t g0) {
 		return (g0 << 2) >= r.beg && ((g0 + kGroupsPerTile) << 2) <= r.end;    // r.end <= n: vector loads stay inside
 	};
-	uint32_t key[8], nkey[8], val[8], ok = 0, nok = 0;
+	uint32_t key[IT], nkey[IT], val[IT], ok = 0, nok = 0;
 	if (PREFETCH && g_beg < g_end) {
-		if (tile_is_full(g_beg)) load_col8<THREADS, true>(nkey, nok, keys, g_beg, g_end, r.beg, r.end, n);
-		else load_col8<THREADS, false>(nkey, nok, keys, g_beg, g_end, r.beg, r.end, n);
+		if (tile_is_full(g_beg)) load_col8<THREADS, G, true>(nkey, nok, keys, g_beg, g_end, r.beg, r.end, n);
+		else load_col8<THREADS, G, false>(nkey, nok, keys, g_beg, g_end, r.beg, r.end, n);
 	}
 	__syncthreads();
 	for (uint64_t g0 = g_beg; g0 < g_end; g0 += kGroupsPerTile) {
@@ -327,31 +328,31 @@ k_scatter(const uint32_t *__restrict__ keys, const uint32_t *__restrict__ vals, 
 		const bool full = tile_is_full(g0);
 		if (PREFETCH) {
 #pragma unroll
-			for (int e = 0; e < 8; ++e) key[e] = nkey[e];
+			for (int e = 0; e < IT; ++e) key[e] = nkey[e];
 			ok = nok;
 		} else {
-			if (full) load_col8<THREADS, true>(key, ok, keys, g0, g_end, r.beg, r.end, n);
-			else load_col8<THREADS, false>(key, ok, keys, g0, g_end, r.beg, r.end, n);
+			if (full) load_col8<THREADS, G, true>(key, ok, keys, g0, g_end, r.beg, r.end, n);
+			else load_col8<THREADS, G, false>(key, ok, keys, g0, g_end, r.beg, r.end, n);
 		}
 		uint32_t vok;
-		if (full) load_col8<THREADS, true>(val, vok, vals, g0, g_end, r.beg, r.end, n);
-		else load_col8<THREADS, false>(val, vok, vals, g0, g_end, r.beg, r.end, n);
+		if (full) load_col8<THREADS, G, true>(val, vok, vals, g0, g_end, r.beg, r.end, n);
+		else load_col8<THREADS, G, false>(val, vok, vals, g0, g_end, r.beg, r.end, n);
 		if (PREFETCH && !last) {
-			if (tile_is_full(g1)) load_col8<THREADS, true>(nkey, nok, keys, g1, g_end, r.beg, r.end, n);
-			else load_col8<THREADS, false>(nkey, nok, keys, g1, g_end, r.beg, r.end, n);
+			if (tile_is_full(g1)) load_col8<THREADS, G, true>(nkey, nok, keys, g1, g_end, r.beg, r.end, n);
+			else load_col8<THREADS, G, false>(nkey, nok, keys, g1, g_end, r.beg, r.end, n);
 		}
 		// (1) rank: digit << 16 | rank-in-digit (rank < TILE <= 2^16, digit < 2^11).  Interior tiles
 		// (all but an item's first and last) have every element valid: no per-element predicate.
-		uint32_t dr[8];
+		uint32_t dr[IT];
 		if (full) {
 #pragma unroll
-			for (int e = 0; e < 8; ++e) {
+			for (int e = 0; e < IT; ++e) {
 				const uint32_t d = radix_digit(hash_mul(key[e], factor), rshift, mask);
 				dr[e] = (d << 16) | atomicAdd(&cnt[d], 1u);
 			}
 		} else {
 #pragma unroll
-			for (int e = 0; e < 8; ++e) {
+			for (int e = 0; e < IT; ++e) {
 				const uint32_t d = radix_digit(hash_mul(key[e], factor), rshift, mask);
 				dr[e] = (ok >> e) & 1u ? (d << 16) | atomicAdd(&cnt[d], 1u) : 0xFFFFFFFFu;
 			}
@@ -409,10 +410,10 @@ k_scatter(const uint32_t *__restrict__ keys, const uint32_t *__restrict__ vals, 
 		// (3) place the tile's tuples; flush the carried tuples of every digit that reached a boundary
 		if (full) {
 #pragma unroll
-			for (int e = 0; e < 8; ++e) buf[base[dr[e] >> 16] + (dr[e] & 0xFFFFu)] = make_uint2(key[e], val[e]);
+			for (int e = 0; e < IT; ++e) buf[base[dr[e] >> 16] + (dr[e] & 0xFFFFu)] = make_uint2(key[e], val[e]);
 		} else {
 #pragma unroll
-			for (int e = 0; e < 8; ++e)
+			for (int e = 0; e < IT; ++e)
 				if (dr[e] != 0xFFFFFFFFu) buf[base[dr[e] >> 16] + (dr[e] & 0xFFFFu)] = make_uint2(key[e], val[e]);
 		}
 		if (wc)
@@ -431,17 +432,20 @@ k_scatter(const uint32_t *__restrict__ keys, const uint32_t *__restrict__ vals, 
 		// golim and before step (3) reads carry.
 		const uint32_t tile_n = s_tile_n;
 		uint32_t *const ko = keys_out, *const vo = vals_out;
-#pragma unroll 4
-		for (uint32_t i = threadIdx.x; i < tile_n; i += THREADS) {
-			const uint2 kv = buf[i];
-			const uint32_t d = radix_digit(hash_mul(kv.x, factor), rshift, mask);
-			const uint2 gl = golim[d];
-			const uint32_t pos = gl.x + i;
-			if (pos < gl.y) {
-				(PEER ? s_pk[d] : ko)[pos] = kv.x;
-				(PEER ? s_pv[d] : vo)[pos] = kv.y;
-			} else {
-				carry[d * kCarry + (pos - gl.y)] = kv;
+#pragma unroll
+		for (int it = 0; it < IT; ++it) {                 // tile_n <= TILE: at most IT rounds, all in flight together
+			const uint32_t i = threadIdx.x + it * THREADS;
+			if (i < tile_n) {
+				const uint2 kv = buf[i];
+				const uint32_t d = radix_digit(hash_mul(kv.x, factor), rshift, mask);
+				const uint2 gl = golim[d];
+				const uint32_t pos = gl.x + i;
+				if (pos < gl.y) {
+					(PEER ? s_pk[d] : ko)[pos] = kv.x;
+					(PEER ? s_pv[d] : vo)[pos] = kv.y;
+				} else {
+					carry[d * kCarry + (pos - gl.y)] = kv;
+				}
 			}
 		}
 	}
@@ -481,6 +485,8 @@ static void scatter_attrs()
 	cudaFuncSetAttribute(k_scatter<1024, 1, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
 	cudaFuncSetAttribute(k_scatter<1024, 2, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
 	cudaFuncSetAttribute(k_scatter<1024, 1, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+	cudaFuncSetAttribute(k_scatter<1024, 2, false, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+	cudaFuncSetAttribute(k_scatter<1024, 2, true, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
 }
 
 // make_items + histogram + scan: after this a.counts holds every item's start offset per digit
@@ -523,14 +529,15 @@ int launch_radix_scatter(const RadixPassArgs &a, cudaStream_t s, KernelTimer *t,
 	if (variant < 0) {
 		const char *e = getenv("HJB_SCATTER_VARIANT");
 		variant = e ? atoi(e) : 3;       // measured best on B200: one 1024-thread CTA per SM, 8192-tuple tiles
-		if (variant < 0 || variant > 4) variant = 3;
+		if (variant < 0 || variant > 6) variant = 3;
 	}
 	const int threads = (variant >= 3 || peers) ? 1024 : 512;
-	const size_t smem = (size_t)F * 32 + (size_t)threads * 8 * 8 + (F <= 256 ? (size_t)F * kCarry * 8 : 0);
+	const int items = (!peers && (variant == 5 || variant == 6)) ? 4 : 8;
+	const size_t smem = (size_t)F * 32 + (size_t)threads * items * 8 + (F <= 256 ? (size_t)F * kCarry * 8 : 0);
 	static const PeerTable no_peers = {};
 	t->start(KK_SCATTER, s);
-#define HJB_LAUNCH_SCATTER(T, M, P, PEER, TABLE)                                                                            \
-	k_scatter<T, M, P, PEER><<<a.max_items, T, smem, s>>>(a.keys, a.vals, a.n, a.np, a.parent_off, a.item_prefix, a.chunk,  \
+#define HJB_LAUNCH_SCATTER(T, M, P, PEER, TABLE, ...)                                                                          \
+	k_scatter<T, M, P, PEER, ##__VA_ARGS__><<<a.max_items, T, smem, s>>>(a.keys, a.vals, a.n, a.np, a.parent_off, a.item_prefix, a.chunk,  \
 	                                                      a.factor, a.rshift, a.bits, a.counts, a.keys_out, a.vals_out, TABLE)
 	if (peers) {
 		HJB_LAUNCH_SCATTER(1024, 1, true, true, *peers);
@@ -540,6 +547,8 @@ int launch_radix_scatter(const RadixPassArgs &a, cudaStream_t s, KernelTimer *t,
 		case 1: HJB_LAUNCH_SCATTER(512, 3, true, false, no_peers); break;
 		case 2: HJB_LAUNCH_SCATTER(512, 3, false, false, no_peers); break;
 		case 4: HJB_LAUNCH_SCATTER(1024, 2, false, false, no_peers); break;
+		case 5: HJB_LAUNCH_SCATTER(1024, 2, false, false, no_peers, 1); break;
+		case 6: HJB_LAUNCH_SCATTER(1024, 2, true, false, no_peers, 1); break;
 		default: HJB_LAUNCH_SCATTER(1024, 1, true, false, no_peers); break;
 		}
 	}
