@@ -915,7 +915,8 @@ extern "C" int hjb_partition_pass(hjb_ctx *ctx, const uint32_t *keys, const uint
 		return fail(ctx, HJB_E_INVALID, "bad partition arguments");
 	if (size > 0xFFFFFFFFull) return fail(ctx, HJB_E_INVALID, "more than 2^32-1 tuples");
 	if (size && (!keys || !vals || !keys_out || !vals_out)) return fail(ctx, HJB_E_INVALID, "null column");
-	if ((((uintptr_t)keys) | ((uintptr_t)vals)) & 15) return fail(ctx, HJB_E_INVALID, "columns must be 16-byte aligned");
+	if ((((uintptr_t)keys) | ((uintptr_t)vals) | ((uintptr_t)keys_out) | ((uintptr_t)vals_out)) & 15)
+		return fail(ctx, HJB_E_INVALID, "columns must be 16-byte aligned");
 	if (shift > 0 && !parent_offsets) return fail(ctx, HJB_E_INVALID, "parent_offsets required when shift > 0");
 	CK(cudaSetDevice(ctx->device));
 	const uint32_t np = 1u << shift, nc = np << bits;
