@@ -864,8 +864,12 @@ extern "C" int hjb_cpra_scatter_peer(hjb_ctx *ctx, int ngpus, void *const *peer_
 		for (int g = 0; g < ngpus; ++g) {
 			// the scan's positions start at pending_off[g] for owner g: shift the column so that they land at base[g]
 			const int64_t shift = (int64_t)base[r][g] - (int64_t)ctx->pending_off[r][g];
-			t.k[g] = (uint32_t *)pk[r][g] + shift;
-			t.v[g] = (uint32_t *)pv[r][g] + shift;
+			// bias: the kernel counts positions as pending_off + bias, congruent to the physical row modulo the
+			// write-combining granule, so that its flush boundaries are line boundaries in the owner's buffer
+			const int64_t bias = ((shift % (int64_t)kPeerCarry) + kPeerCarry) % kPeerCarry;
+			t.bias[g] = (uint32_t)bias;
+			t.k[g] = (uint32_t *)pk[r][g] + (shift - bias);
+			t.v[g] = (uint32_t *)pv[r][g] + (shift - bias);
 		}
 		launches += launch_radix_scatter(a, s, &ctx->timer, &t);
 	}

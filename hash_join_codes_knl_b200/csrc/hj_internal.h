@@ -65,7 +65,10 @@ struct RadixPassArgs {
 struct PeerTable {
 	uint32_t *k[64];
 	uint32_t *v[64];
+	uint32_t bias[64];        // added to the owner's positions so that they are congruent, modulo the
+	                          // write-combining granule, to the physical row in the owner's buffer
 };
+constexpr uint32_t kPeerCarry = 32;       // peer stores are combined to whole 128-byte lines (fan-out <= 64)
 size_t radix_scratch_bytes(uint64_t n, uint32_t np, int bits, uint32_t *chunk, uint32_t *max_items, uint32_t *tiles);
 // launches make_items + histogram + scan + scatter; returns kernels launched
 int launch_radix_pass(const RadixPassArgs &a, cudaStream_t s, int sms, KernelTimer *t = nullptr);

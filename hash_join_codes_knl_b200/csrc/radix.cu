@@ -275,7 +275,7 @@ __device__ __forceinline__ void load_col8(uint32_t (&x)[4 * G], uint32_t &ok, co
 // ends on a sector boundary, so L2 rarely has to fetch the rest of a half-written sector from HBM.
 // (WC is on for fan-outs <= 256, where the carry buffers fit; wider passes write runs as is.)
 // dynamic shared memory: cnt base fpos oldp wpos pend [F] | golim[F] (uint2) | buf[TILE] (uint2) | carry[F*8] (uint2)
-constexpr uint32_t kCarry = 8;         // tuples per 32-byte sector of a 4-byte column
+constexpr uint32_t kLocalCarry = 8;    // tuples per 32-byte sector of a 4-byte column
 
 // PEER: digit d's run does not go to keys_out / vals_out but to peers.k[d] / peers.v[d] -- the
 // receive buffers of GPU d, mapped into this process (CUDA IPC) and pre-offset so that the
@@ -289,6 +289,7 @@ k_scatter(const uint32_t *__restrict__ keys, const uint32_t *__restrict__ vals, 
           uint32_t *__restrict__ keys_out, uint32_t *__restrict__ vals_out, const PeerTable peers)
 {
 	constexpr int IT = 4 * G;                                   // tuples per thread and tile
+	constexpr uint32_t kCarry = PEER ? kPeerCarry : kLocalCarry;  // write-combining granule in tuples
 	constexpr uint32_t TILE = THREADS * IT, kGroupsPerTile = TILE / 4;
 	extern __shared__ __align__(16) uint32_t s_mem[];
 	__shared__ uint32_t warp_totals[34];
@@ -304,7 +305,7 @@ k_scatter(const uint32_t *__restrict__ keys, const uint32_t *__restrict__ vals, 
 	if (!locate_item(item_prefix, np, parent_off, n, chunk, blockIdx.x, &r)) return;
 	const uint32_t *row = offsets + (size_t)blockIdx.x * F;
 	for (uint32_t p = threadIdx.x; p < F; p += THREADS) {
-		wpos[p] = row[p];
+		wpos[p] = row[p] + (PEER ? peers.bias[p & 63] : 0u);
 		pend[p] = 0;
 		cnt[p] = 0;
 	}
@@ -533,7 +534,7 @@ int launch_radix_scatter(const RadixPassArgs &a, cudaStream_t s, KernelTimer *t,
 	}
 	const int threads = (variant >= 3 || peers) ? 1024 : 512;
 	const int items = (!peers && (variant == 5 || variant == 6)) ? 4 : 8;
-	const size_t smem = (size_t)F * 32 + (size_t)threads * items * 8 + (F <= 256 ? (size_t)F * kCarry * 8 : 0);
+	const size_t smem = (size_t)F * 32 + (size_t)threads * items * 8 + (F <= 256 ? (size_t)F * (peers ? kPeerCarry : kLocalCarry) * 8 : 0);
 	static const PeerTable no_peers = {};
 	t->start(KK_SCATTER, s);
 #define HJB_LAUNCH_SCATTER(T, M, P, PEER, TABLE, ...)                                                                          \
