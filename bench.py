@@ -41,42 +41,61 @@ def measured_peak_gbs():
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks + throttle reasons while the timed region runs (B200_PROFILING.md)."""
+    """SM clock + throttle reasons while the timed regions run (B200_PROFILING.md): NVML polled every
+    few milliseconds (the timed region is tens of milliseconds long), nvidia-smi as the fallback."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index):
         super().__init__(daemon=True)
-        self.gpu, self.samples, self._halt = gpu_index, [], threading.Event()
+        self.gpu, self._halt = gpu_index, threading.Event()
+        self.sm, self.max_sm, self.reasons, self.source = [], 0.0, set(), None
 
-    def run(self):
+    def _run_nvml(self):
+        import pynvml as nv
+        nv.nvmlInit()
+        h = nv.nvmlDeviceGetHandleByIndex(self.gpu)
+        self.max_sm = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+        get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+        bits = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40}
+        self.source = "nvml"
+        while not self._halt.is_set():
+            self.sm.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+            r = int(get_reasons(h))
+            for name, bit in bits.items():
+                if r & bit:
+                    self.reasons.add(name)
+            self._halt.wait(0.004)
+
+    def _run_smi(self):
+        self.source = "nvidia-smi"
         while not self._halt.is_set():
             try:
                 out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
                                       "-i", str(self.gpu)], capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.samples.append([x.strip() for x in out.split(",")])
+                s = [x.strip() for x in out.split(",")]
+                self.sm.append(float(s[1]))
+                self.max_sm = max(self.max_sm, float(s[2]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), s[5:9]):
+                    if v.lower().startswith("active"):
+                        self.reasons.add(name)
             except Exception:
                 pass
-            self._halt.wait(0.2)
+            self._halt.wait(0.05)
+
+    def run(self):
+        try:
+            self._run_nvml()
+        except Exception:
+            self._run_smi()
 
     def stop(self):
         self._halt.set()
         self.join(timeout=6)
-        sm, mx, reasons = [], 0.0, set()
-        for s in self.samples:
-            try:
-                sm.append(float(s[1]))
-                mx = max(mx, float(s[2]))
-                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), s[5:9]):
-                    if v.lower().startswith("active"):
-                        reasons.add(name)
-            except Exception:
-                pass
-        sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
-                "samples": len(sm)}
+        sm = sorted(self.sm)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": self.max_sm or None,
+                "reasons": sorted(self.reasons), "samples": len(sm), "source": self.source}
 
 
 def physical_gpu_index(local):
@@ -208,7 +227,7 @@ def expected_checks(eng, sk, sv, ns):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="auto", choices=["auto", "phj_cfg2", "npj_cfg1", "cpra_cfg4"])
