@@ -448,7 +448,7 @@ static int partition_relation(hjb_ctx *ctx, const hjb_rel *rel, const Plan &p, i
 	uint32_t np = 1;
 	int used = consumed;
 	for (int i = 0; i < p.npass; ++i) {
-		RadixPassArgs a;
+		RadixPassArgs a = {};
 		a.keys = ink; a.vals = inv;
 		a.keys_out = bufk[i & 1]; a.vals_out = bufv[i & 1];
 		a.n = rel->tuples;
@@ -701,7 +701,7 @@ extern "C" int hjb_cpra_split(hjb_ctx *ctx, const hjb_rel *R, const hjb_rel *S, 
 			CK(cudaMemsetAsync(off[r], 0, (size_t)(ngpus + 1) * 4, s));
 			continue;
 		}
-		RadixPassArgs a;
+		RadixPassArgs a = {};
 		a.keys = rel[r]->keys; a.vals = rel[r]->vals;
 		a.keys_out = ok[r]; a.vals_out = ov[r];
 		a.n = rel[r]->tuples;
@@ -871,6 +871,11 @@ extern "C" int hjb_cpra_scatter_peer(hjb_ctx *ctx, int ngpus, void *const *peer_
 			t.k[g] = (uint32_t *)pk[r][g] + (shift - bias);
 			t.v[g] = (uint32_t *)pv[r][g] + (shift - bias);
 		}
+		{
+			static int env_ctas = -1;       // experiment knob: HJB_PEER_CTAS limits the peer scatter's grid
+			if (env_ctas < 0) env_ctas = getenv("HJB_PEER_CTAS") ? atoi(getenv("HJB_PEER_CTAS")) : 0;
+			a.peer_ctas = (uint32_t)env_ctas;
+		}
 		launches += launch_radix_scatter(a, s, &ctx->timer, &t);
 	}
 	CK(cudaEventRecord(ctx->ev[7], s));
@@ -937,7 +942,7 @@ extern "C" int hjb_partition_pass(hjb_ctx *ctx, const uint32_t *keys, const uint
 		return HJB_OK;
 	}
 	if (shift > 0) CK(cudaMemcpyAsync(d_parent, parent_offsets, ((size_t)np + 1) * 4, cudaMemcpyHostToDevice, s));
-	RadixPassArgs a;
+	RadixPassArgs a = {};
 	a.keys = keys; a.vals = vals; a.keys_out = keys_out; a.vals_out = vals_out;
 	a.n = size;
 	a.np = np;

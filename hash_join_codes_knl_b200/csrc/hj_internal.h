@@ -55,6 +55,7 @@ struct RadixPassArgs {
 	int rshift, bits;                 // digit = (key*factor >> rshift) & (2^bits - 1)
 	uint32_t chunk;                   // tuples per work item
 	uint32_t max_items;               // upper bound n/chunk + np
+	uint32_t peer_ctas;               // peer scatter only: CTAs to launch (0 = one per item)
 	// scratch (device)
 	uint32_t *item_prefix;            // np + 1
 	uint32_t *counts;                 // max_items * 2^bits  (histogram, then offsets in place)

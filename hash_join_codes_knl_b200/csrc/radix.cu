@@ -452,6 +452,190 @@ k_scatter(const uint32_t *__restrict__ keys, const uint32_t *__restrict__ vals, 
 	}
 }
 
+// ------------------------------------------------------------------ peer scatter with TMA bulk stores
+//
+// The GPU-assign pass of CPRA has a small fan-out (one digit per GPU), so a digit's run in a tile
+// is thousands of tuples long.  Issuing it as per-lane 4-byte remote stores ties up the SM's
+// store path (measured: throughput proportional to the number of CTAs, ~3.5 GB/s per SM).  Here
+// the tile is digit-grouped into two SoA shared-memory buffers laid out with the SAME 128-byte
+// alignment as the destination rows in the owner's buffer, and ONE thread per digit hands each
+// run to the TMA unit as a bulk shared->global copy (cp.async.bulk, UBLKCP in SASS) that then
+// crosses NVLink without occupying the SM.  Tuples beyond a digit's last whole 128-byte line are
+// carried to the next tile (software write-combining as above); an item's first / last few tuples
+// per digit that are not 16-byte aligned take scalar stores.  Fan-out <= 64.
+// dynamic shared memory: cnt wpos pend [64] | place[64] (uint4) | strm[64] (uint4) | cin[64] (uint2) |
+//                        skeys[PAD] svals[PAD] | carry_k[2][32 F] carry_v[2][32 F],  PAD = TILE + 64 F
+constexpr uint32_t kBulkGranule = kPeerCarry;             // 32 tuples = 128 bytes per column
+
+__device__ __forceinline__ void bulk_store(void *gdst, const void *ssrc, uint32_t bytes)
+{
+	asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst),
+	             "r"((uint32_t)__cvta_generic_to_shared(ssrc)), "r"(bytes)
+	             : "memory");
+}
+
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS, 1)
+k_scatter_bulk(const uint32_t *__restrict__ keys, const uint32_t *__restrict__ vals, uint64_t n, uint32_t np,
+               const uint32_t *__restrict__ parent_off, const uint32_t *__restrict__ item_prefix, uint32_t chunk,
+               uint32_t factor, int rshift, int bits, const uint32_t *__restrict__ offsets, const PeerTable peers)
+{
+	constexpr int G = 2, IT = 4 * G;
+	constexpr uint32_t TILE = THREADS * IT, kGroupsPerTile = TILE / 4, GR = kBulkGranule;
+	extern __shared__ __align__(128) uint32_t s_bulk[];
+	__shared__ uint32_t warp_totals[34];
+	__shared__ uint32_t *s_pk[64], *s_pv[64];
+	const uint32_t F = 1u << bits, mask = F - 1;
+	const uint32_t PAD = TILE + 2 * GR * F;
+	uint32_t *cnt = s_bulk, *wpos = cnt + 64, *pend = wpos + 64;
+	uint4 *place = reinterpret_cast<uint4 *>(pend + 64);     // x: slot of new rank 0, y: new tuples that fit the region, z: carry index of rank 0
+	uint4 *strm = place + 64;                                // x: global position of slot 0, y: first valid position, z: end of valid positions
+	uint2 *cin = reinterpret_cast<uint2 *>(strm + 64);       // carried-in tuples: x: destination slot 0 (0xFFFFFFFF: stay carried), y: how many
+	uint32_t *skeys = reinterpret_cast<uint32_t *>(cin + 64);          // byte offset 3*256 + 2*1024 + 512 = 3328 = 26 * 128
+	uint32_t *svals = skeys + PAD;
+	uint32_t *carry_k = svals + PAD, *carry_v = carry_k + 2 * GR * F;
+	if (threadIdx.x < 64) {
+		s_pk[threadIdx.x] = peers.k[threadIdx.x];
+		s_pv[threadIdx.x] = peers.v[threadIdx.x];
+	}
+	for (uint32_t item = blockIdx.x;; item += gridDim.x) {
+		ItemRange r;
+		if (!locate_item(item_prefix, np, parent_off, n, chunk, item, &r)) break;
+		__syncthreads();
+		const uint32_t *row = offsets + (size_t)item * F;
+		if (threadIdx.x < F) {
+			wpos[threadIdx.x] = row[threadIdx.x] + peers.bias[threadIdx.x];
+			pend[threadIdx.x] = 0;
+			cnt[threadIdx.x] = 0;
+		}
+		const uint64_t g_beg = r.beg >> 2, g_end = (r.end + 3) >> 2;
+		auto tile_is_full = [&](uint64_t g0) { return (g0 << 2) >= r.beg && ((g0 + kGroupsPerTile) << 2) <= r.end; };
+		uint32_t key[IT], nkey[IT], val[IT], ok = 0, nok = 0;
+		if (g_beg < g_end) {
+			if (tile_is_full(g_beg)) load_col8<THREADS, G, true>(nkey, nok, keys, g_beg, g_end, r.beg, r.end, n);
+			else load_col8<THREADS, G, false>(nkey, nok, keys, g_beg, g_end, r.beg, r.end, n);
+		}
+		__syncthreads();
+		uint32_t tile_no = 0;
+		for (uint64_t g0 = g_beg; g0 < g_end; g0 += kGroupsPerTile, ++tile_no) {
+			const uint64_t g1 = g0 + kGroupsPerTile;
+			const bool last = g1 >= g_end;
+			const bool full = tile_is_full(g0);
+			uint32_t *const oc_k = carry_k + (tile_no & 1) * GR * F, *const oc_v = carry_v + (tile_no & 1) * GR * F;            // carried in
+			uint32_t *const nc_k = carry_k + ((tile_no & 1) ^ 1) * GR * F, *const nc_v = carry_v + ((tile_no & 1) ^ 1) * GR * F;  // carried out
+#pragma unroll
+			for (int e = 0; e < IT; ++e) key[e] = nkey[e];
+			ok = nok;
+			uint32_t vok;
+			if (full) load_col8<THREADS, G, true>(val, vok, vals, g0, g_end, r.beg, r.end, n);
+			else load_col8<THREADS, G, false>(val, vok, vals, g0, g_end, r.beg, r.end, n);
+			if (!last) {
+				if (tile_is_full(g1)) load_col8<THREADS, G, true>(nkey, nok, keys, g1, g_end, r.beg, r.end, n);
+				else load_col8<THREADS, G, false>(nkey, nok, keys, g1, g_end, r.beg, r.end, n);
+			}
+			// (1) rank
+			uint32_t dr[IT];
+#pragma unroll
+			for (int e = 0; e < IT; ++e) {
+				const uint32_t d = radix_digit(hash_mul(key[e], factor), rshift, mask);
+				dr[e] = (full || ((ok >> e) & 1u)) ? (d << 16) | atomicAdd(&cnt[d], 1u) : 0xFFFFFFFFu;
+			}
+			// the bulk copies of the previous tile must have read their shared-memory source before it is reused
+			if (threadIdx.x < F) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+			__syncthreads();
+			// (2) plan: one digit per thread, all in warp 0/1 (F <= 64)
+			if (threadIdx.x < 64) {
+				const uint32_t p = threadIdx.x;
+				uint32_t c = 0, w = 0, pe = 0, wg = 0, lim = 0, slots = 0;
+				bool flush = false;
+				if (p < F) {
+					c = cnt[p];
+					w = wpos[p];
+					pe = pend[p];
+					const uint32_t endpos = w + pe + c;
+					lim = last ? endpos : (endpos & ~(GR - 1));
+					flush = lim > w;
+					if (!flush) lim = w;
+					wg = w & ~(GR - 1);
+					slots = flush ? ((lim + GR - 1) & ~(GR - 1)) - wg : 0;     // region covers [wg, align_up(lim)), whole lines
+				}
+				const uint32_t incl = warp_inclusive_scan_u32(slots);
+				if (lane_id() == 31) warp_totals[p >> 5] = incl;
+				__syncwarp();
+				asm volatile("bar.sync 1, 64;" ::: "memory");                  // the two planning warps only
+				const uint32_t rb = (p >= 32 ? warp_totals[0] : 0) + incl - slots;    // region start, multiple of GR
+				if (p < F) {
+					const uint32_t room = flush ? lim - (w + pe) : 0;          // new tuples that go to the region
+					place[p] = make_uint4(rb + (w - wg) + pe, room, p * GR + (flush ? 0u - room : pe), 0);
+					strm[p] = make_uint4(wg - rb, w, lim, flush ? 1u : 0u);
+					cin[p] = make_uint2(flush ? rb + (w - wg) : 0xFFFFFFFFu, pe);
+					wpos[p] = lim;
+					pend[p] = w + pe + c - lim;
+					cnt[p] = 0;
+				}
+			}
+			__syncthreads();
+			// (3) place the new tuples and move the carried-in ones
+#pragma unroll
+			for (int e = 0; e < IT; ++e) {
+				if (dr[e] != 0xFFFFFFFFu) {
+					const uint32_t d = dr[e] >> 16, rk_ = dr[e] & 0xFFFFu;
+					const uint4 pl = place[d];
+					if (rk_ < pl.y) {
+						skeys[pl.x + rk_] = key[e];
+						svals[pl.x + rk_] = val[e];
+					} else {
+						nc_k[pl.z + rk_] = key[e];
+						nc_v[pl.z + rk_] = val[e];
+					}
+				}
+			}
+			for (uint32_t t = threadIdx.x; t < F * GR; t += THREADS) {
+				const uint32_t d = t / GR, q = t % GR;
+				const uint2 ci = cin[d];
+				if (q < ci.y) {
+					const uint32_t ck = oc_k[t], cv = oc_v[t];
+					if (ci.x != 0xFFFFFFFFu) {
+						skeys[ci.x + q] = ck;
+						svals[ci.x + q] = cv;
+					} else {
+						nc_k[t] = ck;
+						nc_v[t] = cv;
+					}
+				}
+			}
+			asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy writes -> visible to the bulk copy
+			__syncthreads();
+			// (4) one thread per digit: whole run as bulk copies, unaligned ends as scalar stores
+			if (threadIdx.x < F) {
+				const uint32_t d = threadIdx.x;
+				const uint4 st = strm[d];
+				if (st.w) {
+					uint32_t *const ko = s_pk[d], *const vo = s_pv[d];
+					const uint32_t lo = st.y, hi = st.z;                       // valid global positions [lo, hi)
+					uint32_t blo = (lo + 3) & ~3u, bhi = hi & ~3u;             // 16-byte aligned body
+					if (blo > bhi) blo = bhi = hi;                              // fewer than four tuples: all scalar
+					for (uint32_t pos = lo; pos < min(blo, hi); ++pos) {
+						ko[pos] = skeys[pos - st.x];
+						vo[pos] = svals[pos - st.x];
+					}
+					if (bhi > blo) {
+						bulk_store(ko + blo, skeys + (blo - st.x), (bhi - blo) * 4);
+						bulk_store(vo + blo, svals + (blo - st.x), (bhi - blo) * 4);
+					}
+					for (uint32_t pos = max(bhi, blo); pos < hi; ++pos) {
+						ko[pos] = skeys[pos - st.x];
+						vo[pos] = svals[pos - st.x];
+					}
+				}
+				asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+			}
+		}
+		// the item's last bulk copies must complete before its shared memory is reused / the CTA exits
+		if (threadIdx.x < F) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+	}
+}
+
 // ------------------------------------------------------------------ host launchers
 
 size_t radix_scratch_bytes(uint64_t n, uint32_t np, int bits, uint32_t *chunk, uint32_t *max_items, uint32_t *tiles)
@@ -537,10 +721,26 @@ int launch_radix_scatter(const RadixPassArgs &a, cudaStream_t s, KernelTimer *t,
 	const size_t smem = (size_t)F * 32 + (size_t)threads * items * 8 + (F <= 256 ? (size_t)F * (peers ? kPeerCarry : kLocalCarry) * 8 : 0);
 	static const PeerTable no_peers = {};
 	t->start(KK_SCATTER, s);
+	const uint32_t grid = a.max_items;
 #define HJB_LAUNCH_SCATTER(T, M, P, PEER, TABLE, ...)                                                                          \
-	k_scatter<T, M, P, PEER, ##__VA_ARGS__><<<a.max_items, T, smem, s>>>(a.keys, a.vals, a.n, a.np, a.parent_off, a.item_prefix, a.chunk,  \
+	k_scatter<T, M, P, PEER, ##__VA_ARGS__><<<grid, T, smem, s>>>(a.keys, a.vals, a.n, a.np, a.parent_off, a.item_prefix, a.chunk,  \
 	                                                      a.factor, a.rshift, a.bits, a.counts, a.keys_out, a.vals_out, TABLE)
-	if (peers) {
+	static int peer_bulk = -1;
+	if (peer_bulk < 0) peer_bulk = getenv("HJB_PEER_BULK") ? atoi(getenv("HJB_PEER_BULK")) : 1;
+	if (peers && peer_bulk && F <= 64) {
+		const size_t pad = 8192 + 2 * (size_t)kBulkGranule * F;
+		const size_t smem_b = 3328 + pad * 8 + (size_t)F * kBulkGranule * 16;
+		static bool attr_b = false;
+		if (!attr_b) {
+			cudaFuncSetAttribute(k_scatter_bulk<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+			                     (int)(3328 + (8192 + 2 * kBulkGranule * 64) * 8 + 64 * kBulkGranule * 16));
+			attr_b = true;
+		}
+		// the bulk kernel walks the items with a grid stride: HJB_PEER_CTAS (experiments) can leave SMs to other streams
+		const uint32_t grid_b = (a.peer_ctas && a.peer_ctas < grid) ? a.peer_ctas : grid;
+		k_scatter_bulk<1024><<<grid_b, 1024, smem_b, s>>>(a.keys, a.vals, a.n, a.np, a.parent_off, a.item_prefix, a.chunk, a.factor,
+		                                                a.rshift, a.bits, a.counts, *peers);
+	} else if (peers) {
 		HJB_LAUNCH_SCATTER(1024, 1, true, true, *peers);
 	} else {
 		switch (variant) {
