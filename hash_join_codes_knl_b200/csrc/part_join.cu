@@ -89,13 +89,9 @@ template <int ITEMS>
 __device__ __forceinline__ void emit_round(const OutCols &out, const bool (&found)[ITEMS], const uint32_t (&key)[ITEMS],
                                            const uint32_t (&val)[ITEMS], const uint32_t (&ival)[ITEMS])
 {
-	unsigned m[ITEMS];
-	uint32_t total = 0;
+	uint32_t total = 0;                            // the ballots are recomputed below instead of kept in registers
 #pragma unroll
-	for (int t = 0; t < ITEMS; ++t) {
-		m[t] = __ballot_sync(kFullMask, found[t]);
-		total += __popc(m[t]);
-	}
+	for (int t = 0; t < ITEMS; ++t) total += __popc(__ballot_sync(kFullMask, found[t]));
 	if (total == 0) return;
 	unsigned long long base = 0;
 	if (lane_id() == 0) base = atomicAdd(out.cursor, (unsigned long long)total);
@@ -106,24 +102,26 @@ __device__ __forceinline__ void emit_round(const OutCols &out, const bool (&foun
 		uint32_t off = 0;
 #pragma unroll
 		for (int t = 0; t < ITEMS; ++t) {
-			const uint32_t r = off + __popc(m[t] & lt);
+			const unsigned mt = __ballot_sync(kFullMask, found[t]);
+			const uint32_t r = off + __popc(mt & lt);
 			if (found[t]) {
 				ck[r] = key[t];
 				co[r] = val[t];
 				ci[r] = ival[t];
 			}
-			off += __popc(m[t]);
+			off += __popc(mt);
 		}
 	} else {
 #pragma unroll
 		for (int t = 0; t < ITEMS; ++t) {
-			const uint64_t r = base + __popc(m[t] & lt);
+			const unsigned mt = __ballot_sync(kFullMask, found[t]);
+			const uint64_t r = base + __popc(mt & lt);
 			if (found[t] && r < out.cap) {
 				out.k[r] = key[t];
 				out.o[r] = val[t];
 				out.i[r] = ival[t];
 			}
-			base += __popc(m[t]);
+			base += __popc(mt);
 		}
 	}
 }
@@ -135,7 +133,7 @@ constexpr uint32_t kHashFill = kHashSlots / 4 * 3;       // load <= 0.75
 constexpr size_t kDirectBytes = (size_t)kDirectWords * 8 + (size_t)kDirectFill * 4;
 constexpr size_t kJoinSmemBytes = (size_t)kHashSlots * 8 > kDirectBytes ? (size_t)kHashSlots * 8 : kDirectBytes;
 
-template <int THREADS, int ITEMS, int MINB, bool MATERIALIZE>
+template <int THREADS, int ITEMS, int MINB, bool MATERIALIZE, bool CLOCKS = false>
 __global__ void __launch_bounds__(THREADS, MINB)
 k_partition_join(const uint32_t *__restrict__ rk, const uint32_t *__restrict__ rv,
                  const uint32_t *__restrict__ sk, const uint32_t *__restrict__ sv,
@@ -144,16 +142,16 @@ k_partition_join(const uint32_t *__restrict__ rk, const uint32_t *__restrict__ r
                  uint32_t radix_factor, uint32_t table_factor, int rem_bits, uint32_t owner, int owner_bits,
                  OutCols out, unsigned long long *__restrict__ sums, unsigned long long *__restrict__ phase_clk)
 {
-	// optional phase clocks (HJB_PHASE_CLOCKS=1): thread 0 of every CTA adds the cycles it spent per phase
+	// optional phase clocks (HJB_PHASE_CLOCKS=1 selects the CLOCKS instantiation): thread 0 of every CTA adds the
+	// cycles it spent per phase.  Compiled out of the product kernel: the marks cost registers (spills at 64).
 	long long clk_t = 0;
-	unsigned long long clk_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 #define PHASE_MARK(k)                                              \
-	if (phase_clk && threadIdx.x == 0) {                            \
+	if (CLOCKS && threadIdx.x == 0) {                               \
 		const long long now_ = clock64();                           \
-		clk_acc[k] += (unsigned long long)(now_ - clk_t);           \
+		atomicAdd(&phase_clk[k], (unsigned long long)(now_ - clk_t)); \
 		clk_t = now_;                                               \
 	}
-	if (phase_clk && threadIdx.x == 0) clk_t = clock64();
+	if (CLOCKS && threadIdx.x == 0) clk_t = clock64();
 	extern __shared__ __align__(16) unsigned char s_raw[];
 	// DIRECT view
 	uint32_t *bitmap = reinterpret_cast<uint32_t *>(s_raw);            // kDirectWords
@@ -434,9 +432,6 @@ k_partition_join(const uint32_t *__restrict__ rk, const uint32_t *__restrict__ r
 	}
 	acc.reduce_to_global(sums, scratch);
 	if (foreign) sums[6] = 1;                    // scalars[7]: foreign tuple seen
-	if (phase_clk && threadIdx.x == 0)
-		for (int k = 0; k < 8; ++k)
-			if (clk_acc[k]) atomicAdd(&phase_clk[k], clk_acc[k]);
 #undef PHASE_MARK
 }
 
@@ -467,10 +462,10 @@ int launch_partition_join(const JoinArgs &a, cudaStream_t s, int sms, KernelTime
 	if (clocks < 0) clocks = getenv("HJB_PHASE_CLOCKS") ? 1 : 0;
 	unsigned long long *clk = clocks ? a.scalars + 8 : nullptr;
 	t->start(KK_PART_JOIN, s);
-#define HJB_LAUNCH_JOIN(T, I, MB)                                                                                            \
+#define HJB_LAUNCH_JOIN(T, I, MB, CLK)                                                                                          \
 	do {                                                                                                                   \
-		auto kt = k_partition_join<T, I, MB, true>;                                                                          \
-		auto kf = k_partition_join<T, I, MB, false>;                                                                          \
+		auto kt = k_partition_join<T, I, MB, true, CLK>;                                                                         \
+		auto kf = k_partition_join<T, I, MB, false, CLK>;                                                                         \
 		cudaFuncSetAttribute(kt, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kJoinSmemBytes);                       \
 		cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kJoinSmemBytes);                       \
 		int per_sm = 0;                                                                                                    \
@@ -487,12 +482,13 @@ int launch_partition_join(const JoinArgs &a, cudaStream_t s, int sms, KernelTime
 			                                   a.task_counter, a.s_task, a.radix_factor, a.table_factor, a.rem_bits,       \
 			                                   a.owner, a.owner_bits, out, a.scalars + 1, clk);                                                             \
 	} while (0)
-	switch (variant) {
-	case 1: HJB_LAUNCH_JOIN(256, 8, 3); break;
-	case 2: HJB_LAUNCH_JOIN(256, 4, 4); break;
-	case 3: HJB_LAUNCH_JOIN(256, 4, 5); break;
-	case 4: HJB_LAUNCH_JOIN(128, 8, 8); break;
-	default: HJB_LAUNCH_JOIN(kJoinThreads, kJoinItems, 4); break;
+	switch (clocks ? 5 : variant) {
+	case 1: HJB_LAUNCH_JOIN(256, 8, 3, false); break;
+	case 2: HJB_LAUNCH_JOIN(256, 4, 4, false); break;
+	case 3: HJB_LAUNCH_JOIN(256, 4, 5, false); break;
+	case 4: HJB_LAUNCH_JOIN(128, 8, 8, false); break;
+	case 5: HJB_LAUNCH_JOIN(kJoinThreads, kJoinItems, 4, true); break;
+	default: HJB_LAUNCH_JOIN(kJoinThreads, kJoinItems, 4, false); break;
 	}
 #undef HJB_LAUNCH_JOIN
 	t->stop(s);

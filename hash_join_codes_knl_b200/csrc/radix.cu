@@ -474,27 +474,28 @@ __device__ __forceinline__ void bulk_store(void *gdst, const void *ssrc, uint32_
 	             : "memory");
 }
 
-template <int THREADS>
+template <int THREADS, int GRAN, int MAXF, bool PEER>
 __global__ void __launch_bounds__(THREADS, 1)
 k_scatter_bulk(const uint32_t *__restrict__ keys, const uint32_t *__restrict__ vals, uint64_t n, uint32_t np,
                const uint32_t *__restrict__ parent_off, const uint32_t *__restrict__ item_prefix, uint32_t chunk,
-               uint32_t factor, int rshift, int bits, const uint32_t *__restrict__ offsets, const PeerTable peers)
+               uint32_t factor, int rshift, int bits, const uint32_t *__restrict__ offsets, uint32_t *__restrict__ keys_out,
+               uint32_t *__restrict__ vals_out, const PeerTable peers)
 {
 	constexpr int G = 2, IT = 4 * G;
-	constexpr uint32_t TILE = THREADS * IT, kGroupsPerTile = TILE / 4, GR = kBulkGranule;
+	constexpr uint32_t TILE = THREADS * IT, kGroupsPerTile = TILE / 4, GR = GRAN;
 	extern __shared__ __align__(128) uint32_t s_bulk[];
-	__shared__ uint32_t warp_totals[34];
-	__shared__ uint32_t *s_pk[64], *s_pv[64];
+	__shared__ uint32_t warp_totals[MAXF / 32];
+	__shared__ uint32_t *s_pk[PEER ? 64 : 1], *s_pv[PEER ? 64 : 1];
 	const uint32_t F = 1u << bits, mask = F - 1;
 	const uint32_t PAD = TILE + 2 * GR * F;
-	uint32_t *cnt = s_bulk, *wpos = cnt + 64, *pend = wpos + 64;
-	uint4 *place = reinterpret_cast<uint4 *>(pend + 64);     // x: slot of new rank 0, y: new tuples that fit the region, z: carry index of rank 0
-	uint4 *strm = place + 64;                                // x: global position of slot 0, y: first valid position, z: end of valid positions
-	uint2 *cin = reinterpret_cast<uint2 *>(strm + 64);       // carried-in tuples: x: destination slot 0 (0xFFFFFFFF: stay carried), y: how many
-	uint32_t *skeys = reinterpret_cast<uint32_t *>(cin + 64);          // byte offset 3*256 + 2*1024 + 512 = 3328 = 26 * 128
+	uint32_t *cnt = s_bulk, *wpos = cnt + MAXF, *pend = wpos + MAXF;
+	uint4 *place = reinterpret_cast<uint4 *>(pend + MAXF);     // x: slot of new rank 0, y: new tuples that fit the region, z: carry index of rank 0
+	uint4 *strm = place + MAXF;                                // x: global position of slot 0, y: first valid position, z: end of valid positions
+	uint2 *cin = reinterpret_cast<uint2 *>(strm + MAXF);       // carried-in tuples: x: destination slot 0 (0xFFFFFFFF: stay carried), y: how many
+	uint32_t *skeys = reinterpret_cast<uint32_t *>(cin + MAXF);        // byte offset 52 * MAXF, a multiple of 128
 	uint32_t *svals = skeys + PAD;
 	uint32_t *carry_k = svals + PAD, *carry_v = carry_k + 2 * GR * F;
-	if (threadIdx.x < 64) {
+	if (PEER && threadIdx.x < 64) {
 		s_pk[threadIdx.x] = peers.k[threadIdx.x];
 		s_pv[threadIdx.x] = peers.v[threadIdx.x];
 	}
@@ -504,7 +505,7 @@ k_scatter_bulk(const uint32_t *__restrict__ keys, const uint32_t *__restrict__ v
 		__syncthreads();
 		const uint32_t *row = offsets + (size_t)item * F;
 		if (threadIdx.x < F) {
-			wpos[threadIdx.x] = row[threadIdx.x] + peers.bias[threadIdx.x];
+			wpos[threadIdx.x] = row[threadIdx.x] + (PEER ? peers.bias[threadIdx.x & 63] : 0u);
 			pend[threadIdx.x] = 0;
 			cnt[threadIdx.x] = 0;
 		}
@@ -543,8 +544,8 @@ k_scatter_bulk(const uint32_t *__restrict__ keys, const uint32_t *__restrict__ v
 			// the bulk copies of the previous tile must have read their shared-memory source before it is reused
 			if (threadIdx.x < F) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
 			__syncthreads();
-			// (2) plan: one digit per thread, all in warp 0/1 (F <= 64)
-			if (threadIdx.x < 64) {
+			// (2) plan: one digit per thread in the first MAXF / 32 warps
+			if (threadIdx.x < MAXF) {
 				const uint32_t p = threadIdx.x;
 				uint32_t c = 0, w = 0, pe = 0, wg = 0, lim = 0, slots = 0;
 				bool flush = false;
@@ -562,8 +563,10 @@ k_scatter_bulk(const uint32_t *__restrict__ keys, const uint32_t *__restrict__ v
 				const uint32_t incl = warp_inclusive_scan_u32(slots);
 				if (lane_id() == 31) warp_totals[p >> 5] = incl;
 				__syncwarp();
-				asm volatile("bar.sync 1, 64;" ::: "memory");                  // the two planning warps only
-				const uint32_t rb = (p >= 32 ? warp_totals[0] : 0) + incl - slots;    // region start, multiple of GR
+				asm volatile("bar.sync 1, %0;" ::"n"(MAXF) : "memory");        // the planning warps only
+				uint32_t rb = incl - slots;                                    // region start, multiple of GR
+#pragma unroll
+				for (int wq = 0; wq < MAXF / 32; ++wq) rb += (wq < (int)(p >> 5)) ? warp_totals[wq] : 0u;
 				if (p < F) {
 					const uint32_t room = flush ? lim - (w + pe) : 0;          // new tuples that go to the region
 					place[p] = make_uint4(rb + (w - wg) + pe, room, p * GR + (flush ? 0u - room : pe), 0);
@@ -611,7 +614,7 @@ k_scatter_bulk(const uint32_t *__restrict__ keys, const uint32_t *__restrict__ v
 				const uint32_t d = threadIdx.x;
 				const uint4 st = strm[d];
 				if (st.w) {
-					uint32_t *const ko = s_pk[d], *const vo = s_pv[d];
+					uint32_t *const ko = PEER ? s_pk[d & 63] : keys_out, *const vo = PEER ? s_pv[d & 63] : vals_out;
 					const uint32_t lo = st.y, hi = st.z;                       // valid global positions [lo, hi)
 					uint32_t blo = (lo + 3) & ~3u, bhi = hi & ~3u;             // 16-byte aligned body
 					if (blo > bhi) blo = bhi = hi;                              // fewer than four tuples: all scalar
@@ -714,7 +717,7 @@ int launch_radix_scatter(const RadixPassArgs &a, cudaStream_t s, KernelTimer *t,
 	if (variant < 0) {
 		const char *e = getenv("HJB_SCATTER_VARIANT");
 		variant = e ? atoi(e) : 3;       // measured best on B200: one 1024-thread CTA per SM, 8192-tuple tiles
-		if (variant < 0 || variant > 6) variant = 3;
+		if (variant < 0 || variant > 7) variant = 3;
 	}
 	const int threads = (variant >= 3 || peers) ? 1024 : 512;
 	const int items = (!peers && (variant == 5 || variant == 6)) ? 4 : 8;
@@ -729,19 +732,30 @@ int launch_radix_scatter(const RadixPassArgs &a, cudaStream_t s, KernelTimer *t,
 	if (peer_bulk < 0) peer_bulk = getenv("HJB_PEER_BULK") ? atoi(getenv("HJB_PEER_BULK")) : 1;
 	if (peers && peer_bulk && F <= 64) {
 		const size_t pad = 8192 + 2 * (size_t)kBulkGranule * F;
-		const size_t smem_b = 3328 + pad * 8 + (size_t)F * kBulkGranule * 16;
+		const size_t smem_b = 52 * 64 + pad * 8 + (size_t)F * kBulkGranule * 16;
 		static bool attr_b = false;
 		if (!attr_b) {
-			cudaFuncSetAttribute(k_scatter_bulk<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-			                     (int)(3328 + (8192 + 2 * kBulkGranule * 64) * 8 + 64 * kBulkGranule * 16));
+			cudaFuncSetAttribute(k_scatter_bulk<1024, kBulkGranule, 64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+			                     (int)(52 * 64 + (8192 + 2 * kBulkGranule * 64) * 8 + 64 * kBulkGranule * 16));
 			attr_b = true;
 		}
 		// the bulk kernel walks the items with a grid stride: HJB_PEER_CTAS (experiments) can leave SMs to other streams
 		const uint32_t grid_b = (a.peer_ctas && a.peer_ctas < grid) ? a.peer_ctas : grid;
-		k_scatter_bulk<1024><<<grid_b, 1024, smem_b, s>>>(a.keys, a.vals, a.n, a.np, a.parent_off, a.item_prefix, a.chunk, a.factor,
-		                                                a.rshift, a.bits, a.counts, *peers);
+		k_scatter_bulk<1024, kBulkGranule, 64, true><<<grid_b, 1024, smem_b, s>>>(
+		    a.keys, a.vals, a.n, a.np, a.parent_off, a.item_prefix, a.chunk, a.factor, a.rshift, a.bits, a.counts, nullptr, nullptr, *peers);
 	} else if (peers) {
 		HJB_LAUNCH_SCATTER(1024, 1, true, true, *peers);
+	} else if (variant == 7 && F <= 256) {
+		// experiment: the local scatter with 32-byte granules and one bulk copy per digit, tile and column
+		const size_t smem_b = 52 * 256 + (8192 + 2 * 8 * (size_t)F) * 8 + (size_t)F * 8 * 16;
+		static bool attr_l = false;
+		if (!attr_l) {
+			cudaFuncSetAttribute(k_scatter_bulk<1024, 8, 256, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+			                     (int)(52 * 256 + (8192 + 2 * 8 * 256) * 8 + 256 * 8 * 16));
+			attr_l = true;
+		}
+		k_scatter_bulk<1024, 8, 256, false><<<grid, 1024, smem_b, s>>>(a.keys, a.vals, a.n, a.np, a.parent_off, a.item_prefix, a.chunk,
+		                                                             a.factor, a.rshift, a.bits, a.counts, a.keys_out, a.vals_out, no_peers);
 	} else {
 		switch (variant) {
 		case 0: HJB_LAUNCH_SCATTER(512, 2, true, false, no_peers); break;
