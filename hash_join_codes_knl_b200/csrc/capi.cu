@@ -11,6 +11,17 @@
 
 using namespace hjb;
 
+constexpr int kMaxHostSlices = 16;               // probe-side slices of the pipelined host entry points
+constexpr uint64_t kMinHostSlice = 1u << 22;     // tuples; smaller probe sides are copied in one piece
+
+// HJB_HOST_SLICE=<tuples> overrides the minimum slice (tests exercise the slicing on small inputs)
+static uint64_t host_slice_min()
+{
+	const char *e = getenv("HJB_HOST_SLICE");
+	const long long v = e ? atoll(e) : 0;
+	return v >= 4 ? (uint64_t)v : kMinHostSlice;
+}
+
 struct hjb_ctx {
 	int device, sms;
 	cudaStream_t stream;
@@ -29,6 +40,11 @@ struct hjb_ctx {
 	unsigned long long *d_scalars, *h_scalars;   // 16 each; h_ pinned
 	uint32_t *h_small;        // pinned, 256 uint32
 	cudaEvent_t ev[12];
+	// hjb_*_host pipeline: copy-in / copy-out streams, per-slice events, row cursor after each slice (pinned)
+	cudaStream_t pipe_in, pipe_out;
+	cudaEvent_t pipe_ev[2][kMaxHostSlices + 1];
+	unsigned long long *h_cursor;
+	bool pipe_ready;
 	uint32_t launches;
 	KernelTimer timer;        // per-kernel times of the last join (hjb_set_profiling)
 	char *recv_buf[4];        // CPRA fused exchange: receive columns r_keys r_vals s_keys s_vals
@@ -39,6 +55,7 @@ struct hjb_ctx {
 };
 
 static char g_create_err[512];
+
 
 #define CK(call)                                                                                   \
 	do {                                                                                           \
@@ -127,6 +144,13 @@ extern "C" int hjb_destroy(hjb_ctx *ctx)
 	cudaFreeHost(ctx->h_scalars);
 	cudaFreeHost(ctx->h_small);
 	cudaFreeHost(ctx->h_rows);
+	if (ctx->pipe_ready) {
+		cudaStreamDestroy(ctx->pipe_in);
+		cudaStreamDestroy(ctx->pipe_out);
+		for (int i = 0; i < 2; ++i)
+			for (int k = 0; k <= kMaxHostSlices; ++k) cudaEventDestroy(ctx->pipe_ev[i][k]);
+		cudaFreeHost(ctx->h_cursor);
+	}
 	for (int i = 0; i < 12; ++i) cudaEventDestroy(ctx->ev[i]);
 	for (int i = 0; i < KernelTimer::kMaxLaunches; ++i) {
 		cudaEventDestroy(ctx->timer.beg[i]);
@@ -475,6 +499,93 @@ static int partition_relation(hjb_ctx *ctx, const hjb_rel *rel, const Plan &p, i
 	return HJB_OK;
 }
 
+// One PHJ join in pieces, so that the probe side can arrive in slices (hjb_phj_host overlaps the
+// slices' copies with the kernels): phj_setup plans and carves the workspace, phj_build partitions
+// R, phj_probe partitions one S slice and joins it against R's partitions.  Rows of successive
+// slices are appended (the row cursor d_scalars[0] and the checksums are not reset in between).
+struct PhjState {
+	Plan plan;
+	uint32_t P, owner, radix_factor;
+	int consumed;
+	uint32_t *rbk[2], *rbv[2], *sbk[2], *sbv[2], *roff[2], *soff[2], *task_prefix, *task_counter;
+	char *scratch;
+	Partitioned pr, ps;
+	JoinArgs j;
+};
+
+static int phj_setup(hjb_ctx *ctx, uint64_t nr, uint64_t ns_slice, uint64_t ns_total, const hjb_opts *o, int consumed,
+                     uint32_t owner, PhjState *st)
+{
+	int rc;
+	memset(st, 0, sizeof *st);
+	if ((rc = make_plan(ctx, nr, ns_total, o, consumed, &st->plan))) return rc;
+	const Plan &plan = st->plan;
+	size_t rscratch;
+	const size_t need = phj_workspace(nr, ns_slice, plan, &rscratch);
+	if ((rc = grow_device(ctx, &ctx->ws, &ctx->ws_bytes, need))) return rc;
+	if (o->materialize) {
+		const uint64_t cap = o->out_capacity ? o->out_capacity : (ns_total > nr ? ns_total : nr);
+		if ((rc = grow_out(ctx, cap))) return rc;
+	}
+	st->P = 1u << plan.total_bits;
+	st->consumed = consumed;
+	st->owner = owner;
+	st->radix_factor = hjb_hash_factor(o->seed, 0);
+	Bump b = {ctx->ws, 0};
+	const int nb = plan.npass >= 2 ? 2 : plan.npass;
+	for (int i = 0; i < nb; ++i) {
+		st->rbk[i] = b.take<uint32_t>(nr); st->rbv[i] = b.take<uint32_t>(nr);
+		st->sbk[i] = b.take<uint32_t>(ns_slice); st->sbv[i] = b.take<uint32_t>(ns_slice);
+	}
+	for (int i = 0; i < 2; ++i) st->roff[i] = b.take<uint32_t>(st->P + 1);
+	for (int i = 0; i < 2; ++i) st->soff[i] = b.take<uint32_t>(st->P + 1);
+	st->task_prefix = b.take<uint32_t>(st->P + 1);
+	st->task_counter = b.take<uint32_t>(1);
+	st->scratch = b.take<char>(rscratch);
+	return HJB_OK;
+}
+
+// one side through all radix passes (no pass at all: a single partition [0, n))
+static int phj_partition_side(hjb_ctx *ctx, PhjState *st, const hjb_rel *rel, bool build_side, uint32_t *launches)
+{
+	cudaStream_t s = ctx->stream;
+	Partitioned *res = build_side ? &st->pr : &st->ps;
+	uint32_t **off = build_side ? st->roff : st->soff;
+	if (st->plan.npass == 0) {
+		uint32_t *h = ctx->h_small + (build_side ? 0 : 2);
+		h[0] = 0; h[1] = (uint32_t)rel->tuples;
+		CK(cudaMemcpyAsync(off[0], h, 8, cudaMemcpyHostToDevice, s));
+		res->k = rel->keys; res->v = rel->vals; res->off = off[0];
+		return HJB_OK;
+	}
+	return partition_relation(ctx, rel, st->plan, st->consumed, st->radix_factor, build_side ? st->rbk : st->sbk,
+	                          build_side ? st->rbv : st->sbv, off, st->scratch, res, launches);
+}
+
+static int phj_launch_join(hjb_ctx *ctx, PhjState *st, const hjb_opts *o, uint32_t *launches)
+{
+	JoinArgs &j = st->j;
+	j.rk = st->pr.k; j.rv = st->pr.v; j.sk = st->ps.k; j.sv = st->ps.v;
+	j.r_off = st->pr.off; j.s_off = st->ps.off;
+	j.P = st->P;
+	j.radix_factor = st->radix_factor;
+	j.rem_bits = 32 - st->consumed - st->plan.total_bits;
+	j.owner = st->owner;
+	j.owner_bits = st->consumed;
+	j.table_factor = hjb_hash_factor(o->seed, 1);
+	j.task_prefix = st->task_prefix;
+	j.task_counter = st->task_counter;
+	j.s_task = 16384;
+	j.scalars = ctx->d_scalars;
+	j.materialize = o->materialize;
+	j.out_k = ctx->out_cols;
+	j.out_o = ctx->out_cols + ctx->out_cap;
+	j.out_i = ctx->out_cols + 2 * ctx->out_cap;
+	j.out_cap = o->materialize ? ctx->out_cap : 0;
+	*launches += launch_partition_join(j, ctx->stream, ctx->sms, &ctx->timer);
+	return HJB_OK;
+}
+
 static int phj_device(hjb_ctx *ctx, const hjb_rel *R, const hjb_rel *S, const hjb_opts *o, int consumed,
                       hjb_result *out, uint32_t owner = 0)
 {
@@ -484,69 +595,18 @@ static int phj_device(hjb_ctx *ctx, const hjb_rel *R, const hjb_rel *S, const hj
 	CK(cudaSetDevice(ctx->device));
 	if (consumed == 0) timer_reset(ctx);       // a CPRA join keeps the times of its count / scatter steps
 	if (R->tuples == 0 || S->tuples == 0) return HJB_OK;
-	Plan plan;
-	if ((rc = make_plan(ctx, R->tuples, S->tuples, o, consumed, &plan))) return rc;
-	size_t rscratch;
-	const size_t need = phj_workspace(R->tuples, S->tuples, plan, &rscratch);
-	if ((rc = grow_device(ctx, &ctx->ws, &ctx->ws_bytes, need))) return rc;
-	uint64_t cap = 0;
-	if (o->materialize) {
-		cap = o->out_capacity ? o->out_capacity : (S->tuples > R->tuples ? S->tuples : R->tuples);
-		if ((rc = grow_out(ctx, cap))) return rc;
-	}
-	const uint32_t P = 1u << plan.total_bits;
-	Bump b = {ctx->ws, 0};
-	uint32_t *rbk[2] = {nullptr, nullptr}, *rbv[2] = {nullptr, nullptr}, *sbk[2] = {nullptr, nullptr}, *sbv[2] = {nullptr, nullptr};
-	const int nb = plan.npass >= 2 ? 2 : plan.npass;
-	for (int i = 0; i < nb; ++i) {
-		rbk[i] = b.take<uint32_t>(R->tuples); rbv[i] = b.take<uint32_t>(R->tuples);
-		sbk[i] = b.take<uint32_t>(S->tuples); sbv[i] = b.take<uint32_t>(S->tuples);
-	}
-	uint32_t *roff[2] = {b.take<uint32_t>(P + 1), b.take<uint32_t>(P + 1)};
-	uint32_t *soff[2] = {b.take<uint32_t>(P + 1), b.take<uint32_t>(P + 1)};
-	uint32_t *task_prefix = b.take<uint32_t>(P + 1);
-	uint32_t *task_counter = b.take<uint32_t>(1);
-	char *scratch = b.take<char>(rscratch);
+	PhjState st;
+	if ((rc = phj_setup(ctx, R->tuples, S->tuples, S->tuples, o, consumed, owner, &st))) return rc;
 	cudaStream_t s = ctx->stream;
 	uint32_t launches = 0;
-	const uint32_t radix_factor = hjb_hash_factor(o->seed, 0);
 	CK(cudaEventRecord(ctx->ev[0], s));
 	CK(cudaMemsetAsync(ctx->d_scalars, 0, 16 * 8, s));
-	Partitioned pr, ps;
-	if (plan.npass == 0) {
-		// build side fits one table fill or two: single partition, no scatter
-		ctx->h_small[0] = 0; ctx->h_small[1] = (uint32_t)R->tuples;
-		ctx->h_small[2] = 0; ctx->h_small[3] = (uint32_t)S->tuples;
-		CK(cudaMemcpyAsync(roff[0], &ctx->h_small[0], 8, cudaMemcpyHostToDevice, s));
-		CK(cudaMemcpyAsync(soff[0], &ctx->h_small[2], 8, cudaMemcpyHostToDevice, s));
-		pr.k = R->keys; pr.v = R->vals; pr.off = roff[0];
-		ps.k = S->keys; ps.v = S->vals; ps.off = soff[0];
-	} else {
-		if ((rc = partition_relation(ctx, R, plan, consumed, radix_factor, rbk, rbv, roff, scratch, &pr, &launches))) return rc;
-		CK(cudaEventRecord(ctx->ev[1], s));
-		if ((rc = partition_relation(ctx, S, plan, consumed, radix_factor, sbk, sbv, soff, scratch, &ps, &launches))) return rc;
-	}
+	if ((rc = phj_partition_side(ctx, &st, R, true, &launches))) return rc;
+	CK(cudaEventRecord(ctx->ev[1], s));
+	if ((rc = phj_partition_side(ctx, &st, S, false, &launches))) return rc;
 	CK(cudaEventRecord(ctx->ev[2], s));
-	JoinArgs j;
-	j.rk = pr.k; j.rv = pr.v; j.sk = ps.k; j.sv = ps.v;
-	j.r_off = pr.off; j.s_off = ps.off;
-	j.P = P;
-	j.radix_factor = radix_factor;
-	j.rem_bits = 32 - consumed - plan.total_bits;
-	j.owner = owner;
-	j.owner_bits = consumed;
-	j.table_factor = hjb_hash_factor(o->seed, 1);
-	j.task_prefix = task_prefix;
-	j.task_counter = task_counter;
-	j.s_task = 16384;
-	j.scalars = ctx->d_scalars;
-	j.materialize = o->materialize;
 	for (int attempt = 0; attempt < 2; ++attempt) {
-		j.out_k = ctx->out_cols;
-		j.out_o = ctx->out_cols + ctx->out_cap;
-		j.out_i = ctx->out_cols + 2 * ctx->out_cap;
-		j.out_cap = o->materialize ? ctx->out_cap : 0;
-		launches += launch_partition_join(j, s, ctx->sms, &ctx->timer);
+		if ((rc = phj_launch_join(ctx, &st, o, &launches))) return rc;
 		CK(cudaEventRecord(ctx->ev[3], s));
 		CK(cudaGetLastError());
 		if ((rc = read_scalars(ctx, out))) return rc;
@@ -559,13 +619,13 @@ static int phj_device(hjb_ctx *ctx, const hjb_rel *R, const hjb_rel *S, const hj
 	float ms = 0;
 	CK(cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[3]));
 	out->seconds = ms * 1e-3;
-	if (plan.npass) {
+	if (st.plan.npass) {
 		CK(cudaEventElapsedTime(&out->phase_ms[0], ctx->ev[0], ctx->ev[1]));   // all passes over R
 		CK(cudaEventElapsedTime(&out->phase_ms[1], ctx->ev[1], ctx->ev[2]));   // all passes over S
 	}
 	CK(cudaEventElapsedTime(&out->phase_ms[4], ctx->ev[2], ctx->ev[3]));       // join
 	out->kernel_launches = launches;
-	out->partitions = P;
+	out->partitions = st.P;
 	set_rows(ctx, out, o->materialize);
 	ctx->launches += launches;
 	return HJB_OK;
@@ -586,7 +646,11 @@ static int phj_device0(hjb_ctx *ctx, const hjb_rel *R, const hjb_rel *S, const h
 	return phj_device(ctx, R, S, o, 0, out);
 }
 
-static int host_join(hjb_ctx *ctx, device_join_fn fn, const hjb_rel *R, const hjb_rel *S, const hjb_opts *o,
+static int host_join_pipelined(hjb_ctx *ctx, bool npj, const hjb_rel *R, const hjb_rel *S, const hjb_opts *o,
+                               uint32_t *drk, uint32_t *drv, uint32_t *dsk, uint32_t *dsv, hjb_result *out);
+static int grow_host_rows(hjb_ctx *ctx, uint64_t rows);
+
+static int host_join(hjb_ctx *ctx, device_join_fn fn, bool npj, const hjb_rel *R, const hjb_rel *S, const hjb_opts *o,
                      hjb_result *out)
 {
 	int rc;
@@ -598,12 +662,24 @@ static int host_join(hjb_ctx *ctx, device_join_fn fn, const hjb_rel *R, const hj
 	cudaStream_t s = ctx->stream;
 	uint32_t *drk = (uint32_t *)ctx->in_buf, *drv = (uint32_t *)(ctx->in_buf + rb);
 	uint32_t *dsk = (uint32_t *)(ctx->in_buf + 2 * rb), *dsv = (uint32_t *)(ctx->in_buf + 2 * rb + sb);
+	static int pipeline = -1;               // HJB_HOST_PIPELINE=0: one copy in, the join, one copy out
+	if (pipeline < 0) pipeline = getenv("HJB_HOST_PIPELINE") ? atoi(getenv("HJB_HOST_PIPELINE")) : 1;
+	bool on_device = false;
+	if (pipeline && R->tuples && S->tuples >= 2 * host_slice_min()) {
+		CK(cudaStreamSynchronize(s));
+		rc = host_join_pipelined(ctx, npj, R, S, o, drk, drv, dsk, dsv, out);
+		if (rc <= 0) {
+			if (rc == HJB_OK) out->seconds_e2e = wall_now() - t0;
+			return rc;
+		}
+		on_device = true;                   // more rows than the capacity guess: finish on the plain path
+	}
 	CK(cudaEventRecord(ctx->ev[8], s));
-	if (R->tuples) {
+	if (R->tuples && !on_device) {
 		CK(cudaMemcpyAsync(drk, R->keys, R->tuples * 4, cudaMemcpyHostToDevice, s));
 		CK(cudaMemcpyAsync(drv, R->vals, R->tuples * 4, cudaMemcpyHostToDevice, s));
 	}
-	if (S->tuples) {
+	if (S->tuples && !on_device) {
 		CK(cudaMemcpyAsync(dsk, S->keys, S->tuples * 4, cudaMemcpyHostToDevice, s));
 		CK(cudaMemcpyAsync(dsv, S->vals, S->tuples * 4, cudaMemcpyHostToDevice, s));
 	}
@@ -612,14 +688,7 @@ static int host_join(hjb_ctx *ctx, device_join_fn fn, const hjb_rel *R, const hj
 	if ((rc = fn(ctx, &dR, &dS, o, out))) return rc;
 	float h2d = 0, d2h = 0;
 	if (o->materialize && out->count) {
-		if (out->count > ctx->h_rows_cap) {
-			if (ctx->h_rows) CK(cudaFreeHost(ctx->h_rows));
-			ctx->h_rows = nullptr;
-			ctx->h_rows_cap = 0;
-			const uint64_t rows = (out->count + 4095) & ~4095ull;
-			CK(cudaHostAlloc(&ctx->h_rows, (size_t)rows * 12, cudaHostAllocDefault));
-			ctx->h_rows_cap = rows;
-		}
+		if ((rc = grow_host_rows(ctx, out->count))) return rc;
 		CK(cudaEventRecord(ctx->ev[10], s));
 		const uint32_t *cols[3] = {out->keys, out->outer_vals, out->inner_vals};
 		for (int c = 0; c < 3; ++c)
@@ -643,16 +712,165 @@ static int host_join(hjb_ctx *ctx, device_join_fn fn, const hjb_rel *R, const hj
 	return HJB_OK;
 }
 
+// Host columns, probe side in slices: while slice k+1 crosses PCIe towards the GPU, slice k is
+// partitioned and joined against the (already resident) build side, and the rows of slice k-1 cross
+// PCIe the other way -- three streams, the link busy in both directions.  The reference has no
+// counterpart (its relations are already in the memory its threads read, npj.cpp:1013-1039); this is
+// the loader a host application needs in front of a GPU join.  Row order is slice order, inside a
+// slice unspecified, as for the device entry points.  More rows than the output capacity (a build
+// side with many equal keys): the inputs are on the device by then, the plain path finishes the job.
+static int pipe_setup(hjb_ctx *ctx)
+{
+	if (ctx->pipe_ready) return HJB_OK;
+	CK(cudaStreamCreateWithFlags(&ctx->pipe_in, cudaStreamNonBlocking));
+	CK(cudaStreamCreateWithFlags(&ctx->pipe_out, cudaStreamNonBlocking));
+	for (int i = 0; i < 2; ++i)
+		for (int k = 0; k <= kMaxHostSlices; ++k) CK(cudaEventCreateWithFlags(&ctx->pipe_ev[i][k], cudaEventDisableTiming));
+	CK(cudaHostAlloc(&ctx->h_cursor, (kMaxHostSlices + 1) * 8, cudaHostAllocDefault));
+	ctx->pipe_ready = true;
+	return HJB_OK;
+}
+
+static int grow_host_rows(hjb_ctx *ctx, uint64_t rows)
+{
+	if (rows <= ctx->h_rows_cap) return HJB_OK;
+	if (ctx->h_rows) CK(cudaFreeHost(ctx->h_rows));
+	ctx->h_rows = nullptr;
+	ctx->h_rows_cap = 0;
+	rows = (rows + 4095) & ~4095ull;
+	CK(cudaHostAlloc(&ctx->h_rows, (size_t)rows * 12, cudaHostAllocDefault));
+	ctx->h_rows_cap = rows;
+	return HJB_OK;
+}
+
+// returns 1 when the result did not fit the output capacity (caller falls back), 0 on success, < 0 on error
+static int host_join_pipelined(hjb_ctx *ctx, bool npj, const hjb_rel *R, const hjb_rel *S, const hjb_opts *o,
+                               uint32_t *drk, uint32_t *drv, uint32_t *dsk, uint32_t *dsv, hjb_result *out)
+{
+	int rc;
+	if ((rc = pipe_setup(ctx))) return rc;
+	int K = (int)(S->tuples / host_slice_min());
+	if (K > kMaxHostSlices) K = kMaxHostSlices;
+	if (K < 1) K = 1;
+	const uint64_t slice = ((S->tuples + K - 1) / K + 1023) & ~1023ull;   // whole 4 KB column pieces, 16-byte aligned
+	zero_result(out);
+	timer_reset(ctx);
+	PhjState st;
+	NpjArgs a;
+	if (npj) {
+		const double load = o->npj_load > 0.0 ? o->npj_load : (R->tuples * 16 <= (32u << 20) ? 0.5 : 0.75);
+		if (load > 0.95) return fail(ctx, HJB_E_INVALID, "npj_load must be <= 0.95");
+		const uint64_t buckets = (uint64_t)ceil((double)R->tuples / load / 4.0) + 1;
+		if (buckets > 0xFFFFFFFFull) return fail(ctx, HJB_E_INVALID, "table too large");
+		if ((rc = grow_device(ctx, &ctx->ws, &ctx->ws_bytes, buckets * 32))) return rc;
+		if (o->materialize) {
+			const uint64_t cap = o->out_capacity ? o->out_capacity : (S->tuples > R->tuples ? S->tuples : R->tuples);
+			if ((rc = grow_out(ctx, cap))) return rc;
+		}
+		memset(&a, 0, sizeof a);
+		a.rk = drk; a.rv = drv; a.nr = R->tuples;
+		a.table = (uint64_t *)ctx->ws;
+		a.buckets = buckets;
+		a.factor = hjb_hash_factor(o->seed, 1);
+		a.scalars = ctx->d_scalars;
+		a.materialize = o->materialize;
+		a.out_k = ctx->out_cols;
+		a.out_o = ctx->out_cols + ctx->out_cap;
+		a.out_i = ctx->out_cols + 2 * ctx->out_cap;
+		a.out_cap = o->materialize ? ctx->out_cap : 0;
+	} else {
+		if ((rc = phj_setup(ctx, R->tuples, slice < S->tuples ? slice : S->tuples, S->tuples, o, 0, 0, &st))) return rc;
+	}
+	if (o->materialize && (rc = grow_host_rows(ctx, ctx->out_cap))) return rc;
+	cudaStream_t s = ctx->stream, sin = ctx->pipe_in, sout = ctx->pipe_out;
+	// copy-in stream: R, then the slices of S
+	CK(cudaEventRecord(ctx->ev[8], sin));
+	CK(cudaMemcpyAsync(drk, R->keys, R->tuples * 4, cudaMemcpyHostToDevice, sin));
+	CK(cudaMemcpyAsync(drv, R->vals, R->tuples * 4, cudaMemcpyHostToDevice, sin));
+	CK(cudaEventRecord(ctx->pipe_ev[0][kMaxHostSlices], sin));
+	for (int k = 0; k < K; ++k) {
+		const uint64_t beg = (uint64_t)k * slice, end = beg + slice < S->tuples ? beg + slice : S->tuples;
+		if (beg >= end) { K = k; break; }
+		CK(cudaMemcpyAsync(dsk + beg, S->keys + beg, (end - beg) * 4, cudaMemcpyHostToDevice, sin));
+		CK(cudaMemcpyAsync(dsv + beg, S->vals + beg, (end - beg) * 4, cudaMemcpyHostToDevice, sin));
+		CK(cudaEventRecord(ctx->pipe_ev[0][k], sin));
+	}
+	CK(cudaEventRecord(ctx->ev[9], sin));
+	// compute stream: build side once, then slice after slice
+	uint32_t launches = 0;
+	CK(cudaStreamWaitEvent(s, ctx->pipe_ev[0][kMaxHostSlices], 0));
+	CK(cudaEventRecord(ctx->ev[0], s));
+	CK(cudaMemsetAsync(ctx->d_scalars, 0, 16 * 8, s));
+	hjb_rel dR = {drk, drv, R->tuples};
+	if (npj) launches += launch_npj_build(a, s, ctx->sms, &ctx->timer);
+	else if ((rc = phj_partition_side(ctx, &st, &dR, true, &launches))) return rc;
+	CK(cudaEventRecord(ctx->ev[1], s));
+	for (int k = 0; k < K; ++k) {
+		const uint64_t beg = (uint64_t)k * slice, end = beg + slice < S->tuples ? beg + slice : S->tuples;
+		CK(cudaStreamWaitEvent(s, ctx->pipe_ev[0][k], 0));
+		if (npj) {
+			a.sk = dsk + beg; a.sv = dsv + beg; a.ns = end - beg;
+			launches += launch_npj_probe(a, s, ctx->sms, &ctx->timer);
+		} else {
+			hjb_rel dS = {dsk + beg, dsv + beg, end - beg};
+			if ((rc = phj_partition_side(ctx, &st, &dS, false, &launches))) return rc;
+			if ((rc = phj_launch_join(ctx, &st, o, &launches))) return rc;
+		}
+		CK(cudaMemcpyAsync(&ctx->h_cursor[k], ctx->d_scalars, 8, cudaMemcpyDeviceToHost, s));
+		CK(cudaEventRecord(ctx->pipe_ev[1][k], s));
+	}
+	CK(cudaEventRecord(ctx->ev[3], s));
+	// host: as each slice finishes, send its rows home on the copy-out stream
+	uint64_t prev = 0;
+	bool overflow = false, first_out = true;
+	for (int k = 0; k < K; ++k) {
+		CK(cudaEventSynchronize(ctx->pipe_ev[1][k]));
+		const uint64_t cur = ctx->h_cursor[k];
+		if (!o->materialize) continue;
+		if (cur > ctx->out_cap) { overflow = true; break; }
+		if (cur > prev) {
+			if (first_out) { CK(cudaEventRecord(ctx->ev[10], sout)); first_out = false; }
+			for (int c = 0; c < 3; ++c)
+				CK(cudaMemcpyAsync(ctx->h_rows + (size_t)c * ctx->h_rows_cap + prev, ctx->out_cols + (size_t)c * ctx->out_cap + prev,
+				                   (cur - prev) * 4, cudaMemcpyDeviceToHost, sout));
+			prev = cur;
+		}
+	}
+	if (!first_out) CK(cudaEventRecord(ctx->ev[11], sout));
+	CK(cudaStreamSynchronize(sout));
+	CK(cudaStreamSynchronize(sin));
+	CK(cudaGetLastError());
+	if ((rc = read_scalars(ctx, out))) return rc;          // synchronizes the compute stream
+	ctx->launches += launches;
+	if (overflow) return 1;
+	float ms = 0;
+	CK(cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[3]));
+	out->seconds = ms * 1e-3;                              // compute stream, waits for the copies included
+	CK(cudaEventElapsedTime(&out->phase_ms[npj ? 1 : 0], ctx->ev[0], ctx->ev[1]));
+	CK(cudaEventElapsedTime(&out->phase_ms[npj ? 2 : 4], ctx->ev[1], ctx->ev[3]));
+	CK(cudaEventElapsedTime(&out->phase_ms[5], ctx->ev[8], ctx->ev[9]));
+	if (!first_out) CK(cudaEventElapsedTime(&out->phase_ms[6], ctx->ev[10], ctx->ev[11]));
+	out->kernel_launches = launches;
+	out->partitions = npj ? (uint32_t)a.buckets : st.P;
+	if (o->materialize && out->count) {
+		out->keys = ctx->h_rows;
+		out->outer_vals = ctx->h_rows + ctx->h_rows_cap;
+		out->inner_vals = ctx->h_rows + 2 * ctx->h_rows_cap;
+	}
+	out->rows_on_device = 0;
+	return HJB_OK;
+}
+
 extern "C" int hjb_npj_host(hjb_ctx *ctx, const hjb_rel *R, const hjb_rel *S, const hjb_opts *opts, hjb_result *out)
 {
 	if (!ctx || !out) return HJB_E_INVALID;
-	return host_join(ctx, npj_device, R, S, opts ? opts : &kDefaultOpts, out);
+	return host_join(ctx, npj_device, true, R, S, opts ? opts : &kDefaultOpts, out);
 }
 
 extern "C" int hjb_phj_host(hjb_ctx *ctx, const hjb_rel *R, const hjb_rel *S, const hjb_opts *opts, hjb_result *out)
 {
 	if (!ctx || !out) return HJB_E_INVALID;
-	return host_join(ctx, phj_device0, R, S, opts ? opts : &kDefaultOpts, out);
+	return host_join(ctx, phj_device0, false, R, S, opts ? opts : &kDefaultOpts, out);
 }
 
 // ------------------------------------------------------------------ CPRA

@@ -12,7 +12,7 @@ constexpr int kMaxRadixBits = 11;            // fan-out per pass <= 2048 (shared
 constexpr uint32_t kDefaultPartTuples = 2048; // planner: build tuples per final partition
 constexpr int kJoinLog2Slots = 12;            // shared-memory table slots per CTA (4096 x 8 B = 32 KB)
 constexpr int kJoinThreads = 256;
-constexpr int kJoinItems = 8;                 // probe tuples per thread per round
+constexpr int kJoinItems = 4;                 // probe tuples per thread per round
 constexpr uint32_t kHistThreads = 512;
 constexpr uint32_t kScanThreads = 256;
 constexpr uint32_t kScanItems = 8;

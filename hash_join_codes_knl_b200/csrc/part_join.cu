@@ -227,7 +227,7 @@ k_partition_join(const uint32_t *__restrict__ rk, const uint32_t *__restrict__ r
 				look_ahead();
 				// build tuples are fetched kBatch at a time so that their loads are in flight together; the
 				// first batch (all of a typical partition) stays in registers for step 3
-				constexpr int kBatch = 8;
+				constexpr int kBatch = THREADS >= 512 ? 4 : 8;
 				uint32_t k0[kBatch], v0[kBatch];
 #pragma unroll
 				for (int t = 0; t < kBatch; ++t) {
@@ -456,7 +456,7 @@ int launch_partition_join(const JoinArgs &a, cudaStream_t s, int sms, KernelTime
 	if (variant < 0) {
 		const char *e = getenv("HJB_JOIN_VARIANT");
 		variant = e ? atoi(e) : 0;
-		if (variant < 0 || variant > 4) variant = 0;
+		if (variant < 0 || variant > 6) variant = 0;
 	}
 	static int clocks = -1;
 	if (clocks < 0) clocks = getenv("HJB_PHASE_CLOCKS") ? 1 : 0;
@@ -482,13 +482,15 @@ int launch_partition_join(const JoinArgs &a, cudaStream_t s, int sms, KernelTime
 			                                   a.task_counter, a.s_task, a.radix_factor, a.table_factor, a.rem_bits,       \
 			                                   a.owner, a.owner_bits, out, a.scalars + 1, clk);                                                             \
 	} while (0)
-	switch (clocks ? 5 : variant) {
+	switch (clocks ? 9 : variant) {
 	case 1: HJB_LAUNCH_JOIN(256, 8, 3, false); break;
 	case 2: HJB_LAUNCH_JOIN(256, 4, 4, false); break;
-	case 3: HJB_LAUNCH_JOIN(256, 4, 5, false); break;
+	case 3: HJB_LAUNCH_JOIN(256, 8, 4, false); break;
 	case 4: HJB_LAUNCH_JOIN(128, 8, 8, false); break;
-	case 5: HJB_LAUNCH_JOIN(kJoinThreads, kJoinItems, 4, true); break;
-	default: HJB_LAUNCH_JOIN(kJoinThreads, kJoinItems, 4, false); break;
+	case 5: HJB_LAUNCH_JOIN(512, 4, 2, false); break;
+	case 6: HJB_LAUNCH_JOIN(512, 4, 3, false); break;
+	case 9: HJB_LAUNCH_JOIN(kJoinThreads, kJoinItems, 5, true); break;
+	default: HJB_LAUNCH_JOIN(kJoinThreads, kJoinItems, 5, false); break;       // measured best: five 256-thread CTAs per SM, 48 registers
 	}
 #undef HJB_LAUNCH_JOIN
 	t->stop(s);

@@ -165,6 +165,50 @@ def test_host_entry_equals_device_entry(eng, algo):
     assert (sort_rows(*a.rows_numpy()) == sort_rows(*b.rows_numpy())).all()
 
 
+@pytest.fixture
+def small_host_slices(monkeypatch):
+    """the host entry points slice the probe side from 2 x HJB_HOST_SLICE tuples on (default 2^22)"""
+    monkeypatch.setenv("HJB_HOST_SLICE", "4096")
+
+
+@pytest.mark.parametrize("algo", ALGOS)
+@pytest.mark.parametrize("nr,ns", [(20000, 8192), (50000, 200001), (3000, 70000), (1 << 17, 1 << 20)])
+def test_pipelined_host_entry_matches_oracle(eng, small_host_slices, algo, nr, ns):
+    """probe side copied, joined and copied back slice by slice on three streams: same rows"""
+    rk, rv, sk, sv, _, _ = oracle_generate(nr, ns, threads=2, seed=21)
+    sk[::5] ^= np.uint32(0x40000000)                         # some probe keys without a partner
+    want = oracle_join(algo, rk, rv, sk, sv, threads=2)
+    got = run(eng, algo, rk, rv, sk, sv, where="host")
+    assert not got.rows_on_device and got.seconds_e2e > 0
+    assert_same(got, want)
+    nomat = run(eng, algo, rk, rv, sk, sv, where="host", materialize=False)
+    assert nomat.checks() == want.checks() and not nomat.materialized
+
+
+@pytest.mark.parametrize("algo", ALGOS)
+def test_pipelined_host_entry_falls_back_when_rows_exceed_capacity(eng, small_host_slices, algo):
+    """equal build keys: more rows than max(|R|, |S|) -> the sliced path hands over to the plain one"""
+    rk = np.concatenate([np.full(40, 5, np.uint32), np.arange(100, 1100, dtype=np.uint32)])
+    rv = np.arange(rk.size, dtype=np.uint32)
+    sk = np.concatenate([np.full(3000, 5, np.uint32), np.arange(0, 30000, dtype=np.uint32)])
+    sv = np.arange(sk.size, dtype=np.uint32) * np.uint32(3)
+    want = numpy_join(rk, rv, sk, sv)
+    assert want.count > sk.size
+    assert_same(run(eng, algo, rk, rv, sk, sv, where="host"), want)
+
+
+@pytest.mark.parametrize("algo", ALGOS)
+def test_pipelined_and_plain_host_entries_agree_at_default_slicing(eng, algo):
+    """2^23 probe tuples: two slices of 2^22 without any override"""
+    rk, rv, sk, sv, _, _ = oracle_generate(1 << 20, 1 << 23, threads=4, seed=22)
+    want = oracle_join(algo, rk, rv, sk, sv, threads=4, materialize=False)
+    got = run(eng, algo, rk, rv, sk, sv, where="host")
+    assert got.checks() == want.checks()
+    k, o, i = got.rows_numpy()
+    assert k.size == want.count and int(k.astype(np.uint64).sum()) == want.sum_key
+    assert int(o.astype(np.uint64).sum()) == want.sum_outer and int(i.astype(np.uint64).sum()) == want.sum_inner
+
+
 def test_phj_plans_and_hash_seeds_do_not_change_the_result(eng):
     rk, rv, sk, sv, _, _ = oracle_generate(1 << 17, 1 << 18, threads=2, seed=11)
     want = oracle_join("phj", rk, rv, sk, sv, threads=2)
