@@ -78,6 +78,19 @@ __device__ __forceinline__ void load_group4(const uint32_t *col, uint64_t g, uin
 	}
 }
 
+// Rank for small fan-outs: the lanes of a warp that hold the same digit reserve their ranks with ONE
+// shared-memory atomic (match.any groups them).  With a few digits only, per-lane atomics on the
+// same counter serialise 16-fold and bound the whole pass.
+__device__ __forceinline__ uint32_t rank_aggregated(uint32_t *cnt, uint32_t d, bool valid)
+{
+	const unsigned m = __match_any_sync(kFullMask, valid ? d : 0xFFFFFFFFu);
+	const int leader = __ffs(m) - 1;
+	uint32_t base = 0;
+	if (valid && (int)lane_id() == leader) base = atomicAdd(&cnt[d], (uint32_t)__popc(m));
+	base = __shfl_sync(kFullMask, base, leader);
+	return valid ? (d << 16) | (base + (uint32_t)__popc(m & lanemask_lt())) : 0xFFFFFFFFu;
+}
+
 // ------------------------------------------------------------------ histogram
 
 __global__ void __launch_bounds__(kHistThreads)
@@ -104,6 +117,41 @@ k_hist(const uint32_t *__restrict__ keys, uint64_t n, uint32_t np, const uint32_
 	__syncthreads();
 	uint32_t *row = counts + (size_t)blockIdx.x * F;
 	for (uint32_t p = threadIdx.x; p < F; p += blockDim.x) row[p] = s_hist[p];
+}
+
+// k_hist for at most 8 digits (CPRA's GPU-assign pass): per-lane shared-memory atomics on so few
+// counters serialise 16-fold; private counters in registers, one atomic per warp and digit instead
+__global__ void __launch_bounds__(kHistThreads)
+k_hist_small(const uint32_t *__restrict__ keys, uint64_t n, uint32_t np, const uint32_t *__restrict__ parent_off,
+             const uint32_t *__restrict__ item_prefix, uint32_t chunk, uint32_t factor, int rshift, int bits,
+             uint32_t *__restrict__ counts)
+{
+	__shared__ uint32_t s_hist[8];
+	const uint32_t F = 1u << bits, mask = F - 1;
+	ItemRange r;
+	if (!locate_item(item_prefix, np, parent_off, n, chunk, blockIdx.x, &r)) return;
+	if (threadIdx.x < 8) s_hist[threadIdx.x] = 0;
+	__syncthreads();
+	const uint64_t g_end = (r.end + 3) >> 2;
+	uint32_t c[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+	for (uint64_t g = (r.beg >> 2) + threadIdx.x; g < g_end; g += blockDim.x) {
+		uint32_t k[4];
+		load_group4(keys, g, n, k);
+#pragma unroll
+		for (int e = 0; e < 4; ++e) {
+			const uint64_t idx = (g << 2) + e;
+			const uint32_t d = (idx >= r.beg && idx < r.end) ? radix_digit(hash_mul(k[e], factor), rshift, mask) : 8u;
+#pragma unroll
+			for (int j = 0; j < 8; ++j) c[j] += d == (uint32_t)j;
+		}
+	}
+#pragma unroll
+	for (int j = 0; j < 8; ++j) {
+		const uint32_t t = (uint32_t)warp_sum_u64(c[j]);
+		if (lane_id() == 0 && j < (int)F && t) atomicAdd(&s_hist[j], t);
+	}
+	__syncthreads();
+	if (threadIdx.x < F) counts[(size_t)blockIdx.x * F + threadIdx.x] = s_hist[threadIdx.x];
 }
 
 // whole-column histogram into one global counts[F] (public hjb_histogram)
@@ -345,7 +393,11 @@ k_scatter(const uint32_t *__restrict__ keys, const uint32_t *__restrict__ vals, 
 		// (1) rank: digit << 16 | rank-in-digit (rank < TILE <= 2^16, digit < 2^11).  Interior tiles
 		// (all but an item's first and last) have every element valid: no per-element predicate.
 		uint32_t dr[IT];
-		if (full) {
+		if (bits <= 4) {
+#pragma unroll
+			for (int e = 0; e < IT; ++e)
+				dr[e] = rank_aggregated(cnt, radix_digit(hash_mul(key[e], factor), rshift, mask), full || ((ok >> e) & 1u));
+		} else if (full) {
 #pragma unroll
 			for (int e = 0; e < IT; ++e) {
 				const uint32_t d = radix_digit(hash_mul(key[e], factor), rshift, mask);
@@ -539,7 +591,8 @@ k_scatter_bulk(const uint32_t *__restrict__ keys, const uint32_t *__restrict__ v
 #pragma unroll
 			for (int e = 0; e < IT; ++e) {
 				const uint32_t d = radix_digit(hash_mul(key[e], factor), rshift, mask);
-				dr[e] = (full || ((ok >> e) & 1u)) ? (d << 16) | atomicAdd(&cnt[d], 1u) : 0xFFFFFFFFu;
+				if (bits <= 4) dr[e] = rank_aggregated(cnt, d, full || ((ok >> e) & 1u));
+				else dr[e] = (full || ((ok >> e) & 1u)) ? (d << 16) | atomicAdd(&cnt[d], 1u) : 0xFFFFFFFFu;
 			}
 			// the bulk copies of the previous tile must have read their shared-memory source before it is reused
 			if (threadIdx.x < F) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
@@ -694,8 +747,12 @@ int launch_radix_count(const RadixPassArgs &a, cudaStream_t s, KernelTimer *t)
 	k_make_items<<<1, 1024, 0, s>>>(a.parent_off, a.np, a.n, a.chunk, a.item_prefix, a.child_off, a.np << a.bits);
 	t->stop(s);
 	t->start(KK_HIST, s);
-	k_hist<<<a.max_items, kHistThreads, F * 4, s>>>(a.keys, a.n, a.np, a.parent_off, a.item_prefix, a.chunk,
-	                                                a.factor, a.rshift, a.bits, a.counts);
+	if (a.bits <= 3)
+		k_hist_small<<<a.max_items, kHistThreads, 0, s>>>(a.keys, a.n, a.np, a.parent_off, a.item_prefix, a.chunk,
+		                                                  a.factor, a.rshift, a.bits, a.counts);
+	else
+		k_hist<<<a.max_items, kHistThreads, F * 4, s>>>(a.keys, a.n, a.np, a.parent_off, a.item_prefix, a.chunk,
+		                                                a.factor, a.rshift, a.bits, a.counts);
 	t->stop(s);
 	t->start(KK_SCAN, s);
 	k_scan<<<tiles, kScanThreads, 0, s>>>(a.item_prefix, a.np, a.bits, a.counts, a.child_off, a.scan_status,
