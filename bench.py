@@ -307,42 +307,56 @@ def main():
         torch.cuda.synchronize()
 
     # ---- warm-up (also sizes the workspace so the timed region never allocates)
+    eng.set_profiling(False)
     for _ in range(args.warmup):
         got, _, _ = step_device()
         assert got == want, f"warm-up step produced a wrong result: {got} != {want}"
-    # ---- timed: device-resident
+    # ---- timed: device-resident.  Two timed regions of `steps` steps each: the first as a user runs it
+    # (headline `value`), the second with a CUDA event pair around every kernel (per-kernel times, roofline).
     sampler = ClockSampler(physical_gpu_index(local)) if rank == 0 else None
     if sampler:
         sampler.start()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    launches = 0
     ktimes = {}
     phases = np.zeros(8)
     extra = {"split_ms": 0.0, "exchange_ms": 0.0, "join_ms": 0.0}
-    barrier()
-    ev0.record()
-    for _ in range(args.steps):
-        got, nl, r = step_device()
-        launches += nl
-        if got != want:
-            raise SystemExit(f"timed step produced a wrong result: {got} != {want}")
-        for name, (ms, n) in eng.kernel_times().items():
-            a = ktimes.setdefault(name, [0.0, 0])
-            a[0] += ms
-            a[1] += n
-        if algo == "cpra":
-            for key in extra:
-                extra[key] += r[key]
-            phases += np.array(r["local"].phase_ms)
-        else:
-            phases += np.array(r.phase_ms)
-    ev1.record()
-    barrier()
-    ms_total = ev0.elapsed_time(ev1)
-    if world > 1:
-        t = torch.tensor([ms_total], device=devname)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_total = float(t.item())
+
+    def timed_region(instrumented):
+        eng.set_profiling(instrumented)
+        got, _, _ = step_device()                  # switching the event pairs on or off re-plans the launch path
+        assert got == want
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n_launch = 0
+        barrier()
+        ev0.record()
+        for _ in range(args.steps):
+            got, nl, r = step_device()
+            n_launch += nl
+            if got != want:
+                raise SystemExit(f"timed step produced a wrong result: {got} != {want}")
+            if not instrumented:
+                if algo == "cpra":
+                    for key in extra:
+                        extra[key] += r[key]
+                continue
+            for name, (ms, n) in eng.kernel_times().items():
+                a = ktimes.setdefault(name, [0.0, 0])
+                a[0] += ms
+                a[1] += n
+            phases[:] += np.array(r["local"].phase_ms if algo == "cpra" else r.phase_ms)
+        ev1.record()
+        barrier()
+        ms = ev0.elapsed_time(ev1)
+        if world > 1:
+            t = torch.tensor([ms], device=devname)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, n_launch
+
+    ms_total, launches = timed_region(False)
+    ms_instrumented, launches_instrumented = timed_region(True)
+    if algo == "cpra":
+        launches = launches_instrumented           # counted from the per-kernel event pairs
+    eng.set_profiling(False)
     clocks = sampler.stop() if sampler else None
     ms_step = ms_total / args.steps
     value = (nr_tot + ns_tot) / (ms_step * 1e-3)
@@ -421,7 +435,7 @@ def main():
         roof = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": tr, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": per_launch_bytes, "avg_launch_ms": per_launch_ms,
-                "launches_per_step": launches_k, "share_of_step": ms_k / ms_step,
+                "launches_per_step": launches_k, "share_of_step": ms_k / (ms_instrumented / args.steps),
                 "traffic_source": "profiles/ncu_traffic.json (dram__bytes_read.sum + dram__bytes_write.sum per launch, "
                                   "ncu --set full)" if tr else None}
     if algo == "npj":
@@ -431,7 +445,7 @@ def main():
         step_bytes = n_in * (20 * passes + 8) + 12 * ns_g
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32",
+        "ms_per_step": ms_step, "ms_per_step_instrumented": ms_instrumented / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32",
         "data": "synthetic",
         "config": {"workload": {"phj_cfg2": "PHJ 2^27 x 2^27 unique keys (BASELINE config 2)",
                                 "npj_cfg1": "NPJ 2^24 x 2^28 foreign keys (BASELINE config 1)",

@@ -88,7 +88,7 @@ struct JoinArgs {
 	uint32_t owner;                          // CPRA local join: this GPU's owner id and the bits that encode it
 	int owner_bits;
 	uint32_t *task_prefix;                   // P + 1 scratch
-	uint32_t *task_counter;                  // 1, zeroed by the launcher
+	uint32_t *task_counter;                  // 1 counter at [0], 64-bit block status words from byte 256 on; zeroed by the launcher
 	uint32_t s_task;                         // probe tuples per task
 	uint32_t *out_k, *out_o, *out_i;
 	uint64_t out_cap;

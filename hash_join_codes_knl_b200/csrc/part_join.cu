@@ -30,42 +30,45 @@
 
 namespace hjb {
 
-// tasks per partition -> exclusive prefix; P <= 2^22, one CTA of 32 warps.  Each warp owns a
-// contiguous chunk of partitions and walks it 32 at a time (coalesced offset reads): first to
-// total its chunk, then -- after a scan of the 32 chunk totals -- to write the prefixes.
+// tasks per partition -> exclusive prefix; P <= 2^22.  CTA b owns partitions [1024 b, 1024 b + 1024):
+// it publishes its block total as a status word (bit 63 = ready), then sums the status words of
+// ALL lower blocks -- they were dispatched earlier, so waiting on them cannot deadlock, and the
+// waits are independent loads rather than a chain.
+constexpr uint32_t kTaskBlock = 1024;
 __global__ void __launch_bounds__(1024)
 k_join_tasks(const uint32_t *__restrict__ r_off, const uint32_t *__restrict__ s_off, uint32_t P, uint32_t s_task,
-             uint32_t *__restrict__ task_prefix)
+             uint32_t *__restrict__ task_prefix, unsigned long long *__restrict__ status)
 {
-	__shared__ uint32_t chunk_base[33];
-	const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
-	const uint32_t chunk = ((P + 31) / 32 + 31) & ~31u;          // partitions per warp, multiple of 32
-	const uint32_t beg = warp * chunk, end = min(P, beg + chunk);
-	auto tasks_of = [&](uint32_t p) -> uint32_t {
-		if (p >= end) return 0u;
+	__shared__ uint32_t warp_totals[34];
+	__shared__ uint64_t s_before[32];
+	const uint32_t p = blockIdx.x * kTaskBlock + threadIdx.x;
+	uint32_t v = 0;
+	if (p < P) {
 		const uint32_t rc = r_off[p + 1] - r_off[p], sc = s_off[p + 1] - s_off[p];
-		return (rc && sc) ? (sc + s_task - 1) / s_task : 0u;     // an empty side cannot match
-	};
-	uint32_t local = 0;
-	for (uint32_t p = beg + lane; p < end; p += 32) local += tasks_of(p);
-	local = (uint32_t)warp_sum_u64(local);
-	if (lane == 0) chunk_base[warp] = local;
-	__syncthreads();
-	if (warp == 0) {
-		const uint32_t v = chunk_base[lane];
-		const uint32_t incl = warp_inclusive_scan_u32(v);
-		chunk_base[lane] = incl - v;
-		if (lane == 31) chunk_base[32] = incl;
+		v = (rc && sc) ? (sc + s_task - 1) / s_task : 0u;        // an empty side cannot match
 	}
-	__syncthreads();
-	uint32_t run = chunk_base[warp];
-	for (uint32_t p0 = beg; p0 < end; p0 += 32) {
-		const uint32_t v = tasks_of(p0 + lane);
-		const uint32_t incl = warp_inclusive_scan_u32(v);
-		if (p0 + lane < end) task_prefix[p0 + lane] = run + incl - v;
-		run += __shfl_sync(kFullMask, incl, 31);
+	uint32_t tot;
+	const uint32_t excl = block_exclusive_scan(v, warp_totals, &tot);
+	if (threadIdx.x == 0) {
+		atomicExch(&status[blockIdx.x], (1ull << 63) | tot);
+		__threadfence();
 	}
-	if (threadIdx.x == 0) task_prefix[P] = chunk_base[32];
+	uint64_t before = 0;
+	for (uint32_t b = threadIdx.x; b < blockIdx.x; b += 1024) {
+		unsigned long long w;
+		do {
+			w = *reinterpret_cast<volatile unsigned long long *>(&status[b]);
+		} while (!(w >> 63));
+		before += w & 0xFFFFFFFFull;
+	}
+	before = warp_sum_u64(before);
+	if (lane_id() == 0) s_before[threadIdx.x >> 5] = before;
+	__syncthreads();
+	uint32_t base = 0;
+#pragma unroll 8
+	for (int w = 0; w < 32; ++w) base += (uint32_t)s_before[w];
+	if (p < P) task_prefix[p] = base + excl;
+	if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) task_prefix[P] = base + tot;
 }
 
 // one row, reservation aggregated over whichever lanes of the warp are here together
@@ -441,9 +444,11 @@ int launch_partition_join(const JoinArgs &a, cudaStream_t s, int sms, KernelTime
 	off.enabled = false;
 	off.n = 0;
 	if (!t) t = &off;
-	cudaMemsetAsync(a.task_counter, 0, 4, s);
+	const uint32_t task_blocks = (a.P + kTaskBlock - 1) / kTaskBlock;
+	cudaMemsetAsync(a.task_counter, 0, 256 + (size_t)task_blocks * 8, s);
 	t->start(KK_JOIN_TASKS, s);
-	k_join_tasks<<<1, 1024, 0, s>>>(a.r_off, a.s_off, a.P, a.s_task, a.task_prefix);
+	k_join_tasks<<<task_blocks, 1024, 0, s>>>(a.r_off, a.s_off, a.P, a.s_task, a.task_prefix,
+	                                          reinterpret_cast<unsigned long long *>(a.task_counter + 64));
 	t->stop(s);
 	OutCols out;
 	out.k = a.out_k;

@@ -526,7 +526,7 @@ __device__ __forceinline__ void bulk_store(void *gdst, const void *ssrc, uint32_
 	             : "memory");
 }
 
-template <int THREADS, int GRAN, int MAXF, bool PEER>
+template <int THREADS, int GRAN, int MAXF, bool PEER, bool TMA = true>
 __global__ void __launch_bounds__(THREADS, 1)
 k_scatter_bulk(const uint32_t *__restrict__ keys, const uint32_t *__restrict__ vals, uint64_t n, uint32_t np,
                const uint32_t *__restrict__ parent_off, const uint32_t *__restrict__ item_prefix, uint32_t chunk,
@@ -537,9 +537,15 @@ k_scatter_bulk(const uint32_t *__restrict__ keys, const uint32_t *__restrict__ v
 	constexpr uint32_t TILE = THREADS * IT, kGroupsPerTile = TILE / 4, GR = GRAN;
 	extern __shared__ __align__(128) uint32_t s_bulk[];
 	__shared__ uint32_t warp_totals[MAXF / 32];
+	__shared__ uint32_t s_slots;                  // slots of the digit-grouped tile in use (TMA = false)
 	__shared__ uint32_t *s_pk[PEER ? 64 : 1], *s_pv[PEER ? 64 : 1];
 	const uint32_t F = 1u << bits, mask = F - 1;
 	const uint32_t PAD = TILE + 2 * GR * F;
+	// !TMA: slots of a region that hold no tuple (before an item's first position, behind its last) get a key
+	// that hashes to the region's digit, so that the stream phase can read the digit from any slot
+	uint32_t finv = factor;                       // inverse of the odd factor modulo 2^32 (Newton)
+#pragma unroll
+	for (int t = 0; t < 5; ++t) finv *= 2u - factor * finv;
 	uint32_t *cnt = s_bulk, *wpos = cnt + MAXF, *pend = wpos + MAXF;
 	uint4 *place = reinterpret_cast<uint4 *>(pend + MAXF);     // x: slot of new rank 0, y: new tuples that fit the region, z: carry index of rank 0
 	uint4 *strm = place + MAXF;                                // x: global position of slot 0, y: first valid position, z: end of valid positions
@@ -595,7 +601,7 @@ k_scatter_bulk(const uint32_t *__restrict__ keys, const uint32_t *__restrict__ v
 				else dr[e] = (full || ((ok >> e) & 1u)) ? (d << 16) | atomicAdd(&cnt[d], 1u) : 0xFFFFFFFFu;
 			}
 			// the bulk copies of the previous tile must have read their shared-memory source before it is reused
-			if (threadIdx.x < F) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+			if (TMA && threadIdx.x < F) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
 			__syncthreads();
 			// (2) plan: one digit per thread in the first MAXF / 32 warps
 			if (threadIdx.x < MAXF) {
@@ -628,6 +634,14 @@ k_scatter_bulk(const uint32_t *__restrict__ keys, const uint32_t *__restrict__ v
 					wpos[p] = lim;
 					pend[p] = w + pe + c - lim;
 					cnt[p] = 0;
+					if (!TMA) {
+						if (p == F - 1) s_slots = rb + slots;
+						if (flush && (((w | lim) & (GR - 1)) != 0)) {
+							const uint32_t marker = (p << rshift) * finv;
+							for (uint32_t q = rb; q < rb + (w - wg); ++q) skeys[q] = marker;
+							for (uint32_t q = rb + (lim - wg); q < rb + slots; ++q) skeys[q] = marker;
+						}
+					}
 				}
 			}
 			__syncthreads();
@@ -660,10 +674,33 @@ k_scatter_bulk(const uint32_t *__restrict__ keys, const uint32_t *__restrict__ v
 					}
 				}
 			}
-			asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy writes -> visible to the bulk copy
+			if (TMA) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy writes -> visible to the bulk copy
 			__syncthreads();
+			if (!TMA) {
+				// (4) every thread: four slots at a time, 16-byte stores per column where the four are all valid
+				const uint32_t groups = s_slots >> 2;
+				for (uint32_t q = threadIdx.x; q < groups; q += THREADS) {
+					const uint4 k4 = *reinterpret_cast<const uint4 *>(skeys + 4 * q);
+					const uint4 v4 = *reinterpret_cast<const uint4 *>(svals + 4 * q);
+					const uint32_t d = radix_digit(hash_mul(k4.x, factor), rshift, mask);
+					const uint4 st = strm[d];
+					const uint32_t pos = st.x + 4 * q;                     // global position of the group's first slot
+					if (pos >= st.y && pos + 4 <= st.z) {
+						*reinterpret_cast<uint4 *>(keys_out + pos) = k4;
+						*reinterpret_cast<uint4 *>(vals_out + pos) = v4;
+					} else {
+						const uint32_t kk[4] = {k4.x, k4.y, k4.z, k4.w}, vv[4] = {v4.x, v4.y, v4.z, v4.w};
+#pragma unroll
+						for (int e = 0; e < 4; ++e)
+							if (pos + e >= st.y && pos + e < st.z) {
+								keys_out[pos + e] = kk[e];
+								vals_out[pos + e] = vv[e];
+							}
+					}
+				}
+			}
 			// (4) one thread per digit: whole run as bulk copies, unaligned ends as scalar stores
-			if (threadIdx.x < F) {
+			if (TMA && threadIdx.x < F) {
 				const uint32_t d = threadIdx.x;
 				const uint4 st = strm[d];
 				if (st.w) {
@@ -688,7 +725,7 @@ k_scatter_bulk(const uint32_t *__restrict__ keys, const uint32_t *__restrict__ v
 			}
 		}
 		// the item's last bulk copies must complete before its shared memory is reused / the CTA exits
-		if (threadIdx.x < F) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+		if (TMA && threadIdx.x < F) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 	}
 }
 
@@ -774,7 +811,7 @@ int launch_radix_scatter(const RadixPassArgs &a, cudaStream_t s, KernelTimer *t,
 	if (variant < 0) {
 		const char *e = getenv("HJB_SCATTER_VARIANT");
 		variant = e ? atoi(e) : 3;       // measured best on B200: one 1024-thread CTA per SM, 8192-tuple tiles
-		if (variant < 0 || variant > 7) variant = 3;
+		if (variant < 0 || variant > 8) variant = 3;
 	}
 	const int threads = (variant >= 3 || peers) ? 1024 : 512;
 	const int items = (!peers && (variant == 5 || variant == 6)) ? 4 : 8;
@@ -802,6 +839,18 @@ int launch_radix_scatter(const RadixPassArgs &a, cudaStream_t s, KernelTimer *t,
 		    a.keys, a.vals, a.n, a.np, a.parent_off, a.item_prefix, a.chunk, a.factor, a.rshift, a.bits, a.counts, nullptr, nullptr, *peers);
 	} else if (peers) {
 		HJB_LAUNCH_SCATTER(1024, 1, true, true, *peers);
+	} else if (variant == 8 && F <= 256) {
+		// aligned SoA tile, 16-byte stores per column
+		const size_t smem_b = 52 * 256 + (8192 + 2 * 8 * (size_t)F) * 8 + (size_t)F * 8 * 16;
+		static bool attr_v = false;
+		if (!attr_v) {
+			cudaFuncSetAttribute(k_scatter_bulk<1024, 8, 256, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+			                     (int)(52 * 256 + (8192 + 2 * 8 * 256) * 8 + 256 * 8 * 16));
+			attr_v = true;
+		}
+		k_scatter_bulk<1024, 8, 256, false, false><<<grid, 1024, smem_b, s>>>(a.keys, a.vals, a.n, a.np, a.parent_off, a.item_prefix,
+		                                                                    a.chunk, a.factor, a.rshift, a.bits, a.counts, a.keys_out,
+		                                                                    a.vals_out, no_peers);
 	} else if (variant == 7 && F <= 256) {
 		// experiment: the local scatter with 32-byte granules and one bulk copy per digit, tile and column
 		const size_t smem_b = 52 * 256 + (8192 + 2 * 8 * (size_t)F) * 8 + (size_t)F * 8 * 16;

@@ -209,6 +209,34 @@ def test_pipelined_and_plain_host_entries_agree_at_default_slicing(eng, algo):
     assert int(o.astype(np.uint64).sum()) == want.sum_outer and int(i.astype(np.uint64).sum()) == want.sum_inner
 
 
+def test_repeated_phj_on_the_same_buffers_replays_a_graph_and_rereads_the_data(eng):
+    """second call on identical buffers captures the launch sequence, later calls replay it; the
+    replay must see new CONTENTS of those buffers, and a different size must leave the graph behind"""
+    rk, rv, sk, sv, _, _ = oracle_generate(1 << 16, 1 << 18, threads=2, seed=31)
+    drk, drv, dsk, dsv = dev(rk), dev(rv), dev(sk), dev(sv)
+    want = oracle_join("phj", rk, rv, sk, sv, threads=2)
+    for _ in range(4):
+        assert_same(eng.phj((drk, drv), (dsk, dsv)), want)
+    sk2 = sk.copy()
+    sk2[::3] ^= np.uint32(0x20000000)
+    dsk.copy_(dev(sk2))                                         # same pointer, new keys
+    want2 = oracle_join("phj", rk, rv, sk2, sv, threads=2)
+    assert want2.count != want.count
+    for _ in range(2):
+        assert_same(eng.phj((drk, drv), (dsk, dsv)), want2)
+    assert_same(eng.phj((drk, drv), (dsk[:100000], dsv[:100000])), oracle_join("phj", rk, rv, sk2[:100000], sv[:100000], threads=2))
+    assert_same(eng.phj((drk, drv), (dsk, dsv)), want2)
+    # equal build keys: the replayed graph overflows the result capacity -> eager rerun with a larger buffer
+    rk3 = np.full(3000, 9, np.uint32)
+    d3 = dev(rk3), dev(np.arange(3000, dtype=np.uint32))
+    s3k = np.concatenate([np.full(1500, 9, np.uint32), np.arange(100, 4000, dtype=np.uint32)])
+    s3 = dev(s3k), dev(np.arange(s3k.size, dtype=np.uint32))
+    want3 = numpy_join(rk3, np.arange(3000, dtype=np.uint32), s3k, np.arange(s3k.size, dtype=np.uint32))
+    for _ in range(3):
+        got = eng.phj(d3, s3)
+        assert got.checks() == want3.checks()
+
+
 def test_phj_plans_and_hash_seeds_do_not_change_the_result(eng):
     rk, rv, sk, sv, _, _ = oracle_generate(1 << 17, 1 << 18, threads=2, seed=11)
     want = oracle_join("phj", rk, rv, sk, sv, threads=2)
