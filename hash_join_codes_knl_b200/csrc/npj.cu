@@ -119,52 +119,38 @@ k_npj_probe(const uint32_t *__restrict__ keys, const uint32_t *__restrict__ vals
 			hi[t] = __ldg(bp + 1);
 		}
 		if (!slow) {
+			// home bucket without branches: four key compares, the payload picked by selects.  Only a full
+			// bucket without the key (the chain goes on) and the all-ones probe key (its low word equals an
+			// empty slot's) take the loop below.
 #pragma unroll
 			for (int t = 0; t < kNpjItems; ++t) {
-				bool hit = false;
-				if (found[t]) {
+				const uint64_t s0 = lo[t].x, s1 = lo[t].y, s2 = hi[t].x, s3 = hi[t].y;
+				const bool m0 = (uint32_t)s0 == k[t], m1 = (uint32_t)s1 == k[t], m2 = (uint32_t)s2 == k[t], m3 = (uint32_t)s3 == k[t];
+				ival[t] = m0 ? (uint32_t)(s0 >> 32) : m1 ? (uint32_t)(s1 >> 32) : m2 ? (uint32_t)(s2 >> 32) : (uint32_t)(s3 >> 32);
+				bool hit = found[t] && (m0 || m1 || m2 || m3);
+				const bool special = k[t] == 0xFFFFFFFFu;
+				if (found[t] && (special || (!hit && s3 != kEmptySlot))) {
+					hit = false;
 					uint32_t bb = b[t];
-					uint64_t s0 = lo[t].x, s1 = lo[t].y, s2 = hi[t].x, s3 = hi[t].y;
+					if (!special) bb = bb + 1 == buckets ? 0 : bb + 1;
 					while (true) {
-						if ((uint32_t)s0 == k[t] && s0 != kEmptySlot) { ival[t] = (uint32_t)(s0 >> 32); hit = true; break; }
-						if ((uint32_t)s1 == k[t] && s1 != kEmptySlot) { ival[t] = (uint32_t)(s1 >> 32); hit = true; break; }
-						if ((uint32_t)s2 == k[t] && s2 != kEmptySlot) { ival[t] = (uint32_t)(s2 >> 32); hit = true; break; }
-						if ((uint32_t)s3 == k[t] && s3 != kEmptySlot) { ival[t] = (uint32_t)(s3 >> 32); hit = true; break; }
-						if (s3 == kEmptySlot) break;               // slots fill lowest-first: a free last slot ends the chain
-						bb = bb + 1 == buckets ? 0 : bb + 1;
 						const ulonglong2 *bp = reinterpret_cast<const ulonglong2 *>(table + (uint64_t)bb * 4);
 						const ulonglong2 a = __ldg(bp), c = __ldg(bp + 1);
-						s0 = a.x; s1 = a.y; s2 = c.x; s3 = c.y;
+						const uint64_t q[4] = {a.x, a.y, c.x, c.y};
+#pragma unroll
+						for (int z = 0; z < 4; ++z)
+							if (!hit && (uint32_t)q[z] == k[t] && q[z] != kEmptySlot) {
+								ival[t] = (uint32_t)(q[z] >> 32);
+								hit = true;
+							}
+						if (hit || q[3] == kEmptySlot) break;           // slots fill lowest-first: a free last slot ends the chain
+						bb = bb + 1 == buckets ? 0 : bb + 1;
 					}
 				}
 				found[t] = hit;
-				if (hit) acc.add(k[t], v[t], ival[t]);
+				acc.add_if(hit ? 1u : 0u, k[t], v[t], ival[t]);
 			}
-			if (MATERIALIZE) {
-				unsigned m[kNpjItems];
-				uint32_t total = 0;
-#pragma unroll
-				for (int t = 0; t < kNpjItems; ++t) {
-					m[t] = __ballot_sync(kFullMask, found[t]);
-					total += __popc(m[t]);
-				}
-				if (total) {
-					unsigned long long base = 0;
-					if (lane_id() == 0) base = atomicAdd(out.cursor, (unsigned long long)total);
-					base = __shfl_sync(kFullMask, base, 0);
-					const unsigned lt = lanemask_lt();
-#pragma unroll
-					for (int t = 0; t < kNpjItems; ++t) {
-						const uint64_t r = base + __popc(m[t] & lt);
-						if (found[t] && r < out.cap) {
-							out.k[r] = k[t];
-							out.o[r] = v[t];
-							out.i[r] = ival[t];
-						}
-						base += __popc(m[t]);
-					}
-				}
-			}
+			if (MATERIALIZE) emit_round<kNpjItems>(out, found, k, v, ival);
 		} else {
 #pragma unroll
 			for (int t = 0; t < kNpjItems; ++t) {

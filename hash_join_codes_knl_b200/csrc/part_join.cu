@@ -87,48 +87,6 @@ __device__ __forceinline__ void emit_row_opportunistic(const OutCols &out, uint3
 	}
 }
 
-// warp-collective: at most one match per item and lane, rows of item t of all lanes contiguous
-template <int ITEMS>
-__device__ __forceinline__ void emit_round(const OutCols &out, const bool (&found)[ITEMS], const uint32_t (&key)[ITEMS],
-                                           const uint32_t (&val)[ITEMS], const uint32_t (&ival)[ITEMS])
-{
-	uint32_t total = 0;                            // the ballots are recomputed below instead of kept in registers
-#pragma unroll
-	for (int t = 0; t < ITEMS; ++t) total += __popc(__ballot_sync(kFullMask, found[t]));
-	if (total == 0) return;
-	unsigned long long base = 0;
-	if (lane_id() == 0) base = atomicAdd(out.cursor, (unsigned long long)total);
-	base = __shfl_sync(kFullMask, base, 0);
-	const unsigned lt = lanemask_lt();
-	if (base + total <= out.cap) {                 // common case: no per-row capacity test, 32-bit offsets
-		uint32_t *const ck = out.k + base, *const co = out.o + base, *const ci = out.i + base;
-		uint32_t off = 0;
-#pragma unroll
-		for (int t = 0; t < ITEMS; ++t) {
-			const unsigned mt = __ballot_sync(kFullMask, found[t]);
-			const uint32_t r = off + __popc(mt & lt);
-			if (found[t]) {
-				ck[r] = key[t];
-				co[r] = val[t];
-				ci[r] = ival[t];
-			}
-			off += __popc(mt);
-		}
-	} else {
-#pragma unroll
-		for (int t = 0; t < ITEMS; ++t) {
-			const unsigned mt = __ballot_sync(kFullMask, found[t]);
-			const uint64_t r = base + __popc(mt & lt);
-			if (found[t] && r < out.cap) {
-				out.k[r] = key[t];
-				out.o[r] = val[t];
-				out.i[r] = ival[t];
-			}
-			base += __popc(mt);
-		}
-	}
-}
-
 constexpr uint32_t kDirectWords = 2048;                  // 2^16-bit presence bitmap
 constexpr uint32_t kDirectFill = 6144;                   // build tuples per DIRECT fill (payload array, 24 KB)
 constexpr uint32_t kHashSlots = 1u << kJoinLog2Slots;    // HASH table slots
