@@ -76,6 +76,7 @@ SYMBOLS = {
     "hjb_relation_read": (C.c_int, [C.c_char_p, C.c_int, C.c_uint64, u32p, u32p]),
     "hjb_generate": (C.c_int, [C.c_void_p, C.POINTER(Gen), C.c_void_p, C.c_void_p]),
     "hjb_column_sum": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, u64p]),
+    "hjb_rows_fingerprint": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, u64p]),
 }
 
 _lib = None

@@ -306,12 +306,35 @@ class Engine:
         self.synchronize()
         return keys, vals
 
+    def rows_fingerprint(self, keys_dev, outer_vals_dev, inner_vals_dev):
+        """order-independent (sum, xor) fingerprint of result rows held in device columns"""
+        cols = [_col(c) for c in (keys_dev, outer_vals_dev, inner_vals_dev)]
+        assert all(c[2] for c in cols) and len({c[1] for c in cols}) == 1
+        fp = (C.c_uint64 * 2)()
+        self._check(self._lib.hjb_rows_fingerprint(self._ctx, cols[0][0], cols[1][0], cols[2][0], cols[0][1], fp),
+                    "hjb_rows_fingerprint")
+        return int(fp[0]), int(fp[1])
+
     def column_sum(self, col_dev):
         p, n, on_dev, _ = _col(col_dev)
         assert on_dev
         s = C.c_uint64()
         self._check(self._lib.hjb_column_sum(self._ctx, p, n, C.byref(s)), "hjb_column_sum")
         return int(s.value)
+
+
+def rows_fingerprint_numpy(keys, outer_vals, inner_vals):
+    """numpy mirror of hjb_rows_fingerprint (csrc/gen.cu k_rows_fingerprint): (sum, xor) of
+    splitmix64((key | outer << 32) ^ splitmix64(inner)) over the rows, uint64 wrap-around."""
+    def mix(z):
+        z = z + np.uint64(0x9E3779B97F4A7C15)
+        z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        return z ^ (z >> np.uint64(31))
+    with np.errstate(over="ignore"):
+        k, o, i = (np.ascontiguousarray(c).view(np.uint32).astype(np.uint64) for c in (keys, outer_vals, inner_vals))
+        z = mix((k | (o << np.uint64(32))) ^ mix(i))
+        return int(z.sum(dtype=np.uint64)), int(np.bitwise_xor.reduce(z)) if z.size else 0
 
 
 def relation_write(directory, outer, keys, vals):

@@ -1307,6 +1307,20 @@ extern "C" int hjb_column_sum(hjb_ctx *ctx, const uint32_t *col_dev, uint64_t si
 	return HJB_OK;
 }
 
+extern "C" int hjb_rows_fingerprint(hjb_ctx *ctx, const uint32_t *keys_dev, const uint32_t *outer_vals_dev,
+                                    const uint32_t *inner_vals_dev, uint64_t rows, uint64_t fp[2])
+{
+	if (!ctx || !fp || (rows && (!keys_dev || !outer_vals_dev || !inner_vals_dev))) return HJB_E_INVALID;
+	CK(cudaSetDevice(ctx->device));
+	ctx->launches += launch_rows_fingerprint(keys_dev, outer_vals_dev, inner_vals_dev, rows, ctx->d_scalars + 8, ctx->stream, ctx->sms);
+	CK(cudaMemcpyAsync(ctx->h_scalars + 8, ctx->d_scalars + 8, 16, cudaMemcpyDeviceToHost, ctx->stream));
+	CK(cudaStreamSynchronize(ctx->stream));
+	CK(cudaGetLastError());
+	fp[0] = ctx->h_scalars[8];
+	fp[1] = ctx->h_scalars[9];
+	return HJB_OK;
+}
+
 static int rel_path(char *buf, size_t cap, const char *dir, int outer, char col, uint64_t n)
 {
 	const int w = snprintf(buf, cap, "%s/%c%c_%llu.txt", dir && *dir ? dir : ".", outer ? 'o' : 'i', col,

@@ -122,6 +122,56 @@ k_column_sum(const uint32_t *__restrict__ col, uint64_t n, unsigned long long *_
 	}
 }
 
+// order-independent fingerprint of result rows (hjb_rows_fingerprint): out[0] += z, out[1] ^= z
+__device__ __forceinline__ uint64_t splitmix64(uint64_t z)
+{
+	z += 0x9E3779B97F4A7C15ull;
+	z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+	z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+	return z ^ (z >> 31);
+}
+
+__global__ void __launch_bounds__(256)
+k_rows_fingerprint(const uint32_t *__restrict__ k, const uint32_t *__restrict__ o, const uint32_t *__restrict__ iv, uint64_t n,
+                   unsigned long long *__restrict__ out)
+{
+	__shared__ uint64_t s_sum[8], s_xor[8];
+	uint64_t sum = 0, x = 0;
+	for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+		const uint64_t z = splitmix64(((uint64_t)k[i] | ((uint64_t)o[i] << 32)) ^ splitmix64(iv[i]));
+		sum += z;
+		x ^= z;
+	}
+	sum = warp_sum_u64(sum);
+#pragma unroll
+	for (int off = 16; off; off >>= 1) x ^= __shfl_xor_sync(kFullMask, x, off);
+	if ((threadIdx.x & 31) == 0) {
+		s_sum[threadIdx.x >> 5] = sum;
+		s_xor[threadIdx.x >> 5] = x;
+	}
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		uint64_t a = 0, b = 0;
+		for (int w = 0; w < 8; ++w) {
+			a += s_sum[w];
+			b ^= s_xor[w];
+		}
+		atomicAdd(&out[0], (unsigned long long)a);
+		atomicXor(&out[1], (unsigned long long)b);
+	}
+}
+
+int launch_rows_fingerprint(const uint32_t *k, const uint32_t *o, const uint32_t *iv, uint64_t n, unsigned long long *out_dev,
+                            cudaStream_t s, int sms)
+{
+	cudaMemsetAsync(out_dev, 0, 16, s);
+	uint64_t grid = (n + 255) / 256;
+	if (grid > (uint64_t)sms * 8) grid = (uint64_t)sms * 8;
+	if (grid == 0) grid = 1;
+	k_rows_fingerprint<<<(uint32_t)grid, 256, 0, s>>>(k, o, iv, n, out_dev);
+	return 1;
+}
+
 int launch_column_sum(const uint32_t *col, uint64_t n, unsigned long long *out_dev, cudaStream_t s, int sms)
 {
 	cudaMemsetAsync(out_dev, 0, 8, s);

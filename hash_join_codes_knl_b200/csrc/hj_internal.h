@@ -113,5 +113,7 @@ int launch_npj_probe(const NpjArgs &a, cudaStream_t s, int sms, KernelTimer *t =
 
 int launch_generate(const hjb_gen &g, uint32_t *keys, uint32_t *vals, cudaStream_t s);
 int launch_column_sum(const uint32_t *col, uint64_t n, unsigned long long *out_dev, cudaStream_t s, int sms);
+int launch_rows_fingerprint(const uint32_t *k, const uint32_t *o, const uint32_t *iv, uint64_t n, unsigned long long *out_dev,
+                            cudaStream_t s, int sms);
 
 }  // namespace hjb

@@ -202,6 +202,14 @@ typedef struct hjb_gen {
 int hjb_generate(hjb_ctx *ctx, const hjb_gen *g, uint32_t *keys_dev, uint32_t *vals_dev);
 /* sum of a device column as uint64 (input checksums, cpra2.cpp:1628,1650) */
 int hjb_column_sum(hjb_ctx *ctx, const uint32_t *col_dev, uint64_t size, uint64_t *sum);
+/* Verifier (the reference has none): order-independent fingerprint of `rows`
+ * result rows held in three DEVICE columns -- fp[0] = sum, fp[1] = xor over the rows of
+ * mix64(key | outer_val << 32, inner_val) (splitmix64 finaliser).  Two joins produced the same
+ * multiset of rows iff (with overwhelming probability) count and both words agree, whatever the
+ * row order; lets results of 2^27..2^31 rows be compared across NPJ / PHJ / CPRA and against a
+ * CPU restatement without copying or sorting them. */
+int hjb_rows_fingerprint(hjb_ctx *ctx, const uint32_t *keys_dev, const uint32_t *outer_vals_dev,
+                         const uint32_t *inner_vals_dev, uint64_t rows, uint64_t fp[2]);
 
 #ifdef __cplusplus
 }

@@ -405,6 +405,40 @@ def test_full_size_configs_by_properties(eng, algo, name):
     assert getattr(eng, algo)((rk, rv), (sk, sv), materialize=False).checks() == res.checks()
 
 
+def test_rows_fingerprint_kernel_equals_numpy_mirror_and_ignores_row_order(eng):
+    """the verifier: (sum, xor) of a 64-bit mix of each row -- equal for equal multisets of rows"""
+    from hash_join_codes_knl_b200.api import rows_fingerprint_numpy
+    rk, rv, sk, sv, _, _ = oracle_generate(30000, 100000, threads=2, seed=41)
+    want = oracle_join("npj", rk, rv, sk, sv, threads=2)
+    fp_oracle = rows_fingerprint_numpy(*want.rows)
+    for algo in ALGOS:
+        got = run(eng, algo, rk, rv, sk, sv)
+        assert eng.rows_fingerprint(*got.rows_torch()) == fp_oracle
+    k, o, i = (dev(c) for c in want.rows)
+    perm = torch.randperm(k.numel(), device=k.device)
+    assert eng.rows_fingerprint(k[perm].contiguous(), o[perm].contiguous(), i[perm].contiguous()) == fp_oracle
+    o2 = o.clone()
+    o2[17] ^= 1                                                 # one flipped bit in one row
+    assert eng.rows_fingerprint(k, o2, i) != fp_oracle
+    assert eng.rows_fingerprint(k[:0], o[:0], i[:0]) == (0, 0)
+
+
+def test_full_size_config2_npj_and_phj_emit_the_same_multiset_of_rows(eng):
+    """BASELINE config 2 at full size (2^27 x 2^27): 2^27 rows each from two different algorithms,
+    compared as multisets through the device fingerprint -- no copy, no sort"""
+    n = 1 << 27
+    rk, rv = eng.generate(0, n, n, 42, 1, datagen.INNER_FACTOR)
+    sk, sv = eng.generate(0, n, n, 42, 2, datagen.OUTER_FACTOR)
+    a = eng.phj((rk, rv), (sk, sv))
+    fa, ca = eng.rows_fingerprint(*a.rows_torch()), a.checks()
+    b = eng.npj((rk, rv), (sk, sv))
+    fb, cb = eng.rows_fingerprint(*b.rows_torch()), b.checks()
+    assert ca == cb and ca[0] == n and fa == fb
+    # the same rows rebuilt from S alone (every probe tuple has exactly one partner, payloads are functions of the key)
+    inner = ((sk.to(torch.int64) & 0xFFFFFFFF) * datagen.INNER_FACTOR & 0xFFFFFFFF).to(torch.int32)
+    assert eng.rows_fingerprint(sk, sv, inner) == fa
+
+
 def test_cpra_join_local_rejects_foreign_tuples(eng):
     """the local join trusts that every tuple hashes into its owner's range (the DIRECT tables rely
     on it); a caller that hands it somebody else's tuples gets an error, not a wrong result"""
