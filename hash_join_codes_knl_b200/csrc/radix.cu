@@ -384,16 +384,30 @@ k_scatter(const uint32_t *__restrict__ keys, const uint32_t *__restrict__ vals, 
 			else load_col8<THREADS, G, false>(key, ok, keys, g0, g_end, r.beg, r.end, n);
 		}
 		uint32_t vok;
-		if (full) load_col8<THREADS, G, true>(val, vok, vals, g0, g_end, r.beg, r.end, n);
-		else load_col8<THREADS, G, false>(val, vok, vals, g0, g_end, r.beg, r.end, n);
+		if (G < 4) {          // 16 tuples per thread: the payloads are fetched after step (1) to keep its register need down
+			if (full) load_col8<THREADS, G, true>(val, vok, vals, g0, g_end, r.beg, r.end, n);
+			else load_col8<THREADS, G, false>(val, vok, vals, g0, g_end, r.beg, r.end, n);
+		}
 		if (PREFETCH && !last) {
 			if (tile_is_full(g1)) load_col8<THREADS, G, true>(nkey, nok, keys, g1, g_end, r.beg, r.end, n);
 			else load_col8<THREADS, G, false>(nkey, nok, keys, g1, g_end, r.beg, r.end, n);
 		}
 		// (1) rank: digit << 16 | rank-in-digit (rank < TILE <= 2^16, digit < 2^11).  Interior tiles
 		// (all but an item's first and last) have every element valid: no per-element predicate.
-		uint32_t dr[IT];
-		if (bits <= 4) {
+		// G >= 4 (16 tuples per thread): only the 16-bit ranks are kept, two per register; the digit is
+		// recomputed from the key when the tuple is placed
+		constexpr bool PACK = G >= 4;
+		uint32_t dr[PACK ? IT / 2 : IT];
+		if (PACK) {
+#pragma unroll
+			for (int e = 0; e < IT; e += 2) {
+				const uint32_t d0 = radix_digit(hash_mul(key[e], factor), rshift, mask);
+				const uint32_t d1 = radix_digit(hash_mul(key[e + 1], factor), rshift, mask);
+				const uint32_t r0 = (full || ((ok >> e) & 1u)) ? atomicAdd(&cnt[d0], 1u) : 0xFFFFu;
+				const uint32_t r1 = (full || ((ok >> (e + 1)) & 1u)) ? atomicAdd(&cnt[d1], 1u) : 0xFFFFu;
+				dr[e / 2] = r0 | (r1 << 16);
+			}
+		} else if (bits <= 4) {
 #pragma unroll
 			for (int e = 0; e < IT; ++e)
 				dr[e] = rank_aggregated(cnt, radix_digit(hash_mul(key[e], factor), rshift, mask), full || ((ok >> e) & 1u));
@@ -409,6 +423,10 @@ k_scatter(const uint32_t *__restrict__ keys, const uint32_t *__restrict__ vals, 
 				const uint32_t d = radix_digit(hash_mul(key[e], factor), rshift, mask);
 				dr[e] = (ok >> e) & 1u ? (d << 16) | atomicAdd(&cnt[d], 1u) : 0xFFFFFFFFu;
 			}
+		}
+		if (G >= 4) {
+			if (full) load_col8<THREADS, G, true>(val, vok, vals, g0, g_end, r.beg, r.end, n);
+			else load_col8<THREADS, G, false>(val, vok, vals, g0, g_end, r.beg, r.end, n);
 		}
 		__syncthreads();
 		// (2) per digit: tile offset, global offset, flush limit, what stays pending
@@ -461,7 +479,13 @@ k_scatter(const uint32_t *__restrict__ keys, const uint32_t *__restrict__ vals, 
 			__syncthreads();
 		}
 		// (3) place the tile's tuples; flush the carried tuples of every digit that reached a boundary
-		if (full) {
+		if (PACK) {
+#pragma unroll
+			for (int e = 0; e < IT; ++e) {
+				const uint32_t rk_ = (dr[e / 2] >> (16 * (e & 1))) & 0xFFFFu;
+				if (rk_ != 0xFFFFu) buf[base[radix_digit(hash_mul(key[e], factor), rshift, mask)] + rk_] = make_uint2(key[e], val[e]);
+			}
+		} else if (full) {
 #pragma unroll
 			for (int e = 0; e < IT; ++e) buf[base[dr[e] >> 16] + (dr[e] & 0xFFFFu)] = make_uint2(key[e], val[e]);
 		} else {
@@ -765,6 +789,7 @@ static void scatter_attrs()
 	cudaFuncSetAttribute(k_scatter<1024, 1, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
 	cudaFuncSetAttribute(k_scatter<1024, 2, false, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
 	cudaFuncSetAttribute(k_scatter<1024, 2, true, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+	cudaFuncSetAttribute(k_scatter<512, 2, false, false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
 }
 
 // make_items + histogram + scan: after this a.counts holds every item's start offset per digit
@@ -811,10 +836,10 @@ int launch_radix_scatter(const RadixPassArgs &a, cudaStream_t s, KernelTimer *t,
 	if (variant < 0) {
 		const char *e = getenv("HJB_SCATTER_VARIANT");
 		variant = e ? atoi(e) : 3;       // measured best on B200: one 1024-thread CTA per SM, 8192-tuple tiles
-		if (variant < 0 || variant > 8) variant = 3;
+		if (variant < 0 || variant > 9) variant = 3;
 	}
-	const int threads = (variant >= 3 || peers) ? 1024 : 512;
-	const int items = (!peers && (variant == 5 || variant == 6)) ? 4 : 8;
+	const int threads = ((variant >= 3 && variant != 9) || peers) ? 1024 : 512;
+	const int items = (!peers && (variant == 5 || variant == 6)) ? 4 : (!peers && variant == 9) ? 16 : 8;
 	const size_t smem = (size_t)F * 32 + (size_t)threads * items * 8 + (F <= 256 ? (size_t)F * (peers ? kPeerCarry : kLocalCarry) * 8 : 0);
 	static const PeerTable no_peers = {};
 	t->start(KK_SCATTER, s);
@@ -870,6 +895,7 @@ int launch_radix_scatter(const RadixPassArgs &a, cudaStream_t s, KernelTimer *t,
 		case 4: HJB_LAUNCH_SCATTER(1024, 2, false, false, no_peers); break;
 		case 5: HJB_LAUNCH_SCATTER(1024, 2, false, false, no_peers, 1); break;
 		case 6: HJB_LAUNCH_SCATTER(1024, 2, true, false, no_peers, 1); break;
+		case 9: HJB_LAUNCH_SCATTER(512, 2, false, false, no_peers, 4); break;     // two co-resident CTAs, 16 tuples per thread
 		default: HJB_LAUNCH_SCATTER(1024, 1, true, false, no_peers); break;
 		}
 	}
