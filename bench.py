@@ -492,6 +492,13 @@ def main():
                               "achieved_gbs_per_direction": sent / (line["cpra_ms_per_step"]["split_ms"] * 1e-3) / 1e9
                               if args.exchange == "fused" else sent / (line["cpra_ms_per_step"]["exchange_ms"] * 1e-3) / 1e9,
                               "reference_gbs": 770.0, "note": "measured peer-copy bandwidth per direction (B200_PROFILING.md); nominal 900"}
+            # SURVEY 8d's serial model for CPRA at G GPUs: HBM bytes / HBM bandwidth + NVLink bytes / NVLink bandwidth,
+            # with n_g*(20 GPU-assign + 20 one local pass + 8 join) + 12 M/G algorithmic HBM bytes per GPU
+            hbm_b = n_in * 48 + 12 * ns_g
+            for tag, bw_h, bw_n in (("measured_peaks", peak, 770.0), ("nominal_peaks", 8000.0, 900.0)):
+                t_ms = (hbm_b / bw_h + sent / bw_n) / 1e6
+                line.setdefault("cpra_roofline", {"hbm_bytes_per_gpu": hbm_b, "nvlink_bytes_out_per_gpu": sent})[tag] = {
+                    "hbm_gbs": bw_h, "nvlink_gbs": bw_n, "serial_model_ms": t_ms, "frac": t_ms / ms_step}
     if not args.no_cpu_baseline:
         try:
             base = cpu_join_sample(25 if workload != "npj_cfg1" else 26, 2, 1, "npj_cfg1" if workload == "npj_cfg1" else "phj_cfg2")

@@ -106,6 +106,14 @@ k_hist(const uint32_t *__restrict__ keys, uint64_t n, uint32_t np, const uint32_
 	__syncthreads();
 	const uint64_t g_end = (r.end + 3) >> 2;
 	for (uint64_t g = (r.beg >> 2) + threadIdx.x; g < g_end; g += blockDim.x) {
+		if ((g << 2) >= r.beg && (g << 2) + 4 <= r.end) {          // interior group: one 128-bit load, no per-key range test
+			const uint4 w = ldg_stream_u4(reinterpret_cast<const uint4 *>(keys) + g);
+			atomicAdd(&s_hist[radix_digit(hash_mul(w.x, factor), rshift, mask)], 1u);
+			atomicAdd(&s_hist[radix_digit(hash_mul(w.y, factor), rshift, mask)], 1u);
+			atomicAdd(&s_hist[radix_digit(hash_mul(w.z, factor), rshift, mask)], 1u);
+			atomicAdd(&s_hist[radix_digit(hash_mul(w.w, factor), rshift, mask)], 1u);
+			continue;
+		}
 		uint32_t k[4];
 		load_group4(keys, g, n, k);
 #pragma unroll
