@@ -292,6 +292,14 @@ static void timer_collect(hjb_ctx *ctx)
 extern "C" int hjb_debug_counters(hjb_ctx *ctx, uint64_t *out8)
 {
 	if (!ctx || !out8) return HJB_E_INVALID;
+	if (getenv("HJB_SCATTER_CLOCKS")) {          // the scatter kernel's phase clocks instead (read and cleared)
+		unsigned long long v[8];
+		cudaSetDevice(ctx->device);
+		cudaDeviceSynchronize();
+		scatter_phase_clocks(v);
+		for (int k = 0; k < 8; ++k) out8[k] = v[k];
+		return HJB_OK;
+	}
 	for (int k = 0; k < 8; ++k) out8[k] = ctx->h_scalars[8 + k];
 	return HJB_OK;
 }

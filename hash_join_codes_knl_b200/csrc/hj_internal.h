@@ -75,6 +75,7 @@ size_t radix_scratch_bytes(uint64_t n, uint32_t np, int bits, uint32_t *chunk, u
 int launch_radix_pass(const RadixPassArgs &a, cudaStream_t s, int sms, KernelTimer *t = nullptr);
 int launch_radix_count(const RadixPassArgs &a, cudaStream_t s, KernelTimer *t = nullptr);
 int launch_radix_scatter(const RadixPassArgs &a, cudaStream_t s, KernelTimer *t = nullptr, const PeerTable *peers = nullptr);
+void scatter_phase_clocks(unsigned long long *out8);
 int launch_histogram_only(const uint32_t *keys, uint64_t n, uint32_t *counts_dev, uint32_t factor,
                           int rshift, int bits, cudaStream_t s, int sms);
 

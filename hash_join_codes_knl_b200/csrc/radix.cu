@@ -337,7 +337,10 @@ constexpr uint32_t kLocalCarry = 8;    // tuples per 32-byte sector of a 4-byte 
 // receive buffers of GPU d, mapped into this process (CUDA IPC) and pre-offset so that the
 // position the scan produced indexes them directly.  The stores then travel over NVLink: the
 // GPU-assign pass of CPRA and its all-to-all are one kernel.
-template <int THREADS, int MINB, bool PREFETCH, bool PEER, int G = 2>
+// debug (HJB_SCATTER_CLOCKS=1 selects the CLK instantiation): cycles thread 0 of every CTA spent per phase of a tile
+__device__ unsigned long long g_scatter_clk[8];
+
+template <int THREADS, int MINB, bool PREFETCH, bool PEER, int G = 2, bool CLK = false>
 __global__ void __launch_bounds__(THREADS, MINB)
 k_scatter(const uint32_t *__restrict__ keys, const uint32_t *__restrict__ vals, uint64_t n, uint32_t np,
           const uint32_t *__restrict__ parent_off, const uint32_t *__restrict__ item_prefix, uint32_t chunk,
@@ -379,6 +382,14 @@ k_scatter(const uint32_t *__restrict__ keys, const uint32_t *__restrict__ vals, 
 		else load_col8<THREADS, G, false>(nkey, nok, keys, g_beg, g_end, r.beg, r.end, n);
 	}
 	__syncthreads();
+	long long clk_t = 0;
+#define SCATTER_MARK(k)                                                              \
+	if (CLK && threadIdx.x == 0) {                                                   \
+		const long long now_ = clock64();                                            \
+		atomicAdd(&g_scatter_clk[k], (unsigned long long)(now_ - clk_t));            \
+		clk_t = now_;                                                                \
+	}
+	if (CLK && threadIdx.x == 0) clk_t = clock64();
 	for (uint64_t g0 = g_beg; g0 < g_end; g0 += kGroupsPerTile) {
 		const uint64_t g1 = g0 + kGroupsPerTile;
 		const bool last = g1 >= g_end;
@@ -436,7 +447,9 @@ k_scatter(const uint32_t *__restrict__ keys, const uint32_t *__restrict__ vals, 
 			if (full) load_col8<THREADS, G, true>(val, vok, vals, g0, g_end, r.beg, r.end, n);
 			else load_col8<THREADS, G, false>(val, vok, vals, g0, g_end, r.beg, r.end, n);
 		}
+		SCATTER_MARK(0)        // loads issued, keys arrived, ranks taken
 		__syncthreads();
+		SCATTER_MARK(1)        // waiting for the slowest warp's ranks
 		// (2) per digit: tile offset, global offset, flush limit, what stays pending
 		auto plan_digit = [&](uint32_t p, uint32_t c, uint32_t run) {
 			const uint32_t w = wpos[p], pe = pend[p], endpos = w + pe + c;
@@ -486,6 +499,7 @@ k_scatter(const uint32_t *__restrict__ keys, const uint32_t *__restrict__ vals, 
 			if (threadIdx.x == 0) s_tile_n = tile_total;
 			__syncthreads();
 		}
+		SCATTER_MARK(2)        // plan (two barriers inside)
 		// (3) place the tile's tuples; flush the carried tuples of every digit that reached a boundary
 		if (PACK) {
 #pragma unroll
@@ -511,7 +525,9 @@ k_scatter(const uint32_t *__restrict__ keys, const uint32_t *__restrict__ vals, 
 					(PEER ? s_pv[d] : vals_out)[dst] = kv.y;
 				}
 			}
+		SCATTER_MARK(3)        // place + carry flush
 		__syncthreads();
+		SCATTER_MARK(4)        // waiting for the slowest warp's placement
 		// (4) stream the digit-grouped tile: below the digit's limit to global memory, beyond it into
 		// the carry buffer.  The next tile's step (1) barrier orders this loop before step (2) rewrites
 		// golim and before step (3) reads carry.
@@ -533,7 +549,185 @@ k_scatter(const uint32_t *__restrict__ keys, const uint32_t *__restrict__ vals, 
 				}
 			}
 		}
+		SCATTER_MARK(5)        // stream
 	}
+#undef SCATTER_MARK
+}
+
+// ------------------------------------------------------------------ local scatter, stream overlapped with the next plan
+//
+// Same four steps as k_scatter (1024 threads, 8 tuples per thread, fan-out <= 256), but the steps
+// of successive tiles are skewed: the plan of tile t -- a latency chain of 256 threads that left the
+// other 24 warps idle for ~1250 of a tile's ~10750 cycles (phase clocks, HJB_SCATTER_CLOCKS) -- now runs
+// while those warps stream tile t-1 out.  The stream's work is handed out in 128-tuple chunks from a
+// shared counter, so the planning warps join in when their plan is done.  golim and the tile size
+// are double-buffered; the plan synchronises its 8 warps with a named barrier of its own.
+//
+//   iteration t:  rank(t) | A | plan(t) by warps 0-7  ||  stream(t-1) by all, planners late | B | place(t), carry flush(t) | C
+//
+// dynamic shared memory: cnt base fpos oldp wpos pend [F] | golim[2][F] (uint2) | buf[TILE] (uint2) | carry[F*8] (uint2)
+template <bool CLK>
+__global__ void __launch_bounds__(1024, 1)
+k_scatter_ov(const uint32_t *__restrict__ keys, const uint32_t *__restrict__ vals, uint64_t n, uint32_t np,
+             const uint32_t *__restrict__ parent_off, const uint32_t *__restrict__ item_prefix, uint32_t chunk,
+             uint32_t factor, int rshift, int bits, const uint32_t *__restrict__ offsets,
+             uint32_t *__restrict__ keys_out, uint32_t *__restrict__ vals_out)
+{
+	constexpr int THREADS = 1024, G = 2, IT = 4 * G;
+	constexpr uint32_t kCarry = kLocalCarry, TILE = THREADS * IT, kGroupsPerTile = TILE / 4, kChunk = 128;
+	extern __shared__ __align__(16) uint32_t s_mem[];
+	__shared__ uint32_t warp_totals[8];
+	__shared__ uint32_t s_tile_n[2], s_next[2];
+	const uint32_t F = 1u << bits, mask = F - 1;
+	uint32_t *cnt = s_mem, *base = cnt + F, *fpos = base + F, *oldp = fpos + F, *wpos = oldp + F, *pend = wpos + F;
+	uint2 *golim = reinterpret_cast<uint2 *>(pend + F);                 // [2][F]  x: global offset of tile index 0, y: flush limit
+	uint2 *buf = golim + 2 * F;
+	uint2 *carry = buf + TILE;
+	ItemRange r;
+	if (!locate_item(item_prefix, np, parent_off, n, chunk, blockIdx.x, &r)) return;
+	const uint32_t *row = offsets + (size_t)blockIdx.x * F;
+	for (uint32_t p = threadIdx.x; p < F; p += THREADS) {
+		wpos[p] = row[p];
+		pend[p] = 0;
+		cnt[p] = 0;
+	}
+	if (threadIdx.x < 2) s_next[threadIdx.x] = 0;
+	const uint64_t g_beg = r.beg >> 2, g_end = (r.end + 3) >> 2;
+	auto tile_is_full = [&](uint64_t g0) { return (g0 << 2) >= r.beg && ((g0 + kGroupsPerTile) << 2) <= r.end; };
+	// stream one tile: chunks of 128 consecutive slots, handed out by a shared counter
+	auto stream = [&](uint32_t par) {
+		const uint32_t tile_n = s_tile_n[par];
+		const uint2 *gl_tab = golim + par * F;
+		while (true) {
+			uint32_t c0 = 0;
+			if (lane_id() == 0) c0 = atomicAdd(&s_next[par], kChunk);
+			c0 = __shfl_sync(kFullMask, c0, 0);
+			if (c0 >= tile_n) break;
+#pragma unroll
+			for (uint32_t j = 0; j < kChunk / 32; ++j) {
+				const uint32_t i = c0 + j * 32 + lane_id();
+				if (i < tile_n) {
+					const uint2 kv = buf[i];
+					const uint32_t d = radix_digit(hash_mul(kv.x, factor), rshift, mask);
+					const uint2 gl = gl_tab[d];
+					const uint32_t pos = gl.x + i;
+					if (pos < gl.y) {
+						keys_out[pos] = kv.x;
+						vals_out[pos] = kv.y;
+					} else {
+						carry[d * kCarry + (pos - gl.y)] = kv;
+					}
+				}
+			}
+		}
+	};
+	uint32_t key[IT], nkey[IT], val[IT], ok = 0, nok = 0;
+	if (g_beg < g_end) {
+		if (tile_is_full(g_beg)) load_col8<THREADS, G, true>(nkey, nok, keys, g_beg, g_end, r.beg, r.end, n);
+		else load_col8<THREADS, G, false>(nkey, nok, keys, g_beg, g_end, r.beg, r.end, n);
+	}
+	__syncthreads();
+	long long clk_t = 0;
+#define SCATTER_MARK(k)                                                              \
+	if (CLK && threadIdx.x == 512) {                                                 \
+		const long long now_ = clock64();                                            \
+		atomicAdd(&g_scatter_clk[k], (unsigned long long)(now_ - clk_t));            \
+		clk_t = now_;                                                                \
+	}
+	if (CLK && threadIdx.x == 512) clk_t = clock64();
+	uint32_t t = 0;
+	for (uint64_t g0 = g_beg; g0 < g_end; g0 += kGroupsPerTile, ++t) {
+		const uint64_t g1 = g0 + kGroupsPerTile;
+		const bool last = g1 >= g_end;
+		const bool full = tile_is_full(g0);
+		const uint32_t par = t & 1;
+#pragma unroll
+		for (int e = 0; e < IT; ++e) key[e] = nkey[e];
+		ok = nok;
+		uint32_t vok;
+		if (full) load_col8<THREADS, G, true>(val, vok, vals, g0, g_end, r.beg, r.end, n);
+		else load_col8<THREADS, G, false>(val, vok, vals, g0, g_end, r.beg, r.end, n);
+		if (!last) {
+			if (tile_is_full(g1)) load_col8<THREADS, G, true>(nkey, nok, keys, g1, g_end, r.beg, r.end, n);
+			else load_col8<THREADS, G, false>(nkey, nok, keys, g1, g_end, r.beg, r.end, n);
+		}
+		// (1) rank
+		uint32_t dr[IT];
+		if (full) {
+#pragma unroll
+			for (int e = 0; e < IT; ++e) {
+				const uint32_t d = radix_digit(hash_mul(key[e], factor), rshift, mask);
+				dr[e] = (d << 16) | atomicAdd(&cnt[d], 1u);
+			}
+		} else {
+#pragma unroll
+			for (int e = 0; e < IT; ++e) {
+				const uint32_t d = radix_digit(hash_mul(key[e], factor), rshift, mask);
+				dr[e] = (ok >> e) & 1u ? (d << 16) | atomicAdd(&cnt[d], 1u) : 0xFFFFFFFFu;
+			}
+		}
+		SCATTER_MARK(0)
+		__syncthreads();                                          // A: ranks of tile t taken; tile t-1 fully placed (C of t-1)
+		SCATTER_MARK(1)
+		// (2) plan of tile t by the first 8 warps (one digit per thread) ...
+		if (threadIdx.x < 256) {
+			const uint32_t p = threadIdx.x;
+			const uint32_t c = p < F ? cnt[p] : 0;
+			const uint32_t incl = warp_inclusive_scan_u32(c);
+			if (lane_id() == 31) warp_totals[p >> 5] = incl;
+			asm volatile("bar.sync 1, 256;" ::: "memory");
+			const uint32_t wt = lane_id() < 8 ? warp_totals[lane_id()] : 0;
+			const uint32_t tincl = warp_inclusive_scan_u32(wt);
+			const uint32_t before = __shfl_sync(kFullMask, tincl - wt, p >> 5);
+			if (p < F) {
+				const uint32_t run = before + incl - c;
+				const uint32_t w = wpos[p], pe = pend[p], endpos = w + pe + c;
+				uint32_t lim = last ? endpos : (endpos & ~(kCarry - 1));
+				const bool flush = lim > w;
+				if (!flush) lim = w;
+				base[p] = run;
+				golim[par * F + p] = make_uint2(w + pe - run, lim);
+				fpos[p] = w;
+				oldp[p] = flush ? pe : 0;
+				wpos[p] = lim;
+				pend[p] = endpos - lim;
+				cnt[p] = 0;
+			}
+			const uint32_t tile_total = __shfl_sync(kFullMask, tincl, 31);
+			if (p == 0) {
+				s_tile_n[par] = tile_total;
+				s_next[par] = 0;
+			}
+		}
+		// ... while everybody (the planners once they are done) streams tile t-1
+		if (t > 0) stream(par ^ 1);
+		SCATTER_MARK(2)
+		__syncthreads();                                          // B: plan of tile t visible, tile t-1 streamed (buf and carry free)
+		SCATTER_MARK(3)
+		// (3) place tile t, flush the carried tuples of every digit that reached a boundary
+		if (full) {
+#pragma unroll
+			for (int e = 0; e < IT; ++e) buf[base[dr[e] >> 16] + (dr[e] & 0xFFFFu)] = make_uint2(key[e], val[e]);
+		} else {
+#pragma unroll
+			for (int e = 0; e < IT; ++e)
+				if (dr[e] != 0xFFFFFFFFu) buf[base[dr[e] >> 16] + (dr[e] & 0xFFFFu)] = make_uint2(key[e], val[e]);
+		}
+		for (uint32_t i = threadIdx.x; i < F * kCarry; i += THREADS) {
+			const uint32_t d = i / kCarry, j = i % kCarry;
+			if (j < oldp[d]) {
+				const uint2 kv = carry[i];
+				const uint32_t dst = fpos[d] + j;
+				keys_out[dst] = kv.x;
+				vals_out[dst] = kv.y;
+			}
+		}
+		SCATTER_MARK(4)
+		__syncthreads();                                          // C: tile t placed, its carried tuples flushed
+		SCATTER_MARK(5)
+	}
+	if (t > 0) stream((t - 1) & 1);                                // the item's last tile (its plan flushed every digit completely)
+#undef SCATTER_MARK
 }
 
 // ------------------------------------------------------------------ peer scatter with TMA bulk stores
@@ -798,6 +992,9 @@ static void scatter_attrs()
 	cudaFuncSetAttribute(k_scatter<1024, 2, false, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
 	cudaFuncSetAttribute(k_scatter<1024, 2, true, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
 	cudaFuncSetAttribute(k_scatter<512, 2, false, false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+	cudaFuncSetAttribute(k_scatter<1024, 1, true, false, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+	cudaFuncSetAttribute(k_scatter_ov<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+	cudaFuncSetAttribute(k_scatter_ov<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
 }
 
 // make_items + histogram + scan: after this a.counts holds every item's start offset per digit
@@ -844,7 +1041,7 @@ int launch_radix_scatter(const RadixPassArgs &a, cudaStream_t s, KernelTimer *t,
 	if (variant < 0) {
 		const char *e = getenv("HJB_SCATTER_VARIANT");
 		variant = e ? atoi(e) : 3;       // measured best on B200: one 1024-thread CTA per SM, 8192-tuple tiles
-		if (variant < 0 || variant > 9) variant = 3;
+		if (variant < 0 || variant > 10) variant = 3;
 	}
 	const int threads = ((variant >= 3 && variant != 9) || peers) ? 1024 : 512;
 	const int items = (!peers && (variant == 5 || variant == 6)) ? 4 : (!peers && variant == 9) ? 16 : 8;
@@ -904,12 +1101,41 @@ int launch_radix_scatter(const RadixPassArgs &a, cudaStream_t s, KernelTimer *t,
 		case 5: HJB_LAUNCH_SCATTER(1024, 2, false, false, no_peers, 1); break;
 		case 6: HJB_LAUNCH_SCATTER(1024, 2, true, false, no_peers, 1); break;
 		case 9: HJB_LAUNCH_SCATTER(512, 2, false, false, no_peers, 4); break;     // two co-resident CTAs, 16 tuples per thread
-		default: HJB_LAUNCH_SCATTER(1024, 1, true, false, no_peers); break;
+		case 10: {
+			// experiment: the stream of tile t-1 overlapped with the plan of tile t (k_scatter_ov); measured 2.81 vs 2.59 ms
+			static int clk = -1;
+			if (clk < 0) clk = getenv("HJB_SCATTER_CLOCKS") ? 1 : 0;
+			if (F > 256) {
+				HJB_LAUNCH_SCATTER(1024, 1, true, false, no_peers);
+				break;
+			}
+			const size_t smem_ov = smem + (size_t)F * 8;               // second golim buffer
+			if (clk) k_scatter_ov<true><<<grid, 1024, smem_ov, s>>>(a.keys, a.vals, a.n, a.np, a.parent_off, a.item_prefix, a.chunk, a.factor,
+			                                                      a.rshift, a.bits, a.counts, a.keys_out, a.vals_out);
+			else k_scatter_ov<false><<<grid, 1024, smem_ov, s>>>(a.keys, a.vals, a.n, a.np, a.parent_off, a.item_prefix, a.chunk, a.factor,
+			                                                     a.rshift, a.bits, a.counts, a.keys_out, a.vals_out);
+			break;
+		}
+		default: {
+			static int clk = -1;
+			if (clk < 0) clk = getenv("HJB_SCATTER_CLOCKS") ? 1 : 0;
+			if (clk) HJB_LAUNCH_SCATTER(1024, 1, true, false, no_peers, 2, true);
+			else HJB_LAUNCH_SCATTER(1024, 1, true, false, no_peers);
+			break;
+		}
 		}
 	}
 #undef HJB_LAUNCH_SCATTER
 	t->stop(s);
 	return 1;
+}
+
+// debug: read (and clear) the scatter phase clocks
+void scatter_phase_clocks(unsigned long long *out8)
+{
+	cudaMemcpyFromSymbol(out8, g_scatter_clk, 64);
+	unsigned long long z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+	cudaMemcpyToSymbol(g_scatter_clk, z, 64);
 }
 
 int launch_radix_pass(const RadixPassArgs &a, cudaStream_t s, int /*sms*/, KernelTimer *t)
