@@ -730,6 +730,172 @@ k_scatter_ov(const uint32_t *__restrict__ keys, const uint32_t *__restrict__ val
 #undef SCATTER_MARK
 }
 
+// ------------------------------------------------------------------ local scatter with fixed digit regions
+//
+// The phase clocks of k_scatter (HJB_SCATTER_CLOCKS: rank 18 %, plan 12 %, place + carry flush 31 %,
+// stream 27 %, barrier waits 11 % of a tile's ~10750 cycles) say the tile is a chain of phases each
+// waiting on shared memory.  Here the digit-grouped tile is not packed: digit d owns the slots
+// [d REG, (d+1) REG) with REG = 2 TILE / F, twice its expected share, so
+//   * the rank atomic gives the tuple's slot at once and the tuple is stored there in the same step
+//     (no second look-up of a digit base, no separate placement phase, payloads prefetched like keys);
+//   * the plan needs no prefix scan over the digits: every digit's thread decides alone how far its run
+//     may be flushed;
+//   * a warp streams whole digit regions (the digit is the loop index, not re-hashed from the key).
+// A digit with more than REG tuples in a tile (skewed keys) keeps the excess in registers and writes
+// it to its final position directly after the plan -- slower, never wrong.
+// dynamic shared memory: cnt scnt fpos oldp wpos pend [F] | golim[F] (uint2) | buf[2 TILE] (uint2) | carry[2][F*8] (uint2)
+template <bool CLK>
+__global__ void __launch_bounds__(1024, 1)
+k_scatter_fx(const uint32_t *__restrict__ keys, const uint32_t *__restrict__ vals, uint64_t n, uint32_t np,
+             const uint32_t *__restrict__ parent_off, const uint32_t *__restrict__ item_prefix, uint32_t chunk,
+             uint32_t factor, int rshift, int bits, const uint32_t *__restrict__ offsets,
+             uint32_t *__restrict__ keys_out, uint32_t *__restrict__ vals_out)
+{
+	constexpr int THREADS = 1024, G = 2, IT = 4 * G;
+	constexpr uint32_t kCarry = kLocalCarry, TILE = THREADS * IT, kGroupsPerTile = TILE / 4;
+	extern __shared__ __align__(16) uint32_t s_mem[];
+	const uint32_t F = 1u << bits, mask = F - 1;
+	const int reg_shift = 14 - bits;                            // REG = 2 * 8192 / F slots per digit
+	const uint32_t REG = 1u << reg_shift;
+	uint32_t *cnt = s_mem, *scnt = cnt + F, *fpos = scnt + F, *oldp = fpos + F, *wpos = oldp + F, *pend = wpos + F;
+	uint2 *golim = reinterpret_cast<uint2 *>(pend + F);         // x: global position of the region's slot 0, y: flush limit
+	uint2 *buf = golim + F;
+	uint2 *carry = buf + 2 * TILE;                              // [2][F * kCarry]
+	ItemRange r;
+	if (!locate_item(item_prefix, np, parent_off, n, chunk, blockIdx.x, &r)) return;
+	const uint32_t *row = offsets + (size_t)blockIdx.x * F;
+	for (uint32_t p = threadIdx.x; p < F; p += THREADS) {
+		wpos[p] = row[p];
+		pend[p] = 0;
+		cnt[p] = 0;
+	}
+	const uint64_t g_beg = r.beg >> 2, g_end = (r.end + 3) >> 2;
+	auto tile_is_full = [&](uint64_t g0) { return (g0 << 2) >= r.beg && ((g0 + kGroupsPerTile) << 2) <= r.end; };
+	uint32_t key[IT], val[IT], nkey[IT], nval[IT], ok = 0, nok = 0, vok;
+	if (g_beg < g_end) {
+		if (tile_is_full(g_beg)) {
+			load_col8<THREADS, G, true>(nkey, nok, keys, g_beg, g_end, r.beg, r.end, n);
+			load_col8<THREADS, G, true>(nval, vok, vals, g_beg, g_end, r.beg, r.end, n);
+		} else {
+			load_col8<THREADS, G, false>(nkey, nok, keys, g_beg, g_end, r.beg, r.end, n);
+			load_col8<THREADS, G, false>(nval, vok, vals, g_beg, g_end, r.beg, r.end, n);
+		}
+	}
+	__syncthreads();
+	long long clk_t = 0;
+#define SCATTER_MARK(k)                                                              \
+	if (CLK && threadIdx.x == 512) {                                                 \
+		const long long now_ = clock64();                                            \
+		atomicAdd(&g_scatter_clk[k], (unsigned long long)(now_ - clk_t));            \
+		clk_t = now_;                                                                \
+	}
+	if (CLK && threadIdx.x == 512) clk_t = clock64();
+	uint32_t t = 0;
+	for (uint64_t g0 = g_beg; g0 < g_end; g0 += kGroupsPerTile, ++t) {
+		const uint64_t g1 = g0 + kGroupsPerTile;
+		const bool last = g1 >= g_end;
+		const bool full = tile_is_full(g0);
+		uint2 *const oc = carry + (t & 1) * F * kCarry, *const nc = carry + ((t & 1) ^ 1) * F * kCarry;   // carried in / out
+#pragma unroll
+		for (int e = 0; e < IT; ++e) {
+			key[e] = nkey[e];
+			val[e] = nval[e];
+		}
+		ok = nok;
+		if (!last) {
+			if (tile_is_full(g1)) {
+				load_col8<THREADS, G, true>(nkey, nok, keys, g1, g_end, r.beg, r.end, n);
+				load_col8<THREADS, G, true>(nval, vok, vals, g1, g_end, r.beg, r.end, n);
+			} else {
+				load_col8<THREADS, G, false>(nkey, nok, keys, g1, g_end, r.beg, r.end, n);
+				load_col8<THREADS, G, false>(nval, vok, vals, g1, g_end, r.beg, r.end, n);
+			}
+		}
+		// (1) rank and place in one step; a tuple beyond its digit's region stays in registers (excess != 0)
+		uint32_t dr[IT], excess = 0;
+#pragma unroll
+		for (int e = 0; e < IT; ++e) {
+			if (full || ((ok >> e) & 1u)) {
+				const uint32_t d = radix_digit(hash_mul(key[e], factor), rshift, mask);
+				const uint32_t rk_ = atomicAdd(&cnt[d], 1u);
+				dr[e] = (d << 16) | rk_;
+				if (rk_ < REG) buf[(d << reg_shift) + rk_] = make_uint2(key[e], val[e]);
+				else excess |= 1u << e;
+			}
+		}
+		SCATTER_MARK(0)
+		__syncthreads();                                          // A
+		SCATTER_MARK(1)
+		// (2) plan: every digit on its own
+		for (uint32_t p = threadIdx.x; p < F; p += THREADS) {
+			const uint32_t c = cnt[p], w = wpos[p], pe = pend[p], endpos = w + pe + c;
+			uint32_t lim = last ? endpos : (endpos & ~(kCarry - 1));
+			const bool flush = lim > w;
+			if (!flush) lim = w;
+			golim[p] = make_uint2(w + pe, lim);
+			scnt[p] = min(c, REG);
+			fpos[p] = w;
+			oldp[p] = flush ? pe : 0x80000000u | pe;              // top bit: the carried tuples stay carried
+			wpos[p] = lim;
+			pend[p] = endpos - lim;
+			cnt[p] = 0;
+		}
+		SCATTER_MARK(2)
+		__syncthreads();                                          // B
+		SCATTER_MARK(3)
+		// (3a) the excess of over-full digits, straight from registers
+		if (excess) {
+#pragma unroll
+			for (int e = 0; e < IT; ++e)
+				if ((excess >> e) & 1u) {
+					const uint32_t d = dr[e] >> 16;
+					const uint2 gl = golim[d];
+					const uint32_t pos = gl.x + (dr[e] & 0xFFFFu);
+					if (pos < gl.y) {
+						keys_out[pos] = key[e];
+						vals_out[pos] = val[e];
+					} else {
+						nc[d * kCarry + (pos - gl.y)] = make_uint2(key[e], val[e]);
+					}
+				}
+		}
+		// (3b) the tuples carried in: to their place if the digit flushes, else on to the next tile
+		for (uint32_t i = threadIdx.x; i < F * kCarry; i += THREADS) {
+			const uint32_t d = i / kCarry, j = i % kCarry, op = oldp[d];
+			if (j < (op & 0x7FFFFFFFu)) {
+				const uint2 kv = oc[i];
+				if (op & 0x80000000u) {
+					nc[i] = kv;
+				} else {
+					const uint32_t dst = fpos[d] + j;
+					keys_out[dst] = kv.x;
+					vals_out[dst] = kv.y;
+				}
+			}
+		}
+		// (3c) stream the regions: warp w takes digits w, w + 32, ...; a region's slots are consecutive positions
+		for (uint32_t d = threadIdx.x >> 5; d < F; d += THREADS / 32) {
+			const uint32_t c = scnt[d];
+			const uint2 gl = golim[d];
+			const uint2 *reg = buf + (d << reg_shift);
+			for (uint32_t j = lane_id(); j < c; j += 32) {
+				const uint2 kv = reg[j];
+				const uint32_t pos = gl.x + j;
+				if (pos < gl.y) {
+					keys_out[pos] = kv.x;
+					vals_out[pos] = kv.y;
+				} else {
+					nc[d * kCarry + (pos - gl.y)] = kv;
+				}
+			}
+		}
+		SCATTER_MARK(4)
+		__syncthreads();                                          // C: regions and the old carry buffer are free again
+		SCATTER_MARK(5)
+	}
+#undef SCATTER_MARK
+}
+
 // ------------------------------------------------------------------ peer scatter with TMA bulk stores
 //
 // The GPU-assign pass of CPRA has a small fan-out (one digit per GPU), so a digit's run in a tile
@@ -995,6 +1161,8 @@ static void scatter_attrs()
 	cudaFuncSetAttribute(k_scatter<1024, 1, true, false, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
 	cudaFuncSetAttribute(k_scatter_ov<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
 	cudaFuncSetAttribute(k_scatter_ov<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+	cudaFuncSetAttribute(k_scatter_fx<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 256 * 32 + 2 * 8192 * 8 + 2 * 256 * 8 * 8);
+	cudaFuncSetAttribute(k_scatter_fx<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 256 * 32 + 2 * 8192 * 8 + 2 * 256 * 8 * 8);
 }
 
 // make_items + histogram + scan: after this a.counts holds every item's start offset per digit
@@ -1041,7 +1209,7 @@ int launch_radix_scatter(const RadixPassArgs &a, cudaStream_t s, KernelTimer *t,
 	if (variant < 0) {
 		const char *e = getenv("HJB_SCATTER_VARIANT");
 		variant = e ? atoi(e) : 3;       // measured best on B200: one 1024-thread CTA per SM, 8192-tuple tiles
-		if (variant < 0 || variant > 10) variant = 3;
+		if (variant < 0 || variant > 11) variant = 3;
 	}
 	const int threads = ((variant >= 3 && variant != 9) || peers) ? 1024 : 512;
 	const int items = (!peers && (variant == 5 || variant == 6)) ? 4 : (!peers && variant == 9) ? 16 : 8;
@@ -1113,6 +1281,21 @@ int launch_radix_scatter(const RadixPassArgs &a, cudaStream_t s, KernelTimer *t,
 			if (clk) k_scatter_ov<true><<<grid, 1024, smem_ov, s>>>(a.keys, a.vals, a.n, a.np, a.parent_off, a.item_prefix, a.chunk, a.factor,
 			                                                      a.rshift, a.bits, a.counts, a.keys_out, a.vals_out);
 			else k_scatter_ov<false><<<grid, 1024, smem_ov, s>>>(a.keys, a.vals, a.n, a.np, a.parent_off, a.item_prefix, a.chunk, a.factor,
+			                                                     a.rshift, a.bits, a.counts, a.keys_out, a.vals_out);
+			break;
+		}
+		case 11: {
+			// fixed digit regions (k_scatter_fx): fan-outs 32..256
+			static int clk = -1;
+			if (clk < 0) clk = getenv("HJB_SCATTER_CLOCKS") ? 1 : 0;
+			if (F > 256 || F < 32) {
+				HJB_LAUNCH_SCATTER(1024, 1, true, false, no_peers);
+				break;
+			}
+			const size_t smem_fx = (size_t)F * 32 + 2 * 8192 * 8 + 2 * (size_t)F * kLocalCarry * 8;
+			if (clk) k_scatter_fx<true><<<grid, 1024, smem_fx, s>>>(a.keys, a.vals, a.n, a.np, a.parent_off, a.item_prefix, a.chunk, a.factor,
+			                                                      a.rshift, a.bits, a.counts, a.keys_out, a.vals_out);
+			else k_scatter_fx<false><<<grid, 1024, smem_fx, s>>>(a.keys, a.vals, a.n, a.np, a.parent_off, a.item_prefix, a.chunk, a.factor,
 			                                                     a.rshift, a.bits, a.counts, a.keys_out, a.vals_out);
 			break;
 		}
