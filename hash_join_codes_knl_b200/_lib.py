@@ -66,6 +66,13 @@ SYMBOLS = {
     "hjb_ipc_open": (C.c_int, [C.c_void_p, C.POINTER(C.c_ubyte), C.POINTER(C.c_void_p)]),
     "hjb_ipc_close": (C.c_int, [C.c_void_p, C.c_void_p]),
     "hjb_cpra_count": (C.c_int, [C.c_void_p, C.POINTER(Rel), C.POINTER(Rel), C.c_int, C.POINTER(Opts), u64p, u64p]),
+    "hjb_cpra_scatter_rel": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), u64p,
+                                       C.POINTER(C.c_float)]),
+    "hjb_cpra_stage_rel": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
+    "hjb_cpra_send_staged": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), u64p]),
+    "hjb_cpra_send_wait": (C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
+    "hjb_cpra_join_begin": (C.c_int, [C.c_void_p, C.POINTER(Rel), C.c_uint64, C.c_int, C.c_int, C.POINTER(Opts)]),
+    "hjb_cpra_join_finish": (C.c_int, [C.c_void_p, C.POINTER(Rel), C.POINTER(Opts), C.POINTER(Result)]),
     "hjb_cpra_scatter_peer": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
                                         C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), u64p, u64p, C.POINTER(C.c_float)]),
     "hjb_hash_factor": (C.c_uint32, [C.c_uint32, C.c_int]),

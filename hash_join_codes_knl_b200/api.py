@@ -249,6 +249,49 @@ class Engine:
         self._pending_keep = None
         return float(ms.value)
 
+    # ---- the same with the probe side's exchange overlapped with the build side's local partitioning
+    def cpra_scatter_rel(self, rel, ngpus, peer_keys, peer_vals, base):
+        pk = (C.c_void_p * ngpus)(*[C.c_void_p(p) for p in peer_keys])
+        pv = (C.c_void_p * ngpus)(*[C.c_void_p(p) for p in peer_vals])
+        b = (C.c_uint64 * ngpus)(*[int(x) for x in base])
+        ms = C.c_float()
+        self._check(self._lib.hjb_cpra_scatter_rel(self._ctx, int(rel), int(ngpus), pk, pv, b, C.byref(ms)), "hjb_cpra_scatter_rel")
+        return float(ms.value)
+
+    def cpra_stage_rel(self, rel, ngpus):
+        self._check(self._lib.hjb_cpra_stage_rel(self._ctx, int(rel), int(ngpus)), "hjb_cpra_stage_rel")
+
+    def cpra_send_staged(self, rel, ngpus, me, peer_keys, peer_vals, base):
+        pk = (C.c_void_p * ngpus)(*[C.c_void_p(p) for p in peer_keys])
+        pv = (C.c_void_p * ngpus)(*[C.c_void_p(p) for p in peer_vals])
+        b = (C.c_uint64 * ngpus)(*[int(x) for x in base])
+        self._check(self._lib.hjb_cpra_send_staged(self._ctx, int(rel), int(ngpus), int(me), pk, pv, b), "hjb_cpra_send_staged")
+
+    def cpra_send_wait(self):
+        ms = C.c_float()
+        self._check(self._lib.hjb_cpra_send_wait(self._ctx, C.byref(ms)), "hjb_cpra_send_wait")
+        self._pending_keep = None
+        return float(ms.value)
+
+    def cpra_join_begin(self, inner_recv, s_tuples, gpu, ngpus, **opts):
+        R, _, on_dev, keep = self._rels(inner_recv, inner_recv)
+        if not on_dev:
+            raise HjbError("cpra_join_begin takes device columns")
+        o = self._opts(**opts)
+        self._join_keep = keep
+        self._check(self._lib.hjb_cpra_join_begin(self._ctx, C.byref(R), int(s_tuples), int(gpu), int(ngpus), C.byref(o)),
+                    "hjb_cpra_join_begin")
+
+    def cpra_join_finish(self, outer_recv, **opts):
+        S, _, on_dev, keep = self._rels(outer_recv, outer_recv)
+        if not on_dev:
+            raise HjbError("cpra_join_finish takes device columns")
+        res = Result()
+        o = self._opts(**opts)
+        self._check(self._lib.hjb_cpra_join_finish(self._ctx, C.byref(S), C.byref(o), C.byref(res)), "hjb_cpra_join_finish")
+        self._join_keep = None
+        return JoinResult(res, self)
+
     def device_view(self, ptr, n):
         """int32 CUDA tensor aliasing n elements of library-owned device memory."""
         import torch

@@ -150,3 +150,38 @@ def cpra_join_fused(engine, inner_chunk, outer_chunk, state, group=None, **opts)
     return {"count": count, "sum_key": sum_key, "sum_outer": sum_outer, "sum_inner": sum_inner, "local": local,
             "split_ms": scatter_ms, "exchange_ms": t0.elapsed_time(t1), "join_ms": float(local.seconds) * 1e3,
             "recv_tuples": (r_recv[rank], s_recv[rank])}
+
+
+def cpra_join_overlap(engine, inner_chunk, outer_chunk, state, group=None, **opts):
+    """CPRA with the probe side's exchange overlapped with the build side's local partitioning:
+    R travels through the fused scatter; S is split locally and then moved by the copy engines
+    while the SMs partition the R tuples that have already arrived.  Same result dict as
+    cpra_join_fused (split_ms: fused scatter of R; exchange_ms: the copies of S)."""
+    world, rank = state.world, state.rank
+    dev = torch.device(f"cuda:{engine.device}")
+    r_cnt, s_cnt = engine.cpra_count(inner_chunk, outer_chunk, world, **opts)
+    mine = torch.tensor(r_cnt + s_cnt, dtype=torch.int64, device=dev)
+    allc = torch.empty(world * 2 * world, dtype=torch.int64, device=dev)
+    dist.all_gather_into_tensor(allc, mine, group=group)
+    C = allc.view(world, 2 * world).cpu().tolist()
+    r_recv = [sum(C[s][g] for s in range(world)) for g in range(world)]
+    s_recv = [sum(C[s][world + g] for s in range(world)) for g in range(world)]
+    state.ensure(max(r_recv), max(s_recv))
+    r_base = [sum(C[s][g] for s in range(rank)) for g in range(world)]
+    s_base = [sum(C[s][world + g] for s in range(rank)) for g in range(world)]
+    scatter_ms = engine.cpra_scatter_rel(0, world, state.peers[0], state.peers[1], r_base)
+    engine.cpra_stage_rel(1, world)                          # asynchronous: runs while the ranks meet at the barrier
+    dist.barrier(group=group)                                # every R tuple has landed
+    engine.cpra_send_staged(1, world, rank, state.peers[2], state.peers[3], s_base)
+    own = state.own["ptrs"]
+    rk, rv = engine.device_view(own[0], r_recv[rank]), engine.device_view(own[1], r_recv[rank])
+    engine.cpra_join_begin((rk, rv), s_recv[rank], rank, world, **opts)
+    copy_ms = engine.cpra_send_wait()
+    dist.barrier(group=group)                                # every S tuple has landed
+    sk, sv = engine.device_view(own[2], s_recv[rank]), engine.device_view(own[3], s_recv[rank])
+    local = engine.cpra_join_finish((sk, sv), **opts)
+    count, sum_key, sum_outer, sum_inner = reduce_checks(local.count, local.sum_key, local.sum_outer,
+                                                         local.sum_inner, dev, group)
+    return {"count": count, "sum_key": sum_key, "sum_outer": sum_outer, "sum_inner": sum_inner, "local": local,
+            "split_ms": scatter_ms, "exchange_ms": copy_ms, "join_ms": float(local.seconds) * 1e3,
+            "recv_tuples": (r_recv[rank], s_recv[rank])}

@@ -31,6 +31,8 @@ struct PhjGraphKey {
 	int consumed, materialize, radix_bits[4];
 };
 
+struct PhjState;
+
 struct hjb_ctx {
 	int device, sms;
 	cudaStream_t stream;
@@ -64,6 +66,12 @@ struct hjb_ctx {
 	KernelTimer timer;        // per-kernel times of the last join (hjb_set_profiling)
 	char *recv_buf[4];        // CPRA fused exchange: receive columns r_keys r_vals s_keys s_vals
 	uint64_t recv_cap[2];
+	char *stage_buf;          // CPRA overlapped exchange: locally split probe side waiting for its copy-engine transfer
+	size_t stage_bytes;
+	uint32_t *stage_k, *stage_v;
+	bool cj_active;           // hjb_cpra_join_begin -> hjb_cpra_join_finish
+	uint32_t cj_launches;
+	struct PhjState *cj_state;
 	RadixPassArgs pending[2]; // hjb_cpra_count -> hjb_cpra_scatter_peer
 	uint32_t pending_off[2][65];
 	int pending_gpus;
@@ -154,6 +162,8 @@ extern "C" int hjb_destroy(hjb_ctx *ctx)
 	cudaFree(ctx->out_cols);
 	cudaFree(ctx->in_buf);
 	cudaFree(ctx->split_buf);
+	cudaFree(ctx->stage_buf);
+	free(ctx->cj_state);
 	for (int i = 0; i < 4; ++i) cudaFree(ctx->recv_buf[i]);
 	cudaFree(ctx->d_scalars);
 	cudaFreeHost(ctx->h_scalars);
@@ -1145,6 +1155,31 @@ extern "C" int hjb_cpra_count(hjb_ctx *ctx, const hjb_rel *R, const hjb_rel *S, 
 	return HJB_OK;
 }
 
+// the fused scatter of one counted relation into the owners' columns (asynchronous)
+static int cpra_scatter_one(hjb_ctx *ctx, int r, int ngpus, void *const *pk, void *const *pv, const uint64_t *base,
+                            uint32_t *launches)
+{
+	RadixPassArgs &a = ctx->pending[r];
+	if (a.n == 0) return HJB_OK;
+	PeerTable t;
+	memset(&t, 0, sizeof t);
+	for (int g = 0; g < ngpus; ++g) {
+		// the scan's positions start at pending_off[g] for owner g: shift the column so that they land at base[g]
+		const int64_t shift = (int64_t)base[g] - (int64_t)ctx->pending_off[r][g];
+		// bias: the kernel counts positions as pending_off + bias, congruent to the physical row modulo the
+		// write-combining granule, so that its flush boundaries are line boundaries in the owner's buffer
+		const int64_t bias = ((shift % (int64_t)kPeerCarry) + kPeerCarry) % kPeerCarry;
+		t.bias[g] = (uint32_t)bias;
+		t.k[g] = (uint32_t *)pk[g] + (shift - bias);
+		t.v[g] = (uint32_t *)pv[g] + (shift - bias);
+	}
+	static int env_ctas = -1;       // experiment knob: HJB_PEER_CTAS limits the peer scatter's grid
+	if (env_ctas < 0) env_ctas = getenv("HJB_PEER_CTAS") ? atoi(getenv("HJB_PEER_CTAS")) : 0;
+	a.peer_ctas = (uint32_t)env_ctas;
+	*launches += launch_radix_scatter(a, ctx->stream, &ctx->timer, &t);
+	return HJB_OK;
+}
+
 extern "C" int hjb_cpra_scatter_peer(hjb_ctx *ctx, int ngpus, void *const *peer_r_keys, void *const *peer_r_vals,
                                      void *const *peer_s_keys, void *const *peer_s_vals, const uint64_t *r_base,
                                      const uint64_t *s_base, float *ms)
@@ -1153,32 +1188,11 @@ extern "C" int hjb_cpra_scatter_peer(hjb_ctx *ctx, int ngpus, void *const *peer_
 	if (ngpus != ctx->pending_gpus || ngpus < 2) return fail(ctx, HJB_E_INVALID, "hjb_cpra_count must precede with the same ngpus");
 	CK(cudaSetDevice(ctx->device));
 	cudaStream_t s = ctx->stream;
-	void *const *pk[2] = {peer_r_keys, peer_s_keys}, *const *pv[2] = {peer_r_vals, peer_s_vals};
-	const uint64_t *base[2] = {r_base, s_base};
 	uint32_t launches = 0;
+	int rc;
 	CK(cudaEventRecord(ctx->ev[6], s));
-	for (int r = 0; r < 2; ++r) {
-		RadixPassArgs &a = ctx->pending[r];
-		if (a.n == 0) continue;
-		PeerTable t;
-		memset(&t, 0, sizeof t);
-		for (int g = 0; g < ngpus; ++g) {
-			// the scan's positions start at pending_off[g] for owner g: shift the column so that they land at base[g]
-			const int64_t shift = (int64_t)base[r][g] - (int64_t)ctx->pending_off[r][g];
-			// bias: the kernel counts positions as pending_off + bias, congruent to the physical row modulo the
-			// write-combining granule, so that its flush boundaries are line boundaries in the owner's buffer
-			const int64_t bias = ((shift % (int64_t)kPeerCarry) + kPeerCarry) % kPeerCarry;
-			t.bias[g] = (uint32_t)bias;
-			t.k[g] = (uint32_t *)pk[r][g] + (shift - bias);
-			t.v[g] = (uint32_t *)pv[r][g] + (shift - bias);
-		}
-		{
-			static int env_ctas = -1;       // experiment knob: HJB_PEER_CTAS limits the peer scatter's grid
-			if (env_ctas < 0) env_ctas = getenv("HJB_PEER_CTAS") ? atoi(getenv("HJB_PEER_CTAS")) : 0;
-			a.peer_ctas = (uint32_t)env_ctas;
-		}
-		launches += launch_radix_scatter(a, s, &ctx->timer, &t);
-	}
+	if ((rc = cpra_scatter_one(ctx, 0, ngpus, peer_r_keys, peer_r_vals, r_base, &launches))) return rc;
+	if ((rc = cpra_scatter_one(ctx, 1, ngpus, peer_s_keys, peer_s_vals, s_base, &launches))) return rc;
 	CK(cudaEventRecord(ctx->ev[7], s));
 	CK(cudaStreamSynchronize(s));            // the owners may read once every sender has passed this point
 	CK(cudaGetLastError());
@@ -1189,6 +1203,86 @@ extern "C" int hjb_cpra_scatter_peer(hjb_ctx *ctx, int ngpus, void *const *peer_
 	return HJB_OK;
 }
 
+extern "C" int hjb_cpra_scatter_rel(hjb_ctx *ctx, int rel, int ngpus, void *const *peer_keys, void *const *peer_vals,
+                                    const uint64_t *base, float *ms)
+{
+	if (!ctx || !peer_keys || !peer_vals || !base || rel < 0 || rel > 1) return HJB_E_INVALID;
+	if (ngpus != ctx->pending_gpus || ngpus < 2) return fail(ctx, HJB_E_INVALID, "hjb_cpra_count must precede with the same ngpus");
+	CK(cudaSetDevice(ctx->device));
+	cudaStream_t s = ctx->stream;
+	uint32_t launches = 0;
+	int rc;
+	CK(cudaEventRecord(ctx->ev[6], s));
+	if ((rc = cpra_scatter_one(ctx, rel, ngpus, peer_keys, peer_vals, base, &launches))) return rc;
+	CK(cudaEventRecord(ctx->ev[7], s));
+	CK(cudaStreamSynchronize(s));
+	CK(cudaGetLastError());
+	timer_collect(ctx);
+	if (ms) CK(cudaEventElapsedTime(ms, ctx->ev[6], ctx->ev[7]));
+	ctx->launches += launches;
+	return HJB_OK;
+}
+
+extern "C" int hjb_cpra_stage_rel(hjb_ctx *ctx, int rel, int ngpus)
+{
+	if (!ctx || rel < 0 || rel > 1) return HJB_E_INVALID;
+	if (ngpus != ctx->pending_gpus || ngpus < 2) return fail(ctx, HJB_E_INVALID, "hjb_cpra_count must precede with the same ngpus");
+	CK(cudaSetDevice(ctx->device));
+	int rc;
+	if ((rc = pipe_setup(ctx))) return rc;
+	RadixPassArgs &a = ctx->pending[rel];
+	const size_t col = pad256(a.n * 4);
+	if ((rc = grow_device(ctx, &ctx->stage_buf, &ctx->stage_bytes, 2 * col + 256))) return rc;
+	ctx->stage_k = (uint32_t *)ctx->stage_buf;
+	ctx->stage_v = (uint32_t *)(ctx->stage_buf + col);
+	uint32_t launches = 0;
+	if (a.n) {
+		a.keys_out = ctx->stage_k;
+		a.vals_out = ctx->stage_v;
+		launches += launch_radix_scatter(a, ctx->stream, &ctx->timer, nullptr);
+	}
+	CK(cudaEventRecord(ctx->pipe_ev[1][kMaxHostSlices], ctx->stream));     // the pieces are ready
+	CK(cudaGetLastError());
+	ctx->launches += launches;
+	return HJB_OK;
+}
+
+extern "C" int hjb_cpra_send_staged(hjb_ctx *ctx, int rel, int ngpus, int self, void *const *peer_keys,
+                                    void *const *peer_vals, const uint64_t *base)
+{
+	if (!ctx || !peer_keys || !peer_vals || !base || rel < 0 || rel > 1 || self < 0 || self >= ngpus) return HJB_E_INVALID;
+	if (ngpus != ctx->pending_gpus || !ctx->pipe_ready || !ctx->stage_k)
+		return fail(ctx, HJB_E_INVALID, "hjb_cpra_stage_rel must precede");
+	CK(cudaSetDevice(ctx->device));
+	// two copy streams (keys, payloads) so that two copy engines work at once; this GPU's own piece goes last
+	cudaStream_t ck = ctx->pipe_out, cv = ctx->pipe_in;
+	CK(cudaStreamWaitEvent(ck, ctx->pipe_ev[1][kMaxHostSlices], 0));
+	CK(cudaStreamWaitEvent(cv, ctx->pipe_ev[1][kMaxHostSlices], 0));
+	CK(cudaEventRecord(ctx->ev[10], ck));
+	for (int i = 1; i <= ngpus; ++i) {                        // start with the neighbour: the senders spread over the receivers
+		const int g = (self + i) % ngpus;
+		const uint64_t beg = ctx->pending_off[rel][g], cnt = ctx->pending_off[rel][g + 1] - beg;
+		if (!cnt) continue;
+		CK(cudaMemcpyAsync((uint32_t *)peer_keys[g] + base[g], ctx->stage_k + beg, cnt * 4, cudaMemcpyDeviceToDevice, ck));
+		CK(cudaMemcpyAsync((uint32_t *)peer_vals[g] + base[g], ctx->stage_v + beg, cnt * 4, cudaMemcpyDeviceToDevice, cv));
+	}
+	CK(cudaEventRecord(ctx->pipe_ev[0][kMaxHostSlices], cv));
+	CK(cudaStreamWaitEvent(ck, ctx->pipe_ev[0][kMaxHostSlices], 0));      // ev[11] on ck marks the end of both streams' copies
+	CK(cudaEventRecord(ctx->ev[11], ck));
+	return HJB_OK;
+}
+
+extern "C" int hjb_cpra_send_wait(hjb_ctx *ctx, float *ms)
+{
+	if (!ctx || !ctx->pipe_ready) return HJB_E_INVALID;
+	CK(cudaSetDevice(ctx->device));
+	CK(cudaStreamSynchronize(ctx->pipe_out));        // ordered after the payload stream's copies as well
+	CK(cudaGetLastError());
+	if (ms) CK(cudaEventElapsedTime(ms, ctx->ev[10], ctx->ev[11]));
+	ctx->pending_gpus = 0;
+	return HJB_OK;
+}
+
 extern "C" int hjb_cpra_join_local(hjb_ctx *ctx, const hjb_rel *R, const hjb_rel *S, int gpu, int ngpus,
                                    const hjb_opts *opts, hjb_result *out)
 {
@@ -1196,6 +1290,82 @@ extern "C" int hjb_cpra_join_local(hjb_ctx *ctx, const hjb_rel *R, const hjb_rel
 	const int gbits = log2_exact(ngpus);
 	if (gbits < 0 || ngpus > 64 || gpu < 0 || gpu >= ngpus) return fail(ctx, HJB_E_INVALID, "bad gpu / ngpus");
 	return phj_device(ctx, R, S, opts ? opts : &kDefaultOpts, gbits, out, (uint32_t)gpu);
+}
+
+extern "C" int hjb_cpra_join_begin(hjb_ctx *ctx, const hjb_rel *R, uint64_t s_tuples, int gpu, int ngpus, const hjb_opts *opts)
+{
+	if (!ctx || !R) return HJB_E_INVALID;
+	const hjb_opts *o = opts ? opts : &kDefaultOpts;
+	const int gbits = log2_exact(ngpus);
+	if (gbits < 0 || ngpus > 64 || gpu < 0 || gpu >= ngpus) return fail(ctx, HJB_E_INVALID, "bad gpu / ngpus");
+	int rc;
+	if ((rc = check_rel(ctx, R, true))) return rc;
+	if (s_tuples > 0xFFFFFFFFull) return fail(ctx, HJB_E_INVALID, "more than 2^32-1 tuples per relation per GPU");
+	CK(cudaSetDevice(ctx->device));
+	ctx->cj_active = false;
+	ctx->cj_launches = 0;
+	if (!ctx->cj_state && !(ctx->cj_state = (PhjState *)calloc(1, sizeof(PhjState)))) return HJB_E_NOMEM;
+	if (R->tuples == 0 || s_tuples == 0) {          // nothing to join: finish returns the empty result
+		ctx->cj_active = true;
+		ctx->cj_state->P = 0;
+		return HJB_OK;
+	}
+	PhjState &st = *ctx->cj_state;
+	if ((rc = phj_setup(ctx, R->tuples, s_tuples, s_tuples, o, gbits, (uint32_t)gpu, &st))) return rc;
+	cudaStream_t s = ctx->stream;
+	CK(cudaEventRecord(ctx->ev[0], s));
+	CK(cudaMemsetAsync(ctx->d_scalars, 0, 16 * 8, s));
+	if ((rc = phj_partition_side(ctx, &st, R, true, &ctx->cj_launches))) return rc;
+	CK(cudaEventRecord(ctx->ev[1], s));
+	CK(cudaGetLastError());
+	ctx->cj_active = true;
+	return HJB_OK;
+}
+
+extern "C" int hjb_cpra_join_finish(hjb_ctx *ctx, const hjb_rel *S, const hjb_opts *opts, hjb_result *out)
+{
+	if (!ctx || !S || !out) return HJB_E_INVALID;
+	const hjb_opts *o = opts ? opts : &kDefaultOpts;
+	if (!ctx->cj_active) return fail(ctx, HJB_E_INVALID, "hjb_cpra_join_begin must precede");
+	ctx->cj_active = false;
+	int rc;
+	if ((rc = check_rel(ctx, S, true))) return rc;
+	zero_result(out);
+	CK(cudaSetDevice(ctx->device));
+	PhjState &st = *ctx->cj_state;
+	if (st.P == 0 || S->tuples == 0) {
+		CK(cudaStreamSynchronize(ctx->stream));
+		timer_collect(ctx);
+		return HJB_OK;
+	}
+	cudaStream_t s = ctx->stream;
+	uint32_t launches = ctx->cj_launches;
+	if ((rc = phj_partition_side(ctx, &st, S, false, &launches))) return rc;
+	CK(cudaEventRecord(ctx->ev[2], s));
+	for (int attempt = 0; attempt < 2; ++attempt) {
+		if ((rc = phj_launch_join(ctx, &st, o, &launches))) return rc;
+		CK(cudaEventRecord(ctx->ev[3], s));
+		CK(cudaGetLastError());
+		if ((rc = read_scalars(ctx, out))) return rc;
+		if (ctx->h_scalars[7]) return fail(ctx, HJB_E_INVALID, "hjb_cpra_join_finish: a tuple does not hash into this owner's range");
+		if (!o->materialize || out->count <= ctx->out_cap) break;
+		if (attempt == 1) return fail(ctx, HJB_E_CUDA, "result overflow after regrow");
+		if ((rc = grow_out(ctx, out->count))) return rc;
+		CK(cudaMemsetAsync(ctx->d_scalars, 0, 16 * 8, s));
+	}
+	float ms = 0;
+	CK(cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[3]));
+	out->seconds = ms * 1e-3;                               // from the first build-side kernel: includes the wait for the probe side
+	if (st.plan.npass) {
+		CK(cudaEventElapsedTime(&out->phase_ms[0], ctx->ev[0], ctx->ev[1]));
+		CK(cudaEventElapsedTime(&out->phase_ms[1], ctx->ev[1], ctx->ev[2]));
+	}
+	CK(cudaEventElapsedTime(&out->phase_ms[4], ctx->ev[2], ctx->ev[3]));
+	out->kernel_launches = launches;
+	out->partitions = st.P;
+	set_rows(ctx, out, o->materialize);
+	ctx->launches += launches;
+	return HJB_OK;
 }
 
 // ------------------------------------------------------------------ kernel-level entry points

@@ -157,6 +157,27 @@ int hjb_cpra_scatter_peer(hjb_ctx *ctx, int ngpus, void *const *peer_r_keys, voi
                           void *const *peer_s_keys, void *const *peer_s_vals, const uint64_t *r_base,
                           const uint64_t *s_base, float *ms);
 
+/* ---- the same, with the exchange of the probe side overlapped with the local partitioning of the
+ * build side: R goes through the fused scatter, S is split locally into a send buffer and travels by
+ * copy engine (no SM involved) while the SMs already partition the R tuples that have arrived.
+ *   hjb_cpra_count -> (all-gather) -> hjb_cpra_scatter_rel(rel 0) -> hjb_cpra_stage_rel(rel 1)
+ *   -> (barrier: every R tuple has landed) -> hjb_cpra_send_staged(rel 1) + hjb_cpra_join_begin(R)
+ *   -> hjb_cpra_send_wait -> (barrier: every S tuple has landed) -> hjb_cpra_join_finish(S)          */
+/* the fused scatter of ONE counted relation (rel 0 = R, 1 = S); synchronises the stream */
+int hjb_cpra_scatter_rel(hjb_ctx *ctx, int rel, int ngpus, void *const *peer_keys, void *const *peer_vals,
+                         const uint64_t *base, float *ms);
+/* local split of one counted relation by owner into the context's send buffer (asynchronous) */
+int hjb_cpra_stage_rel(hjb_ctx *ctx, int rel, int ngpus);
+/* copy-engine transfers of the staged pieces into the owners' columns, on the context's copy
+ * stream, ordered after the split (asynchronous); hjb_cpra_send_wait blocks until they are done */
+int hjb_cpra_send_staged(hjb_ctx *ctx, int rel, int ngpus, int self, void *const *peer_keys, void *const *peer_vals,
+                         const uint64_t *base);
+int hjb_cpra_send_wait(hjb_ctx *ctx, float *ms);
+/* hjb_cpra_join_local in two halves: begin partitions the received build side (asynchronous; the
+ * probe side, s_tuples rows, may still be arriving), finish partitions the probe side and joins */
+int hjb_cpra_join_begin(hjb_ctx *ctx, const hjb_rel *R_recv, uint64_t s_tuples, int gpu, int ngpus, const hjb_opts *opts);
+int hjb_cpra_join_finish(hjb_ctx *ctx, const hjb_rel *S_recv, const hjb_opts *opts, hjb_result *out);
+
 /* ---- the kernels, one call each, device pointers: mirror the reference's free functions
  * so intermediate products can be compared with the oracle -------------------------- */
 /* hash h(key,f,N) = ((uint32)(key*f) * N) >> 32, npj.cpp:200-201 / simd_hash npj.cpp:90-106;
