@@ -10,6 +10,7 @@
 // digit, so items never synchronise while scattering.
 #include "hj_device.cuh"
 #include "hj_internal.h"
+#include <atomic>
 #include <stdlib.h>
 
 namespace hjb {
@@ -1145,9 +1146,12 @@ size_t radix_scratch_bytes(uint64_t n, uint32_t np, int bits, uint32_t *chunk, u
 
 static void scatter_attrs()
 {
-	static bool done = false;
-	if (done) return;
-	done = true;
+	// the attribute is per device: a process that drives several GPUs (host/cpra.cpp) sets it once on each
+	static std::atomic<unsigned long long> done_mask{0};
+	int dev = 0;
+	cudaGetDevice(&dev);
+	const unsigned long long bit = 1ull << (dev & 63);
+	if (done_mask.fetch_or(bit) & bit) return;
 	const int big = 2048 * 32 + 1024 * 8 * 8;
 	cudaFuncSetAttribute(k_scatter<512, 2, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
 	cudaFuncSetAttribute(k_scatter<512, 3, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
@@ -1163,6 +1167,12 @@ static void scatter_attrs()
 	cudaFuncSetAttribute(k_scatter_ov<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
 	cudaFuncSetAttribute(k_scatter_fx<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 256 * 32 + 2 * 8192 * 8 + 2 * 256 * 8 * 8);
 	cudaFuncSetAttribute(k_scatter_fx<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 256 * 32 + 2 * 8192 * 8 + 2 * 256 * 8 * 8);
+	cudaFuncSetAttribute(k_scatter_bulk<1024, kBulkGranule, 64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+	                     (int)(52 * 64 + (8192 + 2 * kBulkGranule * 64) * 8 + 64 * kBulkGranule * 16));
+	cudaFuncSetAttribute(k_scatter_bulk<1024, 8, 256, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+	                     (int)(52 * 256 + (8192 + 2 * 8 * 256) * 8 + 256 * 8 * 16));
+	cudaFuncSetAttribute(k_scatter_bulk<1024, 8, 256, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+	                     (int)(52 * 256 + (8192 + 2 * 8 * 256) * 8 + 256 * 8 * 16));
 }
 
 // make_items + histogram + scan: after this a.counts holds every item's start offset per digit
@@ -1225,12 +1235,6 @@ int launch_radix_scatter(const RadixPassArgs &a, cudaStream_t s, KernelTimer *t,
 	if (peers && peer_bulk && F <= 64) {
 		const size_t pad = 8192 + 2 * (size_t)kBulkGranule * F;
 		const size_t smem_b = 52 * 64 + pad * 8 + (size_t)F * kBulkGranule * 16;
-		static bool attr_b = false;
-		if (!attr_b) {
-			cudaFuncSetAttribute(k_scatter_bulk<1024, kBulkGranule, 64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-			                     (int)(52 * 64 + (8192 + 2 * kBulkGranule * 64) * 8 + 64 * kBulkGranule * 16));
-			attr_b = true;
-		}
 		// the bulk kernel walks the items with a grid stride: HJB_PEER_CTAS (experiments) can leave SMs to other streams
 		const uint32_t grid_b = (a.peer_ctas && a.peer_ctas < grid) ? a.peer_ctas : grid;
 		k_scatter_bulk<1024, kBulkGranule, 64, true><<<grid_b, 1024, smem_b, s>>>(
@@ -1240,24 +1244,12 @@ int launch_radix_scatter(const RadixPassArgs &a, cudaStream_t s, KernelTimer *t,
 	} else if (variant == 8 && F <= 256) {
 		// aligned SoA tile, 16-byte stores per column
 		const size_t smem_b = 52 * 256 + (8192 + 2 * 8 * (size_t)F) * 8 + (size_t)F * 8 * 16;
-		static bool attr_v = false;
-		if (!attr_v) {
-			cudaFuncSetAttribute(k_scatter_bulk<1024, 8, 256, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-			                     (int)(52 * 256 + (8192 + 2 * 8 * 256) * 8 + 256 * 8 * 16));
-			attr_v = true;
-		}
 		k_scatter_bulk<1024, 8, 256, false, false><<<grid, 1024, smem_b, s>>>(a.keys, a.vals, a.n, a.np, a.parent_off, a.item_prefix,
 		                                                                    a.chunk, a.factor, a.rshift, a.bits, a.counts, a.keys_out,
 		                                                                    a.vals_out, no_peers);
 	} else if (variant == 7 && F <= 256) {
 		// experiment: the local scatter with 32-byte granules and one bulk copy per digit, tile and column
 		const size_t smem_b = 52 * 256 + (8192 + 2 * 8 * (size_t)F) * 8 + (size_t)F * 8 * 16;
-		static bool attr_l = false;
-		if (!attr_l) {
-			cudaFuncSetAttribute(k_scatter_bulk<1024, 8, 256, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-			                     (int)(52 * 256 + (8192 + 2 * 8 * 256) * 8 + 256 * 8 * 16));
-			attr_l = true;
-		}
 		k_scatter_bulk<1024, 8, 256, false><<<grid, 1024, smem_b, s>>>(a.keys, a.vals, a.n, a.np, a.parent_off, a.item_prefix, a.chunk,
 		                                                             a.factor, a.rshift, a.bits, a.counts, a.keys_out, a.vals_out, no_peers);
 	} else {

@@ -66,6 +66,45 @@ static inline void load_relations(info_t_gpu *d)
 	}
 }
 
+// npj / phj on one GPU.  The reference times the join with both relations already in the memory its
+// threads read (npj.cpp:861-918); so: copy in, one untimed pass that sizes the workspaces (the
+// reference allocates before its timed region), then the timed pass on the resident columns
+// (result.seconds and the phase times).  result.seconds_e2e is a further pass through the host entry
+// point -- copy in, join, rows back to host memory -- which must reproduce the same result.
+typedef int (*hjb_join_fn)(hjb_ctx *, const hjb_rel *, const hjb_rel *, const hjb_opts *, hjb_result *);
+static inline void run_join_single(info_t_gpu *d, const char *name, hjb_join_fn on_device, hjb_join_fn on_host)
+{
+	setenv("HJB_GRAPHS", "0", 0);          // a one-shot program gains nothing from graph replay, and eager launches keep the phase times
+	int rc = hjb_create(0, &d->ctx);
+	if (rc) die("hjb_create", rc, NULL);
+	uint32_t *dev[4];
+	const uint32_t *host[4] = {d->inner_keys, d->inner_vals, d->outer_keys, d->outer_vals};
+	const size_t n[4] = {d->inner_tuples, d->inner_tuples, d->outer_tuples, d->outer_tuples};
+	for (int c = 0; c < 4; ++c)
+		if (cudaMalloc((void **)&dev[c], (n[c] ? n[c] : 1) * 4) != cudaSuccess ||
+		    cudaMemcpy(dev[c], host[c], n[c] * 4, cudaMemcpyHostToDevice) != cudaSuccess) {
+			fprintf(stderr, "cannot place %zu tuples in device memory\n", n[c]);
+			exit(1);
+		}
+	hjb_rel dR = {dev[0], dev[1], d->inner_tuples}, dS = {dev[2], dev[3], d->outer_tuples};
+	hjb_rel hR = {d->inner_keys, d->inner_vals, d->inner_tuples}, hS = {d->outer_keys, d->outer_vals, d->outer_tuples};
+	hjb_opts o;
+	memset(&o, 0, sizeof o);
+	o.materialize = 1;
+	o.seed = d->seed;
+	hjb_result warm, e2e;
+	if ((rc = on_device(d->ctx, &dR, &dS, &o, &warm))) die(name, rc, d->ctx);
+	if ((rc = on_device(d->ctx, &dR, &dS, &o, &d->result))) die(name, rc, d->ctx);
+	if ((rc = on_host(d->ctx, &hR, &hS, &o, &e2e))) die(name, rc, d->ctx);
+	if (e2e.count != d->result.count || e2e.sum_key != d->result.sum_key || e2e.sum_outer != d->result.sum_outer ||
+	    e2e.sum_inner != d->result.sum_inner) {
+		fprintf(stderr, "%s: the host entry point and the device entry point disagree\n", name);
+		exit(1);
+	}
+	d->result.seconds_e2e = e2e.seconds_e2e;
+	for (int c = 0; c < 4; ++c) cudaFree(dev[c]);
+}
+
 // the machine-readable line that follows the reference's own stdout line
 static inline void print_json(const char *algo, const info_t_gpu *d, const hjb_result *r, int gpus)
 {

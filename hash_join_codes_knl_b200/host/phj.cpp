@@ -9,14 +9,7 @@ int main(int argc, char **argv)
 	info_t_gpu d;
 	parse_join_args(argc, argv, &d);
 	load_relations(&d);
-	int rc = hjb_create(0, &d.ctx);
-	if (rc) die("hjb_create", rc, NULL);
-	hjb_rel R = {d.inner_keys, d.inner_vals, d.inner_tuples}, S = {d.outer_keys, d.outer_vals, d.outer_tuples};
-	hjb_opts o;
-	memset(&o, 0, sizeof o);
-	o.materialize = 1;
-	o.seed = d.seed;
-	if ((rc = hjb_phj_host(d.ctx, &R, &S, &o, &d.result))) die("hjb_phj_host", rc, d.ctx);
+	run_join_single(&d, "hjb_phj", hjb_phj_device, hjb_phj_host);
 	const hjb_result *r = &d.result;
 	printf("%lf\t%lf\t%lf\t\n", r->seconds, (r->phase_ms[0] + r->phase_ms[1]) * 1e-3, r->phase_ms[4] * 1e-3);
 	print_json("phj", &d, r, 1);
