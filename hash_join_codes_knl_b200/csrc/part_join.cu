@@ -122,7 +122,7 @@ k_partition_join(const uint32_t *__restrict__ rk, const uint32_t *__restrict__ r
 	uint64_t *table = reinterpret_cast<uint64_t *>(s_raw);             // kHashSlots
 	__shared__ uint64_t scratch[4 * 32];
 	__shared__ uint32_t warp_totals[34];
-	__shared__ uint32_t s_task_id[2], s_dups, s_hdups, s_sentinels;
+	__shared__ uint32_t s_task_id[2], s_hdups, s_sentinels;
 	constexpr uint32_t kMask = kHashSlots - 1;
 	constexpr int kShift = 32 - kJoinLog2Slots;
 	const bool direct_ok = rem_bits <= 16;
@@ -179,10 +179,9 @@ k_partition_join(const uint32_t *__restrict__ rk, const uint32_t *__restrict__ r
 			bool use_hash = !direct_ok;
 			uint32_t fe = min(fb + (use_hash ? kHashFill : kDirectFill), r_end);
 			if (!use_hash) {
-				// ---- DIRECT build, step 1: presence bits; equal keys show up as an already-set bit
+				// ---- DIRECT build, step 1: presence bits (equal keys set the same bit: step 2 counts fewer bits than tuples)
 				for (uint32_t w = threadIdx.x; w < kDirectWords / 4; w += THREADS)
 					reinterpret_cast<uint4 *>(bitmap)[w] = make_uint4(0, 0, 0, 0);
-				if (threadIdx.x == 0) s_dups = 0;
 				__syncthreads();
 				PHASE_MARK(1)      // bitmap clear
 				look_ahead();
@@ -202,7 +201,7 @@ k_partition_join(const uint32_t *__restrict__ rk, const uint32_t *__restrict__ r
 						const uint32_t x = hash_mul(k0[t], radix_factor), lo = x & rem_mask;
 						const uint32_t bit = 1u << (lo & 31);
 						if (owner_bits) foreign |= (x >> owner_shift) ^ owner;
-						if (atomicOr(&bitmap[lo >> 5], bit) & bit) s_dups = 1;
+						atomicOr(&bitmap[lo >> 5], bit);              // result unused: a reduction, no return path
 					}
 				for (uint32_t i0 = fb + threadIdx.x + THREADS * kBatch; i0 < fe; i0 += THREADS * kBatch) {
 					uint32_t bk[kBatch];
@@ -214,14 +213,14 @@ k_partition_join(const uint32_t *__restrict__ rk, const uint32_t *__restrict__ r
 							const uint32_t x = hash_mul(bk[t], radix_factor), lo = x & rem_mask;
 							const uint32_t bit = 1u << (lo & 31);
 							if (owner_bits) foreign |= (x >> owner_shift) ^ owner;
-							if (atomicOr(&bitmap[lo >> 5], bit) & bit) s_dups = 1;
+							atomicOr(&bitmap[lo >> 5], bit);              // result unused: a reduction, no return path
 						}
 				}
 				__syncthreads();
 				PHASE_MARK(2)      // build step 1: key loads + atomicOr
-				use_hash = s_dups != 0;
-				if (!use_hash) {
-					// step 2: rank structure -- prefix[w] = set bits before word w
+				{
+					// step 2: rank structure -- prefix[w] = set bits before word w; fewer bits than build tuples
+					// means equal keys: that fill is redone with the hash table
 					constexpr uint32_t kPer = kDirectWords / THREADS;
 					uint32_t c[kPer], local = 0;
 #pragma unroll
@@ -231,6 +230,7 @@ k_partition_join(const uint32_t *__restrict__ rk, const uint32_t *__restrict__ r
 					}
 					uint32_t tot;
 					uint32_t run = block_exclusive_scan(local, warp_totals, &tot);
+					use_hash = tot != fe - fb;
 #pragma unroll
 					for (uint32_t j = 0; j < kPer; ++j) {
 						prefix[threadIdx.x * kPer + j] = run;
@@ -238,6 +238,8 @@ k_partition_join(const uint32_t *__restrict__ rk, const uint32_t *__restrict__ r
 					}
 					__syncthreads();
 					PHASE_MARK(3)      // rank scan
+				}
+				if (!use_hash) {
 					// step 3: payloads in rank order
 #pragma unroll
 					for (int t = 0; t < kBatch; ++t)
@@ -304,7 +306,7 @@ k_partition_join(const uint32_t *__restrict__ rk, const uint32_t *__restrict__ r
 				for (uint32_t h = threadIdx.x; h < kHashSlots / 2; h += THREADS) t2[h] = make_ulonglong2(kEmptySlot, kEmptySlot);
 			}
 			if (threadIdx.x == 0) {
-				s_hdups = 0;                               // not s_dups: slow threads may still be reading it
+				s_hdups = 0;
 				s_sentinels = 0;
 			}
 			__syncthreads();
