@@ -8,6 +8,17 @@
 // The work item plays the role of the reference's thread: it owns a contiguous chunk of the
 // input, its counts row is the thread's counts[] and the scan hands it one start offset per
 // digit, so items never synchronise while scattering.
+//
+// Also here:
+//   k_hist_small   : k_hist for <= 8 digits (CPRA's GPU-assign pass), register counters
+//   k_scatter_bulk : the scatter whose output columns live in other GPUs' memory; digit runs leave the SM as
+//                    TMA bulk copies (cp.async.bulk) -- the fused exchange of CPRA (product path for N > 1)
+//   k_hist_global  : whole-column histogram behind the public hjb_histogram
+// and three schedule experiments for the local scatter that pass every parity test but measured slower
+// than k_scatter; they stay selectable (HJB_SCATTER_VARIANT) and out of the default path:
+//   k_scatter_bulk<.., PEER=false>  local TMA bulk copies (7) / 16-byte vector stores from a line-aligned tile (8)
+//   k_scatter_ov                    stream of tile t-1 overlapped with the plan of tile t (10)
+//   k_scatter_fx                    fixed digit regions, rank + placement in one step (11)
 #include "hj_device.cuh"
 #include "hj_internal.h"
 #include <atomic>
