@@ -579,6 +579,12 @@ static int phj_setup(hjb_ctx *ctx, uint64_t nr, uint64_t ns_slice, uint64_t ns_t
 	return HJB_OK;
 }
 
+__global__ void k_set_pair(uint32_t *dst, uint32_t a, uint32_t b)
+{
+	dst[0] = a;
+	dst[1] = b;
+}
+
 // one side through all radix passes (no pass at all: a single partition [0, n))
 static int phj_partition_side(hjb_ctx *ctx, PhjState *st, const hjb_rel *rel, bool build_side, uint32_t *launches)
 {
@@ -586,9 +592,8 @@ static int phj_partition_side(hjb_ctx *ctx, PhjState *st, const hjb_rel *rel, bo
 	Partitioned *res = build_side ? &st->pr : &st->ps;
 	uint32_t **off = build_side ? st->roff : st->soff;
 	if (st->plan.npass == 0) {
-		uint32_t *h = ctx->h_small + (build_side ? 0 : 2);
-		h[0] = 0; h[1] = (uint32_t)rel->tuples;
-		CK(cudaMemcpyAsync(off[0], h, 8, cudaMemcpyHostToDevice, s));
+		// by value in the kernel arguments: nothing on the host that a later call (or a graph replay) could find changed
+		k_set_pair<<<1, 1, 0, s>>>(off[0], 0u, (uint32_t)rel->tuples);
 		res->k = rel->keys; res->v = rel->vals; res->off = off[0];
 		return HJB_OK;
 	}

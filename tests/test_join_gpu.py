@@ -172,7 +172,7 @@ def small_host_slices(monkeypatch):
 
 
 @pytest.mark.parametrize("algo", ALGOS)
-@pytest.mark.parametrize("nr,ns", [(20000, 8192), (50000, 200001), (3000, 70000), (1 << 17, 1 << 20)])
+@pytest.mark.parametrize("nr,ns", [(20000, 8192), (50000, 200001), (3000, 70000), (1500, 70001), (1 << 17, 1 << 20)])
 def test_pipelined_host_entry_matches_oracle(eng, small_host_slices, algo, nr, ns):
     """probe side copied, joined and copied back slice by slice on three streams: same rows"""
     rk, rv, sk, sv, _, _ = oracle_generate(nr, ns, threads=2, seed=21)
@@ -226,6 +226,13 @@ def test_repeated_phj_on_the_same_buffers_replays_a_graph_and_rereads_the_data(e
         assert_same(eng.phj((drk, drv), (dsk, dsv)), want2)
     assert_same(eng.phj((drk, drv), (dsk[:100000], dsv[:100000])), oracle_join("phj", rk, rv, sk2[:100000], sv[:100000], threads=2))
     assert_same(eng.phj((drk, drv), (dsk, dsv)), want2)
+    # a build side so small that the plan has no radix pass (one partition, offsets set by a tiny kernel)
+    rk4, rv4, sk4, sv4, _, _ = oracle_generate(1000, 50000, threads=2, seed=32)
+    d4 = dev(rk4), dev(rv4)
+    s4 = dev(sk4), dev(sv4)
+    want4 = oracle_join("phj", rk4, rv4, sk4, sv4, threads=2)
+    for _ in range(3):
+        assert_same(eng.phj(d4, s4), want4)
     # equal build keys: the replayed graph overflows the result capacity -> eager rerun with a larger buffer
     rk3 = np.full(3000, 9, np.uint32)
     d3 = dev(rk3), dev(np.arange(3000, dtype=np.uint32))
