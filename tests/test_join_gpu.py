@@ -271,6 +271,51 @@ def test_histogram_kernel_matches_oracle(eng, bits):
     assert (eng.histogram(dev(sk), f, 0, bits) == want).all()
 
 
+def _canon(k, v, off):                   # order inside a partition is not part of the contract
+    k, v = k.copy(), v.copy()
+    for p in range(off.size - 1):
+        s = slice(int(off[p]), int(off[p + 1]))
+        o = np.lexsort((v[s], k[s]))
+        k[s], v[s] = k[s][o], v[s][o]
+    return k, v
+
+
+def test_partition_kernels_reproduce_the_reference_s_own_partitions(eng):
+    """faithful factors: under the hash factor the reference ran with, the CUDA histogram and
+    scatter must give the counts and the partition contents the reference's compiled histogram() /
+    partition() produced (tests/golden/ref_vectors.npz) -- 64 partitions in one pass, 4096 in two"""
+    sk, sv, f = G["in_small_sk"], G["in_small_sv"], int(G["part_factor"])
+    assert (eng.histogram(dev(sk), f, 0, 6) == G["ref_small_hist_64"]).all()
+    k1, v1, off1 = eng.partition_pass(dev(sk), dev(sv), f, 0, 6)
+    assert (off1 == np.concatenate([[0], np.cumsum(G["ref_small_hist_64"])])).all()
+    got = _canon(k1.cpu().numpy().view(np.uint32), v1.cpu().numpy().view(np.uint32), off1)
+    ref = _canon(G["ref_small_part_keys_64"], G["ref_small_part_vals_64"], off1)
+    assert (got[0] == ref[0]).all() and (got[1] == ref[1]).all()
+    k2, v2, off2 = eng.partition_pass(k1, v1, f, 6, 6, parent_offsets=off1)
+    assert (off2 == np.concatenate([[0], np.cumsum(G["ref_small_hist_4096"])])).all()
+    got = _canon(k2.cpu().numpy().view(np.uint32), v2.cpu().numpy().view(np.uint32), off2)
+    ref = _canon(G["ref_small_part_keys_4096"], G["ref_small_part_vals_4096"], off2)
+    assert (got[0] == ref[0]).all() and (got[1] == ref[1]).all()
+
+
+def test_histogram_under_mt19937_drawn_factors(eng):
+    """the reference draws a fresh odd factor per pass from its MT19937 stream (cpra2.cpp:1787)"""
+    import ctypes as C
+
+    class R32(C.Structure):
+        _fields_ = [("num", C.c_uint32 * 625), ("index", C.c_size_t)]
+    L = olib()
+    L.hjo_rand32_next.restype = C.c_uint32
+    st = R32()
+    L.hjo_rand32_seed(C.byref(st), C.c_uint32(2024))
+    rk, rv, sk, sv, _, _ = oracle_generate(1000, 200003, threads=2, seed=15)
+    for bits in (3, 8, 11):
+        f = int(L.hjo_rand32_next(C.byref(st))) | 1
+        want = np.zeros(1 << bits, np.uint32)
+        L.hjo_histogram(_p(sk), sk.size, _p(want), f, 1 << bits)
+        assert (eng.histogram(dev(sk), f, 0, bits) == want).all()
+
+
 @pytest.mark.parametrize("bits1,bits2", [(6, 6), (8, 8), (3, 11), (11, 0), (1, 1)])
 def test_partition_pass_kernels_match_oracle(eng, bits1, bits2):
     rk, rv, sk, sv, _, _ = oracle_generate(1000, 500003, threads=2, seed=14)
