@@ -26,8 +26,13 @@ def main():
     eng = hj.Engine(local, use_torch_stream=True)
     fused = cpra.FusedExchange(eng)
     ok = True
-    for nr, ns, seed in ((200000, 600000, 16), (1 << 20, 1 << 22, 17), (100003, 70001, 18)):
-        rk, rv, sk, sv, _, _ = oracle_generate(nr, ns, threads=2, seed=seed)
+    for nr, ns, seed in ((200000, 600000, 16), (1 << 20, 1 << 22, 17), (100003, 70001, 18), (150000, 500000, -19)):
+        rk, rv, sk, sv, _, _ = oracle_generate(nr, ns, threads=2, seed=abs(seed))
+        if seed < 0:
+            # skew: a third of the probe side is one heavy-hitter key (all of it lands on one owner), a tenth has no partner
+            sk = sk.copy()
+            sk[::3] = rk[7]
+            sk[5::10] ^= np.uint32(0x10000000)
         want = oracle_join("cpra", rk, rv, sk, sv, threads=4)
         cr = slice(rank * nr // world, (rank + 1) * nr // world)
         cs = slice(rank * ns // world, (rank + 1) * ns // world)
