@@ -14,11 +14,12 @@
 //   k_scatter_bulk : the scatter whose output columns live in other GPUs' memory; digit runs leave the SM as
 //                    TMA bulk copies (cp.async.bulk) -- the fused exchange of CPRA (product path for N > 1)
 //   k_hist_global  : whole-column histogram behind the public hjb_histogram
-// and three schedule experiments for the local scatter that pass every parity test but measured slower
+// and four schedule experiments for the local scatter that pass every parity test but measured slower
 // than k_scatter; they stay selectable (HJB_SCATTER_VARIANT) and out of the default path:
 //   k_scatter_bulk<.., PEER=false>  local TMA bulk copies (7) / 16-byte vector stores from a line-aligned tile (8)
 //   k_scatter_ov                    stream of tile t-1 overlapped with the plan of tile t (10)
 //   k_scatter_fx                    fixed digit regions, rank + placement in one step (11)
+//   k_scatter_2x                    two sub-tiles ranked per plan, 16384 tuples placed and streamed per round (12)
 #include "hj_device.cuh"
 #include "hj_internal.h"
 #include <atomic>
@@ -908,6 +909,140 @@ k_scatter_fx(const uint32_t *__restrict__ keys, const uint32_t *__restrict__ val
 #undef SCATTER_MARK
 }
 
+// ------------------------------------------------------------------ local scatter, two sub-tiles per plan
+//
+// Experiment 12: the plan and the three CTA barriers cost ~2500 of a tile's ~10750 cycles and do not depend
+// on the tile's size, so rank TWO 8192-tuple sub-tiles before one plan and place / stream 16384 tuples per
+// round.  Only the ranks stay in registers between the rank and the placement; the keys are fetched again
+// for the placement (an L2 hit: they were read a few microseconds earlier) and the payloads then for the
+// first time.  128 KB tile, fan-out <= 256.
+// dynamic shared memory: cnt base fpos oldp wpos pend [F] | golim[F] (uint2) | buf[2 * 8192] (uint2) | carry[F*8] (uint2)
+__global__ void __launch_bounds__(1024, 1)
+k_scatter_2x(const uint32_t *__restrict__ keys, const uint32_t *__restrict__ vals, uint64_t n, uint32_t np,
+             const uint32_t *__restrict__ parent_off, const uint32_t *__restrict__ item_prefix, uint32_t chunk,
+             uint32_t factor, int rshift, int bits, const uint32_t *__restrict__ offsets,
+             uint32_t *__restrict__ keys_out, uint32_t *__restrict__ vals_out)
+{
+	constexpr int THREADS = 1024, G = 2, IT = 4 * G;
+	constexpr uint32_t kCarry = kLocalCarry, SUB = THREADS * IT, TILE = 2 * SUB, kGroupsPerSub = SUB / 4;
+	extern __shared__ __align__(16) uint32_t s_mem[];
+	__shared__ uint32_t warp_totals[8];
+	__shared__ uint32_t s_tile_n;
+	const uint32_t F = 1u << bits, mask = F - 1;
+	uint32_t *cnt = s_mem, *base = cnt + F, *fpos = base + F, *oldp = fpos + F, *wpos = oldp + F, *pend = wpos + F;
+	uint2 *golim = reinterpret_cast<uint2 *>(pend + F);
+	uint2 *buf = golim + F;
+	uint2 *carry = buf + TILE;
+	ItemRange r;
+	if (!locate_item(item_prefix, np, parent_off, n, chunk, blockIdx.x, &r)) return;
+	const uint32_t *row = offsets + (size_t)blockIdx.x * F;
+	for (uint32_t p = threadIdx.x; p < F; p += THREADS) {
+		wpos[p] = row[p];
+		pend[p] = 0;
+		cnt[p] = 0;
+	}
+	const uint64_t g_beg = r.beg >> 2, g_end = (r.end + 3) >> 2;
+	auto sub_is_full = [&](uint64_t g0) { return (g0 << 2) >= r.beg && ((g0 + kGroupsPerSub) << 2) <= r.end; };
+	auto load = [&](uint32_t (&x)[IT], uint32_t &ok, const uint32_t *col, uint64_t g0) {
+		if (sub_is_full(g0)) load_col8<THREADS, G, true>(x, ok, col, g0, g_end, r.beg, r.end, n);
+		else load_col8<THREADS, G, false>(x, ok, col, g0, g_end, r.beg, r.end, n);
+	};
+	auto rank = [&](const uint32_t (&k)[IT], uint32_t ok, uint32_t (&dr)[IT]) {
+#pragma unroll
+		for (int e = 0; e < IT; ++e) {
+			const uint32_t d = radix_digit(hash_mul(k[e], factor), rshift, mask);
+			dr[e] = (ok >> e) & 1u ? (d << 16) | atomicAdd(&cnt[d], 1u) : 0xFFFFFFFFu;
+		}
+	};
+	auto place = [&](const uint32_t (&k)[IT], const uint32_t (&v)[IT], const uint32_t (&dr)[IT]) {
+#pragma unroll
+		for (int e = 0; e < IT; ++e)
+			if (dr[e] != 0xFFFFFFFFu) buf[base[dr[e] >> 16] + (dr[e] & 0xFFFFu)] = make_uint2(k[e], v[e]);
+	};
+	uint32_t nkey[IT], nok = 0;
+	if (g_beg < g_end) load(nkey, nok, keys, g_beg);
+	__syncthreads();
+	for (uint64_t g0 = g_beg; g0 < g_end; g0 += 2 * kGroupsPerSub) {
+		const uint64_t gB = g0 + kGroupsPerSub, g1 = g0 + 2 * kGroupsPerSub;
+		const bool last = g1 >= g_end;
+		uint32_t drA[IT], drB[IT], valA[IT], tmp[IT], okB, vok;
+		load(tmp, okB, keys, gB);                                  // sub-tile B's keys on their way while A is ranked
+		rank(nkey, nok, drA);
+		load(valA, vok, vals, g0);                                 // A's payloads: in flight across the plan
+		rank(tmp, okB, drB);
+		if (!last) load(nkey, nok, keys, g1);                      // next round's sub-tile A
+		__syncthreads();
+		// plan: one digit per thread in the first eight warps (fan-out <= 256)
+		if (threadIdx.x < 256) {
+			const uint32_t p = threadIdx.x;
+			const uint32_t c = p < F ? cnt[p] : 0;
+			const uint32_t incl = warp_inclusive_scan_u32(c);
+			if (lane_id() == 31) warp_totals[p >> 5] = incl;
+			asm volatile("bar.sync 1, 256;" ::: "memory");
+			const uint32_t wt = lane_id() < 8 ? warp_totals[lane_id()] : 0;
+			const uint32_t tincl = warp_inclusive_scan_u32(wt);
+			const uint32_t before = __shfl_sync(kFullMask, tincl - wt, p >> 5);
+			const uint32_t tile_total = __shfl_sync(kFullMask, tincl, 31);
+			if (p < F) {
+				const uint32_t run = before + incl - c;
+				const uint32_t w = wpos[p], pe = pend[p], endpos = w + pe + c;
+				uint32_t lim = last ? endpos : (endpos & ~(kCarry - 1));
+				const bool flush = lim > w;
+				if (!flush) lim = w;
+				base[p] = run;
+				golim[p] = make_uint2(w + pe - run, lim);
+				fpos[p] = w;
+				oldp[p] = flush ? pe : 0;
+				wpos[p] = lim;
+				pend[p] = endpos - lim;
+				cnt[p] = 0;
+			}
+			if (p == 0) s_tile_n = tile_total;
+		}
+		__syncthreads();
+		// place A (keys fetched again), then B (keys again, payloads for the first time)
+		{
+			uint32_t okA;
+			load(tmp, okA, keys, g0);
+			place(tmp, valA, drA);
+		}
+		{
+			uint32_t okk;
+			load(tmp, okk, keys, gB);
+			load(valA, vok, vals, gB);
+			place(tmp, valA, drB);
+		}
+		for (uint32_t i = threadIdx.x; i < F * kCarry; i += THREADS) {
+			const uint32_t d = i / kCarry, j = i % kCarry;
+			if (j < oldp[d]) {
+				const uint2 kv = carry[i];
+				const uint32_t dst = fpos[d] + j;
+				keys_out[dst] = kv.x;
+				vals_out[dst] = kv.y;
+			}
+		}
+		__syncthreads();
+		const uint32_t tile_n = s_tile_n;
+#pragma unroll 8
+		for (int it = 0; it < 2 * IT; ++it) {
+			const uint32_t i = threadIdx.x + it * THREADS;
+			if (i < tile_n) {
+				const uint2 kv = buf[i];
+				const uint32_t d = radix_digit(hash_mul(kv.x, factor), rshift, mask);
+				const uint2 gl = golim[d];
+				const uint32_t pos = gl.x + i;
+				if (pos < gl.y) {
+					keys_out[pos] = kv.x;
+					vals_out[pos] = kv.y;
+				} else {
+					carry[d * kCarry + (pos - gl.y)] = kv;
+				}
+			}
+		}
+		// the next round's rank touches only cnt; its plan (after a barrier) rewrites golim and its placement buf
+	}
+}
+
 // ------------------------------------------------------------------ peer scatter with TMA bulk stores
 //
 // The GPU-assign pass of CPRA has a small fan-out (one digit per GPU), so a digit's run in a tile
@@ -1182,6 +1317,7 @@ static void scatter_attrs()
 	cudaFuncSetAttribute(k_scatter_ov<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
 	cudaFuncSetAttribute(k_scatter_fx<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 256 * 32 + 2 * 8192 * 8 + 2 * 256 * 8 * 8);
 	cudaFuncSetAttribute(k_scatter_fx<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 256 * 32 + 2 * 8192 * 8 + 2 * 256 * 8 * 8);
+	cudaFuncSetAttribute(k_scatter_2x, cudaFuncAttributeMaxDynamicSharedMemorySize, 256 * 32 + 2 * 8192 * 8 + 256 * 8 * 8);
 	cudaFuncSetAttribute(k_scatter_bulk<1024, kBulkGranule, 64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
 	                     (int)(52 * 64 + (8192 + 2 * kBulkGranule * 64) * 8 + 64 * kBulkGranule * 16));
 	cudaFuncSetAttribute(k_scatter_bulk<1024, 8, 256, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -1234,7 +1370,7 @@ int launch_radix_scatter(const RadixPassArgs &a, cudaStream_t s, KernelTimer *t,
 	if (variant < 0) {
 		const char *e = getenv("HJB_SCATTER_VARIANT");
 		variant = e ? atoi(e) : 3;       // measured best on B200: one 1024-thread CTA per SM, 8192-tuple tiles
-		if (variant < 0 || variant > 11) variant = 3;
+		if (variant < 0 || variant > 12) variant = 3;
 	}
 	const int threads = ((variant >= 3 && variant != 9) || peers) ? 1024 : 512;
 	const int items = (!peers && (variant == 5 || variant == 6)) ? 4 : (!peers && variant == 9) ? 16 : 8;
@@ -1289,6 +1425,17 @@ int launch_radix_scatter(const RadixPassArgs &a, cudaStream_t s, KernelTimer *t,
 			                                                      a.rshift, a.bits, a.counts, a.keys_out, a.vals_out);
 			else k_scatter_ov<false><<<grid, 1024, smem_ov, s>>>(a.keys, a.vals, a.n, a.np, a.parent_off, a.item_prefix, a.chunk, a.factor,
 			                                                     a.rshift, a.bits, a.counts, a.keys_out, a.vals_out);
+			break;
+		}
+		case 12: {
+			// two sub-tiles per plan (k_scatter_2x)
+			if (F > 256) {
+				HJB_LAUNCH_SCATTER(1024, 1, true, false, no_peers);
+				break;
+			}
+			const size_t smem_2x = (size_t)F * 32 + 2 * 8192 * 8 + (size_t)F * kLocalCarry * 8;
+			k_scatter_2x<<<grid, 1024, smem_2x, s>>>(a.keys, a.vals, a.n, a.np, a.parent_off, a.item_prefix, a.chunk, a.factor, a.rshift,
+			                                         a.bits, a.counts, a.keys_out, a.vals_out);
 			break;
 		}
 		case 11: {

@@ -13,4 +13,4 @@ for ln in open("gpurun_out/bench_v$v.log"):
         d = json.loads(ln); print("variant $v", round(d["ms_per_step"], 3), "ms", d["kernel_ms_per_step"])
 PY
 done
-HJB_SCATTER_VARIANT=$V timeout 120 python scripts/gpu_scatter_clocks.py
+true
