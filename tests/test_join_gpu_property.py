@@ -28,7 +28,7 @@ def dev(a):
 PLANS = [{}, {"radix_bits": (3,)}, {"radix_bits": (8, 8)}, {"radix_bits": (5, 6, 5)}, {"part_tuples": 64}, {"seed": 7}]
 
 
-@settings(max_examples=120, deadline=None, suppress_health_check=[HealthCheck.function_scoped_fixture, HealthCheck.too_slow])
+@settings(max_examples=120, deadline=None, derandomize=True, suppress_health_check=[HealthCheck.function_scoped_fixture, HealthCheck.too_slow])
 @given(nr=st.integers(0, 3000), ns=st.integers(0, 6000), domain_log2=st.integers(1, 32), special=st.booleans(),
        plan=st.sampled_from(PLANS), algo=st.sampled_from(["npj", "phj"]), host=st.booleans(), seed=st.integers(0, 2**31 - 1))
 def test_any_small_join_equals_numpy(eng, nr, ns, domain_log2, special, plan, algo, host, seed):
