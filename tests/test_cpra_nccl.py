@@ -26,7 +26,12 @@ def main():
     eng = hj.Engine(local, use_torch_stream=True)
     fused = cpra.FusedExchange(eng)
     ok = True
-    for nr, ns, seed in ((200000, 600000, 16), (1 << 20, 1 << 22, 17), (100003, 70001, 18), (150000, 500000, -19)):
+    cases = [(200000, 600000, 16), (1 << 20, 1 << 22, 17), (100003, 70001, 18), (150000, 500000, -19),
+             (37, 5, 20), (4096, 33, 21), (1, 70000, 22)]          # pieces of a few tuples: unaligned heads and tails only
+    rnd = np.random.default_rng(int(os.environ.get("HJB_CPRA_RANDOM_SEED", "1")))
+    for i in range(int(os.environ.get("HJB_CPRA_RANDOM", "0"))):   # extra random shapes (same on every rank)
+        cases.append((int(rnd.integers(1, 60000)), int(rnd.integers(1, 200000)), 100 + i if i % 3 else -(100 + i)))
+    for nr, ns, seed in cases:
         rk, rv, sk, sv, _, _ = oracle_generate(nr, ns, threads=2, seed=abs(seed))
         if seed < 0:
             # skew: a third of the probe side is one heavy-hitter key (all of it lands on one owner), a tenth has no partner
