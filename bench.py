@@ -195,6 +195,14 @@ def cpu_join_sample(log2_tuples, steps, warmup, workload):
                       f"mean of {len(secs)} run(s), {sec:.3f} s each", "seconds": sec}
 
 
+def workload_label(workload, world, log2_per_gpu):
+    """config.workload, identical in both arms"""
+    return {"phj_cfg2": "PHJ 2^27 x 2^27 unique keys (BASELINE config 2)",
+            "npj_cfg1": "NPJ 2^24 x 2^28 foreign keys (BASELINE config 1)",
+            "cpra_cfg4": f"CPRA 2^{log2_per_gpu} + 2^{log2_per_gpu} tuples per GPU x {world} GPUs "
+                         f"(N=8 is BASELINE config 4, 2^31 x 2^31)"}[workload]
+
+
 def reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -206,8 +214,10 @@ def reference_arm(args):
     line = {"impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": base["seconds"] * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
-            "config": {"workload": workload, "note": "CPU reference on a bounded sample of the workload; throughput in "
-                       "(R+S) tuples/s does not depend on the GPU count"},
+            "config": {"workload": workload_label(workload, args.gpus, args.log2_per_gpu or 28),
+                       "sample": base["sample"],
+                       "note": "CPU reference on a bounded sample of the workload; throughput in (R+S) tuples/s does not "
+                               "depend on the GPU count"},
             "cpu_baseline": {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0, "wall_s": time.time() - t0}
@@ -471,10 +481,7 @@ def main():
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_step, "ms_per_step_instrumented": ms_instrumented / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32",
         "data": "synthetic",
-        "config": {"workload": {"phj_cfg2": "PHJ 2^27 x 2^27 unique keys (BASELINE config 2)",
-                                "npj_cfg1": "NPJ 2^24 x 2^28 foreign keys (BASELINE config 1)",
-                                "cpra_cfg4": f"CPRA 2^{nr_g.bit_length() - 1} + 2^{ns_g.bit_length() - 1} tuples per GPU "
-                                             f"x {world} GPUs (N=8 is BASELINE config 4, 2^31 x 2^31)"}[workload],
+        "config": {"workload": workload_label(workload, world, nr_g.bit_length() - 1),
                    "inner_tuples": nr_tot, "outer_tuples": ns_tot, "materialize": True, "algorithm": algo,
                    "exchange": (args.exchange if world > 1 else None),
                    "l2_policy": "inputs (%.1f GiB per GPU) and every intermediate exceed the 126 MB L2; no flush needed"
