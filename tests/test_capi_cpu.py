@@ -113,3 +113,20 @@ def test_generator_foreign_keys():
 def test_workloads_named_in_baseline():
     assert datagen.workload("phj_cfg2") == (1 << 27, 1 << 27, 0)
     assert datagen.workload("npj_cfg1") == (1 << 24, 1 << 28, 1)
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` needs no GPU: the reference's own CPU join (oracle/_ref when it was
+    compiled here, else the oracle port) on the host cores, one JSON line with the contract's keys"""
+    import json
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                         capture_output=True, text=True, timeout=600, cwd=root)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads([ln for ln in out.stdout.splitlines() if ln.startswith("{")][-1])
+    assert line["impl"] == "reference" and line["unit"] == "tuples/s" and line["higher_is_better"] is True
+    assert line["value"] > 0 and line["n_gpus"] == 1 and line["gpu_launches"] == 0
+    assert line["config"]["workload"].startswith("PHJ 2^27 x 2^27")
+    assert line["cpu_baseline"]["kind"] in ("reference", "port") and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"] == {"value": line["value"], "unit": "tuples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
