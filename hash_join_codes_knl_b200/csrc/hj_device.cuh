@@ -142,95 +142,12 @@ struct JoinSums {
 	}
 };
 
-// Result rows staged in shared memory so that each CTA reserves output space with ONE
-// global atomic per flush and writes the three result columns coalesced (the reference's
-// 256-entry staging buffer + block allocator, npj.cpp:244-246,292-317).
-struct MatchStage {
-	uint32_t *k, *o, *i;     // shared memory, `cap` entries each
-	uint32_t *cnt;           // shared cursor (may run past cap: overflow)
-	uint32_t cap;
-
-	// warp-collective: all 32 lanes call it, converged.  Rows beyond cap are dropped (counted).
-	__device__ __forceinline__ void emit(bool hit, uint32_t key, uint32_t oval, uint32_t ival) const
-	{
-		const unsigned m = __ballot_sync(kFullMask, hit);
-		if (m == 0) return;
-		const int leader = __ffs(m) - 1;
-		uint32_t base = 0;
-		if ((int)lane_id() == leader) base = atomicAdd(cnt, (uint32_t)__popc(m));
-		base = __shfl_sync(kFullMask, base, leader);
-		if (hit) {
-			const uint32_t pos = base + __popc(m & lanemask_lt());
-			if (pos < cap) {
-				k[pos] = key;
-				o[pos] = oval;
-				i[pos] = ival;
-			}
-		}
-	}
-	// any single thread
-	__device__ __forceinline__ void emit_one(uint32_t key, uint32_t oval, uint32_t ival) const
-	{
-		const uint32_t pos = atomicAdd(cnt, 1u);
-		if (pos < cap) {
-			k[pos] = key;
-			o[pos] = oval;
-			i[pos] = ival;
-		}
-	}
-};
-
 struct OutCols {
 	uint32_t *k, *o, *i;          // global result columns
 	unsigned long long *cursor;   // global row cursor
 	uint64_t cap;                 // rows the columns can hold
 };
 
-// CTA-collective: copy the staged rows to the result columns.  Returns false (and writes
-// nothing) when the stage overflowed; the caller then re-probes in direct mode.  Leaves the
-// stage empty.  s_base: one uint64 of shared memory.
-__device__ __forceinline__ bool stage_flush(const MatchStage &st, const OutCols &out, unsigned long long *s_base)
-{
-	__syncthreads();
-	const uint32_t n = *st.cnt;
-	const bool ok = n <= st.cap;
-	if (ok && n) {
-		if (threadIdx.x == 0) *s_base = atomicAdd(out.cursor, (unsigned long long)n);
-		__syncthreads();
-		const uint64_t base = *s_base;
-		for (uint32_t j = threadIdx.x; j < n; j += blockDim.x) {
-			const uint64_t r = base + j;
-			if (r < out.cap) {
-				out.k[r] = st.k[j];
-				out.o[r] = st.o[j];
-				out.i[r] = st.i[j];
-			}
-		}
-	}
-	__syncthreads();
-	if (threadIdx.x == 0) *st.cnt = 0;
-	__syncthreads();
-	return ok;
-}
-
-// warp-collective direct emission (overflow path: duplicate-heavy build sides)
-__device__ __forceinline__ void emit_direct(const OutCols &out, bool hit, uint32_t key, uint32_t oval, uint32_t ival)
-{
-	const unsigned m = __ballot_sync(kFullMask, hit);
-	if (m == 0) return;
-	const int leader = __ffs(m) - 1;
-	unsigned long long base = 0;
-	if ((int)lane_id() == leader) base = atomicAdd(out.cursor, (unsigned long long)__popc(m));
-	base = __shfl_sync(kFullMask, base, leader);
-	if (hit) {
-		const uint64_t r = base + __popc(m & lanemask_lt());
-		if (r < out.cap) {
-			out.k[r] = key;
-			out.o[r] = oval;
-			out.i[r] = ival;
-		}
-	}
-}
 
 // largest q in [0, n) with a[q] <= x, for a non-decreasing a[0..n] with a[0] <= x < a[n]
 __device__ __forceinline__ uint32_t upper_parent(const uint32_t *a, uint32_t n, uint32_t x)
