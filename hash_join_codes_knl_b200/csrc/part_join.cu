@@ -14,8 +14,8 @@
 //    bits, so the remaining low bits of x identify the key: a 2^16-bit bitmap says whether
 //    a key is present, and the rank of its bit (popcount prefix) addresses its payload in a
 //    dense array.  No key comparison, no collision chain, no divergent loop: build is an
-//    atomicOr + one store, probe is two loads + a popcount.  A fill in which two build
-//    tuples have the SAME key (atomicOr finds the bit already set) falls back to:
+//    OR reduction + one store, probe is two loads + a popcount.  A fill in which two build
+//    tuples have the SAME key (the rank scan counts fewer set bits than tuples) falls back to:
 //  * HASH: open addressing with linear probing over 64-bit slots (payload<<32 | key),
 //    atomicCAS insert as in the reference's build (npj.cpp:206); fills without equal build
 //    keys stop a probe at its first match, the others walk each chain to its end and emit
