@@ -242,7 +242,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="auto", choices=["auto", "phj_cfg2", "npj_cfg1", "cpra_cfg4"])
     ap.add_argument("--log2-per-gpu", type=int, default=0, help="override tuples per relation per GPU (2^k)")
-    ap.add_argument("--exchange", default="fused", choices=["fused", "overlap", "nccl"],
+    ap.add_argument("--exchange", default="fused", choices=["fused", "nccl"],
                     help="N>1: GPU-assign pass storing straight into the owners' buffers over NVLink, or split + NCCL all-to-all")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -276,8 +276,6 @@ def main():
     fused = cpra_mod.FusedExchange(eng) if (world > 1 and args.exchange != "nccl") else None
 
     def cpra_step(inner, outer):
-        if fused is not None and args.exchange == "overlap":
-            return cpra_mod.cpra_join_overlap(eng, inner, outer, fused)
         if fused is not None:
             return cpra_mod.cpra_join_fused(eng, inner, outer, fused)
         return cpra_mod.cpra_join(eng, inner, outer)
@@ -498,10 +496,7 @@ def main():
         if world > 1:
             sent = 8 * n_in * (world - 1) / world                # bytes each GPU stores into its peers per step
             cm = line["cpra_ms_per_step"]
-            if args.exchange == "overlap":       # R through the fused scatter (split_ms), S by copy engine (exchange_ms), half the bytes each
-                ach = {"fused_scatter_R": sent / 2 / (cm["split_ms"] * 1e-3) / 1e9, "copy_engine_S": sent / 2 / (cm["exchange_ms"] * 1e-3) / 1e9}
-            else:
-                ach = sent / (cm["split_ms" if args.exchange == "fused" else "exchange_ms"] * 1e-3) / 1e9
+            ach = sent / (cm["split_ms" if args.exchange == "fused" else "exchange_ms"] * 1e-3) / 1e9
             line["nvlink"] = {"bytes_out_per_gpu": sent, "scatter_ms": cm["split_ms"], "achieved_gbs_per_direction": ach,
                               "reference_gbs": 770.0, "note": "measured peer-copy bandwidth per direction (B200_PROFILING.md); nominal 900"}
             # SURVEY 8d's serial model for CPRA at G GPUs: HBM bytes / HBM bandwidth + NVLink bytes / NVLink bandwidth,

@@ -6,6 +6,8 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libhjb200.so")
 
+HJB_E_CAPACITY = -6
+
 u32p = C.POINTER(C.c_uint32)
 u64p = C.POINTER(C.c_uint64)
 
@@ -55,7 +57,6 @@ SYMBOLS = {
     "hjb_set_profiling": (C.c_int, [C.c_void_p, C.c_int]),
     "hjb_kernel_times": (C.c_int, [C.c_void_p, C.POINTER(C.c_float), u32p, C.c_int]),
     "hjb_kernel_name": (C.c_char_p, [C.c_int]),
-    "hjb_debug_counters": (C.c_int, [C.c_void_p, u64p]),
     "hjb_npj_device": (C.c_int, [C.c_void_p, C.POINTER(Rel), C.POINTER(Rel), C.POINTER(Opts), C.POINTER(Result)]),
     "hjb_phj_device": (C.c_int, [C.c_void_p, C.POINTER(Rel), C.POINTER(Rel), C.POINTER(Opts), C.POINTER(Result)]),
     "hjb_npj_host": (C.c_int, [C.c_void_p, C.POINTER(Rel), C.POINTER(Rel), C.POINTER(Opts), C.POINTER(Result)]),
@@ -66,15 +67,15 @@ SYMBOLS = {
     "hjb_ipc_open": (C.c_int, [C.c_void_p, C.POINTER(C.c_ubyte), C.POINTER(C.c_void_p)]),
     "hjb_ipc_close": (C.c_int, [C.c_void_p, C.c_void_p]),
     "hjb_cpra_count": (C.c_int, [C.c_void_p, C.POINTER(Rel), C.POINTER(Rel), C.c_int, C.POINTER(Opts), u64p, u64p]),
-    "hjb_cpra_scatter_rel": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), u64p,
-                                       C.POINTER(C.c_float)]),
-    "hjb_cpra_stage_rel": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
-    "hjb_cpra_send_staged": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), u64p]),
-    "hjb_cpra_send_wait": (C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
-    "hjb_cpra_join_begin": (C.c_int, [C.c_void_p, C.POINTER(Rel), C.c_uint64, C.c_int, C.c_int, C.POINTER(Opts)]),
-    "hjb_cpra_join_finish": (C.c_int, [C.c_void_p, C.POINTER(Rel), C.POINTER(Opts), C.POINTER(Result)]),
     "hjb_cpra_scatter_peer": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
                                         C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), u64p, u64p, C.POINTER(C.c_float)]),
+    "hjb_cpra_bind": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
+                                C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_uint64, C.c_uint64]),
+    "hjb_cpra_count_async": (C.c_int, [C.c_void_p, C.POINTER(Rel), C.POINTER(Rel), C.POINTER(Opts), C.c_void_p]),
+    "hjb_cpra_scatter_async": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "hjb_cpra_join_async": (C.c_int, [C.c_void_p, C.POINTER(Opts), C.c_uint64, C.c_uint64]),
+    "hjb_cpra_sums_dev": (C.c_void_p, [C.c_void_p]),
+    "hjb_cpra_finish": (C.c_int, [C.c_void_p, C.POINTER(Result), u64p, u64p]),
     "hjb_hash_factor": (C.c_uint32, [C.c_uint32, C.c_int]),
     "hjb_histogram": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, u32p, C.c_uint32, C.c_int, C.c_int]),
     "hjb_partition_pass": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, u32p, C.c_void_p, C.c_void_p, u32p, C.c_uint32, C.c_int, C.c_int]),

@@ -16,6 +16,15 @@ class HjbError(RuntimeError):
     pass
 
 
+class HjbCapacityError(HjbError):
+    """hjb_cpra_finish: an owner's receive buffer was too small (HJB_E_CAPACITY); `largest` = (R rows, S rows)
+    the fullest owner received."""
+
+    def __init__(self, msg, largest):
+        super().__init__(msg)
+        self.largest = largest
+
+
 class _CudaArray:
     """Zero-copy view of library-owned device memory for torch.as_tensor (int32 bit pattern)."""
 
@@ -135,6 +144,8 @@ class Engine:
         ms = (C.c_float * 16)()
         n = (C.c_uint32 * 16)()
         kinds = self._lib.hjb_kernel_times(self._ctx, ms, n, 16)
+        if kinds < 0:
+            self._check(kinds, "hjb_kernel_times")
         return {self._lib.hjb_kernel_name(k).decode(): (float(ms[k]), int(n[k])) for k in range(kinds)}
 
     @staticmethod
@@ -249,48 +260,49 @@ class Engine:
         self._pending_keep = None
         return float(ms.value)
 
-    # ---- the same with the probe side's exchange overlapped with the build side's local partitioning
-    def cpra_scatter_rel(self, rel, ngpus, peer_keys, peer_vals, base):
-        pk = (C.c_void_p * ngpus)(*[C.c_void_p(p) for p in peer_keys])
-        pv = (C.c_void_p * ngpus)(*[C.c_void_p(p) for p in peer_vals])
-        b = (C.c_uint64 * ngpus)(*[int(x) for x in base])
-        ms = C.c_float()
-        self._check(self._lib.hjb_cpra_scatter_rel(self._ctx, int(rel), int(ngpus), pk, pv, b, C.byref(ms)), "hjb_cpra_scatter_rel")
-        return float(ms.value)
+    # ---- the stream-ordered CPRA step (include/hjb200.h: hjb_cpra_bind ... hjb_cpra_finish)
+    def cpra_bind(self, gpu, ngpus, peer_ptrs, r_capacity, s_capacity):
+        cols = [(C.c_void_p * ngpus)(*[C.c_void_p(p) for p in peer_ptrs[c]]) for c in range(4)]
+        self._check(self._lib.hjb_cpra_bind(self._ctx, int(gpu), int(ngpus), cols[0], cols[1], cols[2], cols[3],
+                                            int(r_capacity), int(s_capacity)), "hjb_cpra_bind")
 
-    def cpra_stage_rel(self, rel, ngpus):
-        self._check(self._lib.hjb_cpra_stage_rel(self._ctx, int(rel), int(ngpus)), "hjb_cpra_stage_rel")
-
-    def cpra_send_staged(self, rel, ngpus, me, peer_keys, peer_vals, base):
-        pk = (C.c_void_p * ngpus)(*[C.c_void_p(p) for p in peer_keys])
-        pv = (C.c_void_p * ngpus)(*[C.c_void_p(p) for p in peer_vals])
-        b = (C.c_uint64 * ngpus)(*[int(x) for x in base])
-        self._check(self._lib.hjb_cpra_send_staged(self._ctx, int(rel), int(ngpus), int(me), pk, pv, b), "hjb_cpra_send_staged")
-
-    def cpra_send_wait(self):
-        ms = C.c_float()
-        self._check(self._lib.hjb_cpra_send_wait(self._ctx, C.byref(ms)), "hjb_cpra_send_wait")
-        self._pending_keep = None
-        return float(ms.value)
-
-    def cpra_join_begin(self, inner_recv, s_tuples, gpu, ngpus, **opts):
-        R, _, on_dev, keep = self._rels(inner_recv, inner_recv)
+    def cpra_count_async(self, inner_chunk, outer_chunk, counts_dev, **opts):
+        """counts_dev: int64 CUDA tensor of 2*ngpus elements (the all-gather's input)."""
+        R, S, on_dev, keep = self._rels(inner_chunk, outer_chunk)
         if not on_dev:
-            raise HjbError("cpra_join_begin takes device columns")
+            raise HjbError("cpra_count_async takes device columns")
         o = self._opts(**opts)
-        self._join_keep = keep
-        self._check(self._lib.hjb_cpra_join_begin(self._ctx, C.byref(R), int(s_tuples), int(gpu), int(ngpus), C.byref(o)),
-                    "hjb_cpra_join_begin")
+        self._check(self._lib.hjb_cpra_count_async(self._ctx, C.byref(R), C.byref(S), C.byref(o), C.c_void_p(counts_dev.data_ptr())),
+                    "hjb_cpra_count_async")
+        self._pending_keep = keep          # the chunks must outlive the scatter
 
-    def cpra_join_finish(self, outer_recv, **opts):
-        S, _, on_dev, keep = self._rels(outer_recv, outer_recv)
-        if not on_dev:
-            raise HjbError("cpra_join_finish takes device columns")
+    def cpra_scatter_async(self, matrix_dev):
+        self._check(self._lib.hjb_cpra_scatter_async(self._ctx, C.c_void_p(matrix_dev.data_ptr())), "hjb_cpra_scatter_async")
+
+    def cpra_join_async(self, r_expect=0, s_expect=0, **opts):
+        o = self._opts(**opts)
+        self._check(self._lib.hjb_cpra_join_async(self._ctx, C.byref(o), int(r_expect), int(s_expect)), "hjb_cpra_join_async")
+
+    def cpra_sums_dev(self):
+        """int64 CUDA tensor aliasing this GPU's (count, sum_key, sum_outer, sum_inner) of the enqueued join."""
+        return self.device_view64(self._lib.hjb_cpra_sums_dev(self._ctx), 4)
+
+    def cpra_finish(self):
+        """-> (JoinResult, (R rows, S rows) received here, (R rows, S rows) received by the fullest owner)"""
         res = Result()
-        o = self._opts(**opts)
-        self._check(self._lib.hjb_cpra_join_finish(self._ctx, C.byref(S), C.byref(o), C.byref(res)), "hjb_cpra_join_finish")
-        self._join_keep = None
-        return JoinResult(res, self)
+        got, big = (C.c_uint64 * 2)(), (C.c_uint64 * 2)()
+        rc = self._lib.hjb_cpra_finish(self._ctx, C.byref(res), got, big)
+        self._pending_keep = None
+        if rc == _lib.HJB_E_CAPACITY:
+            raise HjbCapacityError(self._lib.hjb_last_error(self._ctx).decode(), (int(big[0]), int(big[1])))
+        self._check(rc, "hjb_cpra_finish")
+        return JoinResult(res, self), (int(got[0]), int(got[1])), (int(big[0]), int(big[1]))
+
+    def device_view64(self, ptr, n):
+        import torch
+        arr = type("A", (), {"__cuda_array_interface__": {"shape": (int(n),), "typestr": "<i8", "data": (int(ptr), False),
+                                                          "version": 2, "strides": None}})()
+        return torch.as_tensor(arr, device=f"cuda:{self.device}")
 
     def device_view(self, ptr, n):
         """int32 CUDA tensor aliasing n elements of library-owned device memory."""

@@ -84,8 +84,9 @@ def cpra_join(engine, inner_chunk, outer_chunk, group=None, split_fn=None, join_
 
 class FusedExchange:
     """State of the fused GPU-assign + exchange pass for one Engine / process group: this GPU's
-    receive buffers and the peers' buffers mapped through CUDA IPC.  (Re)built collectively
-    whenever some rank would receive more rows than the current capacity."""
+    receive buffers, the peers' buffers mapped through CUDA IPC, and the small device tensors
+    the collectives work on.  (Re)built collectively whenever some rank would receive more rows
+    than the current capacity."""
 
     def __init__(self, engine, group=None):
         self.engine, self.group = engine, group
@@ -94,6 +95,11 @@ class FusedExchange:
         self.own = None
         self.peers = None          # [column][owner] device pointers valid in this process
         self._opened = []
+        dev = torch.device(f"cuda:{engine.device}")
+        self.counts = torch.zeros(2 * self.world, dtype=torch.int64, device=dev)
+        self.matrix = torch.zeros(2 * self.world * self.world, dtype=torch.int64, device=dev)
+        self.token = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.sums = torch.zeros(4, dtype=torch.int64, device=dev)
 
     def ensure(self, r_need, s_need):
         """r_need / s_need: the largest row count any rank receives (identical on every rank)."""
@@ -117,71 +123,50 @@ class FusedExchange:
                 else:
                     self.peers[c][g] = self.engine.ipc_open(handles[g][c])
                     self._opened.append(self.peers[c][g])
+        self.engine.cpra_bind(self.rank, self.world, self.peers, self.r_cap, self.s_cap)
 
 
 def cpra_join_fused(engine, inner_chunk, outer_chunk, state, group=None, **opts):
-    """CPRA with the all-to-all fused into the GPU-assign pass: counts -> all-gather of the
-    count matrix -> every sender scatters straight into the owners' receive buffers over NVLink
-    -> barrier -> local join.  Same result dict as cpra_join."""
-    world, rank = state.world, state.rank
-    dev = torch.device(f"cuda:{engine.device}")
-    r_cnt, s_cnt = engine.cpra_count(inner_chunk, outer_chunk, world, **opts)
-    mine = torch.tensor(r_cnt + s_cnt, dtype=torch.int64, device=dev)
-    allc = torch.empty(world * 2 * world, dtype=torch.int64, device=dev)
-    dist.all_gather_into_tensor(allc, mine, group=group)
-    C = allc.view(world, 2 * world).cpu().tolist()          # C[src][dst] (R), C[src][world + dst] (S)
-    r_recv = [sum(C[s][g] for s in range(world)) for g in range(world)]
-    s_recv = [sum(C[s][world + g] for s in range(world)) for g in range(world)]
-    state.ensure(max(r_recv), max(s_recv))
-    r_base = [sum(C[s][g] for s in range(rank)) for g in range(world)]
-    s_base = [sum(C[s][world + g] for s in range(rank)) for g in range(world)]
-    scatter_ms = engine.cpra_scatter_peer(world, state.peers, r_base, s_base)
-    t0 = torch.cuda.Event(enable_timing=True)
-    t1 = torch.cuda.Event(enable_timing=True)
-    t0.record()
-    dist.barrier(group=group)                                # every sender's stores have landed
-    t1.record()
-    own = state.own["ptrs"]
-    rk, rv = engine.device_view(own[0], r_recv[rank]), engine.device_view(own[1], r_recv[rank])
-    sk, sv = engine.device_view(own[2], s_recv[rank]), engine.device_view(own[3], s_recv[rank])
-    local = engine.cpra_join_local((rk, rv), (sk, sv), rank, world, **opts)
-    count, sum_key, sum_outer, sum_inner = reduce_checks(local.count, local.sum_key, local.sum_outer,
-                                                         local.sum_inner, dev, group)
-    return {"count": count, "sum_key": sum_key, "sum_outer": sum_outer, "sum_inner": sum_inner, "local": local,
-            "split_ms": scatter_ms, "exchange_ms": t0.elapsed_time(t1), "join_ms": float(local.seconds) * 1e3,
-            "recv_tuples": (r_recv[rank], s_recv[rank])}
+    """CPRA with the all-to-all fused into the GPU-assign pass, the whole step enqueued on ONE stream:
+    count -> all-gather of the count matrix (NCCL) -> bases on the device -> every sender scatters
+    straight into the owners' receive buffers over NVLink -> 1-element all-reduce (every sender's stores
+    have landed) -> local join with the received sizes read on the device -> all-reduce of the
+    checksums.  The host synchronises once, at the end.  Same result dict as cpra_join.
 
-
-def cpra_join_overlap(engine, inner_chunk, outer_chunk, state, group=None, **opts):
-    """CPRA with the probe side's exchange overlapped with the build side's local partitioning:
-    R travels through the fused scatter; S is split locally and then moved by the copy engines
-    while the SMs partition the R tuples that have already arrived.  Same result dict as
-    cpra_join_fused (split_ms: fused scatter of R; exchange_ms: the copies of S)."""
+    Requires the Engine to run on torch's current stream (Engine(use_torch_stream=True)): NCCL's
+    collectives are ordered with the library's kernels through that stream."""
     world, rank = state.world, state.rank
-    dev = torch.device(f"cuda:{engine.device}")
-    r_cnt, s_cnt = engine.cpra_count(inner_chunk, outer_chunk, world, **opts)
-    mine = torch.tensor(r_cnt + s_cnt, dtype=torch.int64, device=dev)
-    allc = torch.empty(world * 2 * world, dtype=torch.int64, device=dev)
-    dist.all_gather_into_tensor(allc, mine, group=group)
-    C = allc.view(world, 2 * world).cpu().tolist()
-    r_recv = [sum(C[s][g] for s in range(world)) for g in range(world)]
-    s_recv = [sum(C[s][world + g] for s in range(world)) for g in range(world)]
-    state.ensure(max(r_recv), max(s_recv))
-    r_base = [sum(C[s][g] for s in range(rank)) for g in range(world)]
-    s_base = [sum(C[s][world + g] for s in range(rank)) for g in range(world)]
-    scatter_ms = engine.cpra_scatter_rel(0, world, state.peers[0], state.peers[1], r_base)
-    engine.cpra_stage_rel(1, world)                          # asynchronous: runs while the ranks meet at the barrier
-    dist.barrier(group=group)                                # every R tuple has landed
-    engine.cpra_send_staged(1, world, rank, state.peers[2], state.peers[3], s_base)
-    own = state.own["ptrs"]
-    rk, rv = engine.device_view(own[0], r_recv[rank]), engine.device_view(own[1], r_recv[rank])
-    engine.cpra_join_begin((rk, rv), s_recv[rank], rank, world, **opts)
-    copy_ms = engine.cpra_send_wait()
-    dist.barrier(group=group)                                # every S tuple has landed
-    sk, sv = engine.device_view(own[2], s_recv[rank]), engine.device_view(own[3], s_recv[rank])
-    local = engine.cpra_join_finish((sk, sv), **opts)
-    count, sum_key, sum_outer, sum_inner = reduce_checks(local.count, local.sum_key, local.sum_outer,
-                                                         local.sum_inner, dev, group)
+    from .api import HjbCapacityError
+    nr, ns = int(inner_chunk[0].numel()), int(outer_chunk[0].numel())
+    if state.own is None:
+        # first step: room for a uniform share plus a quarter; a skewed input grows it below
+        tot = torch.tensor([nr, ns], dtype=torch.int64, device=state.counts.device)
+        dist.all_reduce(tot, group=group)
+        tr, ts = (int(x) for x in tot.tolist())
+        state.ensure(tr // world + tr // (4 * world) + 1024, ts // world + ts // (4 * world) + 1024)
+    while True:
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+        ev[0].record()
+        engine.cpra_count_async(inner_chunk, outer_chunk, state.counts, **opts)
+        dist.all_gather_into_tensor(state.matrix, state.counts, group=group)
+        engine.cpra_scatter_async(state.matrix)
+        ev[1].record()
+        dist.all_reduce(state.token, group=group)            # completes here once every rank has passed its scatter
+        ev[2].record()
+        engine.cpra_join_async(r_expect=state.expect[0] if hasattr(state, "expect") else 0,
+                               s_expect=state.expect[1] if hasattr(state, "expect") else 0, **opts)
+        state.sums.copy_(engine.cpra_sums_dev())
+        dist.all_reduce(state.sums, group=group)
+        ev[3].record()
+        try:
+            local, received, largest = engine.cpra_finish()
+        except HjbCapacityError as e:
+            state.ensure(*e.largest)                         # every rank saw the same matrix and takes this branch
+            continue
+        break
+    state.expect = received
+    count, sum_key, sum_outer, sum_inner = (int(x) & ((1 << 64) - 1) for x in state.sums.tolist())
     return {"count": count, "sum_key": sum_key, "sum_outer": sum_outer, "sum_inner": sum_inner, "local": local,
-            "split_ms": scatter_ms, "exchange_ms": copy_ms, "join_ms": float(local.seconds) * 1e3,
-            "recv_tuples": (r_recv[rank], s_recv[rank])}
+            "split_ms": ev[0].elapsed_time(ev[1]), "exchange_ms": ev[1].elapsed_time(ev[2]),
+            "join_ms": float(local.seconds) * 1e3, "step_ms": ev[0].elapsed_time(ev[3]),
+            "recv_tuples": received, "largest_recv": largest}

@@ -66,15 +66,17 @@ struct hjb_ctx {
 	KernelTimer timer;        // per-kernel times of the last join (hjb_set_profiling)
 	char *recv_buf[4];        // CPRA fused exchange: receive columns r_keys r_vals s_keys s_vals
 	uint64_t recv_cap[2];
-	char *stage_buf;          // CPRA overlapped exchange: locally split probe side waiting for its copy-engine transfer
-	size_t stage_bytes;
-	uint32_t *stage_k, *stage_v;
-	bool cj_active;           // hjb_cpra_join_begin -> hjb_cpra_join_finish
-	uint32_t cj_launches;
-	struct PhjState *cj_state;
 	RadixPassArgs pending[2]; // hjb_cpra_count -> hjb_cpra_scatter_peer
-	uint32_t pending_off[2][65];
 	int pending_gpus;
+	uint32_t *cpra_dev;       // device words of the fused exchange: bases, receive ranges, abort flag (enum CD_*)
+	// stream-ordered CPRA (hjb_cpra_bind ... hjb_cpra_finish)
+	void *bind_peer[4][64];
+	int bind_gpu, bind_gpus;
+	uint64_t bind_cap[2];
+	int step_state;           // 0 idle, 1 counted, 2 scattered, 3 join enqueued
+	uint32_t step_launches;
+	struct PhjState *step_phj;
+	hjb_opts step_opts;
 };
 
 static char g_create_err[512];
@@ -162,9 +164,9 @@ extern "C" int hjb_destroy(hjb_ctx *ctx)
 	cudaFree(ctx->out_cols);
 	cudaFree(ctx->in_buf);
 	cudaFree(ctx->split_buf);
-	cudaFree(ctx->stage_buf);
-	free(ctx->cj_state);
 	for (int i = 0; i < 4; ++i) cudaFree(ctx->recv_buf[i]);
+	cudaFree(ctx->cpra_dev);
+	free(ctx->step_phj);
 	cudaFree(ctx->d_scalars);
 	cudaFreeHost(ctx->h_scalars);
 	cudaFreeHost(ctx->h_small);
@@ -280,6 +282,7 @@ static void zero_result(hjb_result *out)
 static void timer_reset(hjb_ctx *ctx)
 {
 	ctx->timer.n = 0;
+	ctx->timer.dropped = 0;
 	memset(ctx->timer.ms, 0, sizeof ctx->timer.ms);
 	memset(ctx->timer.launches, 0, sizeof ctx->timer.launches);
 }
@@ -298,22 +301,6 @@ static void timer_collect(hjb_ctx *ctx)
 	t.n = 0;
 }
 
-// debug: the 8 phase-cycle counters the join kernel fills when HJB_PHASE_CLOCKS is set (d_scalars[8..15])
-extern "C" int hjb_debug_counters(hjb_ctx *ctx, uint64_t *out8)
-{
-	if (!ctx || !out8) return HJB_E_INVALID;
-	if (getenv("HJB_SCATTER_CLOCKS")) {          // the scatter kernel's phase clocks instead (read and cleared)
-		unsigned long long v[8];
-		cudaSetDevice(ctx->device);
-		cudaDeviceSynchronize();
-		scatter_phase_clocks(v);
-		for (int k = 0; k < 8; ++k) out8[k] = v[k];
-		return HJB_OK;
-	}
-	for (int k = 0; k < 8; ++k) out8[k] = ctx->h_scalars[8 + k];
-	return HJB_OK;
-}
-
 extern "C" int hjb_set_profiling(hjb_ctx *ctx, int on)
 {
 	if (!ctx) return HJB_E_INVALID;
@@ -325,13 +312,14 @@ extern "C" int hjb_set_profiling(hjb_ctx *ctx, int on)
 extern "C" const char *hjb_kernel_name(int kind)
 {
 	static const char *names[KK_COUNT] = {"k_make_items", "k_hist", "k_scan", "k_scatter", "k_join_tasks",
-	                                      "k_partition_join", "k_npj_build", "k_npj_probe"};
+	                                      "k_partition_join", "k_npj_build", "k_npj_probe", "k_scatter_bulk"};
 	return kind >= 0 && kind < KK_COUNT ? names[kind] : nullptr;
 }
 
 extern "C" int hjb_kernel_times(hjb_ctx *ctx, float *ms, uint32_t *launches, int max_kinds)
 {
 	if (!ctx || !ms || !launches) return HJB_E_INVALID;
+	if (ctx->timer.dropped) return fail(ctx, HJB_E_NOMEM, "hjb_kernel_times: more launches than event pairs, times incomplete");
 	for (int k = 0; k < max_kinds && k < KK_COUNT; ++k) {
 		ms[k] = ctx->timer.ms[k];
 		launches[k] = ctx->timer.launches[k];
@@ -388,6 +376,7 @@ static int npj_device(hjb_ctx *ctx, const hjb_rel *R, const hjb_rel *S, const hj
 	a.nr = R->tuples; a.ns = S->tuples;
 	a.table = (uint64_t *)ctx->ws;
 	a.buckets = buckets;
+	a.phases = npj_phases(buckets);
 	a.factor = hjb_hash_factor(o->seed, 1);
 	a.scalars = ctx->d_scalars;
 	a.materialize = o->materialize;
@@ -499,10 +488,12 @@ struct Partitioned {
 // all passes over one relation; ping-pongs between two workspace buffers
 static int partition_relation(hjb_ctx *ctx, const hjb_rel *rel, const Plan &p, int consumed, uint32_t factor,
                               uint32_t *bufk[2], uint32_t *bufv[2], uint32_t *off[2], char *scratch,
-                              Partitioned *res, uint32_t *launches)
+                              Partitioned *res, uint32_t *launches, const uint32_t *dev_range = nullptr)
 {
+	// dev_range: {0, tuples} in DEVICE memory -- the relation's size is then only known there (CPRA's receive
+	// buffers in the stream-ordered path) and rel->tuples is an upper bound that sizes grids and scratch
 	const uint32_t *ink = rel->keys, *inv = rel->vals;
-	const uint32_t *parent = nullptr;
+	const uint32_t *parent = dev_range;
 	uint32_t np = 1;
 	int used = consumed;
 	for (int i = 0; i < p.npass; ++i) {
@@ -516,13 +507,7 @@ static int partition_relation(hjb_ctx *ctx, const hjb_rel *rel, const Plan &p, i
 		a.factor = factor;
 		a.bits = p.bits[i];
 		a.rshift = 32 - used - p.bits[i];
-		uint32_t tiles;
-		radix_scratch_bytes(a.n, np, a.bits, &a.chunk, &a.max_items, &tiles);
-		Bump b = {scratch, 0};
-		a.item_prefix = b.take<uint32_t>(np + 1);
-		a.counts = b.take<uint32_t>((size_t)a.max_items << a.bits);
-		a.scan_status = b.take<uint64_t>(tiles);
-		a.scan_counter = b.take<uint32_t>(1);
+		radix_carve(a, scratch, true);
 		*launches += launch_radix_pass(a, ctx->stream, ctx->sms, &ctx->timer);
 		ink = a.keys_out; inv = a.vals_out;
 		parent = a.child_off;
@@ -548,11 +533,13 @@ struct PhjState {
 };
 
 static int phj_setup(hjb_ctx *ctx, uint64_t nr, uint64_t ns_slice, uint64_t ns_total, const hjb_opts *o, int consumed,
-                     uint32_t owner, PhjState *st)
+                     uint32_t owner, PhjState *st, uint64_t nr_plan = 0, uint64_t ns_plan = 0)
 {
+	// nr / ns_slice / ns_total size the buffers; the plan is made for nr_plan / ns_plan tuples when given (sizes
+	// that are only upper bounds here, the expected sizes there)
 	int rc;
 	memset(st, 0, sizeof *st);
-	if ((rc = make_plan(ctx, nr, ns_total, o, consumed, &st->plan))) return rc;
+	if ((rc = make_plan(ctx, nr_plan ? nr_plan : nr, ns_plan ? ns_plan : ns_total, o, consumed, &st->plan))) return rc;
 	const Plan &plan = st->plan;
 	size_t rscratch;
 	const size_t need = phj_workspace(nr, ns_slice, plan, &rscratch);
@@ -579,26 +566,27 @@ static int phj_setup(hjb_ctx *ctx, uint64_t nr, uint64_t ns_slice, uint64_t ns_t
 	return HJB_OK;
 }
 
-__global__ void k_set_pair(uint32_t *dst, uint32_t a, uint32_t b)
+__global__ void k_set_pair(uint32_t *dst, uint32_t a, uint32_t b, const uint32_t *src)
 {
-	dst[0] = a;
-	dst[1] = b;
+	dst[0] = src ? src[0] : a;
+	dst[1] = src ? src[1] : b;
 }
 
 // one side through all radix passes (no pass at all: a single partition [0, n))
-static int phj_partition_side(hjb_ctx *ctx, PhjState *st, const hjb_rel *rel, bool build_side, uint32_t *launches)
+static int phj_partition_side(hjb_ctx *ctx, PhjState *st, const hjb_rel *rel, bool build_side, uint32_t *launches,
+                              const uint32_t *dev_range = nullptr)
 {
 	cudaStream_t s = ctx->stream;
 	Partitioned *res = build_side ? &st->pr : &st->ps;
 	uint32_t **off = build_side ? st->roff : st->soff;
 	if (st->plan.npass == 0) {
 		// by value in the kernel arguments: nothing on the host that a later call (or a graph replay) could find changed
-		k_set_pair<<<1, 1, 0, s>>>(off[0], 0u, (uint32_t)rel->tuples);
+		k_set_pair<<<1, 1, 0, s>>>(off[0], 0u, (uint32_t)rel->tuples, dev_range);
 		res->k = rel->keys; res->v = rel->vals; res->off = off[0];
 		return HJB_OK;
 	}
 	return partition_relation(ctx, rel, st->plan, st->consumed, st->radix_factor, build_side ? st->rbk : st->sbk,
-	                          build_side ? st->rbv : st->sbv, off, st->scratch, res, launches);
+	                          build_side ? st->rbv : st->sbv, off, st->scratch, res, launches, dev_range);
 }
 
 static int phj_launch_join(hjb_ctx *ctx, PhjState *st, const hjb_opts *o, uint32_t *launches)
@@ -869,6 +857,7 @@ static int host_join_pipelined(hjb_ctx *ctx, bool npj, const hjb_rel *R, const h
 		a.rk = drk; a.rv = drv; a.nr = R->tuples;
 		a.table = (uint64_t *)ctx->ws;
 		a.buckets = buckets;
+		a.phases = npj_phases(buckets);
 		a.factor = hjb_hash_factor(o->seed, 1);
 		a.scalars = ctx->d_scalars;
 		a.materialize = o->materialize;
@@ -1027,12 +1016,7 @@ extern "C" int hjb_cpra_split(hjb_ctx *ctx, const hjb_rel *R, const hjb_rel *S, 
 		a.factor = hjb_hash_factor(o->seed, 0);
 		a.bits = gbits;
 		a.rshift = 32 - gbits;
-		radix_scratch_bytes(a.n, 1, gbits, &a.chunk, &a.max_items, &tiles);
-		Bump w = {ctx->ws, 0};
-		a.item_prefix = w.take<uint32_t>(2);
-		a.counts = w.take<uint32_t>((size_t)a.max_items << gbits);
-		a.scan_status = w.take<uint64_t>(tiles);
-		a.scan_counter = w.take<uint32_t>(1);
+		radix_carve(a, ctx->ws, true);
 		launches += launch_radix_pass(a, s, ctx->sms, &ctx->timer);
 	}
 	CK(cudaEventRecord(ctx->ev[5], s));
@@ -1097,6 +1081,42 @@ extern "C" int hjb_ipc_close(hjb_ctx *ctx, void *dev_ptr)
 	return HJB_OK;
 }
 
+// hjb_cpra_count's enqueue half: histogram + scan by owner of both chunks; the counted passes stay in ctx->pending
+static int cpra_count_enqueue(hjb_ctx *ctx, const hjb_rel *R, const hjb_rel *S, int ngpus, const hjb_opts *o,
+                              uint32_t *off_dev[2], uint32_t *launches)
+{
+	int rc;
+	const int gbits = log2_exact(ngpus);
+	const hjb_rel *rel[2] = {R, S};
+	size_t scratch[2], total = 0;
+	for (int r = 0; r < 2; ++r) {
+		uint32_t chunk, mi, tiles;
+		scratch[r] = radix_scratch_bytes(rel[r]->tuples, 1, gbits, &chunk, &mi, &tiles);
+		total += scratch[r] + pad256((size_t)(ngpus + 1) * 4);
+	}
+	if ((rc = grow_device(ctx, &ctx->split_buf, &ctx->split_bytes, total + 4096))) return rc;
+	cudaStream_t s = ctx->stream;
+	Bump w = {ctx->split_buf, 0};
+	for (int r = 0; r < 2; ++r) {
+		RadixPassArgs &a = ctx->pending[r];
+		memset(&a, 0, sizeof a);
+		a.keys = rel[r]->keys; a.vals = rel[r]->vals;
+		a.n = rel[r]->tuples;
+		a.np = 1;
+		a.factor = hjb_hash_factor(o->seed, 0);
+		a.bits = gbits;
+		a.rshift = 32 - gbits;
+		off_dev[r] = a.child_off = w.take<uint32_t>(ngpus + 1);
+		radix_carve(a, w.take<char>(scratch[r]), false);         // the peer scatter ranks its tiles itself: no tile counts
+		if (a.n == 0) {
+			CK(cudaMemsetAsync(a.child_off, 0, (size_t)(ngpus + 1) * 4, s));
+			continue;
+		}
+		*launches += launch_radix_count(a, s, &ctx->timer);
+	}
+	return HJB_OK;
+}
+
 extern "C" int hjb_cpra_count(hjb_ctx *ctx, const hjb_rel *R, const hjb_rel *S, int ngpus, const hjb_opts *opts,
                               uint64_t *r_counts, uint64_t *s_counts)
 {
@@ -1108,60 +1128,36 @@ extern "C" int hjb_cpra_count(hjb_ctx *ctx, const hjb_rel *R, const hjb_rel *S, 
 	if (gbits < 1 || ngpus > 64) return fail(ctx, HJB_E_INVALID, "ngpus must be a power of two in [2, 64]");
 	CK(cudaSetDevice(ctx->device));
 	timer_reset(ctx);
-	const hjb_rel *rel[2] = {R, S};
-	size_t scratch[2], total = 0;
-	for (int r = 0; r < 2; ++r) {
-		uint32_t chunk, mi, tiles;
-		scratch[r] = radix_scratch_bytes(rel[r]->tuples, 1, gbits, &chunk, &mi, &tiles) + pad256((size_t)(ngpus + 1) * 4);
-		total += scratch[r];
-	}
-	if ((rc = grow_device(ctx, &ctx->split_buf, &ctx->split_bytes, total + 4096))) return rc;
 	cudaStream_t s = ctx->stream;
-	Bump w = {ctx->split_buf, 0};
 	uint32_t launches = 0;
 	uint32_t *off_dev[2];
-	for (int r = 0; r < 2; ++r) {
-		RadixPassArgs &a = ctx->pending[r];
-		memset(&a, 0, sizeof a);
-		a.keys = rel[r]->keys; a.vals = rel[r]->vals;
-		a.n = rel[r]->tuples;
-		a.np = 1;
-		a.factor = hjb_hash_factor(o->seed, 0);
-		a.bits = gbits;
-		a.rshift = 32 - gbits;
-		uint32_t tiles;
-		radix_scratch_bytes(a.n, 1, gbits, &a.chunk, &a.max_items, &tiles);
-		off_dev[r] = a.child_off = w.take<uint32_t>(ngpus + 1);
-		a.item_prefix = w.take<uint32_t>(2);
-		a.counts = w.take<uint32_t>((size_t)a.max_items << gbits);
-		a.scan_status = w.take<uint64_t>(tiles);
-		a.scan_counter = w.take<uint32_t>(1);
-		if (a.n == 0) {
-			CK(cudaMemsetAsync(a.child_off, 0, (size_t)(ngpus + 1) * 4, s));
-			continue;
-		}
-		launches += launch_radix_count(a, s, &ctx->timer);
-	}
+	if ((rc = cpra_count_enqueue(ctx, R, S, ngpus, o, off_dev, &launches))) return rc;
 	CK(cudaMemcpyAsync(&ctx->h_small[0], off_dev[0], (size_t)(ngpus + 1) * 4, cudaMemcpyDeviceToHost, s));
 	CK(cudaMemcpyAsync(&ctx->h_small[128], off_dev[1], (size_t)(ngpus + 1) * 4, cudaMemcpyDeviceToHost, s));
 	CK(cudaStreamSynchronize(s));
 	CK(cudaGetLastError());
 	timer_collect(ctx);
-	for (int g = 0; g <= ngpus; ++g) {
-		ctx->pending_off[0][g] = ctx->h_small[g];
-		ctx->pending_off[1][g] = ctx->h_small[128 + g];
-	}
 	for (int g = 0; g < ngpus; ++g) {
-		r_counts[g] = ctx->pending_off[0][g + 1] - ctx->pending_off[0][g];
-		s_counts[g] = ctx->pending_off[1][g + 1] - ctx->pending_off[1][g];
+		r_counts[g] = ctx->h_small[g + 1] - ctx->h_small[g];
+		s_counts[g] = ctx->h_small[128 + g + 1] - ctx->h_small[128 + g];
 	}
 	ctx->pending_gpus = ngpus;
 	ctx->launches += launches;
 	return HJB_OK;
 }
 
+// device words of the fused exchange (ctx->cpra_dev, uint32): the scatter kernel and the local join read them there
+enum { CD_BASE_R = 0, CD_BASE_S = 64, CD_RANGE_R = 128, CD_RANGE_S = 130, CD_ABORT = 132, CD_MAX_R = 133, CD_MAX_S = 134,
+       CD_WORDS = 136 };
+
+static int cpra_dev_alloc(hjb_ctx *ctx)
+{
+	if (!ctx->cpra_dev) CK(cudaMalloc(&ctx->cpra_dev, CD_WORDS * 4));
+	return HJB_OK;
+}
+
 // the fused scatter of one counted relation into the owners' columns (asynchronous)
-static int cpra_scatter_one(hjb_ctx *ctx, int r, int ngpus, void *const *pk, void *const *pv, const uint64_t *base,
+static int cpra_scatter_one(hjb_ctx *ctx, int r, int ngpus, void *const *pk, void *const *pv, bool check_abort,
                             uint32_t *launches)
 {
 	RadixPassArgs &a = ctx->pending[r];
@@ -1169,19 +1165,17 @@ static int cpra_scatter_one(hjb_ctx *ctx, int r, int ngpus, void *const *pk, voi
 	PeerTable t;
 	memset(&t, 0, sizeof t);
 	for (int g = 0; g < ngpus; ++g) {
-		// the scan's positions start at pending_off[g] for owner g: shift the column so that they land at base[g]
-		const int64_t shift = (int64_t)base[g] - (int64_t)ctx->pending_off[r][g];
-		// bias: the kernel counts positions as pending_off + bias, congruent to the physical row modulo the
-		// write-combining granule, so that its flush boundaries are line boundaries in the owner's buffer
-		const int64_t bias = ((shift % (int64_t)kPeerCarry) + kPeerCarry) % kPeerCarry;
-		t.bias[g] = (uint32_t)bias;
-		t.k[g] = (uint32_t *)pk[g] + (shift - bias);
-		t.v[g] = (uint32_t *)pv[g] + (shift - bias);
+		t.k[g] = (uint32_t *)pk[g];
+		t.v[g] = (uint32_t *)pv[g];
 	}
-	static int env_ctas = -1;       // experiment knob: HJB_PEER_CTAS limits the peer scatter's grid
-	if (env_ctas < 0) env_ctas = getenv("HJB_PEER_CTAS") ? atoi(getenv("HJB_PEER_CTAS")) : 0;
+	t.base = ctx->cpra_dev + (r ? CD_BASE_S : CD_BASE_R);
+	t.sender_off = a.child_off;
+	t.abort_flag = check_abort ? ctx->cpra_dev + CD_ABORT : nullptr;
+	static const int env_ctas = getenv("HJB_PEER_CTAS") ? atoi(getenv("HJB_PEER_CTAS")) : 0;   // experiment knob: limits the peer scatter's grid
 	a.peer_ctas = (uint32_t)env_ctas;
-	*launches += launch_radix_scatter(a, ctx->stream, &ctx->timer, &t);
+	const int n = launch_radix_scatter(a, ctx->stream, &ctx->timer, &t);
+	if (n < 0) return fail(ctx, HJB_E_INVALID, "peer scatter: more than 64 owners");
+	*launches += n;
 	return HJB_OK;
 }
 
@@ -1195,9 +1189,16 @@ extern "C" int hjb_cpra_scatter_peer(hjb_ctx *ctx, int ngpus, void *const *peer_
 	cudaStream_t s = ctx->stream;
 	uint32_t launches = 0;
 	int rc;
+	if ((rc = cpra_dev_alloc(ctx))) return rc;
+	for (int g = 0; g < ngpus; ++g) {
+		if (r_base[g] > 0xFFFFFFFFull || s_base[g] > 0xFFFFFFFFull) return fail(ctx, HJB_E_INVALID, "base row beyond 2^32-1");
+		ctx->h_small[CD_BASE_R + g] = (uint32_t)r_base[g];
+		ctx->h_small[CD_BASE_S + g] = (uint32_t)s_base[g];
+	}
+	CK(cudaMemcpyAsync(ctx->cpra_dev, ctx->h_small, 128 * 4, cudaMemcpyHostToDevice, s));
 	CK(cudaEventRecord(ctx->ev[6], s));
-	if ((rc = cpra_scatter_one(ctx, 0, ngpus, peer_r_keys, peer_r_vals, r_base, &launches))) return rc;
-	if ((rc = cpra_scatter_one(ctx, 1, ngpus, peer_s_keys, peer_s_vals, s_base, &launches))) return rc;
+	if ((rc = cpra_scatter_one(ctx, 0, ngpus, peer_r_keys, peer_r_vals, false, &launches))) return rc;
+	if ((rc = cpra_scatter_one(ctx, 1, ngpus, peer_s_keys, peer_s_vals, false, &launches))) return rc;
 	CK(cudaEventRecord(ctx->ev[7], s));
 	CK(cudaStreamSynchronize(s));            // the owners may read once every sender has passed this point
 	CK(cudaGetLastError());
@@ -1205,86 +1206,6 @@ extern "C" int hjb_cpra_scatter_peer(hjb_ctx *ctx, int ngpus, void *const *peer_
 	if (ms) CK(cudaEventElapsedTime(ms, ctx->ev[6], ctx->ev[7]));
 	ctx->pending_gpus = 0;
 	ctx->launches += launches;
-	return HJB_OK;
-}
-
-extern "C" int hjb_cpra_scatter_rel(hjb_ctx *ctx, int rel, int ngpus, void *const *peer_keys, void *const *peer_vals,
-                                    const uint64_t *base, float *ms)
-{
-	if (!ctx || !peer_keys || !peer_vals || !base || rel < 0 || rel > 1) return HJB_E_INVALID;
-	if (ngpus != ctx->pending_gpus || ngpus < 2) return fail(ctx, HJB_E_INVALID, "hjb_cpra_count must precede with the same ngpus");
-	CK(cudaSetDevice(ctx->device));
-	cudaStream_t s = ctx->stream;
-	uint32_t launches = 0;
-	int rc;
-	CK(cudaEventRecord(ctx->ev[6], s));
-	if ((rc = cpra_scatter_one(ctx, rel, ngpus, peer_keys, peer_vals, base, &launches))) return rc;
-	CK(cudaEventRecord(ctx->ev[7], s));
-	CK(cudaStreamSynchronize(s));
-	CK(cudaGetLastError());
-	timer_collect(ctx);
-	if (ms) CK(cudaEventElapsedTime(ms, ctx->ev[6], ctx->ev[7]));
-	ctx->launches += launches;
-	return HJB_OK;
-}
-
-extern "C" int hjb_cpra_stage_rel(hjb_ctx *ctx, int rel, int ngpus)
-{
-	if (!ctx || rel < 0 || rel > 1) return HJB_E_INVALID;
-	if (ngpus != ctx->pending_gpus || ngpus < 2) return fail(ctx, HJB_E_INVALID, "hjb_cpra_count must precede with the same ngpus");
-	CK(cudaSetDevice(ctx->device));
-	int rc;
-	if ((rc = pipe_setup(ctx))) return rc;
-	RadixPassArgs &a = ctx->pending[rel];
-	const size_t col = pad256(a.n * 4);
-	if ((rc = grow_device(ctx, &ctx->stage_buf, &ctx->stage_bytes, 2 * col + 256))) return rc;
-	ctx->stage_k = (uint32_t *)ctx->stage_buf;
-	ctx->stage_v = (uint32_t *)(ctx->stage_buf + col);
-	uint32_t launches = 0;
-	if (a.n) {
-		a.keys_out = ctx->stage_k;
-		a.vals_out = ctx->stage_v;
-		launches += launch_radix_scatter(a, ctx->stream, &ctx->timer, nullptr);
-	}
-	CK(cudaEventRecord(ctx->pipe_ev[1][kMaxHostSlices], ctx->stream));     // the pieces are ready
-	CK(cudaGetLastError());
-	ctx->launches += launches;
-	return HJB_OK;
-}
-
-extern "C" int hjb_cpra_send_staged(hjb_ctx *ctx, int rel, int ngpus, int self, void *const *peer_keys,
-                                    void *const *peer_vals, const uint64_t *base)
-{
-	if (!ctx || !peer_keys || !peer_vals || !base || rel < 0 || rel > 1 || self < 0 || self >= ngpus) return HJB_E_INVALID;
-	if (ngpus != ctx->pending_gpus || !ctx->pipe_ready || !ctx->stage_k)
-		return fail(ctx, HJB_E_INVALID, "hjb_cpra_stage_rel must precede");
-	CK(cudaSetDevice(ctx->device));
-	// two copy streams (keys, payloads) so that two copy engines work at once; this GPU's own piece goes last
-	cudaStream_t ck = ctx->pipe_out, cv = ctx->pipe_in;
-	CK(cudaStreamWaitEvent(ck, ctx->pipe_ev[1][kMaxHostSlices], 0));
-	CK(cudaStreamWaitEvent(cv, ctx->pipe_ev[1][kMaxHostSlices], 0));
-	CK(cudaEventRecord(ctx->ev[10], ck));
-	for (int i = 1; i <= ngpus; ++i) {                        // start with the neighbour: the senders spread over the receivers
-		const int g = (self + i) % ngpus;
-		const uint64_t beg = ctx->pending_off[rel][g], cnt = ctx->pending_off[rel][g + 1] - beg;
-		if (!cnt) continue;
-		CK(cudaMemcpyAsync((uint32_t *)peer_keys[g] + base[g], ctx->stage_k + beg, cnt * 4, cudaMemcpyDeviceToDevice, ck));
-		CK(cudaMemcpyAsync((uint32_t *)peer_vals[g] + base[g], ctx->stage_v + beg, cnt * 4, cudaMemcpyDeviceToDevice, cv));
-	}
-	CK(cudaEventRecord(ctx->pipe_ev[0][kMaxHostSlices], cv));
-	CK(cudaStreamWaitEvent(ck, ctx->pipe_ev[0][kMaxHostSlices], 0));      // ev[11] on ck marks the end of both streams' copies
-	CK(cudaEventRecord(ctx->ev[11], ck));
-	return HJB_OK;
-}
-
-extern "C" int hjb_cpra_send_wait(hjb_ctx *ctx, float *ms)
-{
-	if (!ctx || !ctx->pipe_ready) return HJB_E_INVALID;
-	CK(cudaSetDevice(ctx->device));
-	CK(cudaStreamSynchronize(ctx->pipe_out));        // ordered after the payload stream's copies as well
-	CK(cudaGetLastError());
-	if (ms) CK(cudaEventElapsedTime(ms, ctx->ev[10], ctx->ev[11]));
-	ctx->pending_gpus = 0;
 	return HJB_OK;
 }
 
@@ -1297,74 +1218,194 @@ extern "C" int hjb_cpra_join_local(hjb_ctx *ctx, const hjb_rel *R, const hjb_rel
 	return phj_device(ctx, R, S, opts ? opts : &kDefaultOpts, gbits, out, (uint32_t)gpu);
 }
 
-extern "C" int hjb_cpra_join_begin(hjb_ctx *ctx, const hjb_rel *R, uint64_t s_tuples, int gpu, int ngpus, const hjb_opts *opts)
+// ---- the same exchange, stream-ordered: nothing between the count and the result touches the host ----------
+
+// this sender's tuples per owner, R then S, as the all-gather's input
+__global__ void k_cpra_counts(const uint32_t *__restrict__ r_off, const uint32_t *__restrict__ s_off, int G,
+                              unsigned long long *__restrict__ counts)
 {
-	if (!ctx || !R) return HJB_E_INVALID;
-	const hjb_opts *o = opts ? opts : &kDefaultOpts;
-	const int gbits = log2_exact(ngpus);
-	if (gbits < 0 || ngpus > 64 || gpu < 0 || gpu >= ngpus) return fail(ctx, HJB_E_INVALID, "bad gpu / ngpus");
-	int rc;
-	if ((rc = check_rel(ctx, R, true))) return rc;
-	if (s_tuples > 0xFFFFFFFFull) return fail(ctx, HJB_E_INVALID, "more than 2^32-1 tuples per relation per GPU");
-	CK(cudaSetDevice(ctx->device));
-	ctx->cj_active = false;
-	ctx->cj_launches = 0;
-	if (!ctx->cj_state && !(ctx->cj_state = (PhjState *)calloc(1, sizeof(PhjState)))) return HJB_E_NOMEM;
-	if (R->tuples == 0 || s_tuples == 0) {          // nothing to join: finish returns the empty result
-		ctx->cj_active = true;
-		ctx->cj_state->P = 0;
-		return HJB_OK;
+	const int g = threadIdx.x;
+	if (g < G) {
+		counts[g] = r_off[g + 1] - r_off[g];
+		counts[G + g] = s_off[g + 1] - s_off[g];
 	}
-	PhjState &st = *ctx->cj_state;
-	if ((rc = phj_setup(ctx, R->tuples, s_tuples, s_tuples, o, gbits, (uint32_t)gpu, &st))) return rc;
-	cudaStream_t s = ctx->stream;
-	CK(cudaEventRecord(ctx->ev[0], s));
-	CK(cudaMemsetAsync(ctx->d_scalars, 0, 16 * 8, s));
-	if ((rc = phj_partition_side(ctx, &st, R, true, &ctx->cj_launches))) return rc;
-	CK(cudaEventRecord(ctx->ev[1], s));
-	CK(cudaGetLastError());
-	ctx->cj_active = true;
+}
+
+// From the all-gathered count matrix M[src][2 G] (R counts, then S counts): the first row of every owner's
+// columns reserved for this sender (the senders before it come first, as thread t's pieces precede thread
+// t+1's in the reference's gather, cpra2.cpp:1896-1904), what this GPU receives in total, and whether
+// every owner's buffer is large enough -- every sender reaches the same verdict from the same matrix.
+__global__ void k_cpra_bases(const unsigned long long *__restrict__ M, int G, int me, unsigned long long cap_r,
+                             unsigned long long cap_s, uint32_t *__restrict__ out)
+{
+	__shared__ unsigned long long s_max[2];
+	const int g = threadIdx.x;
+	if (g < 2) s_max[g] = 0;
+	__syncthreads();
+	unsigned long long base_r = 0, base_s = 0, tot_r = 0, tot_s = 0;
+	if (g < G) {
+		for (int src = 0; src < G; ++src) {
+			const unsigned long long cr = M[(size_t)src * 2 * G + g], cs = M[(size_t)src * 2 * G + G + g];
+			if (src < me) {
+				base_r += cr;
+				base_s += cs;
+			}
+			tot_r += cr;
+			tot_s += cs;
+		}
+		atomicMax(&s_max[0], tot_r);
+		atomicMax(&s_max[1], tot_s);
+	}
+	const int abort = __syncthreads_or(g < G && (tot_r > cap_r || tot_s > cap_s));
+	if (g < G) {
+		out[CD_BASE_R + g] = (uint32_t)base_r;
+		out[CD_BASE_S + g] = (uint32_t)base_s;
+		if (g == me) {
+			out[CD_RANGE_R] = 0;
+			out[CD_RANGE_R + 1] = abort ? 0u : (uint32_t)tot_r;
+			out[CD_RANGE_S] = 0;
+			out[CD_RANGE_S + 1] = abort ? 0u : (uint32_t)tot_s;
+		}
+	}
+	if (g == 0) {
+		out[CD_ABORT] = abort ? 1u : 0u;
+		out[CD_MAX_R] = (uint32_t)(s_max[0] > 0xFFFFFFFFull ? 0xFFFFFFFFull : s_max[0]);
+		out[CD_MAX_S] = (uint32_t)(s_max[1] > 0xFFFFFFFFull ? 0xFFFFFFFFull : s_max[1]);
+	}
+}
+
+extern "C" int hjb_cpra_bind(hjb_ctx *ctx, int gpu, int ngpus, void *const *peer_r_keys, void *const *peer_r_vals,
+                             void *const *peer_s_keys, void *const *peer_s_vals, uint64_t r_capacity, uint64_t s_capacity)
+{
+	if (!ctx || !peer_r_keys || !peer_r_vals || !peer_s_keys || !peer_s_vals) return HJB_E_INVALID;
+	const int gbits = log2_exact(ngpus);
+	if (gbits < 1 || ngpus > 64 || gpu < 0 || gpu >= ngpus) return fail(ctx, HJB_E_INVALID, "ngpus must be a power of two in [2, 64], gpu in [0, ngpus)");
+	if (r_capacity > 0xFFFFFFFFull || s_capacity > 0xFFFFFFFFull) return fail(ctx, HJB_E_INVALID, "capacity beyond 2^32-1 rows");
+	CK(cudaSetDevice(ctx->device));
+	int rc;
+	if ((rc = cpra_dev_alloc(ctx))) return rc;
+	void *const *cols[4] = {peer_r_keys, peer_r_vals, peer_s_keys, peer_s_vals};
+	for (int c = 0; c < 4; ++c)
+		for (int g = 0; g < ngpus; ++g) {
+			if (!cols[c][g] || ((uintptr_t)cols[c][g] & 127)) return fail(ctx, HJB_E_INVALID, "peer columns must be 128-byte aligned device memory");
+			ctx->bind_peer[c][g] = cols[c][g];
+		}
+	ctx->bind_gpu = gpu;
+	ctx->bind_gpus = ngpus;
+	ctx->bind_cap[0] = r_capacity;
+	ctx->bind_cap[1] = s_capacity;
+	ctx->step_state = 0;
 	return HJB_OK;
 }
 
-extern "C" int hjb_cpra_join_finish(hjb_ctx *ctx, const hjb_rel *S, const hjb_opts *opts, hjb_result *out)
+extern "C" int hjb_cpra_count_async(hjb_ctx *ctx, const hjb_rel *R, const hjb_rel *S, const hjb_opts *opts, uint64_t *counts_dev)
 {
-	if (!ctx || !S || !out) return HJB_E_INVALID;
+	if (!ctx || !counts_dev) return HJB_E_INVALID;
+	if (!ctx->bind_gpus) return fail(ctx, HJB_E_INVALID, "hjb_cpra_bind must precede");
 	const hjb_opts *o = opts ? opts : &kDefaultOpts;
-	if (!ctx->cj_active) return fail(ctx, HJB_E_INVALID, "hjb_cpra_join_begin must precede");
-	ctx->cj_active = false;
 	int rc;
-	if ((rc = check_rel(ctx, S, true))) return rc;
+	if ((rc = check_rel(ctx, R, true)) || (rc = check_rel(ctx, S, true))) return rc;
+	CK(cudaSetDevice(ctx->device));
+	timer_reset(ctx);
+	uint32_t *off_dev[2];
+	ctx->step_launches = 0;
+	if ((rc = cpra_count_enqueue(ctx, R, S, ctx->bind_gpus, o, off_dev, &ctx->step_launches))) return rc;
+	k_cpra_counts<<<1, 64, 0, ctx->stream>>>(off_dev[0], off_dev[1], ctx->bind_gpus, (unsigned long long *)counts_dev);
+	ctx->step_launches += 1;
+	CK(cudaGetLastError());
+	ctx->pending_gpus = ctx->bind_gpus;
+	ctx->step_state = 1;
+	return HJB_OK;
+}
+
+extern "C" int hjb_cpra_scatter_async(hjb_ctx *ctx, const uint64_t *matrix_dev)
+{
+	if (!ctx || !matrix_dev) return HJB_E_INVALID;
+	if (ctx->step_state != 1) return fail(ctx, HJB_E_INVALID, "hjb_cpra_count_async must precede");
+	CK(cudaSetDevice(ctx->device));
+	const int G = ctx->bind_gpus;
+	int rc;
+	k_cpra_bases<<<1, 64, 0, ctx->stream>>>((const unsigned long long *)matrix_dev, G, ctx->bind_gpu, ctx->bind_cap[0],
+	                                        ctx->bind_cap[1], ctx->cpra_dev);
+	ctx->step_launches += 1;
+	if ((rc = cpra_scatter_one(ctx, 0, G, ctx->bind_peer[0], ctx->bind_peer[1], true, &ctx->step_launches))) return rc;
+	if ((rc = cpra_scatter_one(ctx, 1, G, ctx->bind_peer[2], ctx->bind_peer[3], true, &ctx->step_launches))) return rc;
+	CK(cudaGetLastError());
+	ctx->pending_gpus = 0;
+	ctx->step_state = 2;
+	return HJB_OK;
+}
+
+extern "C" int hjb_cpra_join_async(hjb_ctx *ctx, const hjb_opts *opts, uint64_t r_expect, uint64_t s_expect)
+{
+	if (!ctx) return HJB_E_INVALID;
+	if (ctx->step_state != 2) return fail(ctx, HJB_E_INVALID, "hjb_cpra_scatter_async must precede");
+	const hjb_opts *o = opts ? opts : &kDefaultOpts;
+	CK(cudaSetDevice(ctx->device));
+	const int G = ctx->bind_gpus, me = ctx->bind_gpu;
+	int rc;
+	if (!ctx->step_phj && !(ctx->step_phj = (PhjState *)calloc(1, sizeof(PhjState)))) return HJB_E_NOMEM;
+	PhjState &st = *ctx->step_phj;
+	const uint64_t rc_cap = ctx->bind_cap[0], sc_cap = ctx->bind_cap[1];
+	if (r_expect == 0 || r_expect > rc_cap) r_expect = rc_cap;
+	if (s_expect == 0 || s_expect > sc_cap) s_expect = sc_cap;
+	hjb_opts oo = *o;
+	if (!oo.out_capacity) oo.out_capacity = sc_cap > rc_cap ? sc_cap : rc_cap;
+	if ((rc = phj_setup(ctx, rc_cap, sc_cap, sc_cap, &oo, log2_exact(G), (uint32_t)me, &st, r_expect, s_expect))) return rc;
+	ctx->step_opts = oo;
+	cudaStream_t s = ctx->stream;
+	CK(cudaEventRecord(ctx->ev[0], s));
+	CK(cudaMemsetAsync(ctx->d_scalars, 0, 16 * 8, s));
+	const hjb_rel Rr = {(const uint32_t *)ctx->bind_peer[0][me], (const uint32_t *)ctx->bind_peer[1][me], rc_cap};
+	const hjb_rel Sr = {(const uint32_t *)ctx->bind_peer[2][me], (const uint32_t *)ctx->bind_peer[3][me], sc_cap};
+	if ((rc = phj_partition_side(ctx, &st, &Rr, true, &ctx->step_launches, ctx->cpra_dev + CD_RANGE_R))) return rc;
+	if ((rc = phj_partition_side(ctx, &st, &Sr, false, &ctx->step_launches, ctx->cpra_dev + CD_RANGE_S))) return rc;
+	CK(cudaEventRecord(ctx->ev[2], s));
+	if ((rc = phj_launch_join(ctx, &st, &oo, &ctx->step_launches))) return rc;
+	CK(cudaEventRecord(ctx->ev[3], s));
+	CK(cudaGetLastError());
+	ctx->step_state = 3;
+	return HJB_OK;
+}
+
+extern "C" void *hjb_cpra_sums_dev(hjb_ctx *ctx) { return ctx ? (void *)(ctx->d_scalars + 1) : nullptr; }
+
+extern "C" int hjb_cpra_finish(hjb_ctx *ctx, hjb_result *out, uint64_t received[2], uint64_t largest[2])
+{
+	if (!ctx || !out) return HJB_E_INVALID;
+	if (ctx->step_state != 3) return fail(ctx, HJB_E_INVALID, "hjb_cpra_join_async must precede");
+	ctx->step_state = 0;
 	zero_result(out);
 	CK(cudaSetDevice(ctx->device));
-	PhjState &st = *ctx->cj_state;
-	if (st.P == 0 || S->tuples == 0) {
-		CK(cudaStreamSynchronize(ctx->stream));
-		timer_collect(ctx);
-		return HJB_OK;
-	}
 	cudaStream_t s = ctx->stream;
-	uint32_t launches = ctx->cj_launches;
-	if ((rc = phj_partition_side(ctx, &st, S, false, &launches))) return rc;
-	CK(cudaEventRecord(ctx->ev[2], s));
+	PhjState &st = *ctx->step_phj;
+	const hjb_opts *o = &ctx->step_opts;
+	int rc;
+	CK(cudaMemcpyAsync(&ctx->h_small[128], ctx->cpra_dev + 128, 8 * 4, cudaMemcpyDeviceToHost, s));
+	uint32_t launches = ctx->step_launches;
 	for (int attempt = 0; attempt < 2; ++attempt) {
-		if ((rc = phj_launch_join(ctx, &st, o, &launches))) return rc;
-		CK(cudaEventRecord(ctx->ev[3], s));
-		CK(cudaGetLastError());
 		if ((rc = read_scalars(ctx, out))) return rc;
-		if (ctx->h_scalars[7]) return fail(ctx, HJB_E_INVALID, "hjb_cpra_join_finish: a tuple does not hash into this owner's range");
+		if (received) {
+			received[0] = ctx->h_small[CD_RANGE_R + 1];
+			received[1] = ctx->h_small[CD_RANGE_S + 1];
+		}
+		if (largest) {
+			largest[0] = ctx->h_small[CD_MAX_R];
+			largest[1] = ctx->h_small[CD_MAX_S];
+		}
+		if (ctx->h_small[CD_ABORT]) return fail(ctx, HJB_E_CAPACITY, "hjb_cpra_finish: an owner's receive buffer is too small; nothing was exchanged");
+		if (ctx->h_scalars[7]) return fail(ctx, HJB_E_INVALID, "hjb_cpra_finish: a tuple does not hash into this owner's range");
 		if (!o->materialize || out->count <= ctx->out_cap) break;
 		if (attempt == 1) return fail(ctx, HJB_E_CUDA, "result overflow after regrow");
 		if ((rc = grow_out(ctx, out->count))) return rc;
-		CK(cudaMemsetAsync(ctx->d_scalars, 0, 16 * 8, s));
+		CK(cudaMemsetAsync(ctx->d_scalars, 0, 16 * 8, s));         // rerun the join phase only
+		if ((rc = phj_launch_join(ctx, &st, o, &launches))) return rc;
+		CK(cudaEventRecord(ctx->ev[3], s));
 	}
 	float ms = 0;
 	CK(cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[3]));
-	out->seconds = ms * 1e-3;                               // from the first build-side kernel: includes the wait for the probe side
-	if (st.plan.npass) {
-		CK(cudaEventElapsedTime(&out->phase_ms[0], ctx->ev[0], ctx->ev[1]));
-		CK(cudaEventElapsedTime(&out->phase_ms[1], ctx->ev[1], ctx->ev[2]));
-	}
+	out->seconds = ms * 1e-3;                               // the local join only
+	CK(cudaEventElapsedTime(&out->phase_ms[0], ctx->ev[0], ctx->ev[2]));     // both sides' local passes
 	CK(cudaEventElapsedTime(&out->phase_ms[4], ctx->ev[2], ctx->ev[3]));
 	out->kernel_launches = launches;
 	out->partitions = st.P;
@@ -1427,12 +1468,7 @@ extern "C" int hjb_partition_pass(hjb_ctx *ctx, const uint32_t *keys, const uint
 	a.factor = factor;
 	a.bits = bits;
 	a.rshift = 32 - shift - bits;
-	a.chunk = chunk;
-	a.max_items = mi;
-	a.item_prefix = b.take<uint32_t>(np + 1);
-	a.counts = b.take<uint32_t>((size_t)mi << bits);
-	a.scan_status = b.take<uint64_t>(tiles);
-	a.scan_counter = b.take<uint32_t>(1);
+	radix_carve(a, ctx->ws + b.off, true);
 	ctx->launches += launch_radix_pass(a, s, ctx->sms);
 	CK(cudaMemcpyAsync(child_offsets, d_child, ((size_t)nc + 1) * 4, cudaMemcpyDeviceToHost, s));
 	CK(cudaStreamSynchronize(s));
@@ -1452,6 +1488,7 @@ extern "C" int hjb_npj_build(hjb_ctx *ctx, const uint32_t *keys, const uint32_t 
 	memset(&a, 0, sizeof a);
 	a.rk = keys; a.rv = vals; a.nr = size;
 	a.table = table; a.buckets = buckets; a.factor = factor;
+	a.phases = 1;
 	a.scalars = ctx->d_scalars;
 	CK(cudaMemsetAsync(ctx->d_scalars, 0, 16 * 8, ctx->stream));
 	ctx->launches += launch_npj_build(a, ctx->stream, ctx->sms);

@@ -161,7 +161,9 @@ __device__ __forceinline__ uint32_t upper_parent(const uint32_t *a, uint32_t n, 
 	return lo;
 }
 
-// warp-collective: at most one match per item and lane, rows of item t of all lanes contiguous
+// warp-collective: at most one match per item and lane, rows of item t of all lanes contiguous.
+// Rows that would not fit the result columns are not written at all: the cursor still counts them, the
+// host sees count > capacity, grows the columns and runs the join phase again.
 template <int ITEMS>
 __device__ __forceinline__ void emit_round(const OutCols &out, const bool (&found)[ITEMS], const uint32_t (&key)[ITEMS],
                                            const uint32_t (&val)[ITEMS], const uint32_t (&ival)[ITEMS])
@@ -173,33 +175,20 @@ __device__ __forceinline__ void emit_round(const OutCols &out, const bool (&foun
 	unsigned long long base = 0;
 	if (lane_id() == 0) base = atomicAdd(out.cursor, (unsigned long long)total);
 	base = __shfl_sync(kFullMask, base, 0);
+	if (base + total > out.cap) return;
 	const unsigned lt = lanemask_lt();
-	if (base + total <= out.cap) {                 // common case: no per-row capacity test, 32-bit offsets
-		uint32_t *const ck = out.k + base, *const co = out.o + base, *const ci = out.i + base;
-		uint32_t off = 0;
+	uint32_t *const ck = out.k + base, *const co = out.o + base, *const ci = out.i + base;
+	uint32_t off = 0;
 #pragma unroll
-		for (int t = 0; t < ITEMS; ++t) {
-			const unsigned mt = __ballot_sync(kFullMask, found[t]);
-			const uint32_t r = off + __popc(mt & lt);
-			if (found[t]) {
-				ck[r] = key[t];
-				co[r] = val[t];
-				ci[r] = ival[t];
-			}
-			off += __popc(mt);
+	for (int t = 0; t < ITEMS; ++t) {
+		const unsigned mt = __ballot_sync(kFullMask, found[t]);
+		const uint32_t r = off + __popc(mt & lt);
+		if (found[t]) {
+			ck[r] = key[t];
+			co[r] = val[t];
+			ci[r] = ival[t];
 		}
-	} else {
-#pragma unroll
-		for (int t = 0; t < ITEMS; ++t) {
-			const unsigned mt = __ballot_sync(kFullMask, found[t]);
-			const uint64_t r = base + __popc(mt & lt);
-			if (found[t] && r < out.cap) {
-				out.k[r] = key[t];
-				out.o[r] = val[t];
-				out.i[r] = ival[t];
-			}
-			base += __popc(mt);
-		}
+		off += __popc(mt);
 	}
 }
 

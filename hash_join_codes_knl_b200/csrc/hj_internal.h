@@ -21,18 +21,23 @@ constexpr int kNpjItems = 4;                  // probe tuples per thread per rou
 
 // optional per-launch CUDA-event timing on the launching stream (bench.py's roofline line)
 enum KernelKind { KK_MAKE_ITEMS = 0, KK_HIST, KK_SCAN, KK_SCATTER, KK_JOIN_TASKS, KK_PART_JOIN, KK_NPJ_BUILD,
-                  KK_NPJ_PROBE, KK_COUNT };
+                  KK_NPJ_PROBE, KK_SCATTER_PEER, KK_COUNT };
 struct KernelTimer {
-	static constexpr int kMaxLaunches = 96;
+	static constexpr int kMaxLaunches = 384;     // a sliced host join: 16 probe slices of ~20 kernels + the build side
 	cudaEvent_t beg[kMaxLaunches], end[kMaxLaunches];
 	int kind[kMaxLaunches];
 	int n;
+	int dropped;                                  // launches that found the event pool full (reported by hjb_kernel_times)
 	bool enabled;
 	float ms[KK_COUNT];
 	uint32_t launches[KK_COUNT];
 	void start(int k, cudaStream_t s)
 	{
-		if (!enabled || n >= kMaxLaunches) return;
+		if (!enabled) return;
+		if (n >= kMaxLaunches) {
+			++dropped;
+			return;
+		}
 		kind[n] = k;
 		cudaEventRecord(beg[n], s);
 	}
@@ -56,26 +61,35 @@ struct RadixPassArgs {
 	uint32_t chunk;                   // tuples per work item
 	uint32_t max_items;               // upper bound n/chunk + np
 	uint32_t peer_ctas;               // peer scatter only: CTAs to launch (0 = one per item)
+	uint32_t tiles_per_item;          // rows of tile_counts per item
 	// scratch (device)
 	uint32_t *item_prefix;            // np + 1
 	uint32_t *counts;                 // max_items * 2^bits  (histogram, then offsets in place)
 	uint64_t *scan_status;            // tiles
 	uint32_t *scan_counter;           // 1
+	uint16_t *tile_counts;            // max_items * tiles_per_item * 2^bits digit counts per scatter tile; nullptr: none
+	                                  // (fan-out > 256, or the pass feeds the peer scatter, which ranks its tiles itself)
 };
-// per-owner output columns of the fused GPU-assign pass (CPRA): pointers into the owners' receive buffers
+// per-owner output columns of the fused GPU-assign pass (CPRA): the owners' receive buffers as mapped into this
+// process, and -- in device memory, so that no host round trip sits between the count exchange and the scatter --
+// the first row of every owner's buffer reserved for this sender
 struct PeerTable {
 	uint32_t *k[64];
 	uint32_t *v[64];
-	uint32_t bias[64];        // added to the owner's positions so that they are congruent, modulo the
-	                          // write-combining granule, to the physical row in the owner's buffer
+	const uint32_t *base;        // [fan-out] device: row of owner g's columns where this sender's tuples start
+	const uint32_t *sender_off;  // [fan-out + 1] device: the scan's owner offsets of this sender's chunk (child_off)
+	const uint32_t *abort_flag;  // device, may be null: non-zero = some owner's buffer is too small, scatter nothing
 };
 constexpr uint32_t kPeerCarry = 32;       // peer stores are combined to whole 128-byte lines (fan-out <= 64)
-size_t radix_scratch_bytes(uint64_t n, uint32_t np, int bits, uint32_t *chunk, uint32_t *max_items, uint32_t *tiles);
+size_t radix_scratch_bytes(uint64_t n, uint32_t np, int bits, uint32_t *chunk, uint32_t *max_items, uint32_t *tiles,
+                           uint32_t *tiles_per_item = nullptr);
+// fills a.chunk / max_items / tiles_per_item and carves a's scratch arrays out of `scratch` (radix_scratch_bytes of
+// a.n, a.np, a.bits); tile_counts = false leaves a.tile_counts null
+void radix_carve(RadixPassArgs &a, char *scratch, bool tile_counts);
 // launches make_items + histogram + scan + scatter; returns kernels launched
 int launch_radix_pass(const RadixPassArgs &a, cudaStream_t s, int sms, KernelTimer *t = nullptr);
 int launch_radix_count(const RadixPassArgs &a, cudaStream_t s, KernelTimer *t = nullptr);
 int launch_radix_scatter(const RadixPassArgs &a, cudaStream_t s, KernelTimer *t = nullptr, const PeerTable *peers = nullptr);
-void scatter_phase_clocks(unsigned long long *out8);
 int launch_histogram_only(const uint32_t *keys, uint64_t n, uint32_t *counts_dev, uint32_t factor,
                           int rshift, int bits, cudaStream_t s, int sms);
 
@@ -103,12 +117,14 @@ struct NpjArgs {
 	uint64_t nr, ns;
 	uint64_t *table;
 	uint64_t buckets;                         // x 4 slots
+	uint32_t phases;                          // table slices built / probed one after the other (npj_phases); 0 = 1
 	uint32_t factor;
 	uint32_t *out_k, *out_o, *out_i;
 	uint64_t out_cap;
 	unsigned long long *scalars;              // [0] cursor, [1..4] sums, [5] sentinel build tuples, [6] duplicate build keys seen
 	int materialize;
 };
+uint32_t npj_phases(uint64_t buckets);
 int launch_npj_build(const NpjArgs &a, cudaStream_t s, int sms, KernelTimer *t = nullptr);
 int launch_npj_probe(const NpjArgs &a, cudaStream_t s, int sms, KernelTimer *t = nullptr);
 

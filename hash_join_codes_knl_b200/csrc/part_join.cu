@@ -30,18 +30,23 @@
 
 namespace hjb {
 
-// tasks per partition -> exclusive prefix; P <= 2^22.  CTA b owns partitions [1024 b, 1024 b + 1024):
-// it publishes its block total as a status word (bit 63 = ready), then sums the status words of
-// ALL lower blocks -- they were dispatched earlier, so waiting on them cannot deadlock, and the
-// waits are independent loads rather than a chain.
+// tasks per partition -> exclusive prefix; P <= 2^22.  A CTA takes its block of 1024 partitions from an atomic
+// ticket (so the blocks START in prefix order whatever order the hardware dispatches CTAs in), publishes its
+// block total as a status word (bit 63 = ready), then sums the status words of ALL lower blocks -- their
+// owners hold earlier tickets, i.e. are running, so waiting on them cannot deadlock, and the waits are
+// independent loads rather than a chain.
 constexpr uint32_t kTaskBlock = 1024;
 __global__ void __launch_bounds__(1024)
 k_join_tasks(const uint32_t *__restrict__ r_off, const uint32_t *__restrict__ s_off, uint32_t P, uint32_t s_task,
-             uint32_t *__restrict__ task_prefix, unsigned long long *__restrict__ status)
+             uint32_t *__restrict__ task_prefix, unsigned long long *__restrict__ status, uint32_t *__restrict__ ticket)
 {
 	__shared__ uint32_t warp_totals[34];
 	__shared__ uint64_t s_before[32];
-	const uint32_t p = blockIdx.x * kTaskBlock + threadIdx.x;
+	__shared__ uint32_t s_block;
+	if (threadIdx.x == 0) s_block = atomicAdd(ticket, 1u);
+	__syncthreads();
+	const uint32_t block = s_block;
+	const uint32_t p = block * kTaskBlock + threadIdx.x;
 	uint32_t v = 0;
 	if (p < P) {
 		const uint32_t rc = r_off[p + 1] - r_off[p], sc = s_off[p + 1] - s_off[p];
@@ -50,11 +55,11 @@ k_join_tasks(const uint32_t *__restrict__ r_off, const uint32_t *__restrict__ s_
 	uint32_t tot;
 	const uint32_t excl = block_exclusive_scan(v, warp_totals, &tot);
 	if (threadIdx.x == 0) {
-		atomicExch(&status[blockIdx.x], (1ull << 63) | tot);
+		atomicExch(&status[block], (1ull << 63) | tot);
 		__threadfence();
 	}
 	uint64_t before = 0;
-	for (uint32_t b = threadIdx.x; b < blockIdx.x; b += 1024) {
+	for (uint32_t b = threadIdx.x; b < block; b += 1024) {
 		unsigned long long w;
 		do {
 			w = *reinterpret_cast<volatile unsigned long long *>(&status[b]);
@@ -68,7 +73,7 @@ k_join_tasks(const uint32_t *__restrict__ r_off, const uint32_t *__restrict__ s_
 #pragma unroll 8
 	for (int w = 0; w < 32; ++w) base += (uint32_t)s_before[w];
 	if (p < P) task_prefix[p] = base + excl;
-	if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) task_prefix[P] = base + tot;
+	if (block == gridDim.x - 1 && threadIdx.x == 0) task_prefix[P] = base + tot;
 }
 
 // one row, reservation aggregated over whichever lanes of the warp are here together
@@ -94,30 +99,19 @@ constexpr uint32_t kHashFill = kHashSlots / 4 * 3;       // load <= 0.75
 constexpr size_t kDirectBytes = (size_t)kDirectWords * 8 + (size_t)kDirectFill * 4;
 constexpr size_t kJoinSmemBytes = (size_t)kHashSlots * 8 > kDirectBytes ? (size_t)kHashSlots * 8 : kDirectBytes;
 
-template <int THREADS, int ITEMS, int MINB, bool MATERIALIZE, bool CLOCKS = false>
+template <int THREADS, int ITEMS, int MINB, bool MATERIALIZE, bool OWNER>
 __global__ void __launch_bounds__(THREADS, MINB)
 k_partition_join(const uint32_t *__restrict__ rk, const uint32_t *__restrict__ rv,
                  const uint32_t *__restrict__ sk, const uint32_t *__restrict__ sv,
                  const uint32_t *__restrict__ r_off, const uint32_t *__restrict__ s_off, uint32_t P,
                  const uint32_t *__restrict__ task_prefix, uint32_t *__restrict__ task_counter, uint32_t s_task,
                  uint32_t radix_factor, uint32_t table_factor, int rem_bits, uint32_t owner, int owner_bits,
-                 OutCols out, unsigned long long *__restrict__ sums, unsigned long long *__restrict__ phase_clk)
+                 OutCols out, unsigned long long *__restrict__ sums)
 {
-	// optional phase clocks (HJB_PHASE_CLOCKS=1 selects the CLOCKS instantiation): thread 0 of every CTA adds the
-	// cycles it spent per phase.  Compiled out of the product kernel: the marks cost registers (spills at 64).
-	long long clk_t = 0;
-#define PHASE_MARK(k)                                              \
-	if (CLOCKS && threadIdx.x == 0) {                               \
-		const long long now_ = clock64();                           \
-		atomicAdd(&phase_clk[k], (unsigned long long)(now_ - clk_t)); \
-		clk_t = now_;                                               \
-	}
-	if (CLOCKS && threadIdx.x == 0) clk_t = clock64();
 	extern __shared__ __align__(16) unsigned char s_raw[];
 	// DIRECT view
-	uint32_t *bitmap = reinterpret_cast<uint32_t *>(s_raw);            // kDirectWords
-	uint32_t *prefix = bitmap + kDirectWords;                          // kDirectWords
-	uint32_t *dvals = prefix + kDirectWords;                           // kDirectFill
+	uint2 *bp = reinterpret_cast<uint2 *>(s_raw);                      // kDirectWords x (presence word, set bits before it)
+	uint32_t *dvals = reinterpret_cast<uint32_t *>(bp + kDirectWords); // kDirectFill
 	// HASH view
 	uint64_t *table = reinterpret_cast<uint64_t *>(s_raw);             // kHashSlots
 	__shared__ uint64_t scratch[4 * 32];
@@ -131,7 +125,7 @@ k_partition_join(const uint32_t *__restrict__ rk, const uint32_t *__restrict__ r
 	acc.zero();
 	// CPRA local join: every tuple must hash into this GPU's owner range (top owner_bits bits of
 	// key * radix_factor), else the DIRECT tables would confuse keys; violations are reported, not joined
-	const int owner_shift = owner_bits ? 32 - owner_bits : 0;
+	const int owner_shift = OWNER ? 32 - owner_bits : 0;
 	uint32_t foreign = 0;
 	const uint32_t total_tasks = task_prefix[P];
 	// Every thread resolves a task's ranges itself from uniform (broadcast) loads -- no barrier, no
@@ -172,7 +166,6 @@ k_partition_join(const uint32_t *__restrict__ rk, const uint32_t *__restrict__ r
 			prefetch_col(sk, ns_beg, ns_end);
 			prefetch_col(sv, ns_beg, ns_end);
 		};
-		PHASE_MARK(0)      // task bookkeeping
 
 		uint32_t fb = r_beg;
 		while (fb < r_end) {
@@ -180,10 +173,9 @@ k_partition_join(const uint32_t *__restrict__ rk, const uint32_t *__restrict__ r
 			uint32_t fe = min(fb + (use_hash ? kHashFill : kDirectFill), r_end);
 			if (!use_hash) {
 				// ---- DIRECT build, step 1: presence bits (equal keys set the same bit: step 2 counts fewer bits than tuples)
-				for (uint32_t w = threadIdx.x; w < kDirectWords / 4; w += THREADS)
-					reinterpret_cast<uint4 *>(bitmap)[w] = make_uint4(0, 0, 0, 0);
+				for (uint32_t w = threadIdx.x; w < kDirectWords / 2; w += THREADS)
+					reinterpret_cast<uint4 *>(bp)[w] = make_uint4(0, 0, 0, 0);
 				__syncthreads();
-				PHASE_MARK(1)      // bitmap clear
 				look_ahead();
 				// build tuples are fetched kBatch at a time so that their loads are in flight together; the
 				// first batch (all of a typical partition) stays in registers for step 3
@@ -200,8 +192,8 @@ k_partition_join(const uint32_t *__restrict__ rk, const uint32_t *__restrict__ r
 					if (fb + threadIdx.x + t * THREADS < fe) {
 						const uint32_t x = hash_mul(k0[t], radix_factor), lo = x & rem_mask;
 						const uint32_t bit = 1u << (lo & 31);
-						if (owner_bits) foreign |= (x >> owner_shift) ^ owner;
-						atomicOr(&bitmap[lo >> 5], bit);              // result unused: a reduction, no return path
+						if (OWNER) foreign |= (x >> owner_shift) ^ owner;
+						atomicOr(&bp[lo >> 5].x, bit);                // result unused: a reduction, no return path
 					}
 				for (uint32_t i0 = fb + threadIdx.x + THREADS * kBatch; i0 < fe; i0 += THREADS * kBatch) {
 					uint32_t bk[kBatch];
@@ -212,12 +204,11 @@ k_partition_join(const uint32_t *__restrict__ rk, const uint32_t *__restrict__ r
 						if (i0 + t * THREADS < fe) {
 							const uint32_t x = hash_mul(bk[t], radix_factor), lo = x & rem_mask;
 							const uint32_t bit = 1u << (lo & 31);
-							if (owner_bits) foreign |= (x >> owner_shift) ^ owner;
-							atomicOr(&bitmap[lo >> 5], bit);              // result unused: a reduction, no return path
+							if (OWNER) foreign |= (x >> owner_shift) ^ owner;
+							atomicOr(&bp[lo >> 5].x, bit);                // result unused: a reduction, no return path
 						}
 				}
 				__syncthreads();
-				PHASE_MARK(2)      // build step 1: key loads + atomicOr
 				{
 					// step 2: rank structure -- prefix[w] = set bits before word w; fewer bits than build tuples
 					// means equal keys: that fill is redone with the hash table
@@ -225,7 +216,7 @@ k_partition_join(const uint32_t *__restrict__ rk, const uint32_t *__restrict__ r
 					uint32_t c[kPer], local = 0;
 #pragma unroll
 					for (uint32_t j = 0; j < kPer; ++j) {
-						c[j] = __popc(bitmap[threadIdx.x * kPer + j]);
+						c[j] = __popc(bp[threadIdx.x * kPer + j].x);
 						local += c[j];
 					}
 					uint32_t tot;
@@ -233,11 +224,10 @@ k_partition_join(const uint32_t *__restrict__ rk, const uint32_t *__restrict__ r
 					use_hash = tot != fe - fb;
 #pragma unroll
 					for (uint32_t j = 0; j < kPer; ++j) {
-						prefix[threadIdx.x * kPer + j] = run;
+						bp[threadIdx.x * kPer + j].y = run;
 						run += c[j];
 					}
 					__syncthreads();
-					PHASE_MARK(3)      // rank scan
 				}
 				if (!use_hash) {
 					// step 3: payloads in rank order
@@ -245,8 +235,8 @@ k_partition_join(const uint32_t *__restrict__ rk, const uint32_t *__restrict__ r
 					for (int t = 0; t < kBatch; ++t)
 						if (fb + threadIdx.x + t * THREADS < fe) {
 							const uint32_t lo = hash_mul(k0[t], radix_factor) & rem_mask;
-							const uint32_t w = lo >> 5;
-							dvals[prefix[w] + __popc(bitmap[w] & ((1u << (lo & 31)) - 1))] = v0[t];
+							const uint2 e = bp[lo >> 5];
+							dvals[e.y + __popc(e.x & ((1u << (lo & 31)) - 1))] = v0[t];
 						}
 					for (uint32_t i0 = fb + threadIdx.x + THREADS * kBatch; i0 < fe; i0 += THREADS * kBatch) {
 						uint32_t bk[kBatch], bv[kBatch];
@@ -260,12 +250,11 @@ k_partition_join(const uint32_t *__restrict__ rk, const uint32_t *__restrict__ r
 						for (int t = 0; t < kBatch; ++t)
 							if (i0 + t * THREADS < fe) {
 								const uint32_t lo = hash_mul(bk[t], radix_factor) & rem_mask;
-								const uint32_t w = lo >> 5;
-								dvals[prefix[w] + __popc(bitmap[w] & ((1u << (lo & 31)) - 1))] = bv[t];
+								const uint2 e = bp[lo >> 5];
+								dvals[e.y + __popc(e.x & ((1u << (lo & 31)) - 1))] = bv[t];
 							}
 					}
 					__syncthreads();
-					PHASE_MARK(4)      // build step 3: key + payload loads, placement
 					// ---- DIRECT probe
 					for (uint32_t sb = s_beg; sb < s_end; sb += THREADS * ITEMS) {
 						uint32_t key[ITEMS], val[ITEMS], ival[ITEMS];
@@ -281,11 +270,11 @@ k_partition_join(const uint32_t *__restrict__ rk, const uint32_t *__restrict__ r
 #pragma unroll
 						for (int t = 0; t < ITEMS; ++t) {
 							const uint32_t x = hash_mul(key[t], radix_factor), lo = x & rem_mask;
-							if (owner_bits && found[t]) foreign |= (x >> owner_shift) ^ owner;
-							const uint32_t w = lo >> 5, word = bitmap[w];
-							const uint32_t hit = found[t] ? (word >> (lo & 31)) & 1u : 0u;
+							if (OWNER && found[t]) foreign |= (x >> owner_shift) ^ owner;
+							const uint2 e = bp[lo >> 5];
+							const uint32_t hit = found[t] ? (e.x >> (lo & 31)) & 1u : 0u;
 							// rank < fill size whenever the bit is set; a miss may compute fill size itself: clamp
-							const uint32_t pos = min(prefix[w] + (uint32_t)__popc(word & ((1u << (lo & 31)) - 1)), kDirectFill - 1);
+							const uint32_t pos = min(e.y + (uint32_t)__popc(e.x & ((1u << (lo & 31)) - 1)), kDirectFill - 1);
 							ival[t] = dvals[pos];
 							found[t] = hit != 0;
 							acc.add_if(hit, key[t], val[t], ival[t]);
@@ -293,7 +282,6 @@ k_partition_join(const uint32_t *__restrict__ rk, const uint32_t *__restrict__ r
 						if (MATERIALIZE) emit_round<ITEMS>(out, found, key, val, ival);
 					}
 					__syncthreads();            // the bitmap is cleared next; also publishes the prefetched task id
-					PHASE_MARK(5)      // probe + emit
 					fb = fe;
 					continue;
 				}
@@ -395,7 +383,6 @@ k_partition_join(const uint32_t *__restrict__ rk, const uint32_t *__restrict__ r
 	}
 	acc.reduce_to_global(sums, scratch);
 	if (foreign) sums[6] = 1;                    // scalars[7]: foreign tuple seen
-#undef PHASE_MARK
 }
 
 int launch_partition_join(const JoinArgs &a, cudaStream_t s, int sms, KernelTimer *t)
@@ -408,7 +395,7 @@ int launch_partition_join(const JoinArgs &a, cudaStream_t s, int sms, KernelTime
 	cudaMemsetAsync(a.task_counter, 0, 256 + (size_t)task_blocks * 8, s);
 	t->start(KK_JOIN_TASKS, s);
 	k_join_tasks<<<task_blocks, 1024, 0, s>>>(a.r_off, a.s_off, a.P, a.s_task, a.task_prefix,
-	                                          reinterpret_cast<unsigned long long *>(a.task_counter + 64));
+	                                          reinterpret_cast<unsigned long long *>(a.task_counter + 64), a.task_counter + 1);
 	t->stop(s);
 	OutCols out;
 	out.k = a.out_k;
@@ -416,48 +403,21 @@ int launch_partition_join(const JoinArgs &a, cudaStream_t s, int sms, KernelTime
 	out.i = a.out_i;
 	out.cursor = a.scalars;
 	out.cap = a.materialize ? a.out_cap : 0;
-	// CTA shape; HJB_JOIN_VARIANT picks alternatives for experiments
-	static int variant = -1;
-	if (variant < 0) {
-		const char *e = getenv("HJB_JOIN_VARIANT");
-		variant = e ? atoi(e) : 0;
-		if (variant < 0 || variant > 6) variant = 0;
-	}
-	static int clocks = -1;
-	if (clocks < 0) clocks = getenv("HJB_PHASE_CLOCKS") ? 1 : 0;
-	unsigned long long *clk = clocks ? a.scalars + 8 : nullptr;
+	// five 256-thread CTAs per SM, 48 registers: measured best in round 1 (512-thread CTAs 1.30-1.59 vs 1.11 ms, six CTAs spill)
 	t->start(KK_PART_JOIN, s);
-#define HJB_LAUNCH_JOIN(T, I, MB, CLK)                                                                                          \
-	do {                                                                                                                   \
-		auto kt = k_partition_join<T, I, MB, true, CLK>;                                                                         \
-		auto kf = k_partition_join<T, I, MB, false, CLK>;                                                                         \
-		cudaFuncSetAttribute(kt, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kJoinSmemBytes);                       \
-		cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kJoinSmemBytes);                       \
-		int per_sm = 0;                                                                                                    \
-		if (a.materialize) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kt, T, kJoinSmemBytes);                  \
-		else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kf, T, kJoinSmemBytes);                                \
-		if (per_sm < 1) per_sm = 1;                                                                                        \
-		const uint32_t grid = (uint32_t)(sms * per_sm);                                                                    \
-		if (a.materialize)                                                                                                 \
-			kt<<<grid, T, kJoinSmemBytes, s>>>(a.rk, a.rv, a.sk, a.sv, a.r_off, a.s_off, a.P, a.task_prefix,               \
-			                                   a.task_counter, a.s_task, a.radix_factor, a.table_factor, a.rem_bits,       \
-			                                   a.owner, a.owner_bits, out, a.scalars + 1, clk);                                                             \
-		else                                                                                                               \
-			kf<<<grid, T, kJoinSmemBytes, s>>>(a.rk, a.rv, a.sk, a.sv, a.r_off, a.s_off, a.P, a.task_prefix,               \
-			                                   a.task_counter, a.s_task, a.radix_factor, a.table_factor, a.rem_bits,       \
-			                                   a.owner, a.owner_bits, out, a.scalars + 1, clk);                                                             \
-	} while (0)
-	switch (clocks ? 9 : variant) {
-	case 1: HJB_LAUNCH_JOIN(256, 8, 3, false); break;
-	case 2: HJB_LAUNCH_JOIN(256, 4, 4, false); break;
-	case 3: HJB_LAUNCH_JOIN(256, 8, 4, false); break;
-	case 4: HJB_LAUNCH_JOIN(128, 8, 8, false); break;
-	case 5: HJB_LAUNCH_JOIN(512, 4, 2, false); break;
-	case 6: HJB_LAUNCH_JOIN(512, 4, 3, false); break;
-	case 9: HJB_LAUNCH_JOIN(kJoinThreads, kJoinItems, 5, true); break;
-	default: HJB_LAUNCH_JOIN(kJoinThreads, kJoinItems, 5, false); break;       // measured best: five 256-thread CTAs per SM, 48 registers
-	}
-#undef HJB_LAUNCH_JOIN
+	auto launch = [&](auto kernel) {
+		cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kJoinSmemBytes);
+		int per_sm = 0;
+		cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kJoinThreads, kJoinSmemBytes);
+		if (per_sm < 1) per_sm = 1;
+		kernel<<<(uint32_t)(sms * per_sm), kJoinThreads, kJoinSmemBytes, s>>>(a.rk, a.rv, a.sk, a.sv, a.r_off, a.s_off, a.P, a.task_prefix,
+		                                                                   a.task_counter, a.s_task, a.radix_factor, a.table_factor,
+		                                                                   a.rem_bits, a.owner, a.owner_bits, out, a.scalars + 1);
+	};
+	if (a.materialize && a.owner_bits) launch(k_partition_join<kJoinThreads, kJoinItems, 5, true, true>);
+	else if (a.materialize) launch(k_partition_join<kJoinThreads, kJoinItems, 5, true, false>);
+	else if (a.owner_bits) launch(k_partition_join<kJoinThreads, kJoinItems, 5, false, true>);
+	else launch(k_partition_join<kJoinThreads, kJoinItems, 5, false, false>);
 	t->stop(s);
 	return 2;
 }

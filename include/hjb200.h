@@ -34,7 +34,8 @@ enum {
 	HJB_E_CUDA = -2,      /* CUDA runtime error, see hjb_last_error */
 	HJB_E_NOMEM = -3,     /* device or host allocation failed */
 	HJB_E_IO = -4,        /* relation file missing or of the wrong size */
-	HJB_E_NODEVICE = -5   /* no CUDA device: there is no CPU fallback */
+	HJB_E_NODEVICE = -5,  /* no CUDA device: there is no CPU fallback */
+	HJB_E_CAPACITY = -6   /* hjb_cpra_finish: a receive buffer was too small; nothing was exchanged, re-bind larger ones */
 };
 
 typedef struct hjb_ctx hjb_ctx;        /* one per GPU: device, stream, workspace, output buffers */
@@ -97,9 +98,6 @@ int hjb_synchronize(hjb_ctx *ctx);
 int hjb_set_profiling(hjb_ctx *ctx, int on);
 int hjb_kernel_times(hjb_ctx *ctx, float *ms, uint32_t *launches, int max_kinds);
 const char *hjb_kernel_name(int kind);
-/* debug aid: per-phase SM cycle counters of the last partition join (filled when the environment
- * variable HJB_PHASE_CLOCKS is set; summed over CTAs) */
-int hjb_debug_counters(hjb_ctx *ctx, uint64_t *out8);
 
 /* ---- whole joins: replace run() / run_hj() + main()'s allocation ------------------- */
 /* NPJ, npj.cpp:769-927.  Columns in device memory. */
@@ -157,26 +155,31 @@ int hjb_cpra_scatter_peer(hjb_ctx *ctx, int ngpus, void *const *peer_r_keys, voi
                           void *const *peer_s_keys, void *const *peer_s_vals, const uint64_t *r_base,
                           const uint64_t *s_base, float *ms);
 
-/* ---- the same, with the exchange of the probe side overlapped with the local partitioning of the
- * build side: R goes through the fused scatter, S is split locally into a send buffer and travels by
- * copy engine (no SM involved) while the SMs already partition the R tuples that have arrived.
- *   hjb_cpra_count -> (all-gather) -> hjb_cpra_scatter_rel(rel 0) -> hjb_cpra_stage_rel(rel 1)
- *   -> (barrier: every R tuple has landed) -> hjb_cpra_send_staged(rel 1) + hjb_cpra_join_begin(R)
- *   -> hjb_cpra_send_wait -> (barrier: every S tuple has landed) -> hjb_cpra_join_finish(S)          */
-/* the fused scatter of ONE counted relation (rel 0 = R, 1 = S); synchronises the stream */
-int hjb_cpra_scatter_rel(hjb_ctx *ctx, int rel, int ngpus, void *const *peer_keys, void *const *peer_vals,
-                         const uint64_t *base, float *ms);
-/* local split of one counted relation by owner into the context's send buffer (asynchronous) */
-int hjb_cpra_stage_rel(hjb_ctx *ctx, int rel, int ngpus);
-/* copy-engine transfers of the staged pieces into the owners' columns, on the context's copy
- * stream, ordered after the split (asynchronous); hjb_cpra_send_wait blocks until they are done */
-int hjb_cpra_send_staged(hjb_ctx *ctx, int rel, int ngpus, int self, void *const *peer_keys, void *const *peer_vals,
-                         const uint64_t *base);
-int hjb_cpra_send_wait(hjb_ctx *ctx, float *ms);
-/* hjb_cpra_join_local in two halves: begin partitions the received build side (asynchronous; the
- * probe side, s_tuples rows, may still be arriving), finish partitions the probe side and joins */
-int hjb_cpra_join_begin(hjb_ctx *ctx, const hjb_rel *R_recv, uint64_t s_tuples, int gpu, int ngpus, const hjb_opts *opts);
-int hjb_cpra_join_finish(hjb_ctx *ctx, const hjb_rel *S_recv, const hjb_opts *opts, hjb_result *out);
+/* ---- the same exchange, STREAM-ORDERED: count, scatter and local join are enqueued on the context's stream and
+ * read their sizes from device memory, so the host is not involved between them.  The caller's collectives (NCCL
+ * on the same stream) order the GPUs.  One CPRA step (replaces run_hj, cpra2.cpp:1697-1986, its barriers at
+ * cpra2.cpp:1811,1828,1860 becoming the two collectives):
+ *   hjb_cpra_bind           once per set of receive buffers: every owner's four columns as mapped into this process
+ *   hjb_cpra_count_async    histogram + scan by owner; this sender's 2*ngpus counts (R per owner, then S) -> counts_dev
+ *   (caller)                all-gather of the counts into matrix_dev[ngpus][2*ngpus] (uint64, device)
+ *   hjb_cpra_scatter_async  bases from the matrix (device), then the fused scatter into the owners' buffers
+ *   (caller)                a collective every rank enqueues after its scatter (e.g. a 1-element all-reduce): when it
+ *                           completes here, every sender's stores have landed
+ *   hjb_cpra_join_async     local join of what arrived; the received counts are taken from the matrix on the device
+ *   (caller, optional)      all-reduce of hjb_cpra_sums_dev (count + 3 checksums, uint64[4]) over the ranks
+ *   hjb_cpra_finish         the only synchronisation: waits, returns this GPU's result, rows received and the
+ *                           largest row counts any owner received (for sizing the buffers)
+ * If some owner's buffer is too small (every sender sees that in the same matrix) nothing is scattered or joined
+ * and hjb_cpra_finish returns HJB_E_CAPACITY with `largest` set. */
+int hjb_cpra_bind(hjb_ctx *ctx, int gpu, int ngpus, void *const *peer_r_keys, void *const *peer_r_vals,
+                  void *const *peer_s_keys, void *const *peer_s_vals, uint64_t r_capacity, uint64_t s_capacity);
+int hjb_cpra_count_async(hjb_ctx *ctx, const hjb_rel *R_chunk, const hjb_rel *S_chunk, const hjb_opts *opts,
+                         uint64_t *counts_dev);
+int hjb_cpra_scatter_async(hjb_ctx *ctx, const uint64_t *matrix_dev);
+/* r_expect / s_expect: the row counts the plan is made for (0: the capacities) */
+int hjb_cpra_join_async(hjb_ctx *ctx, const hjb_opts *opts, uint64_t r_expect, uint64_t s_expect);
+void *hjb_cpra_sums_dev(hjb_ctx *ctx);
+int hjb_cpra_finish(hjb_ctx *ctx, hjb_result *out, uint64_t received[2], uint64_t largest[2]);
 
 /* ---- the kernels, one call each, device pointers: mirror the reference's free functions
  * so intermediate products can be compared with the oracle -------------------------- */

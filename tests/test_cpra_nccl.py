@@ -42,13 +42,11 @@ def main():
         cr = slice(rank * nr // world, (rank + 1) * nr // world)
         cs = slice(rank * ns // world, (rank + 1) * ns // world)
         dev = lambda a: torch.from_numpy(np.ascontiguousarray(a).view(np.int32)).cuda()
-        for mode in ("nccl", "fused", "overlap", "overlap"):
+        for mode in ("nccl", "fused", "fused"):              # the fused step twice: the second runs with the first's sizes as its plan
             if mode == "nccl":
                 res = cpra.cpra_join(eng, (dev(rk[cr]), dev(rv[cr])), (dev(sk[cs]), dev(sv[cs])))
-            elif mode == "fused":
-                res = cpra.cpra_join_fused(eng, (dev(rk[cr]), dev(rv[cr])), (dev(sk[cs]), dev(sv[cs])), fused)
             else:
-                res = cpra.cpra_join_overlap(eng, (dev(rk[cr]), dev(rv[cr])), (dev(sk[cs]), dev(sv[cs])), fused)
+                res = cpra.cpra_join_fused(eng, (dev(rk[cr]), dev(rv[cr])), (dev(sk[cs]), dev(sv[cs])), fused)
             got = (res["count"], res["sum_key"], res["sum_outer"], res["sum_inner"])
             rows = list(res["local"].rows_numpy())
             gathered = [None] * world

@@ -433,9 +433,10 @@ def test_cpra_split_exchange_join_single_process(eng, G_):
 
 # ---------------------------------------------------------------- BASELINE sizes: size-independent properties
 
-@pytest.mark.parametrize("algo,name", [("phj", "phj_cfg2"), ("npj", "npj_cfg1"), ("npj", "phj_cfg2")])
+@pytest.mark.parametrize("algo,name", [("phj", "phj_cfg2"), ("npj", "npj_cfg1"), ("npj", "phj_cfg2"), ("phj", "npj_cfg1"),
+                                       ("npj", "small_cfg3"), ("phj", "small_cfg3")])
 def test_full_size_configs_by_properties(eng, algo, name):
-    """BASELINE.json configs 1 and 2 at full size, inputs generated on the device.  Every probe
+    """BASELINE.json configs 1, 2 and 3 at full size, inputs generated on the device.  Every probe
     key has exactly one build partner, so count = |S| and the checksums are plain column sums of
     S: sum_key = sum(S.key), sum_outer = sum(S.val), sum_inner = sum(S.key * f_R mod 2^32)."""
     nr, ns, kind = datagen.workload(name)
@@ -455,6 +456,31 @@ def test_full_size_configs_by_properties(eng, algo, name):
     assert bool(((kk * datagen.INNER_FACTOR & 0xFFFFFFFF) == (i.to(torch.int64) & 0xFFFFFFFF)).all())
     # ... and idempotence: a second run gives the same checks
     assert getattr(eng, algo)((rk, rv), (sk, sv), materialize=False).checks() == res.checks()
+
+
+def test_config5_skewed_probe_scaled_against_numpy_and_full_size_by_properties(eng):
+    """BASELINE.json config 5 (|R| = 2^27, |S| = 2^30, Zipf theta = 1 probe keys, 50 % of the probe tuples match).
+    Scaled by 1/64 the rows are compared with an independent numpy join; at full size NPJ and PHJ -- two unrelated
+    algorithms -- must agree on count, checksums and the multiset of rows (device fingerprint), every row must be
+    internally consistent and about half of S must match."""
+    for shift, exact in ((6, True), (0, False)):
+        nr, ns = (1 << 27) >> shift, (1 << 30) >> shift
+        rk, rv = eng.generate(0, nr, nr, 42, 1, datagen.INNER_FACTOR)
+        sk, sv = eng.generate(2, ns, nr, 42, 2, datagen.OUTER_FACTOR, theta=1.0, selectivity=0.5)
+        a = eng.phj((rk, rv), (sk, sv))
+        fa, ca = eng.rows_fingerprint(*a.rows_torch()), a.checks()
+        k, o, i = a.rows_torch()
+        kk = k.to(torch.int64) & 0xFFFFFFFF
+        assert bool(((kk * datagen.OUTER_FACTOR & 0xFFFFFFFF) == (o.to(torch.int64) & 0xFFFFFFFF)).all())
+        assert bool(((kk * datagen.INNER_FACTOR & 0xFFFFFFFF) == (i.to(torch.int64) & 0xFFFFFFFF)).all())
+        del kk, k, o, i
+        b = eng.npj((rk, rv), (sk, sv))
+        assert b.checks() == ca and eng.rows_fingerprint(*b.rows_torch()) == fa
+        assert abs(ca[0] / ns - 0.5) < 0.01
+        if exact:
+            want = numpy_join(*(t.cpu().numpy().view(np.uint32) for t in (rk, rv, sk, sv)))
+            assert ca == want.checks()
+            assert (sort_rows(*a.rows_numpy()) == want.sorted_rows()).all()
 
 
 def test_rows_fingerprint_kernel_equals_numpy_mirror_and_ignores_row_order(eng):
