@@ -4,16 +4,22 @@
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME]
 
 N = 1 (default): BASELINE.json config 2 -- PHJ, |R| = |S| = 2^27 unique 32-bit keys (S a
-permutation of R's key set), 32-bit payloads, materialised 3-column result.
+permutation of R's key set), 32-bit payloads, materialised 3-column result.  The same run also
+measures configs 1 and 3 (NPJ and PHJ each) and the one-GPU base of the weak-scaling curve; they go
+into the line as `configs` / `weak_scaling_base`.
 N > 1 (under torchrun, one rank per GPU): the CPRA path, weak scaling at 2^28 + 2^28 tuples
-per GPU, so that N = 8 is exactly config 4 (2^31 x 2^31): owner split -> NCCL all-to-all over
-NVLink -> local PHJ -> all-reduce of the checksums.
+per GPU, so that N = 8 is exactly config 4 (2^31 x 2^31): count by owner -> all-gather of the count
+matrix -> GPU-assign scatter straight into the owners' buffers over NVLink -> local PHJ -> all-reduce
+of the checksums, all enqueued on one stream.
 
 A step = one whole join of one batch.  `value` has the inputs resident in HBM (the reference's
-timed region, npj.cpp:861-918); `e2e` goes through the host entry point with pinned host
+timed region, npj.cpp:861-918); `e2e` goes through the host entry points of the C ABI with pinned host
 buffers (H2D of the inputs and D2H of the rows inside the timed region).  Every step's
 count / checksums are checked against the analytic expectation (count = |S|, checksums =
 column sums of S), a wrong step aborts the run.  One JSON line on stdout (rank 0).
+
+--impl reference: the reference's own CPU program (oracle/_ref, compiled from /root/reference where it
+lies) on the box's host cores; nothing of this repository's library is loaded in that arm.
 """
 import argparse
 import json
@@ -30,6 +36,7 @@ sys.path.insert(0, ROOT)
 METRIC = "join throughput (R+S tuples/sec)"
 UNIT = "tuples/s"
 MASK64 = (1 << 64) - 1
+NVLINK_REF_GBS = 770.0          # measured peer-copy bandwidth per direction (B200_PROFILING.md); nominal 900
 
 
 def measured_peak_gbs():
@@ -109,6 +116,10 @@ def physical_gpu_index(local):
 
 
 # ----------------------------------------------------------------------------- reference / CPU arm
+# Nothing below imports hash_join_codes_knl_b200: the relation files are written with numpy.
+
+REF_INNER_FACTOR, REF_OUTER_FACTOR = 0x6587F97D, 0xDF56B8FB
+
 
 def host_threads():
     try:
@@ -126,43 +137,65 @@ def has_avx512():
         return False
 
 
-def run_reference_program(prog, threads, rk, rv, sk, sv, timeout_s):
-    """Runs the UNMODIFIED reference program (oracle/_ref/<prog>, compiled from /root/reference by
-    oracle/Makefile) on the four relation files it expects in its CWD (npj.cpp:1013-1039) and
-    returns the seconds it prints (its own timer)."""
-    from hash_join_codes_knl_b200 import api
-    exe = os.path.join(ROOT, "oracle", "_ref", prog)
-    with tempfile.TemporaryDirectory(prefix="hjref_") as d:
-        api.relation_write(d, False, rk, rv)
-        api.relation_write(d, True, sk, sv)
-        args = [exe, str(threads), str(sk.size), str(rk.size)]
-        if prog != "cpra":
-            args.append("1")
-        out = subprocess.run(args, cwd=d, capture_output=True, text=True, timeout=timeout_s)
-        if out.returncode != 0:
-            raise RuntimeError(f"{prog} exited {out.returncode}: {out.stderr[-300:]}")
-        lines = [ln for ln in out.stdout.strip().splitlines() if ln and not ln.startswith("copy")]
-        return float(lines[-1].split()[0])
+def mem_available_gb():
+    try:
+        with open("/proc/meminfo") as f:
+            for ln in f:
+                if ln.startswith("MemAvailable"):
+                    return int(ln.split()[1]) / 2**20
+    except OSError:
+        pass
+    return 0.0
 
 
-def cpu_join_sample(log2_tuples, steps, warmup, workload):
-    """The reference's CPU implementation on a bounded sample of the workload, all usable host
-    threads.  Preferred: the reference's own program (kind "reference"); else the oracle port.
-    PHJ's shipped program performs no join (its join phase is commented out, phj.cpp:1869-1924),
-    so the partitioned path is timed with the reference's complete partitioned join, cpra."""
+def host_relations(nr, ns, foreign_keys, seed=42):
+    """Relations of the workload's shape, numpy only (write.cpp's semantics: distinct non-zero keys,
+    payload = key * odd factor, S either a permutation of R's key set or foreign keys -- every key once,
+    the rest uniform picks -- and both shuffled)."""
     import numpy as np
-    from hash_join_codes_knl_b200 import datagen
-    sys.path.insert(0, os.path.join(ROOT, "tests"))
-    import _oracle
-    n = 1 << log2_tuples
-    if workload == "npj_cfg1":
-        nr, ns, kind = n >> 4, n, 1
-        prog, algo = "npj", "npj"
+    rng = np.random.default_rng(seed)
+    keys = (np.arange(1, nr + 1, dtype=np.uint32) * np.uint32(0x9E3779B1))          # odd multiplier: distinct, non-zero
+    rk = keys[rng.permutation(nr)]
+    if foreign_keys:
+        sk = np.concatenate([keys, keys[rng.integers(0, nr, ns - nr)]]) if ns > nr else keys[:ns].copy()
+        sk = sk[rng.permutation(ns)]
     else:
-        nr, ns, kind = n, n, 0
-        prog, algo = "cpra", "cpra"
-    rk, rv = datagen.generate(0, nr, nr, 42, 1, datagen.INNER_FACTOR)
-    sk, sv = datagen.generate(kind, ns, nr, 42, 2, datagen.OUTER_FACTOR)
+        sk = keys[rng.permutation(nr)][:ns]
+    with np.errstate(over="ignore"):
+        rv, sv = rk * np.uint32(REF_INNER_FACTOR), sk * np.uint32(REF_OUTER_FACTOR)
+    return rk, rv, sk, sv
+
+
+def write_relation_files(d, rk, rv, sk, sv):
+    """the four raw files the reference reads from its CWD (write.cpp:1824-1865, npj.cpp:1013-1039)"""
+    rk.tofile(os.path.join(d, f"ik_{rk.size}.txt"))
+    rv.tofile(os.path.join(d, f"iv_{rk.size}.txt"))
+    sk.tofile(os.path.join(d, f"ok_{sk.size}.txt"))
+    sv.tofile(os.path.join(d, f"ov_{sk.size}.txt"))
+
+
+def run_reference_program(prog, threads, d, nr, ns, timeout_s):
+    """One run of the UNMODIFIED reference program (oracle/_ref/<prog>, compiled from /root/reference by
+    oracle/Makefile) in directory d; returns the seconds it prints (its own timer)."""
+    exe = os.path.join(ROOT, "oracle", "_ref", prog)
+    args = [exe, str(threads), str(ns), str(nr)]
+    if prog != "cpra":
+        args.append("1")
+    out = subprocess.run(args, cwd=d, capture_output=True, text=True, timeout=timeout_s)
+    if out.returncode != 0:
+        raise RuntimeError(f"{prog} exited {out.returncode}: {out.stderr[-300:]}")
+    lines = [ln for ln in out.stdout.strip().splitlines() if ln and not ln.startswith("copy")]
+    return float(lines[-1].split()[0])
+
+
+def cpu_join(log2_r, log2_s, steps, warmup, npj):
+    """The reference's CPU implementation, all usable host threads.  Preferred: the reference's own program
+    (kind "reference"); else the oracle port.  PHJ's shipped program performs no join (its join phase is
+    commented out, phj.cpp:1869-1924), so the partitioned path is timed with the reference's complete
+    partitioned join, cpra (cpra2.cpp)."""
+    nr, ns = 1 << log2_r, 1 << log2_s
+    prog = "npj" if npj else "cpra"
+    rk, rv, sk, sv = host_relations(nr, ns, foreign_keys=npj)
     cpus = host_threads()
     use_ref = (os.path.exists(os.path.join(ROOT, "oracle", "_ref", prog)) and has_avx512()
                and cpus == list(range(len(cpus))))        # the reference pins thread t to CPU t (makefile -DSCATTER)
@@ -170,20 +203,24 @@ def cpu_join_sample(log2_tuples, steps, warmup, workload):
     secs, kind_used, note = [], None, ""
     if use_ref:
         try:
-            for i in range(warmup + steps):
-                s = run_reference_program(prog, threads, rk, rv, sk, sv, timeout_s=600)
-                if i >= warmup:
-                    secs.append(s)
+            with tempfile.TemporaryDirectory(prefix="hjref_") as d:
+                write_relation_files(d, rk, rv, sk, sv)
+                for i in range(warmup + steps):
+                    s = run_reference_program(prog, threads, d, nr, ns, timeout_s=900)
+                    if i >= warmup:
+                        secs.append(s)
             kind_used = "reference"
             note = f"oracle/_ref/{prog} (unmodified {('cpra2' if prog == 'cpra' else prog)}.cpp, g++ -O3 -march=skylake-avx512)"
         except Exception as e:            # never let the baseline leg take the bench down
             note = f"reference program failed ({type(e).__name__}: {e}); "
             secs = []
     if not secs:
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import _oracle
         _oracle.build_oracle()
         threads = min(len(cpus), 64)
         for i in range(warmup + steps):
-            r = _oracle.oracle_join(algo, rk, rv, sk, sv, threads=threads, materialize=False)
+            r = _oracle.oracle_join(prog, rk, rv, sk, sv, threads=threads, materialize=False)
             assert r.count == ns
             if i >= warmup:
                 secs.append(r.seconds)
@@ -191,8 +228,8 @@ def cpu_join_sample(log2_tuples, steps, warmup, workload):
         note += "oracle/hj_oracle.c scalar restatement"
     sec = sum(secs) / len(secs)
     return {"value": (nr + ns) / sec, "unit": UNIT, "cores": threads, "kind": kind_used,
-            "sample": f"{algo.upper()} |R|=2^{nr.bit_length() - 1} x |S|=2^{ns.bit_length() - 1} ({note}), "
-                      f"mean of {len(secs)} run(s), {sec:.3f} s each", "seconds": sec}
+            "sample": f"{prog.upper()} |R|=2^{log2_r} x |S|=2^{log2_s} ({note}), mean of {len(secs)} run(s), {sec:.3f} s each",
+            "seconds": sec}
 
 
 def workload_label(workload, world, log2_per_gpu):
@@ -208,16 +245,27 @@ def reference_arm(args):
     if rank != 0:
         return 0
     workload = args.workload if args.workload != "auto" else ("phj_cfg2" if args.gpus == 1 else "cpra_cfg4")
-    log2 = 25 if workload != "npj_cfg1" else 26
     t0 = time.time()
-    base = cpu_join_sample(log2, max(1, args.steps), min(args.warmup, 1), "npj_cfg1" if workload == "npj_cfg1" else "phj_cfg2")
+    roomy = mem_available_gb() >= 24.0
+    if workload == "npj_cfg1":
+        shape = (24, 28) if roomy else (22, 26)
+        full = roomy
+    else:
+        # config 2 at full size when the host has the memory; config 4 (2^31 x 2^31) does not fit a CPU run:
+        # the largest power of two that does
+        shape = (27, 27) if roomy else (25, 25)
+        full = roomy and workload == "phj_cfg2"
+    steps = max(1, min(args.steps, 6))              # a run is seconds long: the whole arm ends within minutes
+    base = cpu_join(shape[0], shape[1], steps, min(args.warmup, 1), npj=workload == "npj_cfg1")
+    note = ("CPU reference, throughput in (R+S) tuples/s does not depend on the GPU count. "
+            + ("Full size of the config. " if full else "Bounded sample of the workload. ")
+            + ("" if workload == "npj_cfg1" else "The reference's cpra (cpra2.cpp) stands in for PHJ: the shipped phj.cpp "
+               "performs no join (phj.cpp:1869-1924 commented out); cpra is its complete partitioned join. "))
     line = {"impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT, "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": base["seconds"] * 1e3,
+            "steps": steps, "warmup": min(args.warmup, 1), "ms_per_step": base["seconds"] * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
             "config": {"workload": workload_label(workload, args.gpus, args.log2_per_gpu or 28),
-                       "sample": base["sample"],
-                       "note": "CPU reference on a bounded sample of the workload; throughput in (R+S) tuples/s does not "
-                               "depend on the GPU count"},
+                       "sample": base["sample"], "full_size": full, "note": note},
             "cpu_baseline": {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0, "wall_s": time.time() - t0}
@@ -234,6 +282,70 @@ def expected_checks(eng, sk, sv, ns):
     return (ns, eng.column_sum(sk), eng.column_sum(sv), int(inner.sum().item()) & MASK64)
 
 
+def step_bytes(algo, nr, ns, matches, passes=2, npj_load=0.75):
+    """algorithmic bytes of one whole join"""
+    n = nr + ns
+    if algo == "npj":
+        table = 8 * nr / npj_load
+        return 8 * n + table + 8 * nr + (8 * ns if table > (64 << 20) else 0) + 12 * matches
+    return n * (20 * passes + 8) + 12 * matches
+
+
+def kernel_bytes(nr, ns, matches):
+    """algorithmic bytes per LAUNCH SET of a kernel in one step, given its launches L"""
+    n = nr + ns
+    return {
+        "k_hist": lambda L: 4 * n * (L / 2),                   # 4 B/tuple; R and S launches alternate
+        "k_scatter": lambda L: 16 * n * (L / 2),               # 8 B read + 8 B written per tuple
+        "k_scatter_bulk": lambda L: 16 * n * (L / 2),          # the same bytes, 8 of them over NVLink
+        "k_partition_join": lambda L: 8 * n + 12 * matches,    # read both partitioned relations, write 12 B/match
+        "k_npj_probe": lambda L: 8 * ns + 12 * matches + (0 if nr * 16 <= (64 << 20) else 8 * ns),
+        "k_npj_build": lambda L: 8 * nr + 8 * (4 * nr / 3) + 8 * nr,    # read R, init the table (load 0.75), write slots
+    }
+
+
+def measure_join(eng, algo, R, S, want, steps, warmup, peak, traffic=None):
+    """steps joins of device-resident columns, every one verified; plus one instrumented step for the
+    per-kernel times.  Returns the compact record that goes into `configs`."""
+    import torch
+    nr, ns = R[0].numel(), S[0].numel()
+    eng.set_profiling(False)
+    for _ in range(warmup):
+        r = getattr(eng, algo)(R, S)
+        assert r.checks() == want, f"{algo}: wrong result {r.checks()} != {want}"
+    torch.cuda.synchronize()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    launches = 0
+    for _ in range(steps):
+        r = getattr(eng, algo)(R, S)
+        launches += r.kernel_launches
+        if r.checks() != want:
+            raise SystemExit(f"{algo}: timed step produced a wrong result")
+    ev1.record()
+    torch.cuda.synchronize()
+    ms = ev0.elapsed_time(ev1) / steps
+    eng.set_profiling(True)
+    getattr(eng, algo)(R, S)
+    r = getattr(eng, algo)(R, S)
+    kt = {k: (v[0], v[1]) for k, v in eng.kernel_times().items() if v[1]}
+    eng.set_profiling(False)
+    passes = max(1, round(kt.get("k_scatter", (0, 4))[1] / 2)) if algo == "phj" else 0
+    b = step_bytes(algo, nr, ns, want[0], passes)
+    kb = kernel_bytes(nr, ns, want[0])
+    dom = max(kt.items(), key=lambda kv: kv[1][0])[0] if kt else None
+    rec = {"algorithm": algo, "inner_tuples": nr, "outer_tuples": ns, "ms_per_step": round(ms, 4),
+           "tuples_per_s": (nr + ns) / (ms * 1e-3), "verified": True, "radix_passes": passes,
+           "algorithmic_bytes": b, "step_frac_of_hbm_peak": round(b / (ms * 1e-3) / 1e9 / peak, 4),
+           "kernel_ms": {k: round(v[0], 4) for k, v in sorted(kt.items())}, "gpu_launches_per_step": launches // steps}
+    if dom in kb:
+        per_launch = kb[dom](kt[dom][1]) / kt[dom][1]
+        rec["dominant"] = {"kernel": dom, "frac": round(per_launch / (kt[dom][0] / kt[dom][1] * 1e-3) / 1e9 / peak, 4),
+                           "algorithmic_bytes_per_launch": per_launch, "avg_launch_ms": round(kt[dom][0] / kt[dom][1], 4),
+                           "traffic": (traffic or {}).get(dom)}
+    return rec
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -246,6 +358,7 @@ def main():
                     help="N>1: GPU-assign pass storing straight into the owners' buffers over NVLink, or split + NCCL all-to-all")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="N=1: skip the configs 1 / 3 / weak-scaling-base table")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
@@ -272,7 +385,6 @@ def main():
     workload = args.workload if args.workload != "auto" else ("phj_cfg2" if world == 1 else "cpra_cfg4")
 
     eng = hj.Engine(local, use_torch_stream=True)
-    eng.set_profiling(True)
     fused = cpra_mod.FusedExchange(eng) if (world > 1 and args.exchange != "nccl") else None
 
     def cpra_step(inner, outer):
@@ -307,7 +419,7 @@ def main():
         if algo == "cpra":
             r = cpra_step((rk, rv), (sk, sv))
             got = (r["count"], r["sum_key"], r["sum_outer"], r["sum_inner"])
-            return got, sum(v[1] for v in eng.kernel_times().values()), r
+            return got, r["local"].kernel_launches, r
         r = getattr(eng, algo)((rk, rv), (sk, sv))
         return r.checks(), r.kernel_launches, r
 
@@ -350,7 +462,8 @@ def main():
         sampler.start()
     ktimes = {}
     phases = np.zeros(8)
-    extra = {"split_ms": 0.0, "exchange_ms": 0.0, "join_ms": 0.0}
+    extra = {"split_ms": 0.0, "exchange_ms": 0.0, "join_ms": 0.0, "step_ms": 0.0}
+    recv_stats = []
 
     def timed_region(instrumented):
         eng.set_profiling(instrumented)
@@ -368,7 +481,8 @@ def main():
             if not instrumented:
                 if algo == "cpra":
                     for key in extra:
-                        extra[key] += r[key]
+                        extra[key] += r.get(key, 0.0)
+                    recv_stats.append(r["recv_tuples"])
                 continue
             for name, (ms, n) in eng.kernel_times().items():
                 a = ktimes.setdefault(name, [0.0, 0])
@@ -386,14 +500,12 @@ def main():
 
     ms_total, launches = timed_region(False)
     ms_instrumented, launches_instrumented = timed_region(True)
-    if algo == "cpra":
-        launches = launches_instrumented           # counted from the per-kernel event pairs
     eng.set_profiling(False)
     clocks = sampler.stop() if sampler else None
     ms_step = ms_total / args.steps
     value = (nr_tot + ns_tot) / (ms_step * 1e-3)
 
-    # ---- timed: end to end through the host entry point, pinned host buffers
+    # ---- timed: end to end through the host entry points of the C ABI, pinned host buffers
     e2e = None
     if not args.no_e2e:
         pin = [torch.empty(t.numel(), dtype=torch.int32).pin_memory() for t in (rk, rv, sk, sv)]
@@ -405,21 +517,17 @@ def main():
 
         def step_e2e():
             if algo == "cpra":
-                drk, drv, dsk, dsv = (p.to(devname, non_blocking=True) for p in pin)
-                r = cpra_step((drk, drv), (dsk, dsv))
-                rows = [c.to("cpu", non_blocking=True) for c in r["local"].rows_torch()]   # this rank's share of the rows
-                torch.cuda.synchronize()
-                return (r["count"], r["sum_key"], r["sum_outer"], r["sum_inner"]), r["local"].count, rows
+                r = cpra_step((hrk, hrv), (hsk, hsv))           # hjb_cpra_count_async_host ... hjb_cpra_finish_host
+                return (r["count"], r["sum_key"], r["sum_outer"], r["sum_inner"]), r["local"].count
             r = getattr(eng, algo)((hrk, hrv), (hsk, hsv))
-            return r.checks(), r.count, None
-        got, _, _ = step_e2e()
+            return r.checks(), r.count
+        got, _ = step_e2e()
         assert got == want
         barrier()
         t0 = time.perf_counter()
         rows_out = 0
         for _ in range(e2e_steps):
-            got, cnt, _ = step_e2e()
-            rows_out = cnt
+            got, rows_out = step_e2e()
             if got != want:
                 raise SystemExit("e2e step produced a wrong result")
         barrier()
@@ -430,8 +538,10 @@ def main():
             sec = float(t.item())
         e2e = {"value": (nr_tot + ns_tot) / sec, "unit": UNIT, "h2d_bytes_per_step": 8 * (nr_g + ns_g) * world,
                "d2h_bytes_per_step": 12 * (ns_tot if world > 1 else rows_out), "ms_per_step": sec * 1e3, "steps": e2e_steps,
-               "path": "Engine.%s(host columns) -> hjb_%s_host" % (algo, algo) if algo != "cpra" else
-                       "pinned host -> H2D -> cpra_join -> D2H of each rank's rows"}
+               "path": ("Engine.%s(host columns) -> hjb_%s_host" % (algo, algo)) if algo != "cpra" else
+                       "cpra_join_fused(host columns) -> hjb_cpra_count_async_host / hjb_cpra_scatter_async / "
+                       "hjb_cpra_join_async / hjb_cpra_finish_host (every rank: its chunk in, its share of the rows out)"}
+        del pin, hrk, hrv, hsk, hsv
 
     if rank != 0:
         if world > 1:
@@ -441,14 +551,7 @@ def main():
     # ---- roofline of the dominant kernel, from the per-launch CUDA events of the timed steps
     peak, peak_src = measured_peak_gbs()
     n_in = nr_g + ns_g                              # tuples this GPU partitions per pass / joins
-    # algorithmic bytes per step summed over a kernel's launches
-    alg_bytes_per_step = {
-        "k_hist": lambda L: 4 * n_in * (L / 2),                 # 4 B/tuple; R and S launches alternate
-        "k_scatter": lambda L: 16 * n_in * (L / 2),             # 8 B read + 8 B written per tuple
-        "k_partition_join": lambda L: 8 * n_in + 12 * ns_g,     # read both partitioned relations, write 12 B/match
-        "k_npj_probe": lambda L: 8 * ns_g + 12 * ns_g + (0 if nr_g * 16 <= (64 << 20) else 8 * ns_g),
-        "k_npj_build": lambda L: 8 * nr_g + 8 * (4 * nr_g / 3) + 8 * nr_g,   # read R, init the table (load 0.75), write slots
-    }
+    alg = kernel_bytes(nr_g, ns_g, ns_g)
     per_step = {k: (v[0] / args.steps, v[1] / args.steps) for k, v in ktimes.items() if v[1]}
     dom = max(per_step.items(), key=lambda kv: kv[1][0])[0] if per_step else None
     ncu_traffic = {}
@@ -458,9 +561,9 @@ def main():
     except Exception:
         pass
     roof = None
-    if dom in alg_bytes_per_step:
+    if dom in alg:
         ms_k, launches_k = per_step[dom]
-        per_launch_bytes = alg_bytes_per_step[dom](launches_k) / launches_k
+        per_launch_bytes = alg[dom](launches_k) / launches_k
         per_launch_ms = ms_k / launches_k
         achieved = per_launch_bytes / (per_launch_ms * 1e-3) / 1e9
         tr = ncu_traffic.get(workload, {}).get(dom)
@@ -470,11 +573,10 @@ def main():
                 "launches_per_step": launches_k, "share_of_step": ms_k / (ms_instrumented / args.steps),
                 "traffic_source": "profiles/ncu_traffic.json (dram__bytes_read.sum + dram__bytes_write.sum per launch, "
                                   "ncu --set full)" if tr else None}
-    if algo == "npj":
-        step_bytes = sum(alg_bytes_per_step[k](1) for k in ("k_npj_build", "k_npj_probe"))
-    else:
-        passes = max(1, round(per_step.get("k_scatter", (0, 4))[1] / 2))     # scatter launches come in (R, S) pairs
-        step_bytes = n_in * (20 * passes + 8) + 12 * ns_g
+    passes = max(1, round(per_step.get("k_scatter", (0, 4))[1] / 2))     # local scatter launches come in (R, S) pairs
+    sb = step_bytes("npj" if algo == "npj" else "phj", nr_g, ns_g, ns_g, passes)
+    if algo == "cpra" and world > 1:
+        sb += 20 * n_in + 16 * n_in * (world - 1) / world    # GPU-assign pass (hist + scatter) and the receive-side writes / send-side reads
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_step, "ms_per_step_instrumented": ms_instrumented / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32",
@@ -488,27 +590,64 @@ def main():
         "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roof,
         "kernel_ms_per_step": {k: round(v[0], 4) for k, v in sorted(per_step.items())},
         "phase_ms_per_step": [round(float(x) / args.steps, 4) for x in phases],
-        "step_roofline": {"algorithmic_bytes_per_gpu": step_bytes, "achieved_gbs_per_gpu": step_bytes / (ms_step * 1e-3) / 1e9,
-                          "frac_of_hbm_peak": step_bytes / (ms_step * 1e-3) / 1e9 / peak},
+        "step_roofline": {"algorithmic_bytes_per_gpu": sb, "achieved_gbs_per_gpu": sb / (ms_step * 1e-3) / 1e9,
+                          "frac_of_hbm_peak": sb / (ms_step * 1e-3) / 1e9 / peak, "radix_passes_local": passes},
     }
     if algo == "cpra":
         line["cpra_ms_per_step"] = {k: round(v / args.steps, 4) for k, v in extra.items()}
+        if recv_stats:
+            line["recv_tuples_rank0"] = [int(x) for x in recv_stats[-1]]
         if world > 1:
             sent = 8 * n_in * (world - 1) / world                # bytes each GPU stores into its peers per step
             cm = line["cpra_ms_per_step"]
-            ach = sent / (cm["split_ms" if args.exchange == "fused" else "exchange_ms"] * 1e-3) / 1e9
-            line["nvlink"] = {"bytes_out_per_gpu": sent, "scatter_ms": cm["split_ms"], "achieved_gbs_per_direction": ach,
-                              "reference_gbs": 770.0, "note": "measured peer-copy bandwidth per direction (B200_PROFILING.md); nominal 900"}
-            # SURVEY 8d's serial model for CPRA at G GPUs: HBM bytes / HBM bandwidth + NVLink bytes / NVLink bandwidth,
-            # with n_g*(20 GPU-assign + 20 one local pass + 8 join) + 12 M/G algorithmic HBM bytes per GPU
-            hbm_b = n_in * 48 + 12 * ns_g
-            for tag, bw_h, bw_n in (("measured_peaks", peak, 770.0), ("nominal_peaks", 8000.0, 900.0)):
-                t_ms = (hbm_b / bw_h + sent / bw_n) / 1e6
-                line.setdefault("cpra_roofline", {"hbm_bytes_per_gpu": hbm_b, "nvlink_bytes_out_per_gpu": sent})[tag] = {
-                    "hbm_gbs": bw_h, "nvlink_gbs": bw_n, "serial_model_ms": t_ms, "frac": t_ms / ms_step}
+            bulk_ms = per_step.get("k_scatter_bulk", (0.0, 0))[0]
+            line["nvlink"] = {"bytes_out_per_gpu": sent, "scatter_kernel_ms": round(bulk_ms, 4),
+                              "achieved_gbs_per_direction": sent / (bulk_ms * 1e-3) / 1e9 if bulk_ms else None,
+                              "reference_gbs": NVLINK_REF_GBS,
+                              "note": "k_scatter_bulk's event-timed launches (R and S); measured peer-copy bandwidth per direction 770 GB/s (B200_PROFILING.md), nominal 900"}
+            # SURVEY 8d's serial model for CPRA at G GPUs: HBM bytes / HBM bandwidth + NVLink bytes / NVLink bandwidth.
+            # `as_built`: the bytes this code moves (GPU-assign + `passes` local passes + join); `survey`: the survey's
+            # two-pass figure (GPU-assign + ONE local pass + join) that BASELINE's 12.5 ms target is derived from.
+            rl = {"nvlink_bytes_out_per_gpu": sent}
+            for tag, hbm_b in (("as_built", sb), ("survey", n_in * 48 + 16 * n_in * (world - 1) / world + 12 * ns_g)):
+                for ptag, bw_h, bw_n in (("measured_peaks", peak, NVLINK_REF_GBS), ("nominal_peaks", 8000.0, 900.0)):
+                    t_ms = (hbm_b / bw_h + sent / bw_n) / 1e6
+                    rl.setdefault(tag, {"hbm_bytes_per_gpu": hbm_b})[ptag] = {"hbm_gbs": bw_h, "nvlink_gbs": bw_n, "serial_model_ms": t_ms,
+                                                                              "frac": t_ms / ms_step}
+            line["cpra_roofline"] = rl
+    # ---- N = 1: the other single-GPU configs of BASELINE.json, measured in the same run
+    if world == 1 and not args.no_configs and workload == "phj_cfg2" and not args.log2_per_gpu:
+        del rk, rv, sk, sv
+        torch.cuda.empty_cache()
+        cfgs = {}
+        small = max(3, min(args.steps, 5))
+        for name, label in (("npj_cfg1", "config 1: 2^24 x 2^28 foreign keys"), ("small_cfg3", "config 3: 2^16 x 2^30 foreign keys")):
+            try:
+                nr, ns, kind = datagen.workload(name)
+                R = eng.generate(0, nr, nr, 42, 1, datagen.INNER_FACTOR)
+                S = eng.generate(kind, ns, nr, 42, 2, datagen.OUTER_FACTOR)
+                w = expected_checks(eng, S[0], S[1], ns)
+                cfgs[label] = [measure_join(eng, a, R, S, w, small, 2, peak, ncu_traffic.get(name + "_" + a)) for a in ("npj", "phj")]
+                del R, S
+                torch.cuda.empty_cache()
+            except Exception as e:
+                cfgs[label] = {"error": f"{type(e).__name__}: {e}"}
+        line["configs"] = cfgs
+        try:
+            n = 1 << 28
+            R = eng.generate(0, n, n, 42, 1, datagen.INNER_FACTOR)
+            S = eng.generate(0, n, n, 42, 2, datagen.OUTER_FACTOR)
+            w = expected_checks(eng, S[0], S[1], n)
+            rec = measure_join(eng, "phj", R, S, w, small, 2, peak)
+            rec["note"] = ("what ONE GPU does per step of the weak-scaling run (2^28 + 2^28 tuples) without an exchange: "
+                           "the like-for-like base of the N = 2, 4, 8 CPRA values")
+            line["weak_scaling_base"] = rec
+            del R, S
+        except Exception as e:
+            line["weak_scaling_base"] = {"error": f"{type(e).__name__}: {e}"}
     if not args.no_cpu_baseline:
         try:
-            base = cpu_join_sample(25 if workload != "npj_cfg1" else 26, 2, 1, "npj_cfg1" if workload == "npj_cfg1" else "phj_cfg2")
+            base = cpu_join(25 if workload != "npj_cfg1" else 22, 25 if workload != "npj_cfg1" else 26, 2, 1, npj=workload == "npj_cfg1")
             line["cpu_baseline"] = {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")}
         except Exception as e:
             line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": f"failed: {e}"}

@@ -83,10 +83,18 @@ def _is_torch(x):
     return type(x).__module__.startswith("torch")
 
 
+_own_stream_engines = 0        # Engines that run on a stream of their own (not torch's current stream)
+
+
 def _col(x):
     """-> (pointer, tuples, on_device, keepalive)"""
     if _is_torch(x):
         assert x.dim() == 1 and x.is_contiguous() and x.element_size() == 4, "columns are contiguous 1-D 32-bit"
+        if x.is_cuda and _own_stream_engines:
+            # the tensor may still be being written by kernels queued on torch's stream, which the engine's
+            # non-blocking stream does not wait for
+            import torch
+            torch.cuda.current_stream(x.device).synchronize()
         return x.data_ptr(), x.numel(), x.is_cuda, x
     a = np.ascontiguousarray(x)
     assert a.ndim == 1 and a.dtype.itemsize == 4, "columns are 1-D 32-bit"
@@ -105,14 +113,21 @@ class Engine:
             msg = self._lib.hjb_last_error(None).decode()
             self._ctx = None
             raise HjbError(f"hjb_create({device}) failed ({rc}): {msg}")
+        global _own_stream_engines
+        self._own_stream = not use_torch_stream
         if use_torch_stream:
             import torch
             self.set_stream(torch.cuda.current_stream(self.device).cuda_stream)
+        else:
+            _own_stream_engines += 1
 
     def close(self):
+        global _own_stream_engines
         if getattr(self, "_ctx", None):
             self._lib.hjb_destroy(self._ctx)
             self._ctx = None
+            if getattr(self, "_own_stream", False):
+                _own_stream_engines -= 1
 
     def __del__(self):
         try:
@@ -267,14 +282,15 @@ class Engine:
                                             int(r_capacity), int(s_capacity)), "hjb_cpra_bind")
 
     def cpra_count_async(self, inner_chunk, outer_chunk, counts_dev, **opts):
-        """counts_dev: int64 CUDA tensor of 2*ngpus elements (the all-gather's input)."""
+        """counts_dev: int64 CUDA tensor of 2*ngpus elements (the all-gather's input).  Host columns (numpy /
+        pinned torch CPU tensors) go through hjb_cpra_count_async_host, which copies them in on the stream."""
         R, S, on_dev, keep = self._rels(inner_chunk, outer_chunk)
-        if not on_dev:
-            raise HjbError("cpra_count_async takes device columns")
         o = self._opts(**opts)
-        self._check(self._lib.hjb_cpra_count_async(self._ctx, C.byref(R), C.byref(S), C.byref(o), C.c_void_p(counts_dev.data_ptr())),
-                    "hjb_cpra_count_async")
+        fn = self._lib.hjb_cpra_count_async if on_dev else self._lib.hjb_cpra_count_async_host
+        self._check(fn(self._ctx, C.byref(R), C.byref(S), C.byref(o), C.c_void_p(counts_dev.data_ptr())),
+                    "hjb_cpra_count_async" + ("" if on_dev else "_host"))
         self._pending_keep = keep          # the chunks must outlive the scatter
+        self._step_from_host = not on_dev
 
     def cpra_scatter_async(self, matrix_dev):
         self._check(self._lib.hjb_cpra_scatter_async(self._ctx, C.c_void_p(matrix_dev.data_ptr())), "hjb_cpra_scatter_async")
@@ -291,12 +307,20 @@ class Engine:
         """-> (JoinResult, (R rows, S rows) received here, (R rows, S rows) received by the fullest owner)"""
         res = Result()
         got, big = (C.c_uint64 * 2)(), (C.c_uint64 * 2)()
-        rc = self._lib.hjb_cpra_finish(self._ctx, C.byref(res), got, big)
+        fn = self._lib.hjb_cpra_finish_host if getattr(self, "_step_from_host", False) else self._lib.hjb_cpra_finish
+        rc = fn(self._ctx, C.byref(res), got, big)
         self._pending_keep = None
         if rc == _lib.HJB_E_CAPACITY:
             raise HjbCapacityError(self._lib.hjb_last_error(self._ctx).decode(), (int(big[0]), int(big[1])))
         self._check(rc, "hjb_cpra_finish")
         return JoinResult(res, self), (int(got[0]), int(got[1])), (int(big[0]), int(big[1]))
+
+    def host_register(self, array):
+        """page-locks a caller-owned numpy array in place (hjb_host_register); undo with host_unregister"""
+        self._check(self._lib.hjb_host_register(C.c_void_p(array.ctypes.data), array.nbytes), "hjb_host_register")
+
+    def host_unregister(self, array):
+        self._check(self._lib.hjb_host_unregister(C.c_void_p(array.ctypes.data)), "hjb_host_unregister")
 
     def device_view64(self, ptr, n):
         import torch

@@ -137,7 +137,8 @@ def cpra_join_fused(engine, inner_chunk, outer_chunk, state, group=None, **opts)
     collectives are ordered with the library's kernels through that stream."""
     world, rank = state.world, state.rank
     from .api import HjbCapacityError
-    nr, ns = int(inner_chunk[0].numel()), int(outer_chunk[0].numel())
+    size = lambda col: int(col.numel()) if hasattr(col, "numel") else int(col.size)
+    nr, ns = size(inner_chunk[0]), size(outer_chunk[0])
     if state.own is None:
         # first step: room for a uniform share plus a quarter; a skewed input grows it below
         tot = torch.tensor([nr, ns], dtype=torch.int64, device=state.counts.device)

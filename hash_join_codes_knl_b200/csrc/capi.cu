@@ -1414,6 +1414,75 @@ extern "C" int hjb_cpra_finish(hjb_ctx *ctx, hjb_result *out, uint64_t received[
 	return HJB_OK;
 }
 
+// ---- the stream-ordered step from / to HOST memory: the chunk is copied in by the count call, the rows are
+// copied out by the finish call (what a host application holds after fread, cpra2.cpp:2128-2136)
+
+extern "C" int hjb_host_register(void *ptr, size_t bytes)
+{
+	if (!ptr || !bytes) return HJB_E_INVALID;
+	return cudaHostRegister(ptr, bytes, cudaHostRegisterPortable) == cudaSuccess ? HJB_OK : HJB_E_CUDA;
+}
+
+extern "C" int hjb_host_unregister(void *ptr)
+{
+	if (!ptr) return HJB_E_INVALID;
+	return cudaHostUnregister(ptr) == cudaSuccess ? HJB_OK : HJB_E_CUDA;
+}
+
+extern "C" int hjb_cpra_count_async_host(hjb_ctx *ctx, const hjb_rel *R, const hjb_rel *S, const hjb_opts *opts,
+                                         uint64_t *counts_dev)
+{
+	if (!ctx || !counts_dev) return HJB_E_INVALID;
+	int rc;
+	if ((rc = check_rel(ctx, R, false)) || (rc = check_rel(ctx, S, false))) return rc;
+	CK(cudaSetDevice(ctx->device));
+	const size_t rb = pad256(R->tuples * 4), sb = pad256(S->tuples * 4);
+	if ((rc = grow_device(ctx, &ctx->in_buf, &ctx->in_bytes, 2 * rb + 2 * sb + 256))) return rc;
+	cudaStream_t s = ctx->stream;
+	uint32_t *drk = (uint32_t *)ctx->in_buf, *drv = (uint32_t *)(ctx->in_buf + rb);
+	uint32_t *dsk = (uint32_t *)(ctx->in_buf + 2 * rb), *dsv = (uint32_t *)(ctx->in_buf + 2 * rb + sb);
+	CK(cudaEventRecord(ctx->ev[8], s));
+	if (R->tuples) {
+		CK(cudaMemcpyAsync(drk, R->keys, R->tuples * 4, cudaMemcpyHostToDevice, s));
+		CK(cudaMemcpyAsync(drv, R->vals, R->tuples * 4, cudaMemcpyHostToDevice, s));
+	}
+	if (S->tuples) {
+		CK(cudaMemcpyAsync(dsk, S->keys, S->tuples * 4, cudaMemcpyHostToDevice, s));
+		CK(cudaMemcpyAsync(dsv, S->vals, S->tuples * 4, cudaMemcpyHostToDevice, s));
+	}
+	CK(cudaEventRecord(ctx->ev[9], s));
+	const hjb_rel dR = {drk, drv, R->tuples}, dS = {dsk, dsv, S->tuples};
+	return hjb_cpra_count_async(ctx, &dR, &dS, opts, counts_dev);
+}
+
+extern "C" int hjb_cpra_finish_host(hjb_ctx *ctx, hjb_result *out, uint64_t received[2], uint64_t largest[2])
+{
+	int rc = hjb_cpra_finish(ctx, out, received, largest);
+	if (rc) return rc;
+	cudaStream_t s = ctx->stream;
+	float h2d = 0, d2h = 0;
+	CK(cudaEventElapsedTime(&h2d, ctx->ev[8], ctx->ev[9]));
+	if (out->keys && out->count) {
+		if ((rc = grow_host_rows(ctx, out->count))) return rc;
+		CK(cudaEventRecord(ctx->ev[10], s));
+		const uint32_t *cols[3] = {out->keys, out->outer_vals, out->inner_vals};
+		for (int c = 0; c < 3; ++c)
+			CK(cudaMemcpyAsync(ctx->h_rows + (size_t)c * ctx->h_rows_cap, cols[c], out->count * 4, cudaMemcpyDeviceToHost, s));
+		CK(cudaEventRecord(ctx->ev[11], s));
+		CK(cudaStreamSynchronize(s));
+		CK(cudaEventElapsedTime(&d2h, ctx->ev[10], ctx->ev[11]));
+		out->keys = ctx->h_rows;
+		out->outer_vals = ctx->h_rows + ctx->h_rows_cap;
+		out->inner_vals = ctx->h_rows + 2 * ctx->h_rows_cap;
+	} else {
+		out->keys = out->outer_vals = out->inner_vals = nullptr;
+	}
+	out->rows_on_device = 0;
+	out->phase_ms[5] = h2d;
+	out->phase_ms[6] = d2h;
+	return HJB_OK;
+}
+
 // ------------------------------------------------------------------ kernel-level entry points
 
 extern "C" int hjb_histogram(hjb_ctx *ctx, const uint32_t *keys, uint64_t size, uint32_t *counts, uint32_t factor,

@@ -192,4 +192,48 @@ __device__ __forceinline__ void emit_round(const OutCols &out, const bool (&foun
 	}
 }
 
+// The same, CTA-collective: EVERY thread of the CTA calls it once per round (warps without a match too), and the
+// CTA reserves the rows of all its warps with ONE global atomicAdd.  Same-address atomics are served one after the
+// other by the L2 (measured on B200: ~1 ns each, i.e. a reservation per warp round of 128 tuples caps a join at
+// ~120 G probe tuples/s whatever else it does); per CTA round of THREADS x ITEMS tuples the cap is 8x higher.
+// stage: 2 x (nwarps + 2) uint32 of shared memory, `round` alternates its halves so that two barriers per call suffice.
+template <int ITEMS>
+__device__ __forceinline__ void emit_round_cta(const OutCols &out, uint32_t *stage, uint32_t round, const bool (&found)[ITEMS],
+                                               const uint32_t (&key)[ITEMS], const uint32_t (&val)[ITEMS],
+                                               const uint32_t (&ival)[ITEMS])
+{
+	const uint32_t lane = lane_id(), warp = threadIdx.x >> 5, nwarps = (blockDim.x + 31) >> 5;
+	uint32_t *wt = stage + (round & 1u) * (nwarps + 2);
+	unsigned long long *basep = reinterpret_cast<unsigned long long *>(stage + 2 * (nwarps + 2)) + (round & 1u);
+	uint32_t total = 0;
+#pragma unroll
+	for (int t = 0; t < ITEMS; ++t) total += __popc(__ballot_sync(kFullMask, found[t]));
+	if (lane == 0) wt[warp] = total;
+	__syncthreads();
+	const uint32_t mine = lane < nwarps ? wt[lane] : 0u;
+	const uint32_t incl = warp_inclusive_scan_u32(mine);
+	const uint32_t cta_total = __shfl_sync(kFullMask, incl, 31);
+	const uint32_t before = __shfl_sync(kFullMask, incl - mine, warp);
+	if (cta_total == 0) return;                    // uniform over the CTA
+	if (threadIdx.x == 0) *basep = atomicAdd(out.cursor, (unsigned long long)cta_total);
+	__syncthreads();
+	const unsigned long long cta_base = *basep;
+	if (cta_base + cta_total > out.cap || total == 0) return;
+	const unsigned lt = lanemask_lt();
+	const unsigned long long base = cta_base + before;
+	uint32_t *const ck = out.k + base, *const co = out.o + base, *const ci = out.i + base;
+	uint32_t off = 0;
+#pragma unroll
+	for (int t = 0; t < ITEMS; ++t) {
+		const unsigned mt = __ballot_sync(kFullMask, found[t]);
+		const uint32_t r = off + __popc(mt & lt);
+		if (found[t]) {
+			ck[r] = key[t];
+			co[r] = val[t];
+			ci[r] = ival[t];
+		}
+		off += __popc(mt);
+	}
+}
+
 }  // namespace hjb

@@ -169,13 +169,15 @@ __device__ __forceinline__ void npj_emit_row(const OutCols &out, uint32_t key, u
 // Unique build keys (flags[1] == 0, detected by the build): a lane stops at its first match, the
 // warp reserves rows with one atomicAdd per round and stores them ballot-ranked from registers.
 // Otherwise every match is emitted as it is met.
-template <bool MATERIALIZE>
+template <bool MATERIALIZE, bool CTAEMIT>
 __global__ void __launch_bounds__(kNpjThreads, 3)
 k_npj_probe(const uint32_t *__restrict__ keys, const uint32_t *__restrict__ vals, uint64_t n,
             const uint64_t *__restrict__ table, uint32_t buckets, uint32_t factor, uint32_t b_lo, uint32_t b_hi, int hints, OutCols out,
             unsigned long long *__restrict__ sums, const unsigned long long *__restrict__ flags)
 {
 	__shared__ uint64_t scratch[4 * 32];
+	__shared__ __align__(8) uint32_t s_emit[2 * (kNpjThreads / 32 + 2) + 4];
+	uint32_t emit_rounds = 0;
 	JoinSums acc;
 	acc.zero();
 	const uint32_t sentinels = (uint32_t)flags[0];
@@ -239,7 +241,10 @@ k_npj_probe(const uint32_t *__restrict__ keys, const uint32_t *__restrict__ vals
 				found[t] = hit;
 				acc.add_if(hit ? 1u : 0u, k[t], v[t], ival[t]);
 			}
-			if (MATERIALIZE) emit_round<kNpjItems>(out, found, k, v, ival);
+			if (MATERIALIZE) {
+				if (CTAEMIT) emit_round_cta<kNpjItems>(out, s_emit, emit_rounds++, found, k, v, ival);
+				else emit_round<kNpjItems>(out, found, k, v, ival);
+			}
 		} else {
 #pragma unroll
 			for (int t = 0; t < kNpjItems; ++t) {
@@ -275,8 +280,9 @@ k_npj_probe(const uint32_t *__restrict__ keys, const uint32_t *__restrict__ vals
 // phases of a table of `buckets` buckets: slices of at most HJB_NPJ_PHASE_MB (default 48) megabytes
 uint32_t npj_phases(uint64_t buckets)
 {
-	static const long long mb = getenv("HJB_NPJ_PHASE_MB") ? atoll(getenv("HJB_NPJ_PHASE_MB")) : 48;
-	const uint64_t slice = (uint64_t)(mb > 0 ? mb : 48) << 20;
+	static const long long mb = getenv("HJB_NPJ_PHASE_MB") ? atoll(getenv("HJB_NPJ_PHASE_MB")) : 0;
+	if (mb <= 0) return 1;
+	const uint64_t slice = (uint64_t)mb << 20;
 	const uint64_t bytes = buckets * 32;
 	uint64_t p = (bytes + slice - 1) / slice;
 	if (bytes <= (96ull << 20)) p = 1;                    // fits L2 as a whole
@@ -326,8 +332,9 @@ int launch_npj_probe(const NpjArgs &a, cudaStream_t s, int sms, KernelTimer *t)
 	off.n = 0;
 	if (!t) t = &off;
 	int per_sm = 0;
-	if (a.materialize) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_npj_probe<true>, kNpjThreads, 0);
-	else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_npj_probe<false>, kNpjThreads, 0);
+	static const int cta_emit = getenv("HJB_NPJ_CTA_EMIT") ? atoi(getenv("HJB_NPJ_CTA_EMIT")) : 0;
+	if (a.materialize) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_npj_probe<true, true>, kNpjThreads, 0);
+	else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_npj_probe<false, false>, kNpjThreads, 0);
 	if (per_sm < 1) per_sm = 1;
 	const uint64_t rounds = (a.ns + kNpjThreads * kNpjItems - 1) / (kNpjThreads * kNpjItems);
 	uint64_t grid = rounds;
@@ -344,12 +351,15 @@ int launch_npj_probe(const NpjArgs &a, cudaStream_t s, int sms, KernelTimer *t)
 	for (uint32_t p = 0; p < phases; ++p) {
 		uint32_t lo, hi;
 		phase_range(a.buckets, phases, p, &lo, &hi);
-		if (a.materialize)
-			k_npj_probe<true><<<(uint32_t)grid, kNpjThreads, 0, s>>>(a.sk, a.sv, a.ns, a.table, (uint32_t)a.buckets, a.factor, lo, hi,
-			                                                         npj_hints(), out, a.scalars + 1, a.scalars + 5);
+		if (a.materialize && cta_emit)
+			k_npj_probe<true, true><<<(uint32_t)grid, kNpjThreads, 0, s>>>(a.sk, a.sv, a.ns, a.table, (uint32_t)a.buckets, a.factor, lo, hi,
+			                                                               npj_hints(), out, a.scalars + 1, a.scalars + 5);
+		else if (a.materialize)
+			k_npj_probe<true, false><<<(uint32_t)grid, kNpjThreads, 0, s>>>(a.sk, a.sv, a.ns, a.table, (uint32_t)a.buckets, a.factor, lo, hi,
+			                                                                npj_hints(), out, a.scalars + 1, a.scalars + 5);
 		else
-			k_npj_probe<false><<<(uint32_t)grid, kNpjThreads, 0, s>>>(a.sk, a.sv, a.ns, a.table, (uint32_t)a.buckets, a.factor, lo, hi,
-			                                                          npj_hints(), out, a.scalars + 1, a.scalars + 5);
+			k_npj_probe<false, false><<<(uint32_t)grid, kNpjThreads, 0, s>>>(a.sk, a.sv, a.ns, a.table, (uint32_t)a.buckets, a.factor, lo, hi,
+			                                                                 npj_hints(), out, a.scalars + 1, a.scalars + 5);
 	}
 	t->stop(s);
 	return (int)phases;

@@ -92,14 +92,14 @@ __device__ __forceinline__ void emit_row_opportunistic(const OutCols &out, uint3
 	}
 }
 
-constexpr uint32_t kDirectWords = 2048;                  // 2^16-bit presence bitmap
+constexpr uint32_t kDirectWords = 4096;                  // 2^16 presence bits, 16 per word; the word's high half holds the rank prefix
 constexpr uint32_t kDirectFill = 6144;                   // build tuples per DIRECT fill (payload array, 24 KB)
 constexpr uint32_t kHashSlots = 1u << kJoinLog2Slots;    // HASH table slots
 constexpr uint32_t kHashFill = kHashSlots / 4 * 3;       // load <= 0.75
-constexpr size_t kDirectBytes = (size_t)kDirectWords * 8 + (size_t)kDirectFill * 4;
+constexpr size_t kDirectBytes = (size_t)kDirectWords * 4 + (size_t)kDirectFill * 4;
 constexpr size_t kJoinSmemBytes = (size_t)kHashSlots * 8 > kDirectBytes ? (size_t)kHashSlots * 8 : kDirectBytes;
 
-template <int THREADS, int ITEMS, int MINB, bool MATERIALIZE, bool OWNER>
+template <int THREADS, int ITEMS, int MINB, bool MATERIALIZE, bool OWNER, bool CTAEMIT>
 __global__ void __launch_bounds__(THREADS, MINB)
 k_partition_join(const uint32_t *__restrict__ rk, const uint32_t *__restrict__ rv,
                  const uint32_t *__restrict__ sk, const uint32_t *__restrict__ sv,
@@ -110,13 +110,17 @@ k_partition_join(const uint32_t *__restrict__ rk, const uint32_t *__restrict__ r
 {
 	extern __shared__ __align__(16) unsigned char s_raw[];
 	// DIRECT view
-	uint2 *bp = reinterpret_cast<uint2 *>(s_raw);                      // kDirectWords x (presence word, set bits before it)
-	uint32_t *dvals = reinterpret_cast<uint32_t *>(bp + kDirectWords); // kDirectFill
+	// one word per 16 keys: bits 0..15 presence, bits 16..31 the number of present keys before the word -- a probe
+	// (or a payload placement) is ONE shared-memory load + a popcount
+	uint32_t *dtab = reinterpret_cast<uint32_t *>(s_raw);              // kDirectWords
+	uint32_t *dvals = dtab + kDirectWords;                             // kDirectFill
 	// HASH view
 	uint64_t *table = reinterpret_cast<uint64_t *>(s_raw);             // kHashSlots
 	__shared__ uint64_t scratch[4 * 32];
 	__shared__ uint32_t warp_totals[34];
 	__shared__ uint32_t s_task_id[2], s_hdups, s_sentinels;
+	__shared__ __align__(8) uint32_t s_emit[2 * (THREADS / 32 + 2) + 4];
+	uint32_t emit_rounds = 0;                      // CTA-uniform: which half of s_emit the next round uses
 	constexpr uint32_t kMask = kHashSlots - 1;
 	constexpr int kShift = 32 - kJoinLog2Slots;
 	const bool direct_ok = rem_bits <= 16;
@@ -173,8 +177,8 @@ k_partition_join(const uint32_t *__restrict__ rk, const uint32_t *__restrict__ r
 			uint32_t fe = min(fb + (use_hash ? kHashFill : kDirectFill), r_end);
 			if (!use_hash) {
 				// ---- DIRECT build, step 1: presence bits (equal keys set the same bit: step 2 counts fewer bits than tuples)
-				for (uint32_t w = threadIdx.x; w < kDirectWords / 2; w += THREADS)
-					reinterpret_cast<uint4 *>(bp)[w] = make_uint4(0, 0, 0, 0);
+				for (uint32_t w = threadIdx.x; w < kDirectWords / 4; w += THREADS)
+					reinterpret_cast<uint4 *>(dtab)[w] = make_uint4(0, 0, 0, 0);
 				__syncthreads();
 				look_ahead();
 				// build tuples are fetched kBatch at a time so that their loads are in flight together; the
@@ -191,9 +195,9 @@ k_partition_join(const uint32_t *__restrict__ rk, const uint32_t *__restrict__ r
 				for (int t = 0; t < kBatch; ++t)
 					if (fb + threadIdx.x + t * THREADS < fe) {
 						const uint32_t x = hash_mul(k0[t], radix_factor), lo = x & rem_mask;
-						const uint32_t bit = 1u << (lo & 31);
+						const uint32_t bit = 1u << (lo & 15);
 						if (OWNER) foreign |= (x >> owner_shift) ^ owner;
-						atomicOr(&bp[lo >> 5].x, bit);                // result unused: a reduction, no return path
+						atomicOr(&dtab[lo >> 4], bit);              // result unused: a reduction, no return path
 					}
 				for (uint32_t i0 = fb + threadIdx.x + THREADS * kBatch; i0 < fe; i0 += THREADS * kBatch) {
 					uint32_t bk[kBatch];
@@ -203,41 +207,46 @@ k_partition_join(const uint32_t *__restrict__ rk, const uint32_t *__restrict__ r
 					for (int t = 0; t < kBatch; ++t)
 						if (i0 + t * THREADS < fe) {
 							const uint32_t x = hash_mul(bk[t], radix_factor), lo = x & rem_mask;
-							const uint32_t bit = 1u << (lo & 31);
+							const uint32_t bit = 1u << (lo & 15);
 							if (OWNER) foreign |= (x >> owner_shift) ^ owner;
-							atomicOr(&bp[lo >> 5].x, bit);                // result unused: a reduction, no return path
+							atomicOr(&dtab[lo >> 4], bit);              // result unused: a reduction, no return path
 						}
 				}
 				__syncthreads();
 				{
-					// step 2: rank structure -- prefix[w] = set bits before word w; fewer bits than build tuples
-					// means equal keys: that fill is redone with the hash table
+					// step 2: rank structure -- the high half of word w = set bits before it; fewer bits than build
+					// tuples means equal keys: that fill is redone with the hash table
+					// Thread t owns words t, t + THREADS, ... (conflict-free accesses); ranks are counted in (thread, word)
+					// order -- any fixed order serves, build and probe read the same prefixes.
 					constexpr uint32_t kPer = kDirectWords / THREADS;
-					uint32_t c[kPer], local = 0;
+					uint32_t local = 0;
 #pragma unroll
-					for (uint32_t j = 0; j < kPer; ++j) {
-						c[j] = __popc(bp[threadIdx.x * kPer + j].x);
-						local += c[j];
-					}
+					for (uint32_t j = 0; j < kPer; ++j) local += __popc(dtab[threadIdx.x + j * THREADS]);
 					uint32_t tot;
 					uint32_t run = block_exclusive_scan(local, warp_totals, &tot);
 					use_hash = tot != fe - fb;
 #pragma unroll
-					for (uint32_t j = 0; j < kPer; ++j) {
-						bp[threadIdx.x * kPer + j].y = run;
-						run += c[j];
+					for (uint32_t j = 0; j < kPer; ++j) {                  // read again rather than kept: 16 registers less across the scan
+						const uint32_t w = dtab[threadIdx.x + j * THREADS];
+						dtab[threadIdx.x + j * THREADS] = w | (run << 16);
+						run += __popc(w);
 					}
 					__syncthreads();
 				}
 				if (!use_hash) {
 					// step 3: payloads in rank order
+					// all look-ups before the first store: as far as the compiler knows dvals[] may alias the
+					// bitmap, so look-up and store in one loop would run as a chain
+					uint32_t dpos[kBatch];
+#pragma unroll
+					for (int t = 0; t < kBatch; ++t) {
+						const uint32_t lo = hash_mul(k0[t], radix_factor) & rem_mask;
+						const uint32_t e = dtab[lo >> 4];
+						dpos[t] = (e >> 16) + __popc(e & ((1u << (lo & 15)) - 1));
+					}
 #pragma unroll
 					for (int t = 0; t < kBatch; ++t)
-						if (fb + threadIdx.x + t * THREADS < fe) {
-							const uint32_t lo = hash_mul(k0[t], radix_factor) & rem_mask;
-							const uint2 e = bp[lo >> 5];
-							dvals[e.y + __popc(e.x & ((1u << (lo & 31)) - 1))] = v0[t];
-						}
+						if (fb + threadIdx.x + t * THREADS < fe) dvals[dpos[t]] = v0[t];
 					for (uint32_t i0 = fb + threadIdx.x + THREADS * kBatch; i0 < fe; i0 += THREADS * kBatch) {
 						uint32_t bk[kBatch], bv[kBatch];
 #pragma unroll
@@ -246,13 +255,16 @@ k_partition_join(const uint32_t *__restrict__ rk, const uint32_t *__restrict__ r
 							bk[t] = in ? rk[i0 + t * THREADS] : 0;
 							bv[t] = in ? rv[i0 + t * THREADS] : 0;
 						}
+						uint32_t bpos[kBatch];
+#pragma unroll
+						for (int t = 0; t < kBatch; ++t) {
+							const uint32_t lo = hash_mul(bk[t], radix_factor) & rem_mask;
+							const uint32_t e = dtab[lo >> 4];
+							bpos[t] = (e >> 16) + __popc(e & ((1u << (lo & 15)) - 1));
+						}
 #pragma unroll
 						for (int t = 0; t < kBatch; ++t)
-							if (i0 + t * THREADS < fe) {
-								const uint32_t lo = hash_mul(bk[t], radix_factor) & rem_mask;
-								const uint2 e = bp[lo >> 5];
-								dvals[e.y + __popc(e.x & ((1u << (lo & 31)) - 1))] = bv[t];
-							}
+							if (i0 + t * THREADS < fe) dvals[bpos[t]] = bv[t];
 					}
 					__syncthreads();
 					// ---- DIRECT probe
@@ -271,15 +283,18 @@ k_partition_join(const uint32_t *__restrict__ rk, const uint32_t *__restrict__ r
 						for (int t = 0; t < ITEMS; ++t) {
 							const uint32_t x = hash_mul(key[t], radix_factor), lo = x & rem_mask;
 							if (OWNER && found[t]) foreign |= (x >> owner_shift) ^ owner;
-							const uint2 e = bp[lo >> 5];
-							const uint32_t hit = found[t] ? (e.x >> (lo & 31)) & 1u : 0u;
+							const uint32_t e = dtab[lo >> 4];
+							const uint32_t hit = found[t] ? (e >> (lo & 15)) & 1u : 0u;
 							// rank < fill size whenever the bit is set; a miss may compute fill size itself: clamp
-							const uint32_t pos = min(e.y + (uint32_t)__popc(e.x & ((1u << (lo & 31)) - 1)), kDirectFill - 1);
+							const uint32_t pos = min((e >> 16) + (uint32_t)__popc(e & ((1u << (lo & 15)) - 1)), kDirectFill - 1);
 							ival[t] = dvals[pos];
 							found[t] = hit != 0;
 							acc.add_if(hit, key[t], val[t], ival[t]);
 						}
-						if (MATERIALIZE) emit_round<ITEMS>(out, found, key, val, ival);
+						if (MATERIALIZE) {
+							if (CTAEMIT) emit_round_cta<ITEMS>(out, s_emit, emit_rounds++, found, key, val, ival);
+							else emit_round<ITEMS>(out, found, key, val, ival);
+						}
 					}
 					__syncthreads();            // the bitmap is cleared next; also publishes the prefetched task id
 					fb = fe;
@@ -414,10 +429,15 @@ int launch_partition_join(const JoinArgs &a, cudaStream_t s, int sms, KernelTime
 		                                                                   a.task_counter, a.s_task, a.radix_factor, a.table_factor,
 		                                                                   a.rem_bits, a.owner, a.owner_bits, out, a.scalars + 1);
 	};
-	if (a.materialize && a.owner_bits) launch(k_partition_join<kJoinThreads, kJoinItems, 5, true, true>);
-	else if (a.materialize) launch(k_partition_join<kJoinThreads, kJoinItems, 5, true, false>);
-	else if (a.owner_bits) launch(k_partition_join<kJoinThreads, kJoinItems, 5, false, true>);
-	else launch(k_partition_join<kJoinThreads, kJoinItems, 5, false, false>);
+	static const int cta_emit = getenv("HJB_CTA_EMIT") ? atoi(getenv("HJB_CTA_EMIT")) : 1;
+	static const int minb = getenv("HJB_JOIN_MINB") ? atoi(getenv("HJB_JOIN_MINB")) : 5;
+	if (a.materialize && a.owner_bits && cta_emit) launch(k_partition_join<kJoinThreads, kJoinItems, 5, true, true, true>);
+	else if (a.materialize && a.owner_bits) launch(k_partition_join<kJoinThreads, kJoinItems, 5, true, true, false>);
+	else if (a.materialize && cta_emit && minb == 4) launch(k_partition_join<kJoinThreads, kJoinItems, 4, true, false, true>);
+	else if (a.materialize && cta_emit) launch(k_partition_join<kJoinThreads, kJoinItems, 5, true, false, true>);
+	else if (a.materialize) launch(k_partition_join<kJoinThreads, kJoinItems, 5, true, false, false>);
+	else if (a.owner_bits) launch(k_partition_join<kJoinThreads, kJoinItems, 5, false, true, false>);
+	else launch(k_partition_join<kJoinThreads, kJoinItems, 5, false, false, false>);
 	t->stop(s);
 	return 2;
 }

@@ -322,18 +322,20 @@ __device__ __forceinline__ void hist_add(uint32_t *h, uint32_t d, bool valid, bo
 	if (valid && (int)lane_id() == __ffs(m) - 1) atomicAdd(&h[d], (uint32_t)__popc(m));
 }
 
-// k_hist for fan-outs <= 256.  The item is walked in the scatter's tiles (kTile tuples from the item's
+// k_hist for fan-outs <= 256.  The item is walked in the scatter's tiles (TILE tuples from the item's
 // first aligned group on); besides the item's counts row, the digit counts of every tile go to
-// tile_counts[item][tile][digit] (uint16: a tile holds 8192 tuples).  Two shared-memory histograms
+// tile_counts[item][tile][digit] (uint16: a tile holds at most 16384 tuples).  Two shared-memory histograms
 // take turns so that one barrier per tile suffices.
+template <uint32_t TILE>
 __global__ void __launch_bounds__(kHistThreads)
 k_hist_tiles(const uint32_t *__restrict__ keys, uint64_t n, uint32_t np, const uint32_t *__restrict__ parent_off,
              const uint32_t *__restrict__ item_prefix, uint32_t chunk, uint32_t factor, int rshift, int bits,
              uint32_t *__restrict__ counts, uint16_t *__restrict__ tile_counts, uint32_t tiles_per_item)
 {
 	__shared__ uint32_t s_hist[2][kTcMaxFanout];
-	constexpr int GPT = kTileGroups / kHistThreads;            // groups per thread and tile
-	static_assert(GPT * kHistThreads == kTileGroups, "tile must be a whole number of rounds");
+	constexpr uint32_t TILE_GROUPS = TILE / 4;
+	constexpr int GPT = TILE_GROUPS / kHistThreads;            // groups per thread and tile
+	static_assert(GPT * kHistThreads == TILE_GROUPS, "tile must be a whole number of rounds");
 	const uint32_t F = 1u << bits, mask = F - 1;
 	const bool aggregate = bits <= 4;
 	ItemRange r;
@@ -346,9 +348,9 @@ k_hist_tiles(const uint32_t *__restrict__ keys, uint64_t n, uint32_t np, const u
 	const uint64_t g_beg = r.beg >> 2, g_end = (r.end + 3) >> 2;
 	uint16_t *trow = tile_counts + (size_t)blockIdx.x * tiles_per_item * F;
 	uint32_t total = 0, j = 0;
-	for (uint64_t g0 = g_beg; g0 < g_end; g0 += kTileGroups, ++j) {
+	for (uint64_t g0 = g_beg; g0 < g_end; g0 += TILE_GROUPS, ++j) {
 		uint32_t *h = s_hist[j & 1];
-		const bool full = (g0 << 2) >= r.beg && ((g0 + kTileGroups) << 2) <= r.end;     // r.end <= n: vector loads stay inside
+		const bool full = (g0 << 2) >= r.beg && ((g0 + TILE_GROUPS) << 2) <= r.end;     // r.end <= n: vector loads stay inside
 		if (full) {
 			uint4 w[GPT];
 #pragma unroll
@@ -404,9 +406,9 @@ k_hist_tiles(const uint32_t *__restrict__ keys, uint64_t n, uint32_t np, const u
 // have to fetch the rest of a half-written sector from HBM (measured in round 1: 2.70 -> 2.19 GB of DRAM
 // traffic per 2^27-tuple launch).
 //
-// dynamic shared memory: cursor[256] | cf[256] (uint2) | golim[2][256] (uint2) | buf[kTile] (uint2) | carry[256 * 8] (uint2)
+// dynamic shared memory: cursor[256] | cf[256] (uint2) | golim[2][256] (uint2) | buf[TILE] (uint2) | carry[256 * 8] (uint2)
 constexpr uint32_t kLocalCarry = 8;    // tuples per 32-byte sector of a 4-byte column
-constexpr size_t kScatterTcSmem = 256 * 4 + 256 * 8 + 2 * 256 * 8 + (size_t)kTile * 8 + 256 * kLocalCarry * 8;
+constexpr size_t scatter_tc_smem(uint32_t tile) { return 256 * 4 + 256 * 8 + 2 * 256 * 8 + (size_t)tile * 8 + 256 * kLocalCarry * 8; }
 
 // One tile = THREADS * 4 G tuples = THREADS * G absolutely aligned groups; thread t owns groups t,
 // t + THREADS, ... of the tile (coalesced 128-bit loads).
@@ -444,7 +446,7 @@ k_scatter_tc(const uint32_t *__restrict__ keys, const uint32_t *__restrict__ val
              uint32_t *__restrict__ keys_out, uint32_t *__restrict__ vals_out)
 {
 	constexpr int IT = 4 * G;                                   // tuples per thread and tile
-	static_assert(THREADS * IT == kTile, "CTA shape must cover one tile");
+	constexpr uint32_t TILE = THREADS * IT, TILE_GROUPS = TILE / 4;
 	extern __shared__ __align__(16) uint32_t s_mem[];
 	__shared__ uint32_t warp_totals[8];
 	__shared__ uint32_t s_tile_n[2];
@@ -452,13 +454,13 @@ k_scatter_tc(const uint32_t *__restrict__ keys, const uint32_t *__restrict__ val
 	uint2 *cf = reinterpret_cast<uint2 *>(cursor + 256);          // carried tuples to flush: x = global position of the first, y = how many
 	uint2 *golim = cf + 256;                                      // [2][256]; x: global position of tile slot 0, y: flush limit
 	uint2 *buf = golim + 512;
-	uint2 *carry = buf + kTile;
+	uint2 *carry = buf + TILE;
 	const uint32_t F = 1u << bits, mask = F - 1;
 	const bool aggregate = bits <= 4;
 	ItemRange r;
 	if (!locate_item(item_prefix, np, parent_off, n, chunk, blockIdx.x, &r)) return;
 	const uint64_t g_beg = r.beg >> 2, g_end = (r.end + 3) >> 2;
-	const uint32_t ntiles = (uint32_t)((g_end - g_beg + kTileGroups - 1) / kTileGroups);
+	const uint32_t ntiles = (uint32_t)((g_end - g_beg + TILE_GROUPS - 1) / TILE_GROUPS);
 	if (ntiles == 0) return;
 	const uint16_t *trow = tile_counts + (size_t)blockIdx.x * tiles_per_item * F;
 	// per-digit state lives in the registers of thread d: next output position, tuples waiting in the carry buffer,
@@ -470,7 +472,7 @@ k_scatter_tc(const uint32_t *__restrict__ keys, const uint32_t *__restrict__ val
 		c_next = trow[threadIdx.x];
 	}
 	auto tile_is_full = [&](uint64_t g0) {
-		return (g0 << 2) >= r.beg && ((g0 + kTileGroups) << 2) <= r.end;    // r.end <= n: vector loads stay inside
+		return (g0 << 2) >= r.beg && ((g0 + TILE_GROUPS) << 2) <= r.end;    // r.end <= n: vector loads stay inside
 	};
 	// plan of tile j, by the first plan_threads threads (whole warps): tile offsets by an exclusive scan over the
 	// digits, then per digit how far the item's output may be flushed and what stays carried
@@ -516,7 +518,7 @@ k_scatter_tc(const uint32_t *__restrict__ keys, const uint32_t *__restrict__ val
 	}
 	__syncthreads();
 	for (uint32_t j = 0; j < ntiles; ++j) {
-		const uint64_t g1 = g_beg + (uint64_t)(j + 1) * kTileGroups;
+		const uint64_t g1 = g_beg + (uint64_t)(j + 1) * TILE_GROUPS;
 		// ---- place
 		if (aggregate) {
 #pragma unroll
@@ -555,13 +557,14 @@ k_scatter_tc(const uint32_t *__restrict__ keys, const uint32_t *__restrict__ val
 		}
 		__syncthreads();
 		// ---- next tile: loads on their way, plan on the first F threads
+		constexpr bool kValsEarly = IT <= 8;          // 16 tuples per thread: the payloads are fetched after the stream (registers)
 		if (j + 1 < ntiles) {
 			if (tile_is_full(g1)) {
 				load_tile_col<THREADS, G, true>(key, ok, keys, g1, g_end, r.beg, r.end, n);
-				load_tile_col<THREADS, G, true>(val, ok, vals, g1, g_end, r.beg, r.end, n);
+				if (kValsEarly) load_tile_col<THREADS, G, true>(val, ok, vals, g1, g_end, r.beg, r.end, n);
 			} else {
 				load_tile_col<THREADS, G, false>(key, ok, keys, g1, g_end, r.beg, r.end, n);
-				load_tile_col<THREADS, G, false>(val, ok, vals, g1, g_end, r.beg, r.end, n);
+				if (kValsEarly) load_tile_col<THREADS, G, false>(val, ok, vals, g1, g_end, r.beg, r.end, n);
 			}
 			if (threadIdx.x < plan_threads) {
 				plan(j + 1, j + 2 == ntiles);
@@ -586,6 +589,10 @@ k_scatter_tc(const uint32_t *__restrict__ keys, const uint32_t *__restrict__ val
 					carry[d * kLocalCarry + (pos - gl.y)] = kv;
 				}
 			}
+		}
+		if (!kValsEarly && j + 1 < ntiles) {
+			if (tile_is_full(g1)) load_tile_col<THREADS, G, true>(val, ok, vals, g1, g_end, r.beg, r.end, n);
+			else load_tile_col<THREADS, G, false>(val, ok, vals, g1, g_end, r.beg, r.end, n);
 		}
 		__syncthreads();
 	}
@@ -888,7 +895,9 @@ k_scatter_bulk(const uint32_t *__restrict__ keys, const uint32_t *__restrict__ v
 // experiment knobs, read once (host/cpra.cpp calls the launchers from one thread per GPU)
 struct RadixKnobs {
 	int items;          // HJB_ITEMS: work items per pass
-	int shape;          // HJB_SCATTER_SHAPE: 0 = two 512-thread CTAs per SM, 16 tuples per thread; 1 = one 1024-thread CTA, 8 per thread
+	int shape;          // HJB_SCATTER_SHAPE: 2 = one 1024-thread CTA per SM, 16384-tuple tiles (default, measured best);
+	                    // 1 = one 1024-thread CTA, 8192-tuple tiles; 0 = two 512-thread CTAs, 8192-tuple tiles
+	uint32_t tile;      // tuples per tile of that shape
 };
 static const RadixKnobs &radix_knobs()
 {
@@ -896,7 +905,9 @@ static const RadixKnobs &radix_knobs()
 		RadixKnobs v;
 		v.items = getenv("HJB_ITEMS") ? atoi(getenv("HJB_ITEMS")) : 1184;
 		if (v.items < 64) v.items = 1184;
-		v.shape = getenv("HJB_SCATTER_SHAPE") ? atoi(getenv("HJB_SCATTER_SHAPE")) : 0;
+		v.shape = getenv("HJB_SCATTER_SHAPE") ? atoi(getenv("HJB_SCATTER_SHAPE")) : 2;
+		if (v.shape < 0 || v.shape > 2) v.shape = 2;
+		v.tile = v.shape == 2 ? 2 * kTile : kTile;
 		return v;
 	}();
 	return k;
@@ -909,8 +920,9 @@ size_t radix_scratch_bytes(uint64_t n, uint32_t np, int bits, uint32_t *chunk, u
 	// counts matrix and its scan stay small (measured: 1024-1184 items 4.23 ms per config-2 step, 2048
 	// 4.27, 4096 4.35); chunk is a multiple of the scatter tile
 	const int target = radix_knobs().items;
+	const uint32_t tile = radix_knobs().tile;
 	uint64_t c = (n + target - 1) / target;
-	c = (c + kTile - 1) / kTile * kTile;
+	c = (c + 2 * kTile - 1) / (2 * kTile) * (2 * kTile);       // a multiple of every tile size in use
 	if (c < 2 * kTile) c = 2 * kTile;
 	if (c > (1u << 24)) c = 1u << 24;
 	*chunk = (uint32_t)c;
@@ -918,7 +930,7 @@ size_t radix_scratch_bytes(uint64_t n, uint32_t np, int bits, uint32_t *chunk, u
 	*max_items = (uint32_t)mi;
 	const uint64_t E = mi << bits;
 	*tiles = (uint32_t)((E + kScanThreads * kScanItems - 1) / (kScanThreads * kScanItems));
-	const uint32_t tpi = (uint32_t)(c / kTile) + 1;               // an item starts inside an aligned group: one tile more than chunk / kTile
+	const uint32_t tpi = (uint32_t)(c / tile) + 1;                // an item starts inside an aligned group: one tile more than chunk / tile
 	if (tiles_per_item) *tiles_per_item = tpi;
 	size_t bytes = 0;
 	bytes += ((size_t)(np + 1) * 4 + 255) / 256 * 256;           // item_prefix
@@ -955,10 +967,12 @@ static void scatter_attrs()
 	cudaGetDevice(&dev);
 	const unsigned long long bit = 1ull << (dev & 63);
 	if (done_mask.fetch_or(bit) & bit) return;
-	cudaFuncSetAttribute(k_scatter_tc<512, 4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kScatterTcSmem);
-	cudaFuncSetAttribute(k_scatter_tc<1024, 2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kScatterTcSmem);
+	cudaFuncSetAttribute(k_scatter_tc<512, 4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scatter_tc_smem(kTile));
+	cudaFuncSetAttribute(k_scatter_tc<1024, 2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scatter_tc_smem(kTile));
+	cudaFuncSetAttribute(k_scatter_tc<1024, 4, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scatter_tc_smem(2 * kTile));
 	cudaFuncSetAttribute(k_scatter<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2048 * 12 + (int)kTile * 8);
-	cudaFuncSetAttribute(k_scatter_bulk<1024, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bulk_smem_bytes(64));
+	cudaFuncSetAttribute(k_scatter_bulk<1024, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+	                     (int)(bulk_smem_bytes(32) > bulk_smem_bytes(64) ? bulk_smem_bytes(32) : bulk_smem_bytes(64)));
 }
 
 // make_items + histogram + scan: after this a.counts holds every item's start offset per digit
@@ -978,9 +992,12 @@ int launch_radix_count(const RadixPassArgs &a, cudaStream_t s, KernelTimer *t)
 	k_make_items<<<1, 1024, 0, s>>>(a.parent_off, a.np, a.n, a.chunk, a.item_prefix, a.child_off, a.np << a.bits);
 	t->stop(s);
 	t->start(KK_HIST, s);
-	if (a.tile_counts)
-		k_hist_tiles<<<a.max_items, kHistThreads, 0, s>>>(a.keys, a.n, a.np, a.parent_off, a.item_prefix, a.chunk, a.factor,
-		                                                  a.rshift, a.bits, a.counts, a.tile_counts, a.tiles_per_item);
+	if (a.tile_counts && radix_knobs().tile == 2 * kTile)
+		k_hist_tiles<2 * kTile><<<a.max_items, kHistThreads, 0, s>>>(a.keys, a.n, a.np, a.parent_off, a.item_prefix, a.chunk, a.factor,
+		                                                             a.rshift, a.bits, a.counts, a.tile_counts, a.tiles_per_item);
+	else if (a.tile_counts)
+		k_hist_tiles<kTile><<<a.max_items, kHistThreads, 0, s>>>(a.keys, a.n, a.np, a.parent_off, a.item_prefix, a.chunk, a.factor,
+		                                                         a.rshift, a.bits, a.counts, a.tile_counts, a.tiles_per_item);
 	else if (a.bits <= 3)
 		k_hist_small<<<a.max_items, kHistThreads, 0, s>>>(a.keys, a.n, a.np, a.parent_off, a.item_prefix, a.chunk,
 		                                                  a.factor, a.rshift, a.bits, a.counts);
@@ -1016,14 +1033,18 @@ int launch_radix_scatter(const RadixPassArgs &a, cudaStream_t s, KernelTimer *t,
 		return 1;
 	}
 	t->start(KK_SCATTER, s);
-	if (a.tile_counts && radix_knobs().shape == 1)
-		k_scatter_tc<1024, 2, 1><<<grid, 1024, kScatterTcSmem, s>>>(a.keys, a.vals, a.n, a.np, a.parent_off, a.item_prefix, a.chunk, a.factor,
-		                                                            a.rshift, a.bits, a.counts, a.tile_counts, a.tiles_per_item,
-		                                                            a.keys_out, a.vals_out);
+	if (a.tile_counts && radix_knobs().shape == 2)
+		k_scatter_tc<1024, 4, 1><<<grid, 1024, scatter_tc_smem(2 * kTile), s>>>(a.keys, a.vals, a.n, a.np, a.parent_off, a.item_prefix, a.chunk,
+		                                                                        a.factor, a.rshift, a.bits, a.counts, a.tile_counts,
+		                                                                        a.tiles_per_item, a.keys_out, a.vals_out);
+	else if (a.tile_counts && radix_knobs().shape == 0)
+		k_scatter_tc<512, 4, 2><<<grid, 512, scatter_tc_smem(kTile), s>>>(a.keys, a.vals, a.n, a.np, a.parent_off, a.item_prefix, a.chunk,
+		                                                                  a.factor, a.rshift, a.bits, a.counts, a.tile_counts,
+		                                                                  a.tiles_per_item, a.keys_out, a.vals_out);
 	else if (a.tile_counts)
-		k_scatter_tc<512, 4, 2><<<grid, 512, kScatterTcSmem, s>>>(a.keys, a.vals, a.n, a.np, a.parent_off, a.item_prefix, a.chunk, a.factor,
-		                                                          a.rshift, a.bits, a.counts, a.tile_counts, a.tiles_per_item, a.keys_out,
-		                                                          a.vals_out);
+		k_scatter_tc<1024, 2, 1><<<grid, 1024, scatter_tc_smem(kTile), s>>>(a.keys, a.vals, a.n, a.np, a.parent_off, a.item_prefix, a.chunk,
+		                                                                    a.factor, a.rshift, a.bits, a.counts, a.tile_counts,
+		                                                                    a.tiles_per_item, a.keys_out, a.vals_out);
 	else
 		k_scatter<1024><<<grid, 1024, (size_t)F * 12 + (size_t)kTile * 8, s>>>(a.keys, a.vals, a.n, a.np, a.parent_off, a.item_prefix,
 		                                                                       a.chunk, a.factor, a.rshift, a.bits, a.counts, a.keys_out,

@@ -181,6 +181,18 @@ int hjb_cpra_join_async(hjb_ctx *ctx, const hjb_opts *opts, uint64_t r_expect, u
 void *hjb_cpra_sums_dev(hjb_ctx *ctx);
 int hjb_cpra_finish(hjb_ctx *ctx, hjb_result *out, uint64_t received[2], uint64_t largest[2]);
 
+/* The same step with the chunk in HOST memory (what the reference's main() holds after fread, cpra2.cpp:2128-2136):
+ * hjb_cpra_count_async_host copies the chunk in on the stream before counting, hjb_cpra_finish_host copies this GPU's
+ * rows out to pinned host memory (hjb_result: rows_on_device = 0, phase_ms[5] H2D, phase_ms[6] D2H).  The columns
+ * should be pinned: cudaHostAlloc'ed, or registered once with hjb_host_register (page-locks the caller's own
+ * allocation, e.g. the reference's mamalloc'ed columns, npj.cpp:118-126); pageable memory works but copies slower.
+ * The same holds for hjb_npj_host / hjb_phj_host. */
+int hjb_host_register(void *ptr, size_t bytes);
+int hjb_host_unregister(void *ptr);
+int hjb_cpra_count_async_host(hjb_ctx *ctx, const hjb_rel *R_chunk_host, const hjb_rel *S_chunk_host, const hjb_opts *opts,
+                              uint64_t *counts_dev);
+int hjb_cpra_finish_host(hjb_ctx *ctx, hjb_result *out, uint64_t received[2], uint64_t largest[2]);
+
 /* ---- the kernels, one call each, device pointers: mirror the reference's free functions
  * so intermediate products can be compared with the oracle -------------------------- */
 /* hash h(key,f,N) = ((uint32)(key*f) * N) >> 32, npj.cpp:200-201 / simd_hash npj.cpp:90-106;

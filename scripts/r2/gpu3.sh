@@ -1,0 +1,13 @@
+#!/bin/bash
+cd "$GRAFT_REPO_ROOT" || exit 1
+mkdir -p gpurun_out
+timeout 300 python scripts/r2/sanity.py > gpurun_out/r2_sanity.log 2>&1; rc=$?; tail -2 gpurun_out/r2_sanity.log
+if [ $rc -ne 0 ]; then echo "sanity failed rc=$rc"; tail -30 gpurun_out/r2_sanity.log; exit 1; fi
+for shape in 0 1; do
+HJB_SCATTER_SHAPE=$shape timeout 300 python scripts/r2/exp.py cfg2,cfg1 phj 1 2>&1 | tee -a gpurun_out/r2_exp3.log
+done
+HJB_CTA_EMIT=0 HJB_SCATTER_SHAPE=1 timeout 300 python scripts/r2/exp.py cfg2,cfg1 phj 1 2>&1 | tee -a gpurun_out/r2_exp3.log
+timeout 300 python scripts/r2/exp.py cfg1,cfg3 npj 1 2>&1 | tee -a gpurun_out/r2_exp3.log
+for shape in 0 1; do
+HJB_SCATTER_SHAPE=$shape HJB_GRAPHS=0 timeout 900 ncu --set full --clock-control none --import-source on -k regex:'k_scatter_tc' -s 8 -c 1 -o gpurun_out/r2b_prof_scatter_s$shape -f python scripts/r2/exp.py cfg2 phj 1 > gpurun_out/r2_ncu_s$shape.log 2>&1
+done
