@@ -315,6 +315,39 @@ class Engine:
         self._check(rc, "hjb_cpra_finish")
         return JoinResult(res, self), (int(got[0]), int(got[1])), (int(big[0]), int(big[1]))
 
+    # ---- heavy-hitter handling (include/hjb200.h: hjb_cpra_split_hot / _select_hot / _hot_join)
+    def cpra_split_hot(self, outer_chunk, hot_keys_dev):
+        """-> ((cold keys, cold vals), (hot keys, hot vals)): int32 CUDA tensors aliasing context memory"""
+        kp, kn, kd, ka = _col(outer_chunk[0])
+        vp, vn, vd, va = _col(outer_chunk[1])
+        assert kd and vd and kn == vn
+        S = Rel(kp if kn else None, vp if kn else None, kn)
+        cold, hot = Rel(), Rel()
+        self._check(self._lib.hjb_cpra_split_hot(self._ctx, C.byref(S), C.c_void_p(hot_keys_dev.data_ptr()), int(hot_keys_dev.numel()),
+                                                 C.byref(cold), C.byref(hot)), "hjb_cpra_split_hot")
+        view = lambda r: (self.device_view(r.keys, r.tuples), self.device_view(r.vals, r.tuples))
+        return view(cold), view(hot)
+
+    def cpra_select_hot(self, inner_chunk, hot_keys_dev, keys_out, vals_out):
+        """this chunk's build tuples with hot keys -> keys_out / vals_out (int32 CUDA tensors); returns how many were found"""
+        kp, kn, kd, ka = _col(inner_chunk[0])
+        vp, vn, vd, va = _col(inner_chunk[1])
+        assert kd and vd and kn == vn
+        R = Rel(kp if kn else None, vp if kn else None, kn)
+        found = C.c_uint64()
+        self._check(self._lib.hjb_cpra_select_hot(self._ctx, C.byref(R), C.c_void_p(hot_keys_dev.data_ptr()), int(hot_keys_dev.numel()),
+                                                  C.c_void_p(keys_out.data_ptr()), C.c_void_p(vals_out.data_ptr()),
+                                                  int(keys_out.numel()), C.byref(found)), "hjb_cpra_select_hot")
+        return int(found.value)
+
+    def cpra_hot_join(self, hot_outer, hot_inner):
+        S = Rel(hot_outer[0].data_ptr() if hot_outer[0].numel() else None, hot_outer[1].data_ptr() if hot_outer[0].numel() else None,
+                hot_outer[0].numel())
+        R = Rel(hot_inner[0].data_ptr() if hot_inner[0].numel() else None, hot_inner[1].data_ptr() if hot_inner[0].numel() else None,
+                hot_inner[0].numel())
+        self._check(self._lib.hjb_cpra_hot_join(self._ctx, C.byref(S), C.byref(R)), "hjb_cpra_hot_join")
+        self._hot_keep = (hot_outer, hot_inner)
+
     def host_register(self, array):
         """page-locks a caller-owned numpy array in place (hjb_host_register); undo with host_unregister"""
         self._check(self._lib.hjb_host_register(C.c_void_p(array.ctypes.data), array.nbytes), "hjb_host_register")

@@ -126,18 +126,89 @@ class FusedExchange:
         self.engine.cpra_bind(self.rank, self.world, self.peers, self.r_cap, self.s_cap)
 
 
-def cpra_join_fused(engine, inner_chunk, outer_chunk, state, group=None, **opts):
+MAX_HOT_KEYS = 256          # hjb200.h: hjb_cpra_split_hot
+MAX_HOT_BUILD = 4096        # build tuples with hot keys, all ranks together (hjb_cpra_hot_join)
+
+
+def detect_hot_keys(outer_keys, group=None, sample=1 << 16, per_rank=64, min_share=1.0 / 2048):
+    """Heavy hitters of the probe side, the same list on every rank: every rank counts the keys of a strided
+    sample of its chunk, nominates its most frequent ones, the nominations are all-gathered and a key is hot
+    when its sampled frequency over all ranks reaches `min_share` of the sampled tuples.  Returns a sorted
+    int32 CUDA tensor of at most MAX_HOT_KEYS keys (empty: no skew worth handling)."""
+    world = dist.get_world_size(group)
+    dev = outer_keys.device
+    n = int(outer_keys.numel())
+    m = min(sample, n)
+    nominations = torch.zeros(2, per_rank, dtype=torch.int64, device=dev)
+    if m:
+        picks = outer_keys[:: max(1, n // m)][:m]
+        keys, counts = torch.unique(picks, return_counts=True)
+        top = torch.topk(counts, min(per_rank, int(counts.numel())))
+        nominations[0, : top.indices.numel()] = keys[top.indices].to(torch.int64) & 0xFFFFFFFF
+        nominations[1, : top.indices.numel()] = top.values
+    gathered = torch.empty(world, 2, per_rank, dtype=torch.int64, device=dev)
+    dist.all_gather_into_tensor(gathered.view(-1), nominations.view(-1), group=group)
+    keys, inverse = torch.unique(gathered[:, 0, :].reshape(-1), return_inverse=True)
+    totals = torch.zeros(keys.numel(), dtype=torch.int64, device=dev).index_add_(0, inverse, gathered[:, 1, :].reshape(-1))
+    sampled = torch.tensor([m], dtype=torch.int64, device=dev)
+    dist.all_reduce(sampled, group=group)
+    hot = (totals >= max(8, int(int(sampled.item()) * min_share))) & (keys != 0xFFFFFFFF)     # 0xFFFFFFFF is never declared hot
+    keys, totals = keys[hot], totals[hot]
+    if keys.numel() > MAX_HOT_KEYS:
+        keys = keys[torch.topk(totals, MAX_HOT_KEYS).indices]
+    keys = torch.sort(keys).values
+    return (keys - ((keys >= (1 << 31)).to(torch.int64) << 32)).to(torch.int32).contiguous()     # uint32 bit pattern in int32
+
+
+def split_hot(engine, inner_chunk, outer_chunk, hot_keys, group=None):
+    """-> (cold outer chunk, this rank's hot outer tuples, all ranks' hot inner tuples) or None when the hot build
+    tuples do not fit (then the step runs without the hot path)."""
+    world = dist.get_world_size(group)
+    dev = hot_keys.device
+    mine_k = torch.zeros(MAX_HOT_BUILD, dtype=torch.int32, device=dev)
+    mine_v = torch.zeros(MAX_HOT_BUILD, dtype=torch.int32, device=dev)
+    found = engine.cpra_select_hot(inner_chunk, hot_keys, mine_k, mine_v)
+    counts = torch.empty(world, dtype=torch.int64, device=dev)
+    dist.all_gather_into_tensor(counts, torch.tensor([found], dtype=torch.int64, device=dev), group=group)
+    counts = [int(x) for x in counts.tolist()]
+    if sum(counts) > MAX_HOT_BUILD:
+        return None
+    width = max(1, max(counts))
+    allk = torch.empty(world * width, dtype=torch.int32, device=dev)
+    allv = torch.empty(world * width, dtype=torch.int32, device=dev)
+    dist.all_gather_into_tensor(allk, mine_k[:width].contiguous(), group=group)
+    dist.all_gather_into_tensor(allv, mine_v[:width].contiguous(), group=group)
+    keep = torch.cat([torch.arange(width, device=dev) < c for c in counts])
+    hot_inner = (allk[keep].contiguous(), allv[keep].contiguous())
+    cold, hot_outer = engine.cpra_split_hot(outer_chunk, hot_keys)
+    return cold, hot_outer, hot_inner
+
+
+def cpra_join_fused(engine, inner_chunk, outer_chunk, state, group=None, skew=False, **opts):
     """CPRA with the all-to-all fused into the GPU-assign pass, the whole step enqueued on ONE stream:
     count -> all-gather of the count matrix (NCCL) -> bases on the device -> every sender scatters
     straight into the owners' receive buffers over NVLink -> 1-element all-reduce (every sender's stores
     have landed) -> local join with the received sizes read on the device -> all-reduce of the
     checksums.  The host synchronises once, at the end.  Same result dict as cpra_join.
 
+    skew=True: the probe tuples of heavy-hitter keys (detect_hot_keys) stay on their rank and are joined there
+    against the replicated build tuples of those keys (hjb_cpra_split_hot / _select_hot / _hot_join), the rest
+    takes the normal path -- the owners then receive balanced shares (the reference's static
+    ownership cpra2.cpp:1868-1872 does not).  Device columns only.
+
     Requires the Engine to run on torch's current stream (Engine(use_torch_stream=True)): NCCL's
     collectives are ordered with the library's kernels through that stream."""
     world, rank = state.world, state.rank
     from .api import HjbCapacityError
     size = lambda col: int(col.numel()) if hasattr(col, "numel") else int(col.size)
+    hot_parts, n_hot = None, 0
+    if skew:
+        hot_keys = detect_hot_keys(outer_chunk[0], group)
+        n_hot = int(hot_keys.numel())
+        if n_hot:
+            hot_parts = split_hot(engine, inner_chunk, outer_chunk, hot_keys, group)
+            if hot_parts is not None:
+                outer_chunk = hot_parts[0]
     nr, ns = size(inner_chunk[0]), size(outer_chunk[0])
     if state.own is None:
         # first step: room for a uniform share plus a quarter; a skewed input grows it below
@@ -156,6 +227,8 @@ def cpra_join_fused(engine, inner_chunk, outer_chunk, state, group=None, **opts)
         ev[2].record()
         engine.cpra_join_async(r_expect=state.expect[0] if hasattr(state, "expect") else 0,
                                s_expect=state.expect[1] if hasattr(state, "expect") else 0, **opts)
+        if hot_parts is not None:
+            engine.cpra_hot_join(hot_parts[1], hot_parts[2])
         state.sums.copy_(engine.cpra_sums_dev())
         dist.all_reduce(state.sums, group=group)
         ev[3].record()
@@ -170,4 +243,5 @@ def cpra_join_fused(engine, inner_chunk, outer_chunk, state, group=None, **opts)
     return {"count": count, "sum_key": sum_key, "sum_outer": sum_outer, "sum_inner": sum_inner, "local": local,
             "split_ms": ev[0].elapsed_time(ev[1]), "exchange_ms": ev[1].elapsed_time(ev[2]),
             "join_ms": float(local.seconds) * 1e3, "step_ms": ev[0].elapsed_time(ev[3]),
-            "recv_tuples": received, "largest_recv": largest}
+            "recv_tuples": received, "largest_recv": largest, "hot_keys": n_hot if hot_parts is not None else 0,
+            "hot_outer_tuples": int(hot_parts[1][0].numel()) if hot_parts is not None else 0}

@@ -77,6 +77,11 @@ struct hjb_ctx {
 	uint32_t step_launches;
 	struct PhjState *step_phj;
 	hjb_opts step_opts;
+	// heavy-hitter handling (hjb_cpra_split_hot ... hjb_cpra_hot_join)
+	char *skew_buf;           // cold / hot copies of the probe chunk
+	size_t skew_bytes;
+	hjb_rel hot_s, hot_r;     // arguments of the enqueued hot join (re-run when the result columns had to grow)
+	bool hot_pending;
 };
 
 static char g_create_err[512];
@@ -166,6 +171,7 @@ extern "C" int hjb_destroy(hjb_ctx *ctx)
 	cudaFree(ctx->split_buf);
 	for (int i = 0; i < 4; ++i) cudaFree(ctx->recv_buf[i]);
 	cudaFree(ctx->cpra_dev);
+	cudaFree(ctx->skew_buf);
 	free(ctx->step_phj);
 	cudaFree(ctx->d_scalars);
 	cudaFreeHost(ctx->h_scalars);
@@ -1309,6 +1315,7 @@ extern "C" int hjb_cpra_count_async(hjb_ctx *ctx, const hjb_rel *R, const hjb_re
 	timer_reset(ctx);
 	uint32_t *off_dev[2];
 	ctx->step_launches = 0;
+	ctx->hot_pending = false;
 	if ((rc = cpra_count_enqueue(ctx, R, S, ctx->bind_gpus, o, off_dev, &ctx->step_launches))) return rc;
 	k_cpra_counts<<<1, 64, 0, ctx->stream>>>(off_dev[0], off_dev[1], ctx->bind_gpus, (unsigned long long *)counts_dev);
 	ctx->step_launches += 1;
@@ -1368,6 +1375,8 @@ extern "C" int hjb_cpra_join_async(hjb_ctx *ctx, const hjb_opts *opts, uint64_t 
 	return HJB_OK;
 }
 
+static int hot_join_enqueue(hjb_ctx *ctx, uint32_t *launches);
+
 extern "C" void *hjb_cpra_sums_dev(hjb_ctx *ctx) { return ctx ? (void *)(ctx->d_scalars + 1) : nullptr; }
 
 extern "C" int hjb_cpra_finish(hjb_ctx *ctx, hjb_result *out, uint64_t received[2], uint64_t largest[2])
@@ -1400,8 +1409,10 @@ extern "C" int hjb_cpra_finish(hjb_ctx *ctx, hjb_result *out, uint64_t received[
 		if ((rc = grow_out(ctx, out->count))) return rc;
 		CK(cudaMemsetAsync(ctx->d_scalars, 0, 16 * 8, s));         // rerun the join phase only
 		if ((rc = phj_launch_join(ctx, &st, o, &launches))) return rc;
+		if (ctx->hot_pending && (rc = hot_join_enqueue(ctx, &launches))) return rc;
 		CK(cudaEventRecord(ctx->ev[3], s));
 	}
+	ctx->hot_pending = false;
 	float ms = 0;
 	CK(cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[3]));
 	out->seconds = ms * 1e-3;                               // the local join only
@@ -1412,6 +1423,74 @@ extern "C" int hjb_cpra_finish(hjb_ctx *ctx, hjb_result *out, uint64_t received[
 	set_rows(ctx, out, o->materialize);
 	ctx->launches += launches;
 	return HJB_OK;
+}
+
+// ---- heavy-hitter handling (skew.cu): hot probe tuples stay with their sender, hot build tuples are replicated
+
+extern "C" int hjb_cpra_split_hot(hjb_ctx *ctx, const hjb_rel *S, const uint32_t *hot_keys_dev, uint32_t n_hot, hjb_rel *cold,
+                                  hjb_rel *hot)
+{
+	if (!ctx || !cold || !hot || (n_hot && !hot_keys_dev)) return HJB_E_INVALID;
+	if (n_hot > kMaxHotKeys) return fail(ctx, HJB_E_INVALID, "more than 256 hot keys");
+	int rc;
+	if ((rc = check_rel(ctx, S, true))) return rc;
+	CK(cudaSetDevice(ctx->device));
+	const size_t col = pad256(S->tuples * 4);
+	if ((rc = grow_device(ctx, &ctx->skew_buf, &ctx->skew_bytes, 4 * col + 256))) return rc;
+	uint32_t *ck = (uint32_t *)ctx->skew_buf, *cv = (uint32_t *)(ctx->skew_buf + col);
+	uint32_t *hk = (uint32_t *)(ctx->skew_buf + 2 * col), *hv = (uint32_t *)(ctx->skew_buf + 3 * col);
+	cudaStream_t s = ctx->stream;
+	ctx->launches += launch_split_hot(S->keys, S->vals, S->tuples, hot_keys_dev, n_hot, ck, cv, hk, hv, ctx->d_scalars + 10, s, ctx->sms);
+	CK(cudaMemcpyAsync(ctx->h_scalars + 10, ctx->d_scalars + 10, 16, cudaMemcpyDeviceToHost, s));
+	CK(cudaStreamSynchronize(s));
+	CK(cudaGetLastError());
+	cold->keys = ck; cold->vals = cv; cold->tuples = ctx->h_scalars[10];
+	hot->keys = hk; hot->vals = hv; hot->tuples = ctx->h_scalars[11];
+	if (cold->tuples + hot->tuples != S->tuples) return fail(ctx, HJB_E_CUDA, "hjb_cpra_split_hot: the two parts do not add up");
+	return HJB_OK;
+}
+
+extern "C" int hjb_cpra_select_hot(hjb_ctx *ctx, const hjb_rel *R, const uint32_t *hot_keys_dev, uint32_t n_hot,
+                                   uint32_t *keys_out_dev, uint32_t *vals_out_dev, uint32_t capacity, uint64_t *found)
+{
+	if (!ctx || !found || (n_hot && !hot_keys_dev) || (capacity && (!keys_out_dev || !vals_out_dev))) return HJB_E_INVALID;
+	if (n_hot > kMaxHotKeys) return fail(ctx, HJB_E_INVALID, "more than 256 hot keys");
+	int rc;
+	if ((rc = check_rel(ctx, R, true))) return rc;
+	CK(cudaSetDevice(ctx->device));
+	cudaStream_t s = ctx->stream;
+	ctx->launches += launch_select_hot(R->keys, R->vals, R->tuples, hot_keys_dev, n_hot, keys_out_dev, vals_out_dev, capacity,
+	                                   ctx->d_scalars + 12, s, ctx->sms);
+	CK(cudaMemcpyAsync(ctx->h_scalars + 12, ctx->d_scalars + 12, 8, cudaMemcpyDeviceToHost, s));
+	CK(cudaStreamSynchronize(s));
+	CK(cudaGetLastError());
+	*found = ctx->h_scalars[12];              // may exceed capacity: the caller then gives up on the hot path for this key set
+	return HJB_OK;
+}
+
+static int hot_join_enqueue(hjb_ctx *ctx, uint32_t *launches)
+{
+	const hjb_opts *o = &ctx->step_opts;
+	*launches += launch_hot_join(ctx->hot_s.keys, ctx->hot_s.vals, ctx->hot_s.tuples, ctx->hot_r.keys, ctx->hot_r.vals,
+	                             (uint32_t)ctx->hot_r.tuples, hjb_hash_factor(o->seed, 1), ctx->out_cols, ctx->out_cols + ctx->out_cap,
+	                             ctx->out_cols + 2 * ctx->out_cap, o->materialize ? ctx->out_cap : 0, ctx->d_scalars, ctx->stream, ctx->sms);
+	return HJB_OK;
+}
+
+extern "C" int hjb_cpra_hot_join(hjb_ctx *ctx, const hjb_rel *S_hot, const hjb_rel *R_hot)
+{
+	if (!ctx) return HJB_E_INVALID;
+	if (ctx->step_state != 3) return fail(ctx, HJB_E_INVALID, "hjb_cpra_join_async must precede");
+	int rc;
+	if ((rc = check_rel(ctx, S_hot, true)) || (rc = check_rel(ctx, R_hot, true))) return rc;
+	if (R_hot->tuples > kMaxHotBuild) return fail(ctx, HJB_E_INVALID, "more than 4096 build tuples with hot keys");
+	CK(cudaSetDevice(ctx->device));
+	ctx->hot_s = *S_hot;
+	ctx->hot_r = *R_hot;
+	ctx->hot_pending = true;
+	rc = hot_join_enqueue(ctx, &ctx->step_launches);
+	CK(cudaGetLastError());
+	return rc;
 }
 
 // ---- the stream-ordered step from / to HOST memory: the chunk is copied in by the count call, the rows are

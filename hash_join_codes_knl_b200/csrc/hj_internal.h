@@ -128,6 +128,17 @@ uint32_t npj_phases(uint64_t buckets);
 int launch_npj_build(const NpjArgs &a, cudaStream_t s, int sms, KernelTimer *t = nullptr);
 int launch_npj_probe(const NpjArgs &a, cudaStream_t s, int sms, KernelTimer *t = nullptr);
 
+// heavy-hitter handling of the multi-GPU join (skew.cu)
+constexpr uint32_t kMaxHotKeys = 256;        // keys that may be declared hot
+constexpr uint32_t kMaxHotBuild = 4096;      // build tuples with hot keys, all GPUs together
+int launch_split_hot(const uint32_t *keys, const uint32_t *vals, uint64_t n, const uint32_t *hot, uint32_t n_hot, uint32_t *cold_k,
+                     uint32_t *cold_v, uint32_t *hot_k, uint32_t *hot_v, unsigned long long *cursors, cudaStream_t s, int sms);
+int launch_select_hot(const uint32_t *keys, const uint32_t *vals, uint64_t n, const uint32_t *hot, uint32_t n_hot, uint32_t *out_k,
+                      uint32_t *out_v, uint32_t capacity, unsigned long long *cursor, cudaStream_t s, int sms);
+int launch_hot_join(const uint32_t *sk, const uint32_t *sv, uint64_t ns, const uint32_t *rk, const uint32_t *rv, uint32_t nr,
+                    uint32_t factor, uint32_t *out_k, uint32_t *out_o, uint32_t *out_i, uint64_t out_cap, unsigned long long *scalars,
+                    cudaStream_t s, int sms);
+
 int launch_generate(const hjb_gen &g, uint32_t *keys, uint32_t *vals, cudaStream_t s);
 int launch_column_sum(const uint32_t *col, uint64_t n, unsigned long long *out_dev, cudaStream_t s, int sms);
 int launch_rows_fingerprint(const uint32_t *k, const uint32_t *o, const uint32_t *iv, uint64_t n, unsigned long long *out_dev,

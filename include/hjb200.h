@@ -181,6 +181,21 @@ int hjb_cpra_join_async(hjb_ctx *ctx, const hjb_opts *opts, uint64_t r_expect, u
 void *hjb_cpra_sums_dev(hjb_ctx *ctx);
 int hjb_cpra_finish(hjb_ctx *ctx, hjb_result *out, uint64_t received[2], uint64_t largest[2]);
 
+/* Skew (write.cpp's `zipf` knob, write.cpp:1685-1689; the reference's static ownership par_start / par_end,
+ * cpra2.cpp:1868-1872, sends every tuple of a frequent key to one thread).  The probe tuples of a small set of
+ * hot keys (<= 256, chosen by the caller, e.g. from a sample of the probe chunks) stay with their sender:
+ *   hjb_cpra_split_hot    S chunk -> cold part (takes the normal step) + hot part; both in context-owned memory,
+ *                         valid until the next split on this context
+ *   hjb_cpra_select_hot   this sender's R tuples with hot keys (the caller all-gathers them: <= 4096 in total)
+ *   hjb_cpra_hot_join     after hjb_cpra_join_async: this GPU's hot S tuples x all hot R tuples, rows and checksums
+ *                         appended to the step's result (enqueued; hjb_cpra_finish returns the union)
+ * Key 0xFFFFFFFF must not be declared hot. */
+int hjb_cpra_split_hot(hjb_ctx *ctx, const hjb_rel *S_chunk, const uint32_t *hot_keys_dev, uint32_t n_hot, hjb_rel *cold,
+                       hjb_rel *hot);
+int hjb_cpra_select_hot(hjb_ctx *ctx, const hjb_rel *R_chunk, const uint32_t *hot_keys_dev, uint32_t n_hot,
+                        uint32_t *keys_out_dev, uint32_t *vals_out_dev, uint32_t capacity, uint64_t *found);
+int hjb_cpra_hot_join(hjb_ctx *ctx, const hjb_rel *S_hot, const hjb_rel *R_hot);
+
 /* The same step with the chunk in HOST memory (what the reference's main() holds after fread, cpra2.cpp:2128-2136):
  * hjb_cpra_count_async_host copies the chunk in on the stream before counting, hjb_cpra_finish_host copies this GPU's
  * rows out to pinned host memory (hjb_result: rows_on_device = 0, phase_ms[5] H2D, phase_ms[6] D2H).  The columns

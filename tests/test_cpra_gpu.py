@@ -77,15 +77,29 @@ def run_sync_path(engines, G, rk, rv, sk, sv):
     return tuple(total), rows, (r_recv, s_recv)
 
 
-def run_async_path(engines, G, rk, rv, sk, sv, r_cap, s_cap):
-    """the stream-ordered step; the all-gather is a torch.cat, the cross-GPU ordering a device synchronise"""
+def run_async_path(engines, G, rk, rv, sk, sv, r_cap, s_cap, hot_keys=None):
+    """the stream-ordered step; the all-gather is a torch.cat, the cross-GPU ordering a device synchronise.
+    hot_keys: the probe tuples with these keys stay on their sender and are joined there (skew handling)"""
     bufs, peers = recv_buffers(G, r_cap, s_cap)
     counts = [torch.zeros(2 * G, dtype=torch.int64, device="cuda") for _ in range(G)]
-    keep = []
+    keep, hot_s, hot_r = [], [], None
     for c in range(G):
         engines[c].cpra_bind(c, G, peers, r_cap, s_cap)
         cols = ((dev(chunk(rk, c, G)), dev(chunk(rv, c, G))), (dev(chunk(sk, c, G)), dev(chunk(sv, c, G))))
         keep.append(cols)
+    if hot_keys is not None:
+        hk = dev(np.sort(np.asarray(hot_keys, np.uint32)))
+        parts_k, parts_v = [], []
+        for c in range(G):
+            ok_, ov_ = torch.zeros(4096, dtype=torch.int32, device="cuda"), torch.zeros(4096, dtype=torch.int32, device="cuda")
+            found = engines[c].cpra_select_hot(keep[c][0], hk, ok_, ov_)
+            parts_k.append(ok_[:found].clone())
+            parts_v.append(ov_[:found].clone())
+            cold, hot = engines[c].cpra_split_hot(keep[c][1], hk)
+            assert cold[0].numel() + hot[0].numel() == keep[c][1][0].numel()
+            keep[c] = (keep[c][0], cold)
+            hot_s.append(hot)
+        hot_r = (torch.cat(parts_k).contiguous(), torch.cat(parts_v).contiguous())
     torch.cuda.synchronize()
     for c in range(G):
         engines[c].cpra_count_async(keep[c][0], keep[c][1], counts[c])
@@ -99,6 +113,8 @@ def run_async_path(engines, G, rk, rv, sk, sv, r_cap, s_cap):
     err = None
     for g in range(G):
         engines[g].cpra_join_async()
+        if hot_r is not None:
+            engines[g].cpra_hot_join(hot_s[g], hot_r)
         try:
             res, got, largest = engines[g].cpra_finish()
         except HjbCapacityError as e:
@@ -164,6 +180,25 @@ def test_stream_ordered_step_reports_a_receive_buffer_that_is_too_small(engines)
     assert need_s > sk.size // 3 and need_r >= rk.size // G_ - 4096
     got, rows, _, _ = run_async_path(engines, G_, rk, rv, sk, sv, need_r, need_s)
     assert got == want.checks() and (all_rows(rows) == want.sorted_rows()).all()
+
+
+def test_hot_keys_stay_with_their_sender_and_the_owners_receive_balanced_shares(engines):
+    """skew handling (hjb_cpra_split_hot / _select_hot / _hot_join): a third of the probe side is ONE key, another
+    key takes a tenth and has no partner; with the frequent keys declared hot the rows are still the oracle's, and no owner
+    receives much more than its share"""
+    G_ = 4
+    rk, rv, sk, sv = skewed(150000, 500000, 24)
+    sk = sk.copy()
+    sk[1::10] = np.uint32(0x12345679)                       # frequent, but not a build key
+    assert not (rk == np.uint32(0x12345679)).any()
+    rk[11], rv[11] = rk[7], np.uint32(99)                    # the hot key twice on the build side: every pair is emitted
+    want = oracle_join("cpra", rk, rv, sk, sv, threads=4)
+    _, _, recv_plain, _ = run_async_path(engines, G_, rk, rv, sk, sv, rk.size, sk.size)
+    hot = [rk[7], 0x12345679, rk[7] ^ np.uint32(0x10000000)]    # skewed() also turns every 30th tuple into rk[7] ^ 0x10000000
+    got, rows, recv, _ = run_async_path(engines, G_, rk, rv, sk, sv, rk.size, sk.size, hot_keys=hot)
+    assert got == want.checks() and (all_rows(rows) == want.sorted_rows()).all()
+    share = lambda r: max(x[1] for x in r) / (sum(x[1] for x in r) / G_)
+    assert share(recv_plain) > 2.0 and share(recv) < 1.1
 
 
 def test_fused_exchange_many_tiles_per_item(engines):

@@ -42,11 +42,12 @@ def main():
         cr = slice(rank * nr // world, (rank + 1) * nr // world)
         cs = slice(rank * ns // world, (rank + 1) * ns // world)
         dev = lambda a: torch.from_numpy(np.ascontiguousarray(a).view(np.int32)).cuda()
-        for mode in ("nccl", "fused", "fused"):              # the fused step twice: the second runs with the first's sizes as its plan
+        for mode in ("nccl", "fused", "fused", "fused+skew"):    # the fused step twice: the second runs with the first's sizes as its plan
             if mode == "nccl":
                 res = cpra.cpra_join(eng, (dev(rk[cr]), dev(rv[cr])), (dev(sk[cs]), dev(sv[cs])))
             else:
-                res = cpra.cpra_join_fused(eng, (dev(rk[cr]), dev(rv[cr])), (dev(sk[cs]), dev(sv[cs])), fused)
+                res = cpra.cpra_join_fused(eng, (dev(rk[cr]), dev(rv[cr])), (dev(sk[cs]), dev(sv[cs])), fused,
+                                           skew=mode.endswith("skew"))
             got = (res["count"], res["sum_key"], res["sum_outer"], res["sum_inner"])
             rows = list(res["local"].rows_numpy())
             gathered = [None] * world
@@ -54,7 +55,9 @@ def main():
             if rank == 0:
                 allrows = sort_rows(*(np.concatenate([g[i] for g in gathered]) for i in range(3)))
                 good = got == want.checks() and (allrows == want.sorted_rows()).all()
-                print(f"cpra {mode} world={world} |R|={nr} |S|={ns}: {'OK' if good else 'MISMATCH'} {got} want {want.checks()} "
+                if mode.endswith("skew") and seed < 0 and ns >= 100000:
+                    good = good and res.get("hot_keys", 0) >= 1          # the planted heavy hitter was found
+                print(f"cpra {mode} world={world} |R|={nr} |S|={ns} hot={res.get('hot_keys', 0)}: {'OK' if good else 'MISMATCH'} {got} want {want.checks()} "
                       f"split {res['split_ms']:.3f} ms exchange {res['exchange_ms']:.3f} ms join {res['join_ms']:.3f} ms", flush=True)
                 ok = ok and good
     dist.destroy_process_group()
