@@ -543,6 +543,50 @@ def main():
                        "hjb_cpra_join_async / hjb_cpra_finish_host (every rank: its chunk in, its share of the rows out)"}
         del pin, hrk, hrv, hsk, hsv
 
+    # ---- N > 1: BASELINE config 5 (|R| = 2^27, |S| = 2^30, Zipf theta = 1 probe keys, 50 % of the probe tuples match),
+    # sharded like config 4, with and without the heavy-hitter path; every rank takes part, rank 0 reports
+    cfg5 = None
+    if world > 1 and algo == "cpra" and (world == 8 or os.environ.get("HJB_BENCH_CFG5")) and not args.log2_per_gpu:
+        try:
+            del rk, rv, sk, sv
+            torch.cuda.empty_cache()
+            nr5, ns5 = (1 << 27) // world, (1 << 30) // world
+            r5 = eng.generate(0, nr5, 1 << 27, 42, 1, datagen.INNER_FACTOR, first=rank * nr5, total=1 << 27)
+            s5 = eng.generate(2, ns5, 1 << 27, 42, 2, datagen.OUTER_FACTOR, first=rank * ns5, total=1 << 30, theta=1.0, selectivity=0.5)
+            cfg5 = {"workload": f"config 5: 2^27 x 2^30, Zipf theta = 1 probe keys, 50 % selectivity, {world} GPUs"}
+            checks = {}
+            for mode in ("static_ownership", "hot_keys_local"):
+                skew = mode == "hot_keys_local"
+                for _ in range(2):
+                    r = cpra_mod.cpra_join_fused(eng, r5, s5, fused, skew=skew)
+                barrier()
+                ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                ev0.record()
+                n5 = 4
+                join_ms = 0.0
+                for _ in range(n5):
+                    r = cpra_mod.cpra_join_fused(eng, r5, s5, fused, skew=skew)
+                    join_ms += r["join_ms"]
+                ev1.record()
+                barrier()
+                stats = torch.tensor([ev0.elapsed_time(ev1) / n5, join_ms / n5, float(r["recv_tuples"][1]), float(r["hot_outer_tuples"])],
+                                     dtype=torch.float64, device=devname)
+                allst = torch.empty(world * 4, dtype=torch.float64, device=devname)
+                dist.all_gather_into_tensor(allst, stats)
+                st = allst.view(world, 4).cpu()
+                checks[mode] = (r["count"], r["sum_key"], r["sum_outer"], r["sum_inner"])
+                ms5 = float(st[:, 0].max())
+                cfg5[mode] = {"ms_per_step": round(ms5, 4), "tuples_per_s": ((1 << 27) + (1 << 30)) / (ms5 * 1e-3),
+                              "recv_probe_tuples_max_over_mean": round(float(st[:, 2].max() / st[:, 2].mean()), 4),
+                              "local_join_ms_max_over_mean": round(float(st[:, 1].max() / st[:, 1].mean()), 4),
+                              "hot_keys": r["hot_keys"], "hot_probe_tuples_kept_local": int(st[:, 3].sum()), "count": r["count"]}
+            cfg5["verified"] = (checks["static_ownership"] == checks["hot_keys_local"]
+                                and abs(checks["static_ownership"][0] / (1 << 30) - 0.5) < 0.01)
+            cfg5["check"] = "both modes give the same count and checksums; count / |S| within 0.5 +- 0.01"
+            del r5, s5
+        except Exception as e:
+            cfg5 = {"error": f"{type(e).__name__}: {e}"}
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -615,6 +659,8 @@ def main():
                     rl.setdefault(tag, {"hbm_bytes_per_gpu": hbm_b})[ptag] = {"hbm_gbs": bw_h, "nvlink_gbs": bw_n, "serial_model_ms": t_ms,
                                                                               "frac": t_ms / ms_step}
             line["cpra_roofline"] = rl
+        if cfg5 is not None:
+            line["cpra_cfg5"] = cfg5
     # ---- N = 1: the other single-GPU configs of BASELINE.json, measured in the same run
     if world == 1 and not args.no_configs and workload == "phj_cfg2" and not args.log2_per_gpu:
         del rk, rv, sk, sv

@@ -257,7 +257,8 @@ static size_t pad256(size_t b) { return (b + 255) & ~(size_t)255; }
 static int check_rel(hjb_ctx *ctx, const hjb_rel *r, bool device_cols)
 {
 	if (!r) return fail(ctx, HJB_E_INVALID, "null relation");
-	if (r->tuples > 0xFFFFFFFFull) return fail(ctx, HJB_E_INVALID, "more than 2^32-1 tuples per relation per GPU");
+	// positions are 32-bit; the last 2^16 are kept free so that "position + one table fill" never wraps
+	if (r->tuples > 0xFFFF0000ull) return fail(ctx, HJB_E_INVALID, "more than 2^32 - 2^16 tuples per relation per GPU");
 	if (r->tuples && (!r->keys || !r->vals)) return fail(ctx, HJB_E_INVALID, "null column");
 	if (device_cols && r->tuples && ((((uintptr_t)r->keys) | ((uintptr_t)r->vals)) & 15))
 		return fail(ctx, HJB_E_INVALID, "device columns must be 16-byte aligned");
@@ -382,7 +383,6 @@ static int npj_device(hjb_ctx *ctx, const hjb_rel *R, const hjb_rel *S, const hj
 	a.nr = R->tuples; a.ns = S->tuples;
 	a.table = (uint64_t *)ctx->ws;
 	a.buckets = buckets;
-	a.phases = npj_phases(buckets);
 	a.factor = hjb_hash_factor(o->seed, 1);
 	a.scalars = ctx->d_scalars;
 	a.materialize = o->materialize;
@@ -635,8 +635,7 @@ static int phj_device(hjb_ctx *ctx, const hjb_rel *R, const hjb_rel *S, const hj
 	// The whole sequence (3 memsets, ~14 kernels) depends on nothing the host reads in between, so a
 	// repeated join of the same buffers replays it as ONE graph launch: first call eager, second call
 	// captured, from then on replayed.  Not while per-kernel events are wanted (hjb_set_profiling).
-	static int graphs = -1;
-	if (graphs < 0) graphs = getenv("HJB_GRAPHS") ? atoi(getenv("HJB_GRAPHS")) : 1;
+	static const int graphs = getenv("HJB_GRAPHS") ? atoi(getenv("HJB_GRAPHS")) : 1;
 	PhjGraphKey key;
 	memset(&key, 0, sizeof key);
 	key.rk = R->keys; key.rv = R->vals; key.sk = S->keys; key.sv = S->vals; key.ws = ctx->ws; key.out = ctx->out_cols;
@@ -754,8 +753,7 @@ static int host_join(hjb_ctx *ctx, device_join_fn fn, bool npj, const hjb_rel *R
 	cudaStream_t s = ctx->stream;
 	uint32_t *drk = (uint32_t *)ctx->in_buf, *drv = (uint32_t *)(ctx->in_buf + rb);
 	uint32_t *dsk = (uint32_t *)(ctx->in_buf + 2 * rb), *dsv = (uint32_t *)(ctx->in_buf + 2 * rb + sb);
-	static int pipeline = -1;               // HJB_HOST_PIPELINE=0: one copy in, the join, one copy out
-	if (pipeline < 0) pipeline = getenv("HJB_HOST_PIPELINE") ? atoi(getenv("HJB_HOST_PIPELINE")) : 1;
+	static const int pipeline = getenv("HJB_HOST_PIPELINE") ? atoi(getenv("HJB_HOST_PIPELINE")) : 1;   // 0: one copy in, the join, one copy out
 	bool on_device = false;
 	if (pipeline && R->tuples && S->tuples >= 2 * host_slice_min()) {
 		CK(cudaStreamSynchronize(s));
@@ -863,8 +861,7 @@ static int host_join_pipelined(hjb_ctx *ctx, bool npj, const hjb_rel *R, const h
 		a.rk = drk; a.rv = drv; a.nr = R->tuples;
 		a.table = (uint64_t *)ctx->ws;
 		a.buckets = buckets;
-		a.phases = npj_phases(buckets);
-		a.factor = hjb_hash_factor(o->seed, 1);
+			a.factor = hjb_hash_factor(o->seed, 1);
 		a.scalars = ctx->d_scalars;
 		a.materialize = o->materialize;
 		a.out_k = ctx->out_cols;
@@ -1636,7 +1633,6 @@ extern "C" int hjb_npj_build(hjb_ctx *ctx, const uint32_t *keys, const uint32_t 
 	memset(&a, 0, sizeof a);
 	a.rk = keys; a.rv = vals; a.nr = size;
 	a.table = table; a.buckets = buckets; a.factor = factor;
-	a.phases = 1;
 	a.scalars = ctx->d_scalars;
 	CK(cudaMemsetAsync(ctx->d_scalars, 0, 16 * 8, ctx->stream));
 	ctx->launches += launch_npj_build(a, ctx->stream, ctx->sms);

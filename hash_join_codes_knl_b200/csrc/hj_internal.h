@@ -117,14 +117,12 @@ struct NpjArgs {
 	uint64_t nr, ns;
 	uint64_t *table;
 	uint64_t buckets;                         // x 4 slots
-	uint32_t phases;                          // table slices built / probed one after the other (npj_phases); 0 = 1
 	uint32_t factor;
 	uint32_t *out_k, *out_o, *out_i;
 	uint64_t out_cap;
 	unsigned long long *scalars;              // [0] cursor, [1..4] sums, [5] sentinel build tuples, [6] duplicate build keys seen
 	int materialize;
 };
-uint32_t npj_phases(uint64_t buckets);
 int launch_npj_build(const NpjArgs &a, cudaStream_t s, int sms, KernelTimer *t = nullptr);
 int launch_npj_probe(const NpjArgs &a, cudaStream_t s, int sms, KernelTimer *t = nullptr);
 

@@ -694,13 +694,19 @@ k_scatter(const uint32_t *__restrict__ keys, const uint32_t *__restrict__ vals, 
 // crosses NVLink without occupying the SM.  Tuples beyond a digit's last whole 128-byte line are
 // carried to the next tile (software write-combining as above); an item's first / last few tuples
 // per digit that are not 16-byte aligned take scalar stores.  Fan-out <= 64.
-// For fan-outs <= 32 the digit-grouped tile is double-buffered: the bulk copies of tile t drain
-// over NVLink while tile t+1 is ranked, planned AND placed into the other buffer.
+// The digit-grouped tile is multi-buffered (three tiles for fan-outs <= 8, two up to 32): the bulk copies of
+// tile t drain over NVLink while tiles t+1, t+2 are ranked, planned AND placed into the other buffers.
 // dynamic shared memory: cnt wpos pend [64] | place[64] (uint4) | strm[64] (uint4) | cin[64] (uint2) |
 //                        NB x { skeys[PAD] svals[PAD] } | carry_k[2][32 F] carry_v[2][32 F],  PAD = kTile + 64 F
 constexpr uint32_t kBulkGranule = kPeerCarry;             // 32 tuples = 128 bytes per column
 
-static inline uint32_t bulk_buffers(uint32_t F) { return F <= 32 ? 2u : 1u; }
+// staging tiles of the peer scatter: as many as fit (HJB_BULK_BUFFERS caps it for A/B runs)
+static inline uint32_t bulk_buffers(uint32_t F)
+{
+	static const int cap = getenv("HJB_BULK_BUFFERS") ? atoi(getenv("HJB_BULK_BUFFERS")) : 3;
+	const uint32_t fit = F <= 8 ? 3u : F <= 32 ? 2u : 1u;
+	return cap >= 1 && (uint32_t)cap < fit ? (uint32_t)cap : fit;
+}
 static inline size_t bulk_smem_bytes(uint32_t F)
 {
 	const size_t pad = kTile + 2 * (size_t)kBulkGranule * F;
@@ -718,7 +724,7 @@ template <int THREADS, int MAXF>
 __global__ void __launch_bounds__(THREADS, 1)
 k_scatter_bulk(const uint32_t *__restrict__ keys, const uint32_t *__restrict__ vals, uint64_t n, uint32_t np,
                const uint32_t *__restrict__ parent_off, const uint32_t *__restrict__ item_prefix, uint32_t chunk,
-               uint32_t factor, int rshift, int bits, const uint32_t *__restrict__ offsets, const PeerTable peers)
+               uint32_t factor, int rshift, int bits, const uint32_t *__restrict__ offsets, const PeerTable peers, uint32_t nbuf)
 {
 	constexpr int G = kTile / 4 / THREADS, IT = 4 * G;
 	constexpr uint32_t GR = kBulkGranule;
@@ -728,13 +734,13 @@ k_scatter_bulk(const uint32_t *__restrict__ keys, const uint32_t *__restrict__ v
 	__shared__ uint32_t s_bias[64];
 	const uint32_t F = 1u << bits, mask = F - 1;
 	const uint32_t PAD = kTile + 2 * GR * F;
-	const bool two = F <= 32;                                   // double-buffered tile (bulk_buffers)
+	// nbuf staging tiles (bulk_buffers): the bulk copies of up to nbuf - 1 earlier tiles may still be draining
 	uint32_t *cnt = s_bulk, *wpos = cnt + MAXF, *pend = wpos + MAXF;
 	uint4 *place = reinterpret_cast<uint4 *>(pend + MAXF);     // x: slot of new rank 0, y: new tuples that fit the region, z: carry index of rank 0
 	uint4 *strm = place + MAXF;                                // x: global position of slot 0, y: first valid position, z: end of valid positions
 	uint2 *cin = reinterpret_cast<uint2 *>(strm + MAXF);       // carried-in tuples: x: destination slot 0 (0xFFFFFFFF: stay carried), y: how many
 	uint32_t *tile0 = reinterpret_cast<uint32_t *>(cin + MAXF);        // byte offset 52 * MAXF, a multiple of 128
-	uint32_t *carry_k = tile0 + (two ? 4 : 2) * PAD, *carry_v = carry_k + 2 * GR * F;
+	uint32_t *carry_k = tile0 + 2 * nbuf * PAD, *carry_v = carry_k + 2 * GR * F;
 	if (peers.abort_flag && *peers.abort_flag) return;
 	// The scan's positions start at sender_off[g] for owner g; they must land at base[g] of the owner's columns.
 	// The kernel counts positions as sender_off + bias, congruent to the physical row modulo the write-combining
@@ -768,7 +774,7 @@ k_scatter_bulk(const uint32_t *__restrict__ keys, const uint32_t *__restrict__ v
 		for (uint64_t g0 = g_beg; g0 < g_end; g0 += kTileGroups, ++tile_no) {
 			const uint64_t g1 = g0 + kTileGroups;
 			const bool last = g1 >= g_end;
-			uint32_t *const skeys = tile0 + (two ? (tile_no & 1) * 2 * PAD : 0), *const svals = skeys + PAD;
+			uint32_t *const skeys = tile0 + (tile_no % nbuf) * 2 * PAD, *const svals = skeys + PAD;
 			uint32_t *const oc_k = carry_k + (tile_no & 1) * GR * F, *const oc_v = carry_v + (tile_no & 1) * GR * F;            // carried in
 			uint32_t *const nc_k = carry_k + ((tile_no & 1) ^ 1) * GR * F, *const nc_v = carry_v + ((tile_no & 1) ^ 1) * GR * F;  // carried out
 #pragma unroll
@@ -791,7 +797,8 @@ k_scatter_bulk(const uint32_t *__restrict__ keys, const uint32_t *__restrict__ v
 			}
 			// the bulk copies that last read the buffer about to be refilled must have read their shared-memory source
 			if (threadIdx.x < F) {
-				if (two) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+				if (nbuf == 3) asm volatile("cp.async.bulk.wait_group.read 2;" ::: "memory");
+				else if (nbuf == 2) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
 				else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
 			}
 			__syncthreads();
@@ -971,8 +978,9 @@ static void scatter_attrs()
 	cudaFuncSetAttribute(k_scatter_tc<1024, 2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scatter_tc_smem(kTile));
 	cudaFuncSetAttribute(k_scatter_tc<1024, 4, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scatter_tc_smem(2 * kTile));
 	cudaFuncSetAttribute(k_scatter<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2048 * 12 + (int)kTile * 8);
-	cudaFuncSetAttribute(k_scatter_bulk<1024, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-	                     (int)(bulk_smem_bytes(32) > bulk_smem_bytes(64) ? bulk_smem_bytes(32) : bulk_smem_bytes(64)));
+	size_t bulk_max = 0;
+	for (uint32_t f = 2; f <= 64; f *= 2) bulk_max = bulk_smem_bytes(f) > bulk_max ? bulk_smem_bytes(f) : bulk_max;
+	cudaFuncSetAttribute(k_scatter_bulk<1024, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bulk_max);
 }
 
 // make_items + histogram + scan: after this a.counts holds every item's start offset per digit
@@ -1028,7 +1036,7 @@ int launch_radix_scatter(const RadixPassArgs &a, cudaStream_t s, KernelTimer *t,
 		const uint32_t grid_b = (a.peer_ctas && a.peer_ctas < grid) ? a.peer_ctas : grid;
 		t->start(KK_SCATTER_PEER, s);
 		k_scatter_bulk<1024, 64><<<grid_b, 1024, bulk_smem_bytes(F), s>>>(a.keys, a.vals, a.n, a.np, a.parent_off, a.item_prefix, a.chunk,
-		                                                                   a.factor, a.rshift, a.bits, a.counts, *peers);
+		                                                                   a.factor, a.rshift, a.bits, a.counts, *peers, bulk_buffers(F));
 		t->stop(s);
 		return 1;
 	}

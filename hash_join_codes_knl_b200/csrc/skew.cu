@@ -151,14 +151,18 @@ __device__ __forceinline__ void hot_emit_row(const OutCols &out, uint32_t key, u
 }
 
 // hot S x hot R.  Table: 2 * kMaxHotBuild slots of (payload << 32 | key), linear probing, every build tuple a slot
-// of its own (equal keys allowed), so a probe walks to the first empty slot and emits every equal key on the way.
+// of its own (equal keys allowed), so a probe walks to the first empty slot and emits every equal key on the way:
+// the first match of every tuple goes out with the CTA's round (one reservation per 1024 probe tuples -- a hot
+// key's tuples ALL match, and same-address atomics are served one per ~ns), further matches one by one.
 // The pair (0xFFFFFFFF, 0xFFFFFFFF) looks like an empty slot: the caller never declares key 0xFFFFFFFF hot.
-__global__ void __launch_bounds__(256)
+constexpr int kHotThreads = 256, kHotItems = 4;
+__global__ void __launch_bounds__(kHotThreads)
 k_hot_join(const uint32_t *__restrict__ sk, const uint32_t *__restrict__ sv, uint64_t ns, const uint32_t *__restrict__ rk,
            const uint32_t *__restrict__ rv, uint32_t nr, uint32_t factor, OutCols out, unsigned long long *__restrict__ sums)
 {
 	extern __shared__ __align__(16) uint64_t table[];          // 2 * kMaxHotBuild
 	__shared__ uint64_t scratch[4 * 32];
+	__shared__ __align__(8) uint32_t s_emit[2 * (kHotThreads / 32 + 2) + 4];
 	constexpr uint32_t kSlots = 2 * kMaxHotBuild, kMask = kSlots - 1;
 	for (uint32_t i = threadIdx.x; i < kSlots; i += blockDim.x) table[i] = kEmptySlot;
 	__syncthreads();
@@ -171,17 +175,51 @@ k_hot_join(const uint32_t *__restrict__ sk, const uint32_t *__restrict__ sv, uin
 	__syncthreads();
 	JoinSums acc;
 	acc.zero();
-	for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < ns; i += (uint64_t)gridDim.x * blockDim.x) {
-		const uint32_t k = ldg_stream_u32(&sk[i]), v = ldg_stream_u32(&sv[i]);
-		uint32_t h = (k * factor) & kMask;
-		while (true) {
-			const uint64_t slot = table[h];
-			if (slot == kEmptySlot) break;
-			if ((uint32_t)slot == k) {
-				acc.add(k, v, (uint32_t)(slot >> 32));
-				if (out.cap) hot_emit_row(out, k, v, (uint32_t)(slot >> 32));
+	constexpr uint32_t kRound = kHotThreads * kHotItems;
+	const uint64_t rounds = (ns + kRound - 1) / kRound;
+	uint32_t emit_rounds = 0;
+	for (uint64_t rd = blockIdx.x; rd < rounds; rd += gridDim.x) {
+		const uint64_t wbase = rd * kRound + (uint64_t)(threadIdx.x >> 5) * 32 * kHotItems + lane_id();
+		uint32_t k[kHotItems], v[kHotItems], ival[kHotItems], h[kHotItems];
+		bool found[kHotItems];
+#pragma unroll
+		for (int t = 0; t < kHotItems; ++t) {
+			const uint64_t i = wbase + (uint64_t)t * 32;
+			found[t] = i < ns;
+			k[t] = found[t] ? ldg_stream_u32(&sk[i]) : 0;
+			v[t] = found[t] ? ldg_stream_u32(&sv[i]) : 0;
+		}
+#pragma unroll
+		for (int t = 0; t < kHotItems; ++t) {
+			bool hit = false;
+			h[t] = (k[t] * factor) & kMask;
+			ival[t] = 0;
+			while (found[t]) {
+				const uint64_t slot = table[h[t]];
+				if (slot == kEmptySlot) break;
+				h[t] = (h[t] + 1) & kMask;
+				if ((uint32_t)slot == k[t]) {
+					ival[t] = (uint32_t)(slot >> 32);
+					hit = true;
+					break;
+				}
 			}
-			h = (h + 1) & kMask;
+			found[t] = hit;
+			if (hit) acc.add(k[t], v[t], ival[t]);
+		}
+		if (out.cap) emit_round_cta<kHotItems>(out, s_emit, emit_rounds++, found, k, v, ival);
+		// equal build keys: the walk goes on behind the first match
+#pragma unroll
+		for (int t = 0; t < kHotItems; ++t) {
+			while (found[t]) {
+				const uint64_t slot = table[h[t]];
+				if (slot == kEmptySlot) break;
+				h[t] = (h[t] + 1) & kMask;
+				if ((uint32_t)slot == k[t]) {
+					acc.add(k[t], v[t], (uint32_t)(slot >> 32));
+					if (out.cap) hot_emit_row(out, k[t], v[t], (uint32_t)(slot >> 32));
+				}
+			}
 		}
 	}
 	acc.reduce_to_global(sums, scratch);
@@ -221,9 +259,9 @@ int launch_hot_join(const uint32_t *sk, const uint32_t *sv, uint64_t ns, const u
 	out.i = out_i;
 	out.cursor = scalars;
 	out.cap = out_cap;
-	uint64_t grid = (ns + 255) / 256;
-	if (grid > (uint64_t)sms * 4) grid = (uint64_t)sms * 4;
-	k_hot_join<<<(uint32_t)grid, 256, 2 * kMaxHotBuild * 8, s>>>(sk, sv, ns, rk, rv, nr, factor, out, scalars + 1);
+	uint64_t grid = (ns + kHotThreads * kHotItems - 1) / (kHotThreads * kHotItems);
+	if (grid > (uint64_t)sms * 3) grid = (uint64_t)sms * 3;
+	k_hot_join<<<(uint32_t)grid, kHotThreads, 2 * kMaxHotBuild * 8, s>>>(sk, sv, ns, rk, rv, nr, factor, out, scalars + 1);
 	return 1;
 }
 

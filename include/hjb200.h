@@ -46,7 +46,7 @@ typedef struct hjb_ctx hjb_ctx;        /* one per GPU: device, stream, workspace
 typedef struct hjb_rel {
 	const uint32_t *keys;
 	const uint32_t *vals;
-	uint64_t tuples;                   /* <= 2^32 - 1 per GPU (the reference: uint32 counts, phj.cpp:1722-1727) */
+	uint64_t tuples;                   /* <= 2^32 - 2^16 per GPU (the reference: uint32 counts, phj.cpp:1722-1727) */
 } hjb_rel;
 
 /* Tunables the reference hard-codes in main() (npj.cpp:944-945, phj.cpp:1976-1979,
