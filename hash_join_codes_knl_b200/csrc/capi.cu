@@ -265,6 +265,15 @@ static int check_rel(hjb_ctx *ctx, const hjb_rel *r, bool device_cols)
 	return HJB_OK;
 }
 
+// NPJ table load factor when the caller does not set one: a table that overflows L2 probes fastest at 0.75 (fewer
+// DRAM sectors), a cache-resident one at a low load (few full buckets, so few probes walk into a second bucket --
+// a warp pays that walk's latency as soon as one of its lanes takes it)
+static double npj_default_load(uint64_t build_tuples)
+{
+	static const double small = getenv("HJB_NPJ_SMALL_LOAD") ? atof(getenv("HJB_NPJ_SMALL_LOAD")) : 0.5;
+	return build_tuples * 16 <= (32u << 20) ? small : 0.75;
+}
+
 static const hjb_opts kDefaultOpts = {1, 0, 0.0, {0, 0, 0, 0}, 0, 0, {0}};
 
 extern "C" uint32_t hjb_hash_factor(uint32_t seed, int which)
@@ -368,7 +377,7 @@ static int npj_device(hjb_ctx *ctx, const hjb_rel *R, const hjb_rel *S, const hj
 	if (R->tuples == 0 || S->tuples == 0) return HJB_OK;
 	// measured on B200: a table that overflows L2 probes fastest at 0.75 (fewer DRAM sectors), a
 	// cache-resident one at 0.5 (shorter bucket chains)
-	const double load = o->npj_load > 0.0 ? o->npj_load : (R->tuples * 16 <= (32u << 20) ? 0.5 : 0.75);
+	const double load = o->npj_load > 0.0 ? o->npj_load : npj_default_load(R->tuples);
 	if (load > 0.95) return fail(ctx, HJB_E_INVALID, "npj_load must be <= 0.95");
 	uint64_t buckets = (uint64_t)ceil((double)R->tuples / load / 4.0) + 1;       // +1: at least one empty slot
 	if (buckets > 0xFFFFFFFFull) return fail(ctx, HJB_E_INVALID, "table too large");
@@ -848,7 +857,7 @@ static int host_join_pipelined(hjb_ctx *ctx, bool npj, const hjb_rel *R, const h
 	PhjState st;
 	NpjArgs a;
 	if (npj) {
-		const double load = o->npj_load > 0.0 ? o->npj_load : (R->tuples * 16 <= (32u << 20) ? 0.5 : 0.75);
+		const double load = o->npj_load > 0.0 ? o->npj_load : npj_default_load(R->tuples);
 		if (load > 0.95) return fail(ctx, HJB_E_INVALID, "npj_load must be <= 0.95");
 		const uint64_t buckets = (uint64_t)ceil((double)R->tuples / load / 4.0) + 1;
 		if (buckets > 0xFFFFFFFFull) return fail(ctx, HJB_E_INVALID, "table too large");
