@@ -94,12 +94,12 @@ __device__ __forceinline__ void emit_row_opportunistic(const OutCols &out, uint3
 
 constexpr uint32_t kDirectWords = 4096;                  // 2^16 presence bits, 16 per word; the word's high half holds the rank prefix
 constexpr uint32_t kDirectFill = 6144;                   // build tuples per DIRECT fill (payload array, 24 KB)
-constexpr uint32_t kHashSlots = 1u << kJoinLog2Slots;    // HASH table slots
-constexpr uint32_t kHashFill = kHashSlots / 4 * 3;       // load <= 0.75
+constexpr uint32_t kHashSlots = 1u << kJoinLog2Slots;    // HASH table slots (filled to <= 0.75)
 constexpr size_t kDirectBytes = (size_t)kDirectWords * 4 + (size_t)kDirectFill * 4;
 constexpr size_t kJoinSmemBytes = (size_t)kHashSlots * 8 > kDirectBytes ? (size_t)kHashSlots * 8 : kDirectBytes;
 
-template <int THREADS, int ITEMS, int MINB, bool MATERIALIZE, bool OWNER, bool CTAEMIT>
+template <int THREADS, int ITEMS, int MINB, bool MATERIALIZE, bool OWNER, bool CTAEMIT, uint32_t FILL = kDirectFill,
+          int LOG2HASH = kJoinLog2Slots>
 __global__ void __launch_bounds__(THREADS, MINB)
 k_partition_join(const uint32_t *__restrict__ rk, const uint32_t *__restrict__ rv,
                  const uint32_t *__restrict__ sk, const uint32_t *__restrict__ sv,
@@ -113,7 +113,8 @@ k_partition_join(const uint32_t *__restrict__ rk, const uint32_t *__restrict__ r
 	// one word per 16 keys: bits 0..15 presence, bits 16..31 the number of present keys before the word -- a probe
 	// (or a payload placement) is ONE shared-memory load + a popcount
 	uint32_t *dtab = reinterpret_cast<uint32_t *>(s_raw);              // kDirectWords
-	uint32_t *dvals = dtab + kDirectWords;                             // kDirectFill
+	uint32_t *dvals = dtab + kDirectWords;                             // FILL
+	constexpr uint32_t kHashSlots = 1u << LOG2HASH, kHashFill = kHashSlots / 4 * 3;
 	// HASH view
 	uint64_t *table = reinterpret_cast<uint64_t *>(s_raw);             // kHashSlots
 	__shared__ uint64_t scratch[4 * 32];
@@ -122,7 +123,7 @@ k_partition_join(const uint32_t *__restrict__ rk, const uint32_t *__restrict__ r
 	__shared__ __align__(8) uint32_t s_emit[2 * (THREADS / 32 + 2) + 4];
 	uint32_t emit_rounds = 0;                      // CTA-uniform: which half of s_emit the next round uses
 	constexpr uint32_t kMask = kHashSlots - 1;
-	constexpr int kShift = 32 - kJoinLog2Slots;
+	constexpr int kShift = 32 - LOG2HASH;
 	const bool direct_ok = rem_bits <= 16;
 	const uint32_t rem_mask = rem_bits >= 32 ? 0xFFFFFFFFu : (1u << rem_bits) - 1;
 	JoinSums acc;
@@ -165,16 +166,18 @@ k_partition_join(const uint32_t *__restrict__ rk, const uint32_t *__restrict__ r
 			const uint32_t ntask = s_task_id[(it + 1) & 1];
 			if (ntask >= total_tasks) return;
 			resolve(ntask, nr_beg, nr_end, ns_beg, ns_end);
-			prefetch_col(rk, nr_beg, min(nr_end, nr_beg + kDirectFill));
-			prefetch_col(rv, nr_beg, min(nr_end, nr_beg + kDirectFill));
-			prefetch_col(sk, ns_beg, ns_end);
-			prefetch_col(sv, ns_beg, ns_end);
+			prefetch_col(rk, nr_beg, min(nr_end, nr_beg + FILL));
+			prefetch_col(rv, nr_beg, min(nr_end, nr_beg + FILL));
+			// at most the first rounds of a long probe slice: 740 CTAs x 128 KB of prefetched lines do not survive in L2
+			// beside the streamed rows (config 3: 31.0 GB of DRAM traffic for 21.5 GB algorithmic with whole slices)
+			prefetch_col(sk, ns_beg, min(ns_end, ns_beg + 4096u));
+			prefetch_col(sv, ns_beg, min(ns_end, ns_beg + 4096u));
 		};
 
 		uint32_t fb = r_beg;
 		while (fb < r_end) {
 			bool use_hash = !direct_ok;
-			uint32_t fe = min(fb + (use_hash ? kHashFill : kDirectFill), r_end);
+			uint32_t fe = min(fb + (use_hash ? kHashFill : FILL), r_end);
 			if (!use_hash) {
 				// ---- DIRECT build, step 1: presence bits (equal keys set the same bit: step 2 counts fewer bits than tuples)
 				for (uint32_t w = threadIdx.x; w < kDirectWords / 4; w += THREADS)
@@ -183,7 +186,7 @@ k_partition_join(const uint32_t *__restrict__ rk, const uint32_t *__restrict__ r
 				look_ahead();
 				// build tuples are fetched kBatch at a time so that their loads are in flight together; the
 				// first batch (all of a typical partition) stays in registers for step 3
-				constexpr int kBatch = THREADS >= 512 ? 4 : 8;
+				constexpr int kBatch = THREADS >= 512 ? 4 : THREADS >= 256 ? 8 : 16;
 				uint32_t k0[kBatch], v0[kBatch];
 #pragma unroll
 				for (int t = 0; t < kBatch; ++t) {
@@ -286,7 +289,7 @@ k_partition_join(const uint32_t *__restrict__ rk, const uint32_t *__restrict__ r
 							const uint32_t e = dtab[lo >> 4];
 							const uint32_t hit = found[t] ? (e >> (lo & 15)) & 1u : 0u;
 							// rank < fill size whenever the bit is set; a miss may compute fill size itself: clamp
-							const uint32_t pos = min((e >> 16) + (uint32_t)__popc(e & ((1u << (lo & 15)) - 1)), kDirectFill - 1);
+							const uint32_t pos = min((e >> 16) + (uint32_t)__popc(e & ((1u << (lo & 15)) - 1)), FILL - 1);
 							ival[t] = dvals[pos];
 							found[t] = hit != 0;
 							acc.add_if(hit, key[t], val[t], ival[t]);
@@ -420,20 +423,19 @@ int launch_partition_join(const JoinArgs &a, cudaStream_t s, int sms, KernelTime
 	out.cap = a.materialize ? a.out_cap : 0;
 	// five 256-thread CTAs per SM, 48 registers: measured best in round 1 (512-thread CTAs 1.30-1.59 vs 1.11 ms, six CTAs spill)
 	t->start(KK_PART_JOIN, s);
-	auto launch = [&](auto kernel) {
-		cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kJoinSmemBytes);
+	auto launch_shape = [&](auto kernel, int threads, size_t smem) {
+		cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 		int per_sm = 0;
-		cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kJoinThreads, kJoinSmemBytes);
+		cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem);
 		if (per_sm < 1) per_sm = 1;
-		kernel<<<(uint32_t)(sms * per_sm), kJoinThreads, kJoinSmemBytes, s>>>(a.rk, a.rv, a.sk, a.sv, a.r_off, a.s_off, a.P, a.task_prefix,
-		                                                                   a.task_counter, a.s_task, a.radix_factor, a.table_factor,
-		                                                                   a.rem_bits, a.owner, a.owner_bits, out, a.scalars + 1);
+		kernel<<<(uint32_t)(sms * per_sm), threads, smem, s>>>(a.rk, a.rv, a.sk, a.sv, a.r_off, a.s_off, a.P, a.task_prefix, a.task_counter,
+		                                                       a.s_task, a.radix_factor, a.table_factor, a.rem_bits, a.owner, a.owner_bits,
+		                                                       out, a.scalars + 1);
 	};
+	auto launch = [&](auto kernel) { launch_shape(kernel, kJoinThreads, kJoinSmemBytes); };
 	static const int cta_emit = getenv("HJB_CTA_EMIT") ? atoi(getenv("HJB_CTA_EMIT")) : 1;
-	static const int minb = getenv("HJB_JOIN_MINB") ? atoi(getenv("HJB_JOIN_MINB")) : 5;
 	if (a.materialize && a.owner_bits && cta_emit) launch(k_partition_join<kJoinThreads, kJoinItems, 5, true, true, true>);
 	else if (a.materialize && a.owner_bits) launch(k_partition_join<kJoinThreads, kJoinItems, 5, true, true, false>);
-	else if (a.materialize && cta_emit && minb == 4) launch(k_partition_join<kJoinThreads, kJoinItems, 4, true, false, true>);
 	else if (a.materialize && cta_emit) launch(k_partition_join<kJoinThreads, kJoinItems, 5, true, false, true>);
 	else if (a.materialize) launch(k_partition_join<kJoinThreads, kJoinItems, 5, true, false, false>);
 	else if (a.owner_bits) launch(k_partition_join<kJoinThreads, kJoinItems, 5, false, true, false>);

@@ -437,7 +437,7 @@ __device__ __forceinline__ void load_tile_col(uint32_t (&x)[4 * G], uint32_t &ok
 	if (FULL) ok = 0xFFFFFFFFu;
 }
 
-template <int THREADS, int G, int MINB>
+template <int THREADS, int G, int MINB, bool VALS_EARLY = true>
 __global__ void __launch_bounds__(THREADS, MINB)
 k_scatter_tc(const uint32_t *__restrict__ keys, const uint32_t *__restrict__ vals, uint64_t n, uint32_t np,
              const uint32_t *__restrict__ parent_off, const uint32_t *__restrict__ item_prefix, uint32_t chunk,
@@ -557,7 +557,7 @@ k_scatter_tc(const uint32_t *__restrict__ keys, const uint32_t *__restrict__ val
 		}
 		__syncthreads();
 		// ---- next tile: loads on their way, plan on the first F threads
-		constexpr bool kValsEarly = IT <= 8;          // 16 tuples per thread: the payloads are fetched after the stream (registers)
+		constexpr bool kValsEarly = VALS_EARLY;       // false: the payloads are fetched after the stream (fewer registers held through it)
 		if (j + 1 < ntiles) {
 			if (tile_is_full(g1)) {
 				load_tile_col<THREADS, G, true>(key, ok, keys, g1, g_end, r.beg, r.end, n);
@@ -974,7 +974,7 @@ static void scatter_attrs()
 	cudaGetDevice(&dev);
 	const unsigned long long bit = 1ull << (dev & 63);
 	if (done_mask.fetch_or(bit) & bit) return;
-	cudaFuncSetAttribute(k_scatter_tc<512, 4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scatter_tc_smem(kTile));
+	cudaFuncSetAttribute(k_scatter_tc<512, 4, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scatter_tc_smem(kTile));
 	cudaFuncSetAttribute(k_scatter_tc<1024, 2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scatter_tc_smem(kTile));
 	cudaFuncSetAttribute(k_scatter_tc<1024, 4, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scatter_tc_smem(2 * kTile));
 	cudaFuncSetAttribute(k_scatter<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2048 * 12 + (int)kTile * 8);
@@ -1046,7 +1046,7 @@ int launch_radix_scatter(const RadixPassArgs &a, cudaStream_t s, KernelTimer *t,
 		                                                                        a.factor, a.rshift, a.bits, a.counts, a.tile_counts,
 		                                                                        a.tiles_per_item, a.keys_out, a.vals_out);
 	else if (a.tile_counts && radix_knobs().shape == 0)
-		k_scatter_tc<512, 4, 2><<<grid, 512, scatter_tc_smem(kTile), s>>>(a.keys, a.vals, a.n, a.np, a.parent_off, a.item_prefix, a.chunk,
+		k_scatter_tc<512, 4, 2, false><<<grid, 512, scatter_tc_smem(kTile), s>>>(a.keys, a.vals, a.n, a.np, a.parent_off, a.item_prefix, a.chunk,
 		                                                                  a.factor, a.rshift, a.bits, a.counts, a.tile_counts,
 		                                                                  a.tiles_per_item, a.keys_out, a.vals_out);
 	else if (a.tile_counts)
