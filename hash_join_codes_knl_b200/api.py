@@ -315,6 +315,40 @@ class Engine:
         self._check(rc, "hjb_cpra_finish")
         return JoinResult(res, self), (int(got[0]), int(got[1])), (int(big[0]), int(big[1]))
 
+    # ---- the staged exchange (include/hjb200.h: hjb_cpra_stage_*)
+    def cpra_stage_plan(self, ngpus, r_expect, s_expect, **opts):
+        """-> (abits, bbits, big_fill) or None when two passes do not suffice (use the fused path)"""
+        a, b, f = C.c_int(), C.c_int(), C.c_int()
+        o = self._opts(**opts)
+        rc = self._lib.hjb_cpra_stage_plan(self._ctx, int(ngpus), int(r_expect), int(s_expect), C.byref(o), C.byref(a), C.byref(b),
+                                           C.byref(f))
+        return None if rc != 0 else (int(a.value), int(b.value), int(f.value))
+
+    def cpra_stage_count_async(self, inner_chunk, outer_chunk, abits, counts_dev, **opts):
+        """counts_dev: int64 CUDA tensor of 2 * 2^abits elements (the all-gather's input)"""
+        R, S, on_dev, keep = self._rels(inner_chunk, outer_chunk)
+        if not on_dev:
+            raise HjbError("cpra_stage_count_async takes device columns")
+        o = self._opts(**opts)
+        self._check(self._lib.hjb_cpra_stage_count_async(self._ctx, C.byref(R), C.byref(S), C.byref(o), int(abits),
+                                                         C.c_void_p(counts_dev.data_ptr())), "hjb_cpra_stage_count_async")
+        self._pending_keep = keep
+        self._step_from_host = False
+
+    def cpra_stage_scatter_async(self, matrix_dev, rel):
+        self._check(self._lib.hjb_cpra_stage_scatter_async(self._ctx, C.c_void_p(matrix_dev.data_ptr()), int(rel)),
+                    "hjb_cpra_stage_scatter_async")
+
+    def cpra_stage_copy_async(self, rel, cuda_stream=None):
+        """cuda_stream: raw cudaStream_t of a side stream that already waits for the scatter (None: the engine's stream)"""
+        self._check(self._lib.hjb_cpra_stage_copy_async(self._ctx, int(rel), C.c_void_p(int(cuda_stream) if cuda_stream else None)),
+                    "hjb_cpra_stage_copy_async")
+
+    def cpra_stage_local_async(self, bbits, big_fill, rel, **opts):
+        o = self._opts(**opts)
+        self._check(self._lib.hjb_cpra_stage_local_async(self._ctx, C.byref(o), int(bbits), int(big_fill), int(rel)),
+                    "hjb_cpra_stage_local_async")
+
     # ---- heavy-hitter handling (include/hjb200.h: hjb_cpra_split_hot / _select_hot / _hot_join)
     def cpra_split_hot(self, outer_chunk, hot_keys_dev):
         """-> ((cold keys, cold vals), (hot keys, hot vals)): int32 CUDA tensors aliasing context memory"""

@@ -10,7 +10,7 @@ CSRC = os.path.join(HERE, "csrc")
 HOST = os.path.join(HERE, "host")
 LIB = os.path.join(HERE, "libhjb200.so")
 BIN = os.path.join(HERE, "bin")
-KERNEL_SOURCES = ["radix.cu", "part_join.cu", "npj.cu", "skew.cu", "gen.cu", "capi.cu"]
+KERNEL_SOURCES = ["radix.cu", "part_join.cu", "npj.cu", "skew.cu", "stage.cu", "gen.cu", "capi.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-Wall"] + os.environ.get("HJB_NVCC_EXTRA", "").split()
 

@@ -99,7 +99,12 @@ class FusedExchange:
         self.counts = torch.zeros(2 * self.world, dtype=torch.int64, device=dev)
         self.matrix = torch.zeros(2 * self.world * self.world, dtype=torch.int64, device=dev)
         self.token = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.token2 = torch.zeros(1, dtype=torch.int32, device=dev)
         self.sums = torch.zeros(4, dtype=torch.int64, device=dev)
+        # staged exchange: the plan of a step (made once for this state), its count tensors, the copies' side stream
+        self.stage_plan = None
+        self.stage_counts = self.stage_matrix = None
+        self.side = torch.cuda.Stream(device=dev, priority=-1)
 
     def ensure(self, r_need, s_need):
         """r_need / s_need: the largest row count any rank receives (identical on every rank)."""
@@ -245,3 +250,74 @@ def cpra_join_fused(engine, inner_chunk, outer_chunk, state, group=None, skew=Fa
             "join_ms": float(local.seconds) * 1e3, "step_ms": ev[0].elapsed_time(ev[3]),
             "recv_tuples": received, "largest_recv": largest, "hot_keys": n_hot if hot_parts is not None else 0,
             "hot_outer_tuples": int(hot_parts[1][0].numel()) if hot_parts is not None else 0}
+
+
+def cpra_join_staged(engine, inner_chunk, outer_chunk, state, group=None, overlap=True, **opts):
+    """CPRA with the STAGED exchange (csrc/stage.cu; the reference's own order -- chunk-local passes, then the gather of
+    whole partition pieces, cpra2.cpp:1783-1827,1861-1905): stage A partitions the chunk locally by owner and
+    sub-partition, TMA copies on a high-priority side stream push the runs into the owners' columns while the SMs
+    work on the other relation, one local pass and the join follow.  Two radix passes over the data where the fused
+    path needs three.  The plan (how the radix bits are split) is made once per `state` from the first step's sizes;
+    inputs that need more than two 9-bit passes take cpra_join_fused.  Same result dict as cpra_join_fused.
+
+    overlap=False runs the copies on the main stream (no side stream): for A/B runs."""
+    world = state.world
+    from .api import HjbCapacityError
+    size = lambda col: int(col.numel()) if hasattr(col, "numel") else int(col.size)
+    dev = state.counts.device
+    if state.stage_plan is None:
+        tot = torch.tensor([size(inner_chunk[0]), size(outer_chunk[0])], dtype=torch.int64, device=dev)
+        dist.all_reduce(tot, group=group)
+        tr, ts = (int(x) for x in tot.tolist())
+        plan = engine.cpra_stage_plan(world, max(1, tr // world), max(1, ts // world), **opts)
+        state.stage_plan = plan if plan is not None else "fused"
+        if plan is not None:
+            f = 1 << plan[0]
+            state.stage_counts = torch.zeros(2 * f, dtype=torch.int64, device=dev)
+            state.stage_matrix = torch.zeros(2 * f * world, dtype=torch.int64, device=dev)
+        if state.own is None:
+            state.ensure(tr // world + tr // (4 * world) + 1024, ts // world + ts // (4 * world) + 1024)
+    if state.stage_plan == "fused":
+        return cpra_join_fused(engine, inner_chunk, outer_chunk, state, group, **opts)
+    abits, bbits, big_fill = state.stage_plan
+    main = torch.cuda.current_stream(dev)
+    side = state.side if overlap else main
+    while True:
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(6)]
+        ev[0].record()
+        engine.cpra_stage_count_async(inner_chunk, outer_chunk, abits, state.stage_counts, **opts)
+        dist.all_gather_into_tensor(state.stage_matrix, state.stage_counts, group=group)
+        engine.cpra_stage_scatter_async(state.stage_matrix, 0)
+        ev[1].record()                                       # R is staged
+        engine.cpra_stage_scatter_async(state.stage_matrix, 1)
+        ev[2].record()                                       # S is staged
+        with torch.cuda.stream(side):
+            side.wait_event(ev[1])
+            engine.cpra_stage_copy_async(0, side.cuda_stream)
+            dist.all_reduce(state.token, group=group)        # completes once every rank's copies of R are through
+            ev[3].record()
+            side.wait_event(ev[2])
+            engine.cpra_stage_copy_async(1, side.cuda_stream)
+            dist.all_reduce(state.token2, group=group)
+            ev[4].record()
+        main.wait_event(ev[3])
+        engine.cpra_stage_local_async(bbits, big_fill, 0, **opts)
+        main.wait_event(ev[4])
+        engine.cpra_stage_local_async(bbits, big_fill, 1, **opts)
+        state.sums.copy_(engine.cpra_sums_dev())
+        dist.all_reduce(state.sums, group=group)
+        ev[5].record()
+        try:
+            local, received, largest = engine.cpra_finish()
+        except HjbCapacityError as e:
+            state.ensure(*e.largest)                         # every rank saw the same matrix and takes this branch
+            continue
+        break
+    state.expect = received
+    count, sum_key, sum_outer, sum_inner = (int(x) & ((1 << 64) - 1) for x in state.sums.tolist())
+    return {"count": count, "sum_key": sum_key, "sum_outer": sum_outer, "sum_inner": sum_inner, "local": local,
+            "split_ms": ev[0].elapsed_time(ev[2]), "exchange_ms": ev[1].elapsed_time(ev[4]),
+            "join_ms": float(local.seconds) * 1e3, "step_ms": ev[0].elapsed_time(ev[5]),
+            "recv_tuples": received, "largest_recv": largest, "hot_keys": 0, "hot_outer_tuples": 0,
+            "stage_plan": {"stage_a_bits": abits, "local_bits": bbits, "big_fill": big_fill},
+            "copy_r_done_ms": ev[0].elapsed_time(ev[3]), "copy_s_done_ms": ev[0].elapsed_time(ev[4])}

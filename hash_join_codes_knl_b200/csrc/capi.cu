@@ -77,6 +77,10 @@ struct hjb_ctx {
 	uint32_t step_launches;
 	struct PhjState *step_phj;
 	hjb_opts step_opts;
+	// staged exchange (hjb_cpra_stage_*): stage A's output columns live in split_buf
+	uint32_t *stage_dev;      // device words of k_stage_bases (enum SD_*)
+	uint32_t *stage_k[2], *stage_v[2];
+	int stage_abits, stage_state[2];   // per relation: 0 idle, 1 counted, 2 scattered, 3 copied
 	// heavy-hitter handling (hjb_cpra_split_hot ... hjb_cpra_hot_join)
 	char *skew_buf;           // cold / hot copies of the probe chunk
 	size_t skew_bytes;
@@ -171,6 +175,7 @@ extern "C" int hjb_destroy(hjb_ctx *ctx)
 	cudaFree(ctx->split_buf);
 	for (int i = 0; i < 4; ++i) cudaFree(ctx->recv_buf[i]);
 	cudaFree(ctx->cpra_dev);
+	cudaFree(ctx->stage_dev);
 	cudaFree(ctx->skew_buf);
 	free(ctx->step_phj);
 	cudaFree(ctx->d_scalars);
@@ -328,7 +333,7 @@ extern "C" int hjb_set_profiling(hjb_ctx *ctx, int on)
 extern "C" const char *hjb_kernel_name(int kind)
 {
 	static const char *names[KK_COUNT] = {"k_make_items", "k_hist", "k_scan", "k_scatter", "k_join_tasks",
-	                                      "k_partition_join", "k_npj_build", "k_npj_probe", "k_scatter_bulk"};
+	                                      "k_partition_join", "k_npj_build", "k_npj_probe", "k_scatter_bulk", "k_peer_copy"};
 	return kind >= 0 && kind < KK_COUNT ? names[kind] : nullptr;
 }
 
@@ -473,16 +478,16 @@ static int make_plan(hjb_ctx *ctx, uint64_t nr, uint64_t ns, const hjb_opts *o, 
 	return HJB_OK;
 }
 
-static size_t phj_workspace(uint64_t nr, uint64_t ns, const Plan &p, size_t *radix_scratch)
+static size_t phj_workspace(uint64_t nr, uint64_t ns, const Plan &p, size_t *radix_scratch, int pre_bits = 0)
 {
 	size_t total = 0;
 	const int nb = p.npass >= 2 ? 2 : p.npass;
 	total += (size_t)nb * 2 * (pad256(nr * 4) + pad256(ns * 4));
-	const uint32_t P = 1u << p.total_bits;
+	const uint32_t P = 1u << (pre_bits + p.total_bits);
 	total += 4 * pad256(((size_t)P + 1) * 4);          // r_off / s_off, two generations each
 	total += pad256(((size_t)P + 1) * 4) + pad256(256 + 8 * (((size_t)P >> 10) + 1));   // task prefix, counter + block status words
 	size_t rs = 0;
-	uint32_t np = 1;
+	uint32_t np = 1u << pre_bits;
 	for (int i = 0; i < p.npass; ++i) {
 		uint32_t chunk, mi, tiles;
 		size_t a = radix_scratch_bytes(nr, np, p.bits[i], &chunk, &mi, &tiles);
@@ -503,14 +508,16 @@ struct Partitioned {
 // all passes over one relation; ping-pongs between two workspace buffers
 static int partition_relation(hjb_ctx *ctx, const hjb_rel *rel, const Plan &p, int consumed, uint32_t factor,
                               uint32_t *bufk[2], uint32_t *bufv[2], uint32_t *off[2], char *scratch,
-                              Partitioned *res, uint32_t *launches, const uint32_t *dev_range = nullptr)
+                              Partitioned *res, uint32_t *launches, const uint32_t *dev_range = nullptr, int pre_bits = 0)
 {
 	// dev_range: {0, tuples} in DEVICE memory -- the relation's size is then only known there (CPRA's receive
-	// buffers in the stream-ordered path) and rel->tuples is an upper bound that sizes grids and scratch
+	// buffers in the stream-ordered path) and rel->tuples is an upper bound that sizes grids and scratch.
+	// pre_bits > 0: the relation arrives cut into 2^pre_bits partitions by the bits below `consumed` (the staged
+	// exchange); dev_range then holds their 2^pre_bits + 1 offsets.
 	const uint32_t *ink = rel->keys, *inv = rel->vals;
 	const uint32_t *parent = dev_range;
-	uint32_t np = 1;
-	int used = consumed;
+	uint32_t np = 1u << pre_bits;
+	int used = consumed + pre_bits;
 	for (int i = 0; i < p.npass; ++i) {
 		RadixPassArgs a = {};
 		a.keys = ink; a.vals = inv;
@@ -540,7 +547,7 @@ static int partition_relation(hjb_ctx *ctx, const hjb_rel *rel, const Plan &p, i
 struct PhjState {
 	Plan plan;
 	uint32_t P, owner, radix_factor;
-	int consumed;
+	int consumed, pre_bits, big_fill;
 	uint32_t *rbk[2], *rbv[2], *sbk[2], *sbv[2], *roff[2], *soff[2], *task_prefix, *task_counter;
 	char *scratch;
 	Partitioned pr, ps;
@@ -548,22 +555,26 @@ struct PhjState {
 };
 
 static int phj_setup(hjb_ctx *ctx, uint64_t nr, uint64_t ns_slice, uint64_t ns_total, const hjb_opts *o, int consumed,
-                     uint32_t owner, PhjState *st, uint64_t nr_plan = 0, uint64_t ns_plan = 0)
+                     uint32_t owner, PhjState *st, uint64_t nr_plan = 0, uint64_t ns_plan = 0, const Plan *given = nullptr,
+                     int pre_bits = 0)
 {
 	// nr / ns_slice / ns_total size the buffers; the plan is made for nr_plan / ns_plan tuples when given (sizes
-	// that are only upper bounds here, the expected sizes there)
+	// that are only upper bounds here, the expected sizes there), or is `given` (the staged exchange: pre_bits of
+	// the partition id are already in place when the relation arrives)
 	int rc;
 	memset(st, 0, sizeof *st);
-	if ((rc = make_plan(ctx, nr_plan ? nr_plan : nr, ns_plan ? ns_plan : ns_total, o, consumed, &st->plan))) return rc;
+	if (given) st->plan = *given;
+	else if ((rc = make_plan(ctx, nr_plan ? nr_plan : nr, ns_plan ? ns_plan : ns_total, o, consumed, &st->plan))) return rc;
+	st->pre_bits = pre_bits;
 	const Plan &plan = st->plan;
 	size_t rscratch;
-	const size_t need = phj_workspace(nr, ns_slice, plan, &rscratch);
+	const size_t need = phj_workspace(nr, ns_slice, plan, &rscratch, pre_bits);
 	if ((rc = grow_device(ctx, &ctx->ws, &ctx->ws_bytes, need))) return rc;
 	if (o->materialize) {
 		const uint64_t cap = o->out_capacity ? o->out_capacity : (ns_total > nr ? ns_total : nr);
 		if ((rc = grow_out(ctx, cap))) return rc;
 	}
-	st->P = 1u << plan.total_bits;
+	st->P = 1u << (pre_bits + plan.total_bits);
 	st->consumed = consumed;
 	st->owner = owner;
 	st->radix_factor = hjb_hash_factor(o->seed, 0);
@@ -594,6 +605,10 @@ static int phj_partition_side(hjb_ctx *ctx, PhjState *st, const hjb_rel *rel, bo
 	cudaStream_t s = ctx->stream;
 	Partitioned *res = build_side ? &st->pr : &st->ps;
 	uint32_t **off = build_side ? st->roff : st->soff;
+	if (st->plan.npass == 0 && st->pre_bits) {       // the partitions the relation arrived in are the final ones
+		res->k = rel->keys; res->v = rel->vals; res->off = dev_range;
+		return HJB_OK;
+	}
 	if (st->plan.npass == 0) {
 		// by value in the kernel arguments: nothing on the host that a later call (or a graph replay) could find changed
 		k_set_pair<<<1, 1, 0, s>>>(off[0], 0u, (uint32_t)rel->tuples, dev_range);
@@ -601,7 +616,7 @@ static int phj_partition_side(hjb_ctx *ctx, PhjState *st, const hjb_rel *rel, bo
 		return HJB_OK;
 	}
 	return partition_relation(ctx, rel, st->plan, st->consumed, st->radix_factor, build_side ? st->rbk : st->sbk,
-	                          build_side ? st->rbv : st->sbv, off, st->scratch, res, launches, dev_range);
+	                          build_side ? st->rbv : st->sbv, off, st->scratch, res, launches, dev_range, st->pre_bits);
 }
 
 static int phj_launch_join(hjb_ctx *ctx, PhjState *st, const hjb_opts *o, uint32_t *launches)
@@ -611,7 +626,8 @@ static int phj_launch_join(hjb_ctx *ctx, PhjState *st, const hjb_opts *o, uint32
 	j.r_off = st->pr.off; j.s_off = st->ps.off;
 	j.P = st->P;
 	j.radix_factor = st->radix_factor;
-	j.rem_bits = 32 - st->consumed - st->plan.total_bits;
+	j.rem_bits = 32 - st->consumed - st->pre_bits - st->plan.total_bits;
+	j.big_fill = st->big_fill;
 	j.owner = st->owner;
 	j.owner_bits = st->consumed;
 	j.table_factor = hjb_hash_factor(o->seed, 1);
@@ -1428,6 +1444,198 @@ extern "C" int hjb_cpra_finish(hjb_ctx *ctx, hjb_result *out, uint64_t received[
 	out->partitions = st.P;
 	set_rows(ctx, out, o->materialize);
 	ctx->launches += launches;
+	return HJB_OK;
+}
+
+// ---- the STAGED exchange (stage.cu): stage A partitions the chunk locally by owner AND sub-partition, TMA copies push
+// whole runs into the owners' columns, one local pass and the join follow.  Two radix passes over the data instead
+// of the fused path's three (GPU-assign + two local ones), and the copies leave the SMs to the passes beside them.
+
+constexpr int kStageMaxBits = 9;                  // fan-out of a pass of the tile-count scatter
+
+// How the radix bits of one step are split: stage A takes abits (>= the owner bits), the local pass bbits.
+// Every rank must call this with the same expected sizes.  Returns HJB_E_INVALID when two passes do not suffice
+// (the caller then uses the fused path).
+extern "C" int hjb_cpra_stage_plan(hjb_ctx *ctx, int ngpus, uint64_t r_expect, uint64_t s_expect, const hjb_opts *opts,
+                                   int *abits, int *bbits, int *big_fill)
+{
+	if (!ctx || !abits || !bbits || !big_fill) return HJB_E_INVALID;
+	const hjb_opts *o = opts ? opts : &kDefaultOpts;
+	const int gbits = log2_exact(ngpus);
+	if (gbits < 1 || ngpus > 64) return fail(ctx, HJB_E_INVALID, "ngpus must be a power of two in [2, 64]");
+	Plan p;
+	int rc;
+	hjb_opts oo = *o;
+	memset(oo.radix_bits, 0, sizeof oo.radix_bits);
+	if ((rc = make_plan(ctx, r_expect ? r_expect : 1, s_expect, &oo, gbits, &p))) return rc;
+	int total = gbits + p.total_bits;
+	*big_fill = 0;
+	// DIRECT tables (>= 16 bits in all): partitions may average 8192 build tuples when the join takes 12288-tuple fills
+	if (total > 2 * kStageMaxBits && total - 1 <= 2 * kStageMaxBits && total - 1 >= 18) {
+		total -= 1;
+		*big_fill = 1;
+	}
+	if (total > 2 * kStageMaxBits) return fail(ctx, HJB_E_INVALID, "staged exchange: more radix bits than two passes take");
+	int a = (total + 1) / 2;
+	if (a < gbits) a = gbits;
+	if (a < 2) a = 2;                              // the copy kernel's piece tables assume at least two sub-... owners x subs >= 4
+	*abits = a;
+	*bbits = total > a ? total - a : 0;
+	return HJB_OK;
+}
+
+static int stage_dev_alloc(hjb_ctx *ctx)
+{
+	int rc;
+	if ((rc = cpra_dev_alloc(ctx))) return rc;
+	if (!ctx->stage_dev) CK(cudaMalloc(&ctx->stage_dev, SD_WORDS * 4));
+	return HJB_OK;
+}
+
+// stage A's histogram + scan of both chunks; counts_dev[rel * 2^abits + digit] = this sender's tuples (uint64)
+extern "C" int hjb_cpra_stage_count_async(hjb_ctx *ctx, const hjb_rel *R, const hjb_rel *S, const hjb_opts *opts, int abits,
+                                          uint64_t *counts_dev)
+{
+	if (!ctx || !counts_dev) return HJB_E_INVALID;
+	if (!ctx->bind_gpus) return fail(ctx, HJB_E_INVALID, "hjb_cpra_bind must precede");
+	const hjb_opts *o = opts ? opts : &kDefaultOpts;
+	const int gbits = log2_exact(ctx->bind_gpus);
+	if (abits < gbits || abits < 2 || abits > kStageMaxBits) return fail(ctx, HJB_E_INVALID, "stage A takes between max(2, owner bits) and 9 bits");
+	int rc;
+	if ((rc = check_rel(ctx, R, true)) || (rc = check_rel(ctx, S, true))) return rc;
+	CK(cudaSetDevice(ctx->device));
+	if ((rc = stage_dev_alloc(ctx))) return rc;
+	timer_reset(ctx);
+	ctx->step_launches = 0;
+	ctx->hot_pending = false;
+	const hjb_rel *rel[2] = {R, S};
+	const uint32_t F = 1u << abits;
+	size_t scratch[2], total = 0, cols[2];
+	for (int r = 0; r < 2; ++r) {
+		uint32_t chunk, mi, tiles;
+		scratch[r] = radix_scratch_bytes(rel[r]->tuples, 1, abits, &chunk, &mi, &tiles);
+		cols[r] = rel[r]->tuples + 8 * (size_t)F + 64;          // every run may start up to 3 rows late and end up to 3 rows early
+		total += scratch[r] + pad256((size_t)(F + 1) * 4) + 2 * pad256(cols[r] * 4);
+	}
+	if ((rc = grow_device(ctx, &ctx->split_buf, &ctx->split_bytes, total + 4096))) return rc;
+	cudaStream_t s = ctx->stream;
+	Bump w = {ctx->split_buf, 0};
+	for (int r = 0; r < 2; ++r) {
+		RadixPassArgs &a = ctx->pending[r];
+		memset(&a, 0, sizeof a);
+		a.keys = rel[r]->keys; a.vals = rel[r]->vals;
+		a.n = rel[r]->tuples;
+		a.np = 1;
+		a.factor = hjb_hash_factor(o->seed, 0);
+		a.bits = abits;
+		a.rshift = 32 - abits;
+		a.child_off = w.take<uint32_t>(F + 1);
+		ctx->stage_k[r] = a.keys_out = w.take<uint32_t>(cols[r]);
+		ctx->stage_v[r] = a.vals_out = w.take<uint32_t>(cols[r]);
+		a.shift = reinterpret_cast<const int32_t *>(ctx->stage_dev + (r ? SD_REL_S : SD_REL_R) + SD_SHIFT);
+		radix_carve(a, w.take<char>(scratch[r]), true);
+		if (a.n == 0) CK(cudaMemsetAsync(a.child_off, 0, (size_t)(F + 1) * 4, s));
+		else ctx->step_launches += launch_radix_count(a, s, &ctx->timer);
+		ctx->stage_state[r] = 1;
+	}
+	ctx->step_launches += launch_stage_counts(ctx->pending[0].child_off, ctx->pending[1].child_off, abits,
+	                                          (unsigned long long *)counts_dev, s);
+	CK(cudaGetLastError());
+	ctx->stage_abits = abits;
+	ctx->step_state = 10;
+	return HJB_OK;
+}
+
+// rel 0: the bases from the all-gathered matrix (G x 2 x 2^abits uint64), then stage A's scatter of R; rel 1: of S
+extern "C" int hjb_cpra_stage_scatter_async(hjb_ctx *ctx, const uint64_t *matrix_dev, int rel)
+{
+	if (!ctx || !matrix_dev || rel < 0 || rel > 1) return HJB_E_INVALID;
+	if (ctx->step_state != 10 || ctx->stage_state[rel] != 1 || (rel == 1 && ctx->stage_state[0] < 2))
+		return fail(ctx, HJB_E_INVALID, "hjb_cpra_stage_count_async must precede; R is scattered before S");
+	CK(cudaSetDevice(ctx->device));
+	const int G = ctx->bind_gpus;
+	cudaStream_t s = ctx->stream;
+	if (rel == 0)
+		ctx->step_launches += launch_stage_bases((const unsigned long long *)matrix_dev, G, ctx->bind_gpu, ctx->stage_abits, log2_exact(G),
+		                                         ctx->bind_cap[0], ctx->bind_cap[1], ctx->pending[0].child_off, ctx->pending[1].child_off,
+		                                         ctx->stage_dev, ctx->cpra_dev + CD_RANGE_R, s);
+	RadixPassArgs &a = ctx->pending[rel];
+	if (a.n) ctx->step_launches += launch_radix_scatter(a, s, &ctx->timer, nullptr);
+	CK(cudaGetLastError());
+	ctx->stage_state[rel] = 2;
+	return HJB_OK;
+}
+
+// the copies of one relation's runs into the owners' columns, on `cuda_stream` (null: the context's stream) -- a side
+// stream that waits for the scatter lets them cross NVLink beside the passes: the copies need 21 SMs, not the GPU
+extern "C" int hjb_cpra_stage_copy_async(hjb_ctx *ctx, int rel, void *cuda_stream)
+{
+	if (!ctx || rel < 0 || rel > 1) return HJB_E_INVALID;
+	if (ctx->step_state != 10 || ctx->stage_state[rel] != 2) return fail(ctx, HJB_E_INVALID, "hjb_cpra_stage_scatter_async must precede");
+	CK(cudaSetDevice(ctx->device));
+	const int G = ctx->bind_gpus;
+	PeerCols pc;
+	memset(&pc, 0, sizeof pc);
+	for (int g = 0; g < G; ++g) {
+		pc.k[g] = (uint32_t *)ctx->bind_peer[rel ? 2 : 0][g];
+		pc.v[g] = (uint32_t *)ctx->bind_peer[rel ? 3 : 1][g];
+	}
+	if (ctx->pending[rel].n)
+		ctx->step_launches += launch_peer_copy(ctx->stage_k[rel], ctx->stage_v[rel], pc, ctx->stage_dev + (rel ? SD_REL_S : SD_REL_R),
+		                                       ctx->cpra_dev + CD_ABORT, ctx->stage_abits, log2_exact(G), ctx->bind_gpu,
+		                                       cuda_stream ? (cudaStream_t)cuda_stream : ctx->stream, cuda_stream ? nullptr : &ctx->timer);
+	CK(cudaGetLastError());
+	ctx->stage_state[rel] = 3;
+	return HJB_OK;
+}
+
+// rel 0: the local pass over what this GPU received of R (call once every sender's copies of R have landed); rel 1: the
+// same for S, then the join.  hjb_cpra_finish follows.
+extern "C" int hjb_cpra_stage_local_async(hjb_ctx *ctx, const hjb_opts *opts, int bbits, int big_fill, int rel)
+{
+	if (!ctx || rel < 0 || rel > 1) return HJB_E_INVALID;
+	if (ctx->step_state != (rel ? 11 : 10) || ctx->stage_state[rel] != 3)
+		return fail(ctx, HJB_E_INVALID, "hjb_cpra_stage_copy_async must precede; R's local pass comes before S's");
+	if (bbits < 0 || bbits > kStageMaxBits) return fail(ctx, HJB_E_INVALID, "the local pass takes at most 9 bits");
+	const hjb_opts *o = opts ? opts : &kDefaultOpts;
+	CK(cudaSetDevice(ctx->device));
+	const int G = ctx->bind_gpus, me = ctx->bind_gpu, gbits = log2_exact(G), pre = ctx->stage_abits - gbits;
+	int rc;
+	cudaStream_t s = ctx->stream;
+	const uint64_t rc_cap = ctx->bind_cap[0], sc_cap = ctx->bind_cap[1];
+	if (rel == 0) {
+		if (!ctx->step_phj && !(ctx->step_phj = (PhjState *)calloc(1, sizeof(PhjState)))) return HJB_E_NOMEM;
+		hjb_opts oo = *o;
+		if (!oo.out_capacity) oo.out_capacity = sc_cap > rc_cap ? sc_cap : rc_cap;
+		Plan p;
+		memset(&p, 0, sizeof p);
+		if (bbits) {
+			p.npass = 1;
+			p.bits[0] = bbits;
+			p.total_bits = bbits;
+		}
+		if (32 - ctx->stage_abits - bbits > (big_fill ? 14 : 32)) return fail(ctx, HJB_E_INVALID, "12288-tuple fills need <= 14 hash bits below the partition id");
+		if ((rc = phj_setup(ctx, rc_cap, sc_cap, sc_cap, &oo, gbits, (uint32_t)me, ctx->step_phj, 0, 0, &p, pre))) return rc;
+		ctx->step_phj->big_fill = big_fill;
+		ctx->step_opts = oo;
+		CK(cudaEventRecord(ctx->ev[0], s));
+		CK(cudaMemsetAsync(ctx->d_scalars, 0, 16 * 8, s));
+		const hjb_rel Rr = {(const uint32_t *)ctx->bind_peer[0][me], (const uint32_t *)ctx->bind_peer[1][me], rc_cap};
+		if ((rc = phj_partition_side(ctx, ctx->step_phj, &Rr, true, &ctx->step_launches, ctx->stage_dev + SD_POFF_R))) return rc;
+		CK(cudaGetLastError());
+		ctx->step_state = 11;
+		return HJB_OK;
+	}
+	PhjState &st = *ctx->step_phj;
+	const hjb_rel Sr = {(const uint32_t *)ctx->bind_peer[2][me], (const uint32_t *)ctx->bind_peer[3][me], sc_cap};
+	if ((rc = phj_partition_side(ctx, &st, &Sr, false, &ctx->step_launches, ctx->stage_dev + SD_POFF_S))) return rc;
+	CK(cudaEventRecord(ctx->ev[2], s));
+	if ((rc = phj_launch_join(ctx, &st, &ctx->step_opts, &ctx->step_launches))) return rc;
+	CK(cudaEventRecord(ctx->ev[3], s));
+	CK(cudaGetLastError());
+	ctx->stage_state[0] = ctx->stage_state[1] = 0;
+	ctx->pending_gpus = 0;
+	ctx->step_state = 3;
 	return HJB_OK;
 }
 

@@ -21,7 +21,7 @@ constexpr int kNpjItems = 4;                  // probe tuples per thread per rou
 
 // optional per-launch CUDA-event timing on the launching stream (bench.py's roofline line)
 enum KernelKind { KK_MAKE_ITEMS = 0, KK_HIST, KK_SCAN, KK_SCATTER, KK_JOIN_TASKS, KK_PART_JOIN, KK_NPJ_BUILD,
-                  KK_NPJ_PROBE, KK_SCATTER_PEER, KK_COUNT };
+                  KK_NPJ_PROBE, KK_SCATTER_PEER, KK_PEER_COPY, KK_COUNT };
 struct KernelTimer {
 	static constexpr int kMaxLaunches = 384;     // a sliced host join: 16 probe slices of ~20 kernels + the build side
 	cudaEvent_t beg[kMaxLaunches], end[kMaxLaunches];
@@ -68,7 +68,9 @@ struct RadixPassArgs {
 	uint64_t *scan_status;            // tiles
 	uint32_t *scan_counter;           // 1
 	uint16_t *tile_counts;            // max_items * tiles_per_item * 2^bits digit counts per scatter tile; nullptr: none
-	                                  // (fan-out > 256, or the pass feeds the peer scatter, which ranks its tiles itself)
+	                                  // (fan-out > 512, or the pass feeds the peer scatter, which ranks its tiles itself)
+	const int32_t *shift;             // device, 2^bits entries or nullptr: added to every digit's output positions (staged CPRA
+	                                  // exchange, np == 1: each digit's run starts with the 16-byte phase of its destination row)
 };
 // per-owner output columns of the fused GPU-assign pass (CPRA): the owners' receive buffers as mapped into this
 // process, and -- in device memory, so that no host round trip sits between the count exchange and the scatter --
@@ -93,6 +95,22 @@ int launch_radix_scatter(const RadixPassArgs &a, cudaStream_t s, KernelTimer *t 
 int launch_histogram_only(const uint32_t *keys, uint64_t n, uint32_t *counts_dev, uint32_t factor,
                           int rshift, int bits, cudaStream_t s, int sms);
 
+// ---- staged CPRA exchange (stage.cu)
+// device words written by k_stage_bases (uint32), per relation: tuples of this sender per digit, first row of the digit's run
+// in the staging columns, first row of the run in its owner's columns, and what stage A's scatter adds to the scan's positions
+enum { SD_N = 0, SD_S0 = 512, SD_T0 = 1024, SD_SHIFT = 1536, SD_REL_R = 0, SD_REL_S = 2048,
+       SD_POFF_R = 4096, SD_POFF_S = 4096 + 520,      // offsets of the sub-partitions this GPU receives (parents of the local pass)
+       SD_WORDS = 4096 + 1040 };
+struct PeerCols {
+	uint32_t *k[64];
+	uint32_t *v[64];
+};
+int launch_stage_counts(const uint32_t *r_off, const uint32_t *s_off, int abits, unsigned long long *counts, cudaStream_t s);
+int launch_stage_bases(const unsigned long long *M, int G, int me, int abits, int gbits, uint64_t cap_r, uint64_t cap_s,
+                       const uint32_t *child_r, const uint32_t *child_s, uint32_t *out, uint32_t *status, cudaStream_t s);
+int launch_peer_copy(const uint32_t *sk, const uint32_t *sv, const PeerCols &peers, const uint32_t *desc, const uint32_t *abort_flag,
+                     int abits, int gbits, int me, cudaStream_t s, KernelTimer *t = nullptr);
+
 struct JoinArgs {
 	const uint32_t *rk, *rv, *sk, *sv;       // partitioned columns
 	const uint32_t *r_off, *s_off;           // P + 1 entries each
@@ -109,6 +127,7 @@ struct JoinArgs {
 	uint64_t out_cap;
 	unsigned long long *scalars;             // [0] cursor, [1..4] count, sum_key, sum_outer, sum_inner
 	int materialize;
+	int big_fill;                            // partitions average 8192 build tuples (needs rem_bits <= 14): 12288-tuple DIRECT fills
 };
 int launch_partition_join(const JoinArgs &a, cudaStream_t s, int sms, KernelTimer *t = nullptr);
 

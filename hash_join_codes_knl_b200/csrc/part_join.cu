@@ -98,8 +98,11 @@ constexpr uint32_t kHashSlots = 1u << kJoinLog2Slots;    // HASH table slots (fi
 constexpr size_t kDirectBytes = (size_t)kDirectWords * 4 + (size_t)kDirectFill * 4;
 constexpr size_t kJoinSmemBytes = (size_t)kHashSlots * 8 > kDirectBytes ? (size_t)kHashSlots * 8 : kDirectBytes;
 
+// FILL / WORDS: build tuples per DIRECT fill and words of the presence bitmap.  The default serves partitions that
+// average 4096 build tuples below <= 16 hash bits; 12288 / 1024 (52 KB, four CTAs per SM) serves the staged CPRA
+// exchange at 2^31 tuples, where two 9-bit passes leave partitions of 8192 build tuples and 14 hash bits.
 template <int THREADS, int ITEMS, int MINB, bool MATERIALIZE, bool OWNER, bool CTAEMIT, uint32_t FILL = kDirectFill,
-          int LOG2HASH = kJoinLog2Slots>
+          int LOG2HASH = kJoinLog2Slots, uint32_t WORDS = kDirectWords>
 __global__ void __launch_bounds__(THREADS, MINB)
 k_partition_join(const uint32_t *__restrict__ rk, const uint32_t *__restrict__ rv,
                  const uint32_t *__restrict__ sk, const uint32_t *__restrict__ sv,
@@ -112,8 +115,8 @@ k_partition_join(const uint32_t *__restrict__ rk, const uint32_t *__restrict__ r
 	// DIRECT view
 	// one word per 16 keys: bits 0..15 presence, bits 16..31 the number of present keys before the word -- a probe
 	// (or a payload placement) is ONE shared-memory load + a popcount
-	uint32_t *dtab = reinterpret_cast<uint32_t *>(s_raw);              // kDirectWords
-	uint32_t *dvals = dtab + kDirectWords;                             // FILL
+	uint32_t *dtab = reinterpret_cast<uint32_t *>(s_raw);              // WORDS
+	uint32_t *dvals = dtab + WORDS;                             // FILL
 	constexpr uint32_t kHashSlots = 1u << LOG2HASH, kHashFill = kHashSlots / 4 * 3;
 	// HASH view
 	uint64_t *table = reinterpret_cast<uint64_t *>(s_raw);             // kHashSlots
@@ -124,7 +127,7 @@ k_partition_join(const uint32_t *__restrict__ rk, const uint32_t *__restrict__ r
 	uint32_t emit_rounds = 0;                      // CTA-uniform: which half of s_emit the next round uses
 	constexpr uint32_t kMask = kHashSlots - 1;
 	constexpr int kShift = 32 - LOG2HASH;
-	const bool direct_ok = rem_bits <= 16;
+	const bool direct_ok = (1ull << rem_bits) <= (unsigned long long)WORDS * 16;
 	const uint32_t rem_mask = rem_bits >= 32 ? 0xFFFFFFFFu : (1u << rem_bits) - 1;
 	JoinSums acc;
 	acc.zero();
@@ -180,7 +183,7 @@ k_partition_join(const uint32_t *__restrict__ rk, const uint32_t *__restrict__ r
 			uint32_t fe = min(fb + (use_hash ? kHashFill : FILL), r_end);
 			if (!use_hash) {
 				// ---- DIRECT build, step 1: presence bits (equal keys set the same bit: step 2 counts fewer bits than tuples)
-				for (uint32_t w = threadIdx.x; w < kDirectWords / 4; w += THREADS)
+				for (uint32_t w = threadIdx.x; w < WORDS / 4; w += THREADS)
 					reinterpret_cast<uint4 *>(dtab)[w] = make_uint4(0, 0, 0, 0);
 				__syncthreads();
 				look_ahead();
@@ -221,7 +224,7 @@ k_partition_join(const uint32_t *__restrict__ rk, const uint32_t *__restrict__ r
 					// tuples means equal keys: that fill is redone with the hash table
 					// Thread t owns words t, t + THREADS, ... (conflict-free accesses); ranks are counted in (thread, word)
 					// order -- any fixed order serves, build and probe read the same prefixes.
-					constexpr uint32_t kPer = kDirectWords / THREADS;
+					constexpr uint32_t kPer = WORDS / THREADS;
 					uint32_t local = 0;
 #pragma unroll
 					for (uint32_t j = 0; j < kPer; ++j) local += __popc(dtab[threadIdx.x + j * THREADS]);
@@ -434,7 +437,12 @@ int launch_partition_join(const JoinArgs &a, cudaStream_t s, int sms, KernelTime
 	};
 	auto launch = [&](auto kernel) { launch_shape(kernel, kJoinThreads, kJoinSmemBytes); };
 	static const int cta_emit = getenv("HJB_CTA_EMIT") ? atoi(getenv("HJB_CTA_EMIT")) : 1;
-	if (a.materialize && a.owner_bits && cta_emit) launch(k_partition_join<kJoinThreads, kJoinItems, 5, true, true, true>);
+	constexpr size_t kBigBytes = 1024 * 4 + 12288 * 4;
+	if (a.big_fill && a.rem_bits <= 14 && a.materialize)
+		launch_shape(k_partition_join<kJoinThreads, kJoinItems, 4, true, true, true, 12288, kJoinLog2Slots, 1024>, kJoinThreads, kBigBytes);
+	else if (a.big_fill && a.rem_bits <= 14)
+		launch_shape(k_partition_join<kJoinThreads, kJoinItems, 4, false, true, false, 12288, kJoinLog2Slots, 1024>, kJoinThreads, kBigBytes);
+	else if (a.materialize && a.owner_bits && cta_emit) launch(k_partition_join<kJoinThreads, kJoinItems, 5, true, true, true>);
 	else if (a.materialize && a.owner_bits) launch(k_partition_join<kJoinThreads, kJoinItems, 5, true, true, false>);
 	else if (a.materialize && cta_emit) launch(k_partition_join<kJoinThreads, kJoinItems, 5, true, false, true>);
 	else if (a.materialize) launch(k_partition_join<kJoinThreads, kJoinItems, 5, true, false, false>);

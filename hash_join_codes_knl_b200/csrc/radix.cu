@@ -305,9 +305,10 @@ k_scan(const uint32_t *__restrict__ item_prefix, uint32_t np, int bits, uint32_t
 
 // ------------------------------------------------------------------ histogram with tile counts
 
-constexpr uint32_t kTile = 8192;                 // tuples per scatter tile
+constexpr uint32_t kTile = 8192;                 // tuples per tile of k_scatter / k_scatter_bulk
 constexpr uint32_t kTileGroups = kTile / 4;      // absolutely aligned groups of four tuples per tile
-constexpr uint32_t kTcMaxFanout = 256;           // widest pass of the tile-count path
+constexpr uint32_t kTcTile = 16384;              // tuples per tile of the tile-count path (k_hist_tiles / k_scatter_tc)
+constexpr uint32_t kTcMaxFanout = 512;           // widest pass of the tile-count path
 
 // One more count for digit d: a shared-memory atomic per lane, or -- for fan-outs <= 16, where the lanes
 // of a warp would serialise on a handful of counters -- one atomic per warp and digit (match.any).
@@ -406,9 +407,10 @@ k_hist_tiles(const uint32_t *__restrict__ keys, uint64_t n, uint32_t np, const u
 // have to fetch the rest of a half-written sector from HBM (measured in round 1: 2.70 -> 2.19 GB of DRAM
 // traffic per 2^27-tuple launch).
 //
-// dynamic shared memory: cursor[256] | cf[256] (uint2) | golim[2][256] (uint2) | buf[TILE] (uint2) | carry[256 * 8] (uint2)
+// dynamic shared memory: cursor[MAXF] | cf[MAXF] (uint2) | golim[2][MAXF] (uint2) | buf[TILE] (uint2) | carry[MAXF * 8] (uint2)
+// MAXF = 256, or 512 for the 9-bit passes of the staged CPRA exchange (174 KB with the 16384-tuple tile)
 constexpr uint32_t kLocalCarry = 8;    // tuples per 32-byte sector of a 4-byte column
-constexpr size_t scatter_tc_smem(uint32_t tile) { return 256 * 4 + 256 * 8 + 2 * 256 * 8 + (size_t)tile * 8 + 256 * kLocalCarry * 8; }
+constexpr size_t scatter_tc_smem(uint32_t tile, uint32_t maxf) { return (size_t)maxf * (4 + 8 + 16 + kLocalCarry * 8) + (size_t)tile * 8; }
 
 // One tile = THREADS * 4 G tuples = THREADS * G absolutely aligned groups; thread t owns groups t,
 // t + THREADS, ... of the tile (coalesced 128-bit loads).
@@ -437,23 +439,25 @@ __device__ __forceinline__ void load_tile_col(uint32_t (&x)[4 * G], uint32_t &ok
 	if (FULL) ok = 0xFFFFFFFFu;
 }
 
-template <int THREADS, int G, int MINB, bool VALS_EARLY = true>
+// `shift` (may be null): added to every digit's output positions -- the staged CPRA exchange lays the digits'
+// runs out with the 16-byte phase of their destination rows in the owners' buffers (k_stage_bases)
+template <int THREADS, int G, int MINB, uint32_t MAXF>
 __global__ void __launch_bounds__(THREADS, MINB)
 k_scatter_tc(const uint32_t *__restrict__ keys, const uint32_t *__restrict__ vals, uint64_t n, uint32_t np,
              const uint32_t *__restrict__ parent_off, const uint32_t *__restrict__ item_prefix, uint32_t chunk,
              uint32_t factor, int rshift, int bits, const uint32_t *__restrict__ offsets,
-             const uint16_t *__restrict__ tile_counts, uint32_t tiles_per_item,
+             const uint16_t *__restrict__ tile_counts, uint32_t tiles_per_item, const int32_t *__restrict__ shift,
              uint32_t *__restrict__ keys_out, uint32_t *__restrict__ vals_out)
 {
 	constexpr int IT = 4 * G;                                   // tuples per thread and tile
 	constexpr uint32_t TILE = THREADS * IT, TILE_GROUPS = TILE / 4;
 	extern __shared__ __align__(16) uint32_t s_mem[];
-	__shared__ uint32_t warp_totals[8];
+	__shared__ uint32_t warp_totals[MAXF / 32];
 	__shared__ uint32_t s_tile_n[2];
 	uint32_t *cursor = s_mem;
-	uint2 *cf = reinterpret_cast<uint2 *>(cursor + 256);          // carried tuples to flush: x = global position of the first, y = how many
-	uint2 *golim = cf + 256;                                      // [2][256]; x: global position of tile slot 0, y: flush limit
-	uint2 *buf = golim + 512;
+	uint2 *cf = reinterpret_cast<uint2 *>(cursor + MAXF);         // carried tuples to flush: x = global position of the first, y = how many
+	uint2 *golim = cf + MAXF;                                     // [2][MAXF]; x: global position of tile slot 0, y: flush limit
+	uint2 *buf = golim + 2 * MAXF;
 	uint2 *carry = buf + TILE;
 	const uint32_t F = 1u << bits, mask = F - 1;
 	const bool aggregate = bits <= 4;
@@ -468,7 +472,7 @@ k_scatter_tc(const uint32_t *__restrict__ keys, const uint32_t *__restrict__ val
 	const uint32_t plan_threads = F <= 32 ? 32u : F;
 	uint32_t wpos = 0, pend = 0, c_next = 0;
 	if (threadIdx.x < F) {
-		wpos = offsets[(size_t)blockIdx.x * F + threadIdx.x];
+		wpos = offsets[(size_t)blockIdx.x * F + threadIdx.x] + (shift ? (uint32_t)shift[threadIdx.x] : 0u);
 		c_next = trow[threadIdx.x];
 	}
 	auto tile_is_full = [&](uint64_t g0) {
@@ -498,7 +502,7 @@ k_scatter_tc(const uint32_t *__restrict__ keys, const uint32_t *__restrict__ val
 			const bool flush = lim > wpos;
 			if (!flush) lim = wpos;
 			cursor[p] = lbase;
-			golim[(j & 1) * 256 + p] = make_uint2(wpos + pend - lbase, lim);
+			golim[(j & 1) * MAXF + p] = make_uint2(wpos + pend - lbase, lim);
 			cf[p] = make_uint2(wpos, flush ? pend : 0u);
 			wpos = lim;
 			pend = endpos - lim;
@@ -557,14 +561,13 @@ k_scatter_tc(const uint32_t *__restrict__ keys, const uint32_t *__restrict__ val
 		}
 		__syncthreads();
 		// ---- next tile: loads on their way, plan on the first F threads
-		constexpr bool kValsEarly = VALS_EARLY;       // false: the payloads are fetched after the stream (fewer registers held through it)
 		if (j + 1 < ntiles) {
 			if (tile_is_full(g1)) {
 				load_tile_col<THREADS, G, true>(key, ok, keys, g1, g_end, r.beg, r.end, n);
-				if (kValsEarly) load_tile_col<THREADS, G, true>(val, ok, vals, g1, g_end, r.beg, r.end, n);
+				load_tile_col<THREADS, G, true>(val, ok, vals, g1, g_end, r.beg, r.end, n);
 			} else {
 				load_tile_col<THREADS, G, false>(key, ok, keys, g1, g_end, r.beg, r.end, n);
-				if (kValsEarly) load_tile_col<THREADS, G, false>(val, ok, vals, g1, g_end, r.beg, r.end, n);
+				load_tile_col<THREADS, G, false>(val, ok, vals, g1, g_end, r.beg, r.end, n);
 			}
 			if (threadIdx.x < plan_threads) {
 				plan(j + 1, j + 2 == ntiles);
@@ -573,7 +576,7 @@ k_scatter_tc(const uint32_t *__restrict__ keys, const uint32_t *__restrict__ val
 		}
 		// ---- stream tile j: below the digit's limit to global memory, beyond it into the carry buffer
 		const uint32_t tile_n = s_tile_n[j & 1];
-		const uint2 *gl_tab = golim + (j & 1) * 256;
+		const uint2 *gl_tab = golim + (j & 1) * MAXF;
 #pragma unroll 4
 		for (int it = 0; it < IT; ++it) {
 			const uint32_t i = threadIdx.x + it * THREADS;
@@ -589,10 +592,6 @@ k_scatter_tc(const uint32_t *__restrict__ keys, const uint32_t *__restrict__ val
 					carry[d * kLocalCarry + (pos - gl.y)] = kv;
 				}
 			}
-		}
-		if (!kValsEarly && j + 1 < ntiles) {
-			if (tile_is_full(g1)) load_tile_col<THREADS, G, true>(val, ok, vals, g1, g_end, r.beg, r.end, n);
-			else load_tile_col<THREADS, G, false>(val, ok, vals, g1, g_end, r.beg, r.end, n);
 		}
 		__syncthreads();
 	}
@@ -899,25 +898,14 @@ k_scatter_bulk(const uint32_t *__restrict__ keys, const uint32_t *__restrict__ v
 
 // ------------------------------------------------------------------ host launchers
 
-// experiment knobs, read once (host/cpra.cpp calls the launchers from one thread per GPU)
-struct RadixKnobs {
-	int items;          // HJB_ITEMS: work items per pass
-	int shape;          // HJB_SCATTER_SHAPE: 2 = one 1024-thread CTA per SM, 16384-tuple tiles (default, measured best);
-	                    // 1 = one 1024-thread CTA, 8192-tuple tiles; 0 = two 512-thread CTAs, 8192-tuple tiles
-	uint32_t tile;      // tuples per tile of that shape
-};
-static const RadixKnobs &radix_knobs()
+// experiment knob, read once (host/cpra.cpp calls the launchers from one thread per GPU)
+static int radix_items()
 {
-	static const RadixKnobs k = [] {
-		RadixKnobs v;
-		v.items = getenv("HJB_ITEMS") ? atoi(getenv("HJB_ITEMS")) : 1184;
-		if (v.items < 64) v.items = 1184;
-		v.shape = getenv("HJB_SCATTER_SHAPE") ? atoi(getenv("HJB_SCATTER_SHAPE")) : 2;
-		if (v.shape < 0 || v.shape > 2) v.shape = 2;
-		v.tile = v.shape == 2 ? 2 * kTile : kTile;
-		return v;
+	static const int items = [] {
+		const int v = getenv("HJB_ITEMS") ? atoi(getenv("HJB_ITEMS")) : 1184;      // work items per pass
+		return v < 64 ? 1184 : v;
 	}();
-	return k;
+	return items;
 }
 
 size_t radix_scratch_bytes(uint64_t n, uint32_t np, int bits, uint32_t *chunk, uint32_t *max_items, uint32_t *tiles,
@@ -926,11 +914,11 @@ size_t radix_scratch_bytes(uint64_t n, uint32_t np, int bits, uint32_t *chunk, u
 	// ~1.2K items (eight per SM of a B200): enough to balance the SMs over a pass, few enough that the
 	// counts matrix and its scan stay small (measured: 1024-1184 items 4.23 ms per config-2 step, 2048
 	// 4.27, 4096 4.35); chunk is a multiple of the scatter tile
-	const int target = radix_knobs().items;
-	const uint32_t tile = radix_knobs().tile;
+	const int target = radix_items();
+	const uint32_t tile = kTcTile;
 	uint64_t c = (n + target - 1) / target;
-	c = (c + 2 * kTile - 1) / (2 * kTile) * (2 * kTile);       // a multiple of every tile size in use
-	if (c < 2 * kTile) c = 2 * kTile;
+	c = (c + kTcTile - 1) / kTcTile * kTcTile;                 // a multiple of every tile size in use
+	if (c < kTcTile) c = kTcTile;
 	if (c > (1u << 24)) c = 1u << 24;
 	*chunk = (uint32_t)c;
 	const uint64_t mi = n / c + np + 1;
@@ -974,9 +962,8 @@ static void scatter_attrs()
 	cudaGetDevice(&dev);
 	const unsigned long long bit = 1ull << (dev & 63);
 	if (done_mask.fetch_or(bit) & bit) return;
-	cudaFuncSetAttribute(k_scatter_tc<512, 4, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scatter_tc_smem(kTile));
-	cudaFuncSetAttribute(k_scatter_tc<1024, 2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scatter_tc_smem(kTile));
-	cudaFuncSetAttribute(k_scatter_tc<1024, 4, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scatter_tc_smem(2 * kTile));
+	cudaFuncSetAttribute(k_scatter_tc<1024, 4, 1, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scatter_tc_smem(kTcTile, 256));
+	cudaFuncSetAttribute(k_scatter_tc<1024, 4, 1, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scatter_tc_smem(kTcTile, 512));
 	cudaFuncSetAttribute(k_scatter<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2048 * 12 + (int)kTile * 8);
 	size_t bulk_max = 0;
 	for (uint32_t f = 2; f <= 64; f *= 2) bulk_max = bulk_smem_bytes(f) > bulk_max ? bulk_smem_bytes(f) : bulk_max;
@@ -1000,12 +987,9 @@ int launch_radix_count(const RadixPassArgs &a, cudaStream_t s, KernelTimer *t)
 	k_make_items<<<1, 1024, 0, s>>>(a.parent_off, a.np, a.n, a.chunk, a.item_prefix, a.child_off, a.np << a.bits);
 	t->stop(s);
 	t->start(KK_HIST, s);
-	if (a.tile_counts && radix_knobs().tile == 2 * kTile)
-		k_hist_tiles<2 * kTile><<<a.max_items, kHistThreads, 0, s>>>(a.keys, a.n, a.np, a.parent_off, a.item_prefix, a.chunk, a.factor,
-		                                                             a.rshift, a.bits, a.counts, a.tile_counts, a.tiles_per_item);
-	else if (a.tile_counts)
-		k_hist_tiles<kTile><<<a.max_items, kHistThreads, 0, s>>>(a.keys, a.n, a.np, a.parent_off, a.item_prefix, a.chunk, a.factor,
-		                                                         a.rshift, a.bits, a.counts, a.tile_counts, a.tiles_per_item);
+	if (a.tile_counts)
+		k_hist_tiles<kTcTile><<<a.max_items, kHistThreads, 0, s>>>(a.keys, a.n, a.np, a.parent_off, a.item_prefix, a.chunk, a.factor,
+		                                                           a.rshift, a.bits, a.counts, a.tile_counts, a.tiles_per_item);
 	else if (a.bits <= 3)
 		k_hist_small<<<a.max_items, kHistThreads, 0, s>>>(a.keys, a.n, a.np, a.parent_off, a.item_prefix, a.chunk,
 		                                                  a.factor, a.rshift, a.bits, a.counts);
@@ -1041,18 +1025,14 @@ int launch_radix_scatter(const RadixPassArgs &a, cudaStream_t s, KernelTimer *t,
 		return 1;
 	}
 	t->start(KK_SCATTER, s);
-	if (a.tile_counts && radix_knobs().shape == 2)
-		k_scatter_tc<1024, 4, 1><<<grid, 1024, scatter_tc_smem(2 * kTile), s>>>(a.keys, a.vals, a.n, a.np, a.parent_off, a.item_prefix, a.chunk,
-		                                                                        a.factor, a.rshift, a.bits, a.counts, a.tile_counts,
-		                                                                        a.tiles_per_item, a.keys_out, a.vals_out);
-	else if (a.tile_counts && radix_knobs().shape == 0)
-		k_scatter_tc<512, 4, 2, false><<<grid, 512, scatter_tc_smem(kTile), s>>>(a.keys, a.vals, a.n, a.np, a.parent_off, a.item_prefix, a.chunk,
-		                                                                  a.factor, a.rshift, a.bits, a.counts, a.tile_counts,
-		                                                                  a.tiles_per_item, a.keys_out, a.vals_out);
+	if (a.tile_counts && F > 256)
+		k_scatter_tc<1024, 4, 1, 512><<<grid, 1024, scatter_tc_smem(kTcTile, 512), s>>>(a.keys, a.vals, a.n, a.np, a.parent_off, a.item_prefix,
+		                                                                                a.chunk, a.factor, a.rshift, a.bits, a.counts, a.tile_counts,
+		                                                                                a.tiles_per_item, a.shift, a.keys_out, a.vals_out);
 	else if (a.tile_counts)
-		k_scatter_tc<1024, 2, 1><<<grid, 1024, scatter_tc_smem(kTile), s>>>(a.keys, a.vals, a.n, a.np, a.parent_off, a.item_prefix, a.chunk,
-		                                                                    a.factor, a.rshift, a.bits, a.counts, a.tile_counts,
-		                                                                    a.tiles_per_item, a.keys_out, a.vals_out);
+		k_scatter_tc<1024, 4, 1, 256><<<grid, 1024, scatter_tc_smem(kTcTile, 256), s>>>(a.keys, a.vals, a.n, a.np, a.parent_off, a.item_prefix,
+		                                                                                a.chunk, a.factor, a.rshift, a.bits, a.counts, a.tile_counts,
+		                                                                                a.tiles_per_item, a.shift, a.keys_out, a.vals_out);
 	else
 		k_scatter<1024><<<grid, 1024, (size_t)F * 12 + (size_t)kTile * 8, s>>>(a.keys, a.vals, a.n, a.np, a.parent_off, a.item_prefix,
 		                                                                       a.chunk, a.factor, a.rshift, a.bits, a.counts, a.keys_out,

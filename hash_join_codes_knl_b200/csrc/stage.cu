@@ -1,0 +1,309 @@
+// stage.cu -- the STAGED exchange of CPRA (reference: the chunk-local passes cpra2.cpp:1783-1827 followed by the
+// per-owner memcpy gather cpra2.cpp:1861-1905,1940-1959, timed there as "copy:").
+//
+// Stage A partitions this GPU's chunk LOCALLY by the top `abits` bits of key * factor with the ordinary pass of
+// radix.cu (digit = owner << sub_bits | sub-partition), so that an owner's share is already cut into 2^sub_bits
+// sub-partitions when it leaves.  The exchange is then nothing but copies of whole digit runs:
+//   k_stage_counts : this sender's tuples per digit, R then S -- the all-gather's input
+//   k_stage_bases  : from the all-gathered G x 2 x 2^abits count matrix: for every digit the first row of its run in
+//                    the owner's columns (sub-partition-major, sender-minor -- the reference's interleave order,
+//                    cpra2.cpp:1426-1440), the offsets of the sub-partitions this GPU receives, whether every
+//                    owner's buffer is large enough, and where stage A must START each run in the staging columns
+//                    so that source and destination rows have the same 16-byte phase
+//   k_peer_copy    : a handful of one-warp CTAs drive the TMA unit: cp.async.bulk global -> shared (mbarrier) and
+//                    shared -> the owner's global memory over NVLink, 16 KB per column and piece, six stages.
+//                    Measured (scripts/r2/peer_copy_bench.cu, 2 GPUs): 16 such CTAs move 705 GB/s, the copy
+//                    engine 776 GB/s -- the SMs beside them stay free for stage A of the other relation and the
+//                    local pass of the relation that has arrived.
+// The receiver continues with ONE local pass over the 2^sub_bits sub-partitions (parents with device-resident
+// offsets) and the shared-memory join.
+#include "hj_device.cuh"
+#include "hj_internal.h"
+#include <atomic>
+#include <stdlib.h>
+
+namespace hjb {
+
+__global__ void __launch_bounds__(512)
+k_stage_counts(const uint32_t *__restrict__ r_off, const uint32_t *__restrict__ s_off, uint32_t F,
+               unsigned long long *__restrict__ counts)
+{
+	const uint32_t d = threadIdx.x;
+	if (d < F) {
+		counts[d] = r_off[d + 1] - r_off[d];
+		counts[F + d] = s_off[d + 1] - s_off[d];
+	}
+}
+
+// exclusive scan of one uint64 per thread over a 512-thread CTA; *total = the sum
+__device__ __forceinline__ unsigned long long block_exclusive_scan_u64(unsigned long long v, unsigned long long *warp_tot,
+                                                                      unsigned long long *total)
+{
+	unsigned long long incl = v;
+#pragma unroll
+	for (int o = 1; o < 32; o <<= 1) {
+		const unsigned long long t = __shfl_up_sync(kFullMask, incl, o);
+		if ((int)lane_id() >= o) incl += t;
+	}
+	__syncthreads();                                  // warp_tot may still be read from an earlier call
+	if (lane_id() == 31) warp_tot[threadIdx.x >> 5] = incl;
+	__syncthreads();
+	unsigned long long before = 0, all = 0;
+	for (uint32_t w = 0; w < (blockDim.x >> 5); ++w) {
+		const unsigned long long t = warp_tot[w];
+		if (w < (threadIdx.x >> 5)) before += t;
+		all += t;
+	}
+	*total = all;
+	return before + incl - v;
+}
+
+// M[src][rel][digit] (uint64): the all-gathered counts.  One CTA of 512 threads, one digit per thread, R then S.
+__global__ void __launch_bounds__(512)
+k_stage_bases(const unsigned long long *__restrict__ M, int G, int me, int abits, int gbits, unsigned long long cap_r,
+              unsigned long long cap_s, const uint32_t *__restrict__ child_r, const uint32_t *__restrict__ child_s,
+              uint32_t *__restrict__ out, uint32_t *__restrict__ status)
+{
+	__shared__ unsigned long long warp_tot[16];
+	__shared__ unsigned long long s_e[513];
+	__shared__ unsigned long long s_max[2];
+	__shared__ int s_abort;
+	const uint32_t F = 1u << abits, nsub = F >> gbits, d = threadIdx.x;
+	if (d == 0) {
+		s_abort = 0;
+		s_max[0] = s_max[1] = 0;
+	}
+	unsigned long long t0v[2] = {0, 0}, mine[2] = {0, 0};
+	for (int rel = 0; rel < 2; ++rel) {
+		unsigned long long col = 0, before = 0;
+		if (d < F)
+			for (int src = 0; src < G; ++src) {
+				const unsigned long long c = M[((size_t)src * 2 + rel) * F + d];
+				col += c;
+				if (src < me) before += c;
+				if (src == me) mine[rel] = c;
+			}
+		unsigned long long total;
+		const unsigned long long e = block_exclusive_scan_u64(col, warp_tot, &total);
+		if (d < F) s_e[d] = e;
+		if (d == 0) s_e[F] = total;
+		__syncthreads();
+		if (d < F) {
+			const uint32_t o = d / nsub;
+			t0v[rel] = e - s_e[o * nsub] + before;
+			if (d % nsub == 0) {
+				const unsigned long long tot_o = s_e[(o + 1) * nsub] - s_e[o * nsub];
+				atomicMax(&s_max[rel], tot_o);
+				if (tot_o > (rel ? cap_s : cap_r)) s_abort = 1;
+			}
+		}
+		__syncthreads();
+		// this GPU's sub-partition offsets (parents of the local pass); filled below once the verdict is known
+		if (d <= nsub) {
+			const unsigned long long p = s_e[(size_t)me * nsub + d] - s_e[(size_t)me * nsub];
+			out[(rel ? SD_POFF_S : SD_POFF_R) + d] = (uint32_t)p;       // provisional: zeroed below on abort
+		}
+		__syncthreads();
+	}
+	const int abort = s_abort;
+	for (int rel = 0; rel < 2; ++rel) {
+		// the run of digit d starts in the staging columns at a row with the 16-byte phase of its destination row
+		const uint32_t a = (uint32_t)(t0v[rel] & 3);
+		const unsigned long long w = (d < F && mine[rel]) ? ((a + mine[rel] + 3) & ~3ull) : 0ull;
+		unsigned long long total;
+		const unsigned long long before = block_exclusive_scan_u64(w, warp_tot, &total);
+		const uint32_t *child = rel ? child_s : child_r;
+		uint32_t *o = out + (rel ? SD_REL_S : SD_REL_R);
+		if (d < F) {
+			const uint32_t s0 = (uint32_t)before + a;
+			o[SD_N + d] = (uint32_t)mine[rel];
+			o[SD_S0 + d] = s0;
+			o[SD_T0 + d] = (uint32_t)t0v[rel];
+			o[SD_SHIFT + d] = s0 - child[d];
+		}
+		if (abort && d <= nsub) out[(rel ? SD_POFF_S : SD_POFF_R) + d] = 0;
+	}
+	// what hjb_cpra_finish reports: rows received here, the verdict, the fullest owner's rows
+	if (d == 0) {
+		status[0] = 0;
+		status[1] = abort ? 0u : out[SD_POFF_R + nsub];
+		status[2] = 0;
+		status[3] = abort ? 0u : out[SD_POFF_S + nsub];
+		status[4] = abort ? 1u : 0u;
+		status[5] = (uint32_t)(s_max[0] > 0xFFFFFFFFull ? 0xFFFFFFFFull : s_max[0]);
+		status[6] = (uint32_t)(s_max[1] > 0xFFFFFFFFull ? 0xFFFFFFFFull : s_max[1]);
+	}
+}
+
+// ------------------------------------------------------------------ the copy
+
+constexpr uint32_t kCopyChunk = 4096;          // tuples per piece and column: 16 KB
+constexpr int kCopyStages = 6;                 // stages of 2 x 16 KB
+constexpr int kCopyAhead = 3;                  // loads in flight before the piece being stored; kCopyStages - kCopyAhead stores may drain
+constexpr size_t kCopySmem = (size_t)kCopyStages * 2 * kCopyChunk * 4;
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+struct CopyPiece {
+	uint32_t src, dst, rows, owner;            // rows of the 16-byte aligned body piece (may be 0), its first row on both sides
+};
+
+__global__ void __launch_bounds__(32)
+k_peer_copy(const uint32_t *__restrict__ sk, const uint32_t *__restrict__ sv, const PeerCols peers,
+            const uint32_t *__restrict__ desc, const uint32_t *__restrict__ abort_flag, int abits, int gbits, int me)
+{
+	extern __shared__ __align__(128) unsigned char s_stage[];
+	__shared__ uint64_t full[kCopyStages];
+	__shared__ uint32_t s_n[512], s_s0[512], s_t0[512], s_pref[512], s_total[64];
+	__shared__ CopyPiece ring[kCopyStages];
+	if (*abort_flag) return;
+	const uint32_t F = 1u << abits, nsub = F >> gbits, G = 1u << gbits, lane = threadIdx.x;
+	const uint32_t *dn = desc + SD_N, *ds0 = desc + SD_S0, *dt0 = desc + SD_T0;
+	for (uint32_t d = lane; d < F; d += 32) {
+		s_n[d] = dn[d];
+		s_s0[d] = ds0[d];
+		s_t0[d] = dt0[d];
+	}
+	if (lane == 0) {
+		for (int i = 0; i < kCopyStages; ++i)
+			asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&full[i])));
+		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+	}
+	__syncwarp();
+	// head: rows before the first 16-byte aligned destination row; body: whole 16-byte words; tail: the rest
+	auto head_of = [&](uint32_t d) { return min(s_n[d], (4u - (s_t0[d] & 3u)) & 3u); };
+	auto body_of = [&](uint32_t d) { return (s_n[d] - head_of(d)) & ~3u; };
+	uint32_t maxp = 0;
+	for (uint32_t o = lane; o < G; o += 32) {
+		uint32_t run = 0;
+		for (uint32_t sub = 0; sub < nsub; ++sub) {
+			const uint32_t d = o * nsub + sub;
+			s_pref[d] = run;
+			if (s_n[d]) run += max(1u, (body_of(d) + kCopyChunk - 1) / kCopyChunk);
+		}
+		s_total[o] = run;
+		maxp = max(maxp, run);
+	}
+#pragma unroll
+	for (int o = 16; o; o >>= 1) maxp = max(maxp, __shfl_xor_sync(kFullMask, maxp, o));
+	__syncwarp();
+	// Virtual piece v = (index within the owner) * G + slot, slot s = owner (me + 1 + s) mod G: consecutive pieces go to
+	// different owners, so every sender spreads its traffic over all receivers at all times.  CTA b takes v = b, b + grid, ...
+	const unsigned long long vmax = (unsigned long long)maxp * G;
+	unsigned long long v = blockIdx.x;
+	auto next_piece = [&](CopyPiece *p) -> bool {
+		for (; v < vmax; v += gridDim.x) {
+			const uint32_t owner = (uint32_t)((me + 1 + v % G) % G), idx = (uint32_t)(v / G);
+			if (idx >= s_total[owner]) continue;
+			const uint32_t *pref = s_pref + owner * nsub;
+			uint32_t lo = 0, hi = nsub;
+			while (hi - lo > 1) {
+				const uint32_t mid = (lo + hi) >> 1;
+				if (pref[mid] <= idx) lo = mid;
+				else hi = mid;
+			}
+			const uint32_t d = owner * nsub + lo, c = idx - pref[lo];
+			const uint32_t h = head_of(d), body = body_of(d);
+			const uint32_t off = c * kCopyChunk;
+			p->rows = body > off ? min(kCopyChunk, body - off) : 0u;
+			p->src = s_s0[d] + h + off;
+			p->dst = s_t0[d] + h + off;
+			p->owner = owner;
+			if (c == 0) {
+				// the unaligned ends of the run: at most three rows each, plain stores
+				const uint32_t tail = s_n[d] - h - body;
+				if (lane < h + tail) {
+					const uint32_t row = lane < h ? lane : h + body + (lane - h);
+					peers.k[owner][s_t0[d] + row] = sk[s_s0[d] + row];
+					peers.v[owner][s_t0[d] + row] = sv[s_s0[d] + row];
+				}
+			}
+			v += gridDim.x;
+			return true;
+		}
+		return false;
+	};
+	auto issue_load = [&](uint32_t n, const CopyPiece &p) {
+		const int st = (int)(n % kCopyStages);
+		if (lane == 0) {
+			ring[st] = p;
+			const uint32_t bytes = p.rows * 4;
+			unsigned char *buf = s_stage + (size_t)st * 2 * kCopyChunk * 4;
+			asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&full[st])), "r"(2 * bytes) : "memory");
+			if (bytes) {
+				asm volatile("cp.async.bulk.shared::cta.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(buf)),
+				             "l"(sk + p.src), "r"(bytes), "r"(smem_u32(&full[st])) : "memory");
+				asm volatile("cp.async.bulk.shared::cta.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(buf + kCopyChunk * 4)),
+				             "l"(sv + p.src), "r"(bytes), "r"(smem_u32(&full[st])) : "memory");
+			}
+		}
+	};
+	uint32_t issued = 0, done = 0;
+	CopyPiece p;
+	while (issued < (uint32_t)kCopyAhead && next_piece(&p)) issue_load(issued++, p);
+	while (done < issued) {
+		const int st = (int)(done % kCopyStages);
+		if (lane == 0) {
+			const uint32_t phase = (done / kCopyStages) & 1u;
+			asm volatile("{\n.reg .pred p;\nWAIT_%=: mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n@p bra DONE_%=;\nbra WAIT_%=;\nDONE_%=:\n}" ::"r"(
+			                 smem_u32(&full[st])),
+			             "r"(phase)
+			             : "memory");
+			const CopyPiece q = ring[st];
+			unsigned char *buf = s_stage + (size_t)st * 2 * kCopyChunk * 4;
+			if (q.rows) {
+				asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(peers.k[q.owner] + q.dst), "r"(smem_u32(buf)),
+				             "r"(q.rows * 4) : "memory");
+				asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(peers.v[q.owner] + q.dst),
+				             "r"(smem_u32(buf + kCopyChunk * 4)), "r"(q.rows * 4) : "memory");
+			}
+			asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+		}
+		++done;
+		__syncwarp();
+		if (next_piece(&p)) {
+			// the stage about to be refilled was read by the store of piece issued - kCopyStages; stores are committed in
+			// order, so at most kCopyStages - kCopyAhead of them may still be reading shared memory
+			if (lane == 0) asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(kCopyStages - kCopyAhead) : "memory");
+			issue_load(issued++, p);
+		}
+	}
+	if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+
+int launch_stage_counts(const uint32_t *r_off, const uint32_t *s_off, int abits, unsigned long long *counts, cudaStream_t s)
+{
+	k_stage_counts<<<1, 512, 0, s>>>(r_off, s_off, 1u << abits, counts);
+	return 1;
+}
+
+int launch_stage_bases(const unsigned long long *M, int G, int me, int abits, int gbits, uint64_t cap_r, uint64_t cap_s,
+                       const uint32_t *child_r, const uint32_t *child_s, uint32_t *out, uint32_t *status, cudaStream_t s)
+{
+	k_stage_bases<<<1, 512, 0, s>>>(M, G, me, abits, gbits, cap_r, cap_s, child_r, child_s, out, status);
+	return 1;
+}
+
+int launch_peer_copy(const uint32_t *sk, const uint32_t *sv, const PeerCols &peers, const uint32_t *desc, const uint32_t *abort_flag,
+                     int abits, int gbits, int me, cudaStream_t s, KernelTimer *t)
+{
+	KernelTimer off;
+	off.enabled = false;
+	off.n = 0;
+	if (!t) t = &off;
+	static const int ctas = [] {
+		const int v = getenv("HJB_COPY_CTAS") ? atoi(getenv("HJB_COPY_CTAS")) : 21;
+		return v < 1 ? 21 : v;
+	}();
+	static std::atomic<unsigned long long> done_mask{0};         // the attribute is per device
+	int dev = 0;
+	cudaGetDevice(&dev);
+	const unsigned long long bit = 1ull << (dev & 63);
+	if (!(done_mask.fetch_or(bit) & bit)) cudaFuncSetAttribute(k_peer_copy, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCopySmem);
+	t->start(KK_PEER_COPY, s);
+	k_peer_copy<<<ctas, 32, kCopySmem, s>>>(sk, sv, peers, desc, abort_flag, abits, gbits, me);
+	t->stop(s);
+	return 1;
+}
+
+}  // namespace hjb

@@ -181,6 +181,33 @@ int hjb_cpra_join_async(hjb_ctx *ctx, const hjb_opts *opts, uint64_t r_expect, u
 void *hjb_cpra_sums_dev(hjb_ctx *ctx);
 int hjb_cpra_finish(hjb_ctx *ctx, hjb_result *out, uint64_t received[2], uint64_t largest[2]);
 
+/* ---- the STAGED exchange: two radix passes over the data instead of the fused path's three, and an exchange that
+ * leaves the SMs alone.  The reference's own order -- chunk-local passes first (cpra2.cpp:1783-1827), then the
+ * per-owner gather of whole partition pieces with memcpy (cpra2.cpp:1861-1905,1940-1959):
+ *   hjb_cpra_stage_plan          how one step's radix bits are split (same arguments on every rank): stage A takes
+ *                                abits = owner bits + sub-partition bits, the local pass bbits
+ *   hjb_cpra_stage_count_async   stage A's histogram + scan of both chunks; this sender's 2 * 2^abits counts
+ *                                (R per digit, then S) -> counts_dev
+ *   (caller)                     all-gather into matrix_dev[ngpus][2][2^abits] (uint64, device)
+ *   hjb_cpra_stage_scatter_async rel 0: every run's row in its owner's columns from the matrix (sub-partition-major,
+ *                                sender-minor -- the reference's interleave), then stage A's scatter of R into staging
+ *                                columns where each run starts with the 16-byte phase of its destination; rel 1: S
+ *   hjb_cpra_stage_copy_async    the runs of one relation -> the owners' columns: a few one-warp CTAs driving TMA bulk
+ *                                copies (k_peer_copy), on `cuda_stream` (null: the context's stream): on a side stream
+ *                                that waits for the scatter, the copies of R cross NVLink while stage A works on S,
+ *                                those of S while R's local pass runs
+ *   (caller)                     per relation, a collective after the copy: when it completes every sender's runs are in
+ *   hjb_cpra_stage_local_async   rel 0: the local pass over R's received sub-partitions; rel 1: S's, then the join
+ *   hjb_cpra_finish              as above
+ * hjb_cpra_bind precedes as for the fused path; capacity failures are reported the same way. */
+int hjb_cpra_stage_plan(hjb_ctx *ctx, int ngpus, uint64_t r_expect, uint64_t s_expect, const hjb_opts *opts, int *abits,
+                        int *bbits, int *big_fill);
+int hjb_cpra_stage_count_async(hjb_ctx *ctx, const hjb_rel *R_chunk, const hjb_rel *S_chunk, const hjb_opts *opts, int abits,
+                               uint64_t *counts_dev);
+int hjb_cpra_stage_scatter_async(hjb_ctx *ctx, const uint64_t *matrix_dev, int rel);
+int hjb_cpra_stage_copy_async(hjb_ctx *ctx, int rel, void *cuda_stream);
+int hjb_cpra_stage_local_async(hjb_ctx *ctx, const hjb_opts *opts, int bbits, int big_fill, int rel);
+
 /* Skew (write.cpp's `zipf` knob, write.cpp:1685-1689; the reference's static ownership par_start / par_end,
  * cpra2.cpp:1868-1872, sends every tuple of a frequent key to one thread).  The probe tuples of a small set of
  * hot keys (<= 256, chosen by the caller, e.g. from a sample of the probe chunks) stay with their sender:

@@ -231,6 +231,130 @@ def test_fused_exchange_many_tiles_per_item(engines):
     assert tuple(fp) == e0.rows_fingerprint(sk, sv, inner.to(torch.int32))
 
 
+def run_staged_path(engines, G, rk, rv, sk, sv, r_cap, s_cap, plan=None):
+    """the staged exchange (hjb_cpra_stage_*): stage A locally by owner and sub-partition, TMA copies of whole runs
+    into the owners' buffers, one local pass, join; the all-gather is a torch.cat, the cross-GPU ordering a device
+    synchronise"""
+    bufs, peers = recv_buffers(G, r_cap, s_cap)
+    plan = plan or engines[0].cpra_stage_plan(G, max(1, rk.size // G), max(1, sk.size // G))
+    assert plan is not None
+    abits, bbits, big = plan
+    counts = [torch.zeros(2 << abits, dtype=torch.int64, device="cuda") for _ in range(G)]
+    keep = []
+    for c in range(G):
+        engines[c].cpra_bind(c, G, peers, r_cap, s_cap)
+        keep.append(((dev(chunk(rk, c, G)), dev(chunk(rv, c, G))), (dev(chunk(sk, c, G)), dev(chunk(sv, c, G)))))
+    torch.cuda.synchronize()
+    for c in range(G):
+        engines[c].cpra_stage_count_async(keep[c][0], keep[c][1], abits, counts[c])
+    torch.cuda.synchronize()
+    matrix = torch.cat(counts).contiguous()
+    torch.cuda.synchronize()
+    for c in range(G):
+        engines[c].cpra_stage_scatter_async(matrix, 0)
+        engines[c].cpra_stage_scatter_async(matrix, 1)
+    torch.cuda.synchronize()
+    for c in range(G):
+        engines[c].cpra_stage_copy_async(0)
+        engines[c].cpra_stage_copy_async(1)
+    torch.cuda.synchronize()
+    total, rows, recv = [0, 0, 0, 0], [], []
+    err = None
+    for g in range(G):
+        engines[g].cpra_stage_local_async(bbits, big, 0)
+        engines[g].cpra_stage_local_async(bbits, big, 1)
+        try:
+            res, got, largest = engines[g].cpra_finish()
+        except HjbCapacityError as e:
+            err = e
+            continue
+        total = add_checks(total, res)
+        rows.append(res.rows_numpy())
+        recv.append(got)
+    if err is not None:
+        raise err
+    return tuple(total), rows, recv, matrix.view(G, 2, 1 << abits).cpu().numpy()
+
+
+@pytest.mark.parametrize("G_", [2, 4, 8])
+@pytest.mark.parametrize("name,nr,ns,seed", CASES)
+def test_staged_exchange_with_virtual_owners_matches_oracle(engines, G_, name, nr, ns, seed):
+    rk, rv, sk, sv = skewed(nr, ns, seed) if name == "skewed" else oracle_generate(nr, ns, threads=2, seed=seed)[:4]
+    want = oracle_join("cpra", rk, rv, sk, sv, threads=4)
+    got, rows, recv, matrix = run_staged_path(engines, G_, rk, rv, sk, sv, nr + 1024, ns + 1024)
+    assert got == want.checks()
+    assert (all_rows(rows) == want.sorted_rows()).all()
+    per_owner = matrix.reshape(G_, 2, G_, -1).sum(axis=(0, 3))          # [rel][owner]
+    assert [r[0] for r in recv] == [int(x) for x in per_owner[0]]
+    assert [r[1] for r in recv] == [int(x) for x in per_owner[1]]
+
+
+@pytest.mark.parametrize("G_,plan", [(2, (9, 9, 1)), (8, (9, 9, 1)), (4, (9, 0, 0)), (2, (2, 0, 0)), (4, (2, 9, 0)), (8, (3, 5, 0)),
+                                     (2, (8, 8, 0)), (4, (5, 7, 0))])
+def test_staged_exchange_under_explicit_plans(engines, G_, plan):
+    """512-way stage A, 12288-tuple join fills, no local pass at all, stage A with the owner bits only"""
+    rk, rv, sk, sv = skewed(150000, 500000, 31)
+    want = oracle_join("cpra", rk, rv, sk, sv, threads=4)
+    got, rows, _, _ = run_staged_path(engines, G_, rk, rv, sk, sv, rk.size, sk.size, plan=plan)
+    assert got == want.checks()
+    assert (all_rows(rows) == want.sorted_rows()).all()
+
+
+def test_staged_exchange_reports_a_receive_buffer_that_is_too_small(engines):
+    rk, rv, sk, sv = skewed(150000, 500000, 23)
+    want = oracle_join("cpra", rk, rv, sk, sv, threads=4)
+    G_ = 4
+    with pytest.raises(HjbCapacityError) as info:
+        run_staged_path(engines, G_, rk, rv, sk, sv, rk.size // G_ + 4096, sk.size // G_ + 4096)
+    need_r, need_s = info.value.largest
+    assert need_s > sk.size // 3 and need_r >= rk.size // G_ - 4096
+    got, rows, _, _ = run_staged_path(engines, G_, rk, rv, sk, sv, need_r, need_s)
+    assert got == want.checks() and (all_rows(rows) == want.sorted_rows()).all()
+
+
+@pytest.mark.parametrize("plan", [None, (9, 9, 1)])
+def test_staged_exchange_many_pieces_per_run(engines, plan):
+    """2^25 x 2^25 over 4 virtual owners: runs of many 16 KB pieces, every copy stage in use; checked by count,
+    checksums and the device fingerprint of the rows against the rows rebuilt from S"""
+    G_, n = 4, 1 << 25
+    e0 = engines[0]
+    rk, rv = e0.generate(0, n, n, 42, 1, datagen.INNER_FACTOR)
+    sk, sv = e0.generate(0, n, n, 42, 2, datagen.OUTER_FACTOR)
+    e0.synchronize()
+    per = n // G_
+    plan = plan or e0.cpra_stage_plan(G_, per, per)
+    abits, bbits, big = plan
+    cap = per + per // 8
+    bufs, peers = recv_buffers(G_, cap, cap)
+    counts = [torch.zeros(2 << abits, dtype=torch.int64, device="cuda") for _ in range(G_)]
+    for c in range(G_):
+        engines[c].cpra_bind(c, G_, peers, cap, cap)
+        engines[c].cpra_stage_count_async((rk[c * per:(c + 1) * per], rv[c * per:(c + 1) * per]),
+                                          (sk[c * per:(c + 1) * per], sv[c * per:(c + 1) * per]), abits, counts[c])
+    torch.cuda.synchronize()
+    matrix = torch.cat(counts).contiguous()
+    torch.cuda.synchronize()
+    for rel in (0, 1):
+        for c in range(G_):
+            engines[c].cpra_stage_scatter_async(matrix, rel)
+    torch.cuda.synchronize()
+    for c in range(G_):
+        engines[c].cpra_stage_copy_async(0)
+        engines[c].cpra_stage_copy_async(1)
+    torch.cuda.synchronize()
+    total, fp = [0, 0, 0, 0], [0, 0]
+    for g in range(G_):
+        engines[g].cpra_stage_local_async(bbits, big, 0)
+        engines[g].cpra_stage_local_async(bbits, big, 1)
+        res, _, _ = engines[g].cpra_finish()
+        total = add_checks(total, res)
+        f = engines[g].rows_fingerprint(*res.rows_torch())
+        fp = [(fp[0] + f[0]) & MASK64, fp[1] ^ f[1]]
+    inner = ((sk.to(torch.int64) & 0xFFFFFFFF) * datagen.INNER_FACTOR & 0xFFFFFFFF)
+    assert tuple(total) == (n, e0.column_sum(sk), e0.column_sum(sv), int(inner.sum().item()) & MASK64)
+    assert tuple(fp) == e0.rows_fingerprint(sk, sv, inner.to(torch.int32))
+
+
 @pytest.mark.parametrize("nproc", [2, 4, 8])
 def test_cpra_over_nccl_and_cuda_ipc(nproc):
     """one process per GPU, NCCL collectives and peer-mapped receive buffers: tests/test_cpra_nccl.py under torchrun"""

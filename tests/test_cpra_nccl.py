@@ -42,9 +42,13 @@ def main():
         cr = slice(rank * nr // world, (rank + 1) * nr // world)
         cs = slice(rank * ns // world, (rank + 1) * ns // world)
         dev = lambda a: torch.from_numpy(np.ascontiguousarray(a).view(np.int32)).cuda()
-        for mode in ("nccl", "fused", "fused", "fused+skew"):    # the fused step twice: the second runs with the first's sizes as its plan
+        fused.stage_plan = None                                  # the staged plan is made per input shape
+        for mode in ("nccl", "fused", "fused", "fused+skew", "staged", "staged", "staged-serial"):    # twice: the second step reuses plans / buffers
             if mode == "nccl":
                 res = cpra.cpra_join(eng, (dev(rk[cr]), dev(rv[cr])), (dev(sk[cs]), dev(sv[cs])))
+            elif mode.startswith("staged"):
+                res = cpra.cpra_join_staged(eng, (dev(rk[cr]), dev(rv[cr])), (dev(sk[cs]), dev(sv[cs])), fused,
+                                            overlap=not mode.endswith("serial"))
             else:
                 res = cpra.cpra_join_fused(eng, (dev(rk[cr]), dev(rv[cr])), (dev(sk[cs]), dev(sv[cs])), fused,
                                            skew=mode.endswith("skew"))

@@ -247,7 +247,7 @@ def test_repeated_phj_on_the_same_buffers_replays_a_graph_and_rereads_the_data(e
 def test_phj_plans_and_hash_seeds_do_not_change_the_result(eng):
     rk, rv, sk, sv, _, _ = oracle_generate(1 << 17, 1 << 18, threads=2, seed=11)
     want = oracle_join("phj", rk, rv, sk, sv, threads=2)
-    for opts in ({"radix_bits": (4,)}, {"radix_bits": (8, 8)}, {"radix_bits": (3, 4, 2)}, {"radix_bits": (11, 5)},
+    for opts in ({"radix_bits": (4,)}, {"radix_bits": (8, 8)}, {"radix_bits": (3, 4, 2)}, {"radix_bits": (11, 5)}, {"radix_bits": (9, 7)}, {"radix_bits": (9, 9)},
                  {"radix_bits": (2, 2, 2, 2)}, {"part_tuples": 100}, {"part_tuples": 1 << 20}, {"seed": 12345},
                  {"npj_load": 0.9}):
         assert_same(run(eng, "phj", rk, rv, sk, sv, **opts), want)

@@ -25,7 +25,7 @@ def dev(a):
     return torch.from_numpy(np.ascontiguousarray(a).view(np.int32)).cuda()
 
 
-PLANS = [{}, {"radix_bits": (3,)}, {"radix_bits": (8, 8)}, {"radix_bits": (5, 6, 5)}, {"part_tuples": 64}, {"seed": 7}]
+PLANS = [{}, {"radix_bits": (3,)}, {"radix_bits": (8, 8)}, {"radix_bits": (5, 6, 5)}, {"radix_bits": (9, 2)}, {"part_tuples": 64}, {"seed": 7}]
 
 
 @settings(max_examples=120, deadline=None, derandomize=True, suppress_health_check=[HealthCheck.function_scoped_fixture, HealthCheck.too_slow])
