@@ -354,8 +354,10 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="auto", choices=["auto", "phj_cfg2", "npj_cfg1", "cpra_cfg4"])
     ap.add_argument("--log2-per-gpu", type=int, default=0, help="override tuples per relation per GPU (2^k)")
-    ap.add_argument("--exchange", default="fused", choices=["fused", "nccl"],
-                    help="N>1: GPU-assign pass storing straight into the owners' buffers over NVLink, or split + NCCL all-to-all")
+    ap.add_argument("--exchange", default="staged", choices=["staged", "staged-serial", "fused", "nccl"],
+                    help="N>1: staged (local pass by owner and sub-partition, TMA copies of whole runs beside the passes; "
+                         "-serial: copies on the main stream), fused (GPU-assign pass storing straight into the owners' buffers), "
+                         "or split + NCCL all-to-all")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-configs", action="store_true", help="N=1: skip the configs 1 / 3 / weak-scaling-base table")
@@ -381,6 +383,7 @@ def main():
     devname = f"cuda:{local}"
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("TORCH_NCCL_HIGH_PRIORITY", "1")      # the small collectives between the passes must not queue behind them
         dist.init_process_group("nccl", device_id=torch.device(devname))
     workload = args.workload if args.workload != "auto" else ("phj_cfg2" if world == 1 else "cpra_cfg4")
 
@@ -388,8 +391,10 @@ def main():
     fused = cpra_mod.FusedExchange(eng) if (world > 1 and args.exchange != "nccl") else None
 
     def cpra_step(inner, outer):
+        if fused is not None and args.exchange.startswith("staged") and hasattr(inner[0], "is_cuda"):
+            return cpra_mod.cpra_join_staged(eng, inner, outer, fused, overlap=args.exchange == "staged")
         if fused is not None:
-            return cpra_mod.cpra_join_fused(eng, inner, outer, fused)
+            return cpra_mod.cpra_join_fused(eng, inner, outer, fused)       # also the host-memory step of every exchange mode
         return cpra_mod.cpra_join(eng, inner, outer)
 
     # ---- synthetic inputs, generated on the device (identical to datagen's numpy mirror)
@@ -462,7 +467,7 @@ def main():
         sampler.start()
     ktimes = {}
     phases = np.zeros(8)
-    extra = {"split_ms": 0.0, "exchange_ms": 0.0, "join_ms": 0.0, "step_ms": 0.0}
+    extra = {"split_ms": 0.0, "exchange_ms": 0.0, "join_ms": 0.0, "step_ms": 0.0, "copy_r_done_ms": 0.0, "copy_s_done_ms": 0.0}
     recv_stats = []
 
     def timed_region(instrumented):
@@ -619,7 +624,10 @@ def main():
                                   "ncu --set full)" if tr else None}
     passes = max(1, round(per_step.get("k_scatter", (0, 4))[1] / 2))     # local scatter launches come in (R, S) pairs
     sb = step_bytes("npj" if algo == "npj" else "phj", nr_g, ns_g, ns_g, passes)
-    if algo == "cpra" and world > 1:
+    staged = algo == "cpra" and world > 1 and args.exchange.startswith("staged")
+    if staged:
+        sb += 16 * n_in                                      # the copies: every run read from the staging columns, written into an owner's columns
+    elif algo == "cpra" and world > 1:
         sb += 20 * n_in + 16 * n_in * (world - 1) / world    # GPU-assign pass (hist + scatter) and the receive-side writes / send-side reads
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -645,10 +653,15 @@ def main():
             sent = 8 * n_in * (world - 1) / world                # bytes each GPU stores into its peers per step
             cm = line["cpra_ms_per_step"]
             bulk_ms = per_step.get("k_scatter_bulk", (0.0, 0))[0]
+            if staged:
+                # the copies run on a side stream beside the passes: from "R is staged" to "every rank's copies of S are through"
+                bulk_ms = cm["exchange_ms"]
             line["nvlink"] = {"bytes_out_per_gpu": sent, "scatter_kernel_ms": round(bulk_ms, 4),
                               "achieved_gbs_per_direction": sent / (bulk_ms * 1e-3) / 1e9 if bulk_ms else None,
                               "reference_gbs": NVLINK_REF_GBS,
-                              "note": "k_scatter_bulk's event-timed launches (R and S); measured peer-copy bandwidth per direction 770 GB/s (B200_PROFILING.md), nominal 900"}
+                              "note": ("k_peer_copy on the side stream: span from the first relation staged to the last copy through on every rank "
+                                       "(includes stage A of S running beside it)" if staged else "k_scatter_bulk's event-timed launches (R and S)")
+                                      + "; measured peer-copy bandwidth per direction 770 GB/s (B200_PROFILING.md), nominal 900"}
             # SURVEY 8d's serial model for CPRA at G GPUs: HBM bytes / HBM bandwidth + NVLink bytes / NVLink bandwidth.
             # `as_built`: the bytes this code moves (GPU-assign + `passes` local passes + join); `survey`: the survey's
             # two-pass figure (GPU-assign + ONE local pass + join) that BASELINE's 12.5 ms target is derived from.

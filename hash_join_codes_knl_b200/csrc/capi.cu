@@ -81,6 +81,9 @@ struct hjb_ctx {
 	uint32_t *stage_dev;      // device words of k_stage_bases (enum SD_*)
 	uint32_t *stage_k[2], *stage_v[2];
 	int stage_abits, stage_state[2];   // per relation: 0 idle, 1 counted, 2 scattered, 3 copied
+	uint64_t recv_stage_off[2], recv_stage_cap[2];   // the staging region behind the receive region of recv_buf's columns (rows)
+	int stage_inplace;        // stage A writes into recv_buf's columns: own runs at their final rows, the others into the staging region
+	uint32_t stage_base[2];
 	// heavy-hitter handling (hjb_cpra_split_hot ... hjb_cpra_hot_join)
 	char *skew_buf;           // cold / hot copies of the probe chunk
 	size_t skew_bytes;
@@ -1071,10 +1074,16 @@ extern "C" int hjb_cpra_recv_alloc(hjb_ctx *ctx, uint64_t r_capacity, uint64_t s
 	CK(cudaSetDevice(ctx->device));
 	CK(cudaStreamSynchronize(ctx->stream));
 	const uint64_t cap[2] = {r_capacity ? r_capacity : 1, s_capacity ? s_capacity : 1};
+	// behind every receive column, in the same allocation: room for the staged exchange's outgoing runs of a chunk of
+	// about the same size (stage A then writes this GPU's own runs straight to their final rows with 32-bit positions)
+	for (int r = 0; r < 2; ++r) {
+		ctx->recv_stage_off[r] = (cap[r] + 63) & ~63ull;
+		ctx->recv_stage_cap[r] = cap[r] + 64 * 512 + 64;
+	}
 	for (int i = 0; i < 4; ++i) {
 		if (ctx->recv_buf[i]) CK(cudaFree(ctx->recv_buf[i]));
 		ctx->recv_buf[i] = nullptr;
-		CK(cudaMalloc(&ctx->recv_buf[i], cap[i / 2] * 4 + 256));
+		CK(cudaMalloc(&ctx->recv_buf[i], (ctx->recv_stage_off[i / 2] + ctx->recv_stage_cap[i / 2]) * 4 + 256));
 		cudaIpcMemHandle_t h;
 		CK(cudaIpcGetMemHandle(&h, ctx->recv_buf[i]));
 		static_assert(sizeof(h) == 64, "cudaIpcMemHandle_t is 64 bytes");
@@ -1511,12 +1520,21 @@ extern "C" int hjb_cpra_stage_count_async(hjb_ctx *ctx, const hjb_rel *R, const 
 	const hjb_rel *rel[2] = {R, S};
 	const uint32_t F = 1u << abits;
 	size_t scratch[2], total = 0, cols[2];
+	const int me = ctx->bind_gpu;
+	bool inplace = true;
+	for (int r = 0; r < 2; ++r) {
+		cols[r] = rel[r]->tuples + 64 * (size_t)F + 64;         // every run may start up to 31 rows late and end up to 31 rows early
+		inplace = inplace && ctx->bind_peer[2 * r][me] == ctx->recv_buf[2 * r] && ctx->bind_peer[2 * r + 1][me] == ctx->recv_buf[2 * r + 1] &&
+		          cols[r] <= ctx->recv_stage_cap[r] && ctx->recv_stage_off[r] + ctx->recv_stage_cap[r] < 0xFFFFFFFFull;
+	}
+	static const int env_inplace = getenv("HJB_STAGE_INPLACE") ? atoi(getenv("HJB_STAGE_INPLACE")) : 1;
+	inplace = inplace && env_inplace;
 	for (int r = 0; r < 2; ++r) {
 		uint32_t chunk, mi, tiles;
 		scratch[r] = radix_scratch_bytes(rel[r]->tuples, 1, abits, &chunk, &mi, &tiles);
-		cols[r] = rel[r]->tuples + 8 * (size_t)F + 64;          // every run may start up to 3 rows late and end up to 3 rows early
-		total += scratch[r] + pad256((size_t)(F + 1) * 4) + 2 * pad256(cols[r] * 4);
+		total += scratch[r] + pad256((size_t)(F + 1) * 4) + (inplace ? 0 : 2 * pad256(cols[r] * 4));
 	}
+	ctx->stage_inplace = inplace;
 	if ((rc = grow_device(ctx, &ctx->split_buf, &ctx->split_bytes, total + 4096))) return rc;
 	cudaStream_t s = ctx->stream;
 	Bump w = {ctx->split_buf, 0};
@@ -1530,8 +1548,15 @@ extern "C" int hjb_cpra_stage_count_async(hjb_ctx *ctx, const hjb_rel *R, const 
 		a.bits = abits;
 		a.rshift = 32 - abits;
 		a.child_off = w.take<uint32_t>(F + 1);
-		ctx->stage_k[r] = a.keys_out = w.take<uint32_t>(cols[r]);
-		ctx->stage_v[r] = a.vals_out = w.take<uint32_t>(cols[r]);
+		if (inplace) {
+			ctx->stage_k[r] = a.keys_out = (uint32_t *)ctx->recv_buf[2 * r];
+			ctx->stage_v[r] = a.vals_out = (uint32_t *)ctx->recv_buf[2 * r + 1];
+			ctx->stage_base[r] = (uint32_t)ctx->recv_stage_off[r];
+		} else {
+			ctx->stage_k[r] = a.keys_out = w.take<uint32_t>(cols[r]);
+			ctx->stage_v[r] = a.vals_out = w.take<uint32_t>(cols[r]);
+			ctx->stage_base[r] = 0;
+		}
 		a.shift = reinterpret_cast<const int32_t *>(ctx->stage_dev + (r ? SD_REL_S : SD_REL_R) + SD_SHIFT);
 		radix_carve(a, w.take<char>(scratch[r]), true);
 		if (a.n == 0) CK(cudaMemsetAsync(a.child_off, 0, (size_t)(F + 1) * 4, s));
@@ -1558,7 +1583,8 @@ extern "C" int hjb_cpra_stage_scatter_async(hjb_ctx *ctx, const uint64_t *matrix
 	if (rel == 0)
 		ctx->step_launches += launch_stage_bases((const unsigned long long *)matrix_dev, G, ctx->bind_gpu, ctx->stage_abits, log2_exact(G),
 		                                         ctx->bind_cap[0], ctx->bind_cap[1], ctx->pending[0].child_off, ctx->pending[1].child_off,
-		                                         ctx->stage_dev, ctx->cpra_dev + CD_RANGE_R, s);
+		                                         ctx->stage_base[0], ctx->stage_base[1], ctx->stage_inplace, ctx->stage_dev,
+		                                         ctx->cpra_dev + CD_RANGE_R, s);
 	RadixPassArgs &a = ctx->pending[rel];
 	if (a.n) ctx->step_launches += launch_radix_scatter(a, s, &ctx->timer, nullptr);
 	CK(cudaGetLastError());
@@ -1567,7 +1593,7 @@ extern "C" int hjb_cpra_stage_scatter_async(hjb_ctx *ctx, const uint64_t *matrix
 }
 
 // the copies of one relation's runs into the owners' columns, on `cuda_stream` (null: the context's stream) -- a side
-// stream that waits for the scatter lets them cross NVLink beside the passes: the copies need 21 SMs, not the GPU
+// stream that waits for the scatter lets them cross NVLink beside the passes: the copies need 16 SMs, not the GPU
 extern "C" int hjb_cpra_stage_copy_async(hjb_ctx *ctx, int rel, void *cuda_stream)
 {
 	if (!ctx || rel < 0 || rel > 1) return HJB_E_INVALID;
@@ -1582,7 +1608,7 @@ extern "C" int hjb_cpra_stage_copy_async(hjb_ctx *ctx, int rel, void *cuda_strea
 	}
 	if (ctx->pending[rel].n)
 		ctx->step_launches += launch_peer_copy(ctx->stage_k[rel], ctx->stage_v[rel], pc, ctx->stage_dev + (rel ? SD_REL_S : SD_REL_R),
-		                                       ctx->cpra_dev + CD_ABORT, ctx->stage_abits, log2_exact(G), ctx->bind_gpu,
+		                                       ctx->cpra_dev + CD_ABORT, ctx->stage_abits, log2_exact(G), ctx->bind_gpu, ctx->stage_inplace,
 		                                       cuda_stream ? (cudaStream_t)cuda_stream : ctx->stream, cuda_stream ? nullptr : &ctx->timer);
 	CK(cudaGetLastError());
 	ctx->stage_state[rel] = 3;

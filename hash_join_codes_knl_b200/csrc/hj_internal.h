@@ -107,9 +107,10 @@ struct PeerCols {
 };
 int launch_stage_counts(const uint32_t *r_off, const uint32_t *s_off, int abits, unsigned long long *counts, cudaStream_t s);
 int launch_stage_bases(const unsigned long long *M, int G, int me, int abits, int gbits, uint64_t cap_r, uint64_t cap_s,
-                       const uint32_t *child_r, const uint32_t *child_s, uint32_t *out, uint32_t *status, cudaStream_t s);
+                       const uint32_t *child_r, const uint32_t *child_s, uint32_t stage_base_r, uint32_t stage_base_s, int inplace,
+                       uint32_t *out, uint32_t *status, cudaStream_t s);
 int launch_peer_copy(const uint32_t *sk, const uint32_t *sv, const PeerCols &peers, const uint32_t *desc, const uint32_t *abort_flag,
-                     int abits, int gbits, int me, cudaStream_t s, KernelTimer *t = nullptr);
+                     int abits, int gbits, int me, int skip_me, cudaStream_t s, KernelTimer *t = nullptr);
 
 struct JoinArgs {
 	const uint32_t *rk, *rv, *sk, *sv;       // partitioned columns

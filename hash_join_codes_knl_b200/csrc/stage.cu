@@ -9,8 +9,8 @@
 //                    the owner's columns (sub-partition-major, sender-minor -- the reference's interleave order,
 //                    cpra2.cpp:1426-1440), the offsets of the sub-partitions this GPU receives, whether every
 //                    owner's buffer is large enough, and where stage A must START each run in the staging columns
-//                    so that source and destination rows have the same 16-byte phase
-//   k_peer_copy    : a handful of one-warp CTAs drive the TMA unit: cp.async.bulk global -> shared (mbarrier) and
+//                    so that source and destination rows have the same 128-byte phase
+//   k_peer_copy    : a handful of two-warp CTAs drive the TMA unit: cp.async.bulk global -> shared (mbarrier) and
 //                    shared -> the owner's global memory over NVLink, 16 KB per column and piece, six stages.
 //                    Measured (scripts/r2/peer_copy_bench.cu, 2 GPUs): 16 such CTAs move 705 GB/s, the copy
 //                    engine 776 GB/s -- the SMs beside them stay free for stage A of the other relation and the
@@ -58,12 +58,20 @@ __device__ __forceinline__ unsigned long long block_exclusive_scan_u64(unsigned 
 	return before + incl - v;
 }
 
+// Source and destination rows of a run agree modulo kCopyPhase rows = 128 bytes: the bulk copies then move whole,
+// identically aligned 128-byte lines on both sides (measured at 2 GPUs: with 16-byte agreement only, a 32 KB piece took
+// 5.4 us to leave shared memory and 23 CTAs moved 540 GB/s).
+constexpr uint32_t kCopyPhase = 32;
+
 // M[src][rel][digit] (uint64): the all-gathered counts.  One CTA of 512 threads, one digit per thread, R then S.
 __global__ void __launch_bounds__(512)
 k_stage_bases(const unsigned long long *__restrict__ M, int G, int me, int abits, int gbits, unsigned long long cap_r,
               unsigned long long cap_s, const uint32_t *__restrict__ child_r, const uint32_t *__restrict__ child_s,
-              uint32_t *__restrict__ out, uint32_t *__restrict__ status)
+              uint32_t stage_base_r, uint32_t stage_base_s, int inplace, uint32_t *__restrict__ out, uint32_t *__restrict__ status)
 {
+	// stage_base_*: first row of the staging region in stage A's output columns.  inplace: those columns ARE this GPU's
+	// receive columns (staging region behind the receive region): the runs this GPU owns itself are then scattered
+	// straight to their final rows and never copied.
 	__shared__ unsigned long long warp_tot[16];
 	__shared__ unsigned long long s_e[513];
 	__shared__ unsigned long long s_max[2];
@@ -108,14 +116,15 @@ k_stage_bases(const unsigned long long *__restrict__ M, int G, int me, int abits
 	const int abort = s_abort;
 	for (int rel = 0; rel < 2; ++rel) {
 		// the run of digit d starts in the staging columns at a row with the 16-byte phase of its destination row
-		const uint32_t a = (uint32_t)(t0v[rel] & 3);
-		const unsigned long long w = (d < F && mine[rel]) ? ((a + mine[rel] + 3) & ~3ull) : 0ull;
+		const uint32_t a = (uint32_t)(t0v[rel] & (kCopyPhase - 1));
+		const bool home = inplace && !abort && d < F && d / nsub == (uint32_t)me;
+		const unsigned long long w = (d < F && mine[rel] && !home) ? ((a + mine[rel] + kCopyPhase - 1) & ~(unsigned long long)(kCopyPhase - 1)) : 0ull;
 		unsigned long long total;
 		const unsigned long long before = block_exclusive_scan_u64(w, warp_tot, &total);
 		const uint32_t *child = rel ? child_s : child_r;
 		uint32_t *o = out + (rel ? SD_REL_S : SD_REL_R);
 		if (d < F) {
-			const uint32_t s0 = (uint32_t)before + a;
+			const uint32_t s0 = home ? (uint32_t)t0v[rel] : (rel ? stage_base_s : stage_base_r) + (uint32_t)before + a;
 			o[SD_N + d] = (uint32_t)mine[rel];
 			o[SD_S0 + d] = s0;
 			o[SD_T0 + d] = (uint32_t)t0v[rel];
@@ -137,138 +146,162 @@ k_stage_bases(const unsigned long long *__restrict__ M, int G, int me, int abits
 
 // ------------------------------------------------------------------ the copy
 
-constexpr uint32_t kCopyChunk = 4096;          // tuples per piece and column: 16 KB
-constexpr int kCopyStages = 6;                 // stages of 2 x 16 KB
-constexpr int kCopyAhead = 3;                  // loads in flight before the piece being stored; kCopyStages - kCopyAhead stores may drain
+#ifndef HJB_COPY_CHUNK
+#define HJB_COPY_CHUNK 4096
+#define HJB_COPY_STAGES 6
+#define HJB_COPY_DRAIN 2
+#endif
+constexpr uint32_t kCopyChunk = HJB_COPY_CHUNK;     // tuples per piece and column: 16 KB
+constexpr int kCopyStages = HJB_COPY_STAGES;        // stages of 2 x 16 KB
+constexpr int kCopyDrain = HJB_COPY_DRAIN;          // stores that may still be reading shared memory when a stage is handed back
 constexpr size_t kCopySmem = (size_t)kCopyStages * 2 * kCopyChunk * 4;
+constexpr uint32_t kCopyEnd = 0xFFFFFFFFu;
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+	asm volatile("{\n.reg .pred p;\nWAIT_%=: mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n@p bra DONE_%=;\nbra WAIT_%=;\nDONE_%=:\n}" ::"r"(
+	                 smem_u32(bar)),
+	             "r"(parity)
+	             : "memory");
+}
 
 struct CopyPiece {
-	uint32_t src, dst, rows, owner;            // rows of the 16-byte aligned body piece (may be 0), its first row on both sides
+	uint32_t src, dst, rows, owner;            // rows of the 128-byte aligned body piece (may be 0), its first row on both sides
 };
 
-__global__ void __launch_bounds__(32)
+// Two warps per CTA.  Warp 0 walks this CTA's pieces and issues the loads (global -> shared, completion on full[stage]);
+// warp 1 waits for a piece, issues its two stores (shared -> the owner's columns) and hands a stage back (empty[stage])
+// once its store has read shared memory.  Neither waits for the other's bookkeeping.
+__global__ void __launch_bounds__(64)
 k_peer_copy(const uint32_t *__restrict__ sk, const uint32_t *__restrict__ sv, const PeerCols peers,
-            const uint32_t *__restrict__ desc, const uint32_t *__restrict__ abort_flag, int abits, int gbits, int me)
+            const uint32_t *__restrict__ desc, const uint32_t *__restrict__ abort_flag, int abits, int gbits, int me, int skip_me)
 {
 	extern __shared__ __align__(128) unsigned char s_stage[];
-	__shared__ uint64_t full[kCopyStages];
-	__shared__ uint32_t s_n[512], s_s0[512], s_t0[512], s_pref[512], s_total[64];
+	__shared__ uint64_t full[kCopyStages], empty[kCopyStages];
+	__shared__ uint32_t s_n[512], s_s0[512], s_t0[512], s_end[512], s_total[64], s_cur[64];
+	__shared__ uint32_t *s_pk[64], *s_pv[64];
 	__shared__ CopyPiece ring[kCopyStages];
+	__shared__ uint32_t s_maxp;
 	if (*abort_flag) return;
-	const uint32_t F = 1u << abits, nsub = F >> gbits, G = 1u << gbits, lane = threadIdx.x;
+	const uint32_t F = 1u << abits, nsub = F >> gbits, G = 1u << gbits, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 	const uint32_t *dn = desc + SD_N, *ds0 = desc + SD_S0, *dt0 = desc + SD_T0;
-	for (uint32_t d = lane; d < F; d += 32) {
+	for (uint32_t d = threadIdx.x; d < F; d += 64) {
 		s_n[d] = dn[d];
 		s_s0[d] = ds0[d];
 		s_t0[d] = dt0[d];
 	}
-	if (lane == 0) {
-		for (int i = 0; i < kCopyStages; ++i)
+	if (threadIdx.x < 64) {
+		s_pk[threadIdx.x] = peers.k[threadIdx.x];
+		s_pv[threadIdx.x] = peers.v[threadIdx.x];
+		s_cur[threadIdx.x] = 0;
+	}
+	if (threadIdx.x == 0) {
+		for (int i = 0; i < kCopyStages; ++i) {
 			asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&full[i])));
+			asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&empty[i])));
+		}
 		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 	}
-	__syncwarp();
-	// head: rows before the first 16-byte aligned destination row; body: whole 16-byte words; tail: the rest
-	auto head_of = [&](uint32_t d) { return min(s_n[d], (4u - (s_t0[d] & 3u)) & 3u); };
-	auto body_of = [&](uint32_t d) { return (s_n[d] - head_of(d)) & ~3u; };
-	uint32_t maxp = 0;
-	for (uint32_t o = lane; o < G; o += 32) {
-		uint32_t run = 0;
-		for (uint32_t sub = 0; sub < nsub; ++sub) {
-			const uint32_t d = o * nsub + sub;
-			s_pref[d] = run;
-			if (s_n[d]) run += max(1u, (body_of(d) + kCopyChunk - 1) / kCopyChunk);
-		}
-		s_total[o] = run;
-		maxp = max(maxp, run);
-	}
-#pragma unroll
-	for (int o = 16; o; o >>= 1) maxp = max(maxp, __shfl_xor_sync(kFullMask, maxp, o));
-	__syncwarp();
-	// Virtual piece v = (index within the owner) * G + slot, slot s = owner (me + 1 + s) mod G: consecutive pieces go to
-	// different owners, so every sender spreads its traffic over all receivers at all times.  CTA b takes v = b, b + grid, ...
-	const unsigned long long vmax = (unsigned long long)maxp * G;
-	unsigned long long v = blockIdx.x;
-	auto next_piece = [&](CopyPiece *p) -> bool {
-		for (; v < vmax; v += gridDim.x) {
-			const uint32_t owner = (uint32_t)((me + 1 + v % G) % G), idx = (uint32_t)(v / G);
-			if (idx >= s_total[owner]) continue;
-			const uint32_t *pref = s_pref + owner * nsub;
-			uint32_t lo = 0, hi = nsub;
-			while (hi - lo > 1) {
-				const uint32_t mid = (lo + hi) >> 1;
-				if (pref[mid] <= idx) lo = mid;
-				else hi = mid;
+	__syncthreads();
+	// head: rows before the first 128-byte aligned destination row; body: whole 128-byte lines; tail: the rest
+	auto head_of = [&](uint32_t d) { return min(s_n[d], (kCopyPhase - (s_t0[d] & (kCopyPhase - 1))) & (kCopyPhase - 1)); };
+	auto body_of = [&](uint32_t d) { return (s_n[d] - head_of(d)) & ~(kCopyPhase - 1); };
+	if (warp == 0) {
+		uint32_t maxp = 0;
+		for (uint32_t o = lane; o < G; o += 32) {
+			uint32_t run = 0;
+			for (uint32_t sub = 0; sub < nsub; ++sub) {
+				const uint32_t d = o * nsub + sub;
+				if (s_n[d] && !(skip_me && o == (uint32_t)me)) run += max(1u, (body_of(d) + kCopyChunk - 1) / kCopyChunk);
+				s_end[d] = run;                       // pieces of the owner's runs up to and including this one
 			}
-			const uint32_t d = owner * nsub + lo, c = idx - pref[lo];
-			const uint32_t h = head_of(d), body = body_of(d);
-			const uint32_t off = c * kCopyChunk;
-			p->rows = body > off ? min(kCopyChunk, body - off) : 0u;
-			p->src = s_s0[d] + h + off;
-			p->dst = s_t0[d] + h + off;
-			p->owner = owner;
+			s_total[o] = run;
+			maxp = max(maxp, run);
+		}
+#pragma unroll
+		for (int o = 16; o; o >>= 1) maxp = max(maxp, __shfl_xor_sync(kFullMask, maxp, o));
+		if (lane == 0) s_maxp = maxp;
+	}
+	__syncthreads();
+	if (warp == 0) {
+		// Virtual piece v = (index within the owner) * na + slot over the na owners that get copies (me + 1, me + 2, ... and
+		// this GPU last unless its own runs are already in place): consecutive pieces go to different owners, so every
+		// sender spreads its traffic over all receivers at all times.  CTA b takes v = b, b + grid, ...
+		const uint32_t na = G - (skip_me ? 1u : 0u);
+		const uint32_t vmax = s_maxp * na;
+		uint32_t k = 0;
+		for (uint32_t v = blockIdx.x; v < vmax; v += gridDim.x) {
+			const uint32_t slot = v % na, idx = v / na;
+			const uint32_t owner = ((uint32_t)me + 1u + slot) & (G - 1);
+			if (idx >= s_total[owner]) continue;
+			const uint32_t *end = s_end + owner * nsub;
+			uint32_t cur = s_cur[owner];              // this CTA's pieces of an owner come in increasing order
+			while (end[cur] <= idx) ++cur;
+			__syncwarp();
+			if (lane == 0) s_cur[owner] = cur;
+			const uint32_t d = owner * nsub + cur, c = idx - (cur ? end[cur - 1] : 0u);
+			const uint32_t h = head_of(d), body = body_of(d), off = c * kCopyChunk;
+			CopyPiece p;
+			p.rows = body > off ? min(kCopyChunk, body - off) : 0u;
+			p.src = s_s0[d] + h + off;
+			p.dst = s_t0[d] + h + off;
+			p.owner = owner;
 			if (c == 0) {
-				// the unaligned ends of the run: at most three rows each, plain stores
+				// the unaligned ends of the run: at most 31 rows each, plain stores
 				const uint32_t tail = s_n[d] - h - body;
-				if (lane < h + tail) {
-					const uint32_t row = lane < h ? lane : h + body + (lane - h);
-					peers.k[owner][s_t0[d] + row] = sk[s_s0[d] + row];
-					peers.v[owner][s_t0[d] + row] = sv[s_s0[d] + row];
+				if (lane < h) {
+					s_pk[owner][s_t0[d] + lane] = sk[s_s0[d] + lane];
+					s_pv[owner][s_t0[d] + lane] = sv[s_s0[d] + lane];
+				}
+				if (lane < tail) {
+					const uint32_t row = h + body + lane;
+					s_pk[owner][s_t0[d] + row] = sk[s_s0[d] + row];
+					s_pv[owner][s_t0[d] + row] = sv[s_s0[d] + row];
 				}
 			}
-			v += gridDim.x;
-			return true;
-		}
-		return false;
-	};
-	auto issue_load = [&](uint32_t n, const CopyPiece &p) {
-		const int st = (int)(n % kCopyStages);
-		if (lane == 0) {
-			ring[st] = p;
-			const uint32_t bytes = p.rows * 4;
-			unsigned char *buf = s_stage + (size_t)st * 2 * kCopyChunk * 4;
-			asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&full[st])), "r"(2 * bytes) : "memory");
-			if (bytes) {
+			if (p.rows == 0) continue;                // a run shorter than one line: its ends were all of it
+			const int st = (int)(k % kCopyStages);
+			if (lane == 0) {
+				if (k >= (uint32_t)kCopyStages) mbar_wait(&empty[st], ((k / kCopyStages) - 1) & 1u);
+				ring[st] = p;
+				const uint32_t bytes = p.rows * 4;
+				unsigned char *buf = s_stage + (size_t)st * 2 * kCopyChunk * 4;
+				asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&full[st])), "r"(2 * bytes) : "memory");
 				asm volatile("cp.async.bulk.shared::cta.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(buf)),
 				             "l"(sk + p.src), "r"(bytes), "r"(smem_u32(&full[st])) : "memory");
 				asm volatile("cp.async.bulk.shared::cta.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(buf + kCopyChunk * 4)),
 				             "l"(sv + p.src), "r"(bytes), "r"(smem_u32(&full[st])) : "memory");
 			}
+			++k;
 		}
-	};
-	uint32_t issued = 0, done = 0;
-	CopyPiece p;
-	while (issued < (uint32_t)kCopyAhead && next_piece(&p)) issue_load(issued++, p);
-	while (done < issued) {
-		const int st = (int)(done % kCopyStages);
+		// the end mark travels through the same ring
 		if (lane == 0) {
-			const uint32_t phase = (done / kCopyStages) & 1u;
-			asm volatile("{\n.reg .pred p;\nWAIT_%=: mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n@p bra DONE_%=;\nbra WAIT_%=;\nDONE_%=:\n}" ::"r"(
-			                 smem_u32(&full[st])),
-			             "r"(phase)
-			             : "memory");
+			const int st = (int)(k % kCopyStages);
+			if (k >= (uint32_t)kCopyStages) mbar_wait(&empty[st], ((k / kCopyStages) - 1) & 1u);
+			ring[st].owner = kCopyEnd;
+			asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&full[st])) : "memory");
+		}
+	} else if (lane == 0) {
+		for (uint32_t k = 0;; ++k) {
+			const int st = (int)(k % kCopyStages);
+			mbar_wait(&full[st], (k / kCopyStages) & 1u);
 			const CopyPiece q = ring[st];
+			if (q.owner == kCopyEnd) break;
 			unsigned char *buf = s_stage + (size_t)st * 2 * kCopyChunk * 4;
-			if (q.rows) {
-				asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(peers.k[q.owner] + q.dst), "r"(smem_u32(buf)),
-				             "r"(q.rows * 4) : "memory");
-				asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(peers.v[q.owner] + q.dst),
-				             "r"(smem_u32(buf + kCopyChunk * 4)), "r"(q.rows * 4) : "memory");
-			}
+			asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(s_pk[q.owner] + q.dst), "r"(smem_u32(buf)),
+			             "r"(q.rows * 4) : "memory");
+			asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(s_pv[q.owner] + q.dst),
+			             "r"(smem_u32(buf + kCopyChunk * 4)), "r"(q.rows * 4) : "memory");
 			asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+			if (k >= (uint32_t)kCopyDrain) {
+				// stores are committed in order: all but the last kCopyDrain have read their stage
+				asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(kCopyDrain) : "memory");
+				asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&empty[(k - kCopyDrain) % kCopyStages])) : "memory");
+			}
 		}
-		++done;
-		__syncwarp();
-		if (next_piece(&p)) {
-			// the stage about to be refilled was read by the store of piece issued - kCopyStages; stores are committed in
-			// order, so at most kCopyStages - kCopyAhead of them may still be reading shared memory
-			if (lane == 0) asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(kCopyStages - kCopyAhead) : "memory");
-			issue_load(issued++, p);
-		}
+		asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 	}
-	if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
 
 int launch_stage_counts(const uint32_t *r_off, const uint32_t *s_off, int abits, unsigned long long *counts, cudaStream_t s)
@@ -278,22 +311,23 @@ int launch_stage_counts(const uint32_t *r_off, const uint32_t *s_off, int abits,
 }
 
 int launch_stage_bases(const unsigned long long *M, int G, int me, int abits, int gbits, uint64_t cap_r, uint64_t cap_s,
-                       const uint32_t *child_r, const uint32_t *child_s, uint32_t *out, uint32_t *status, cudaStream_t s)
+                       const uint32_t *child_r, const uint32_t *child_s, uint32_t stage_base_r, uint32_t stage_base_s, int inplace,
+                       uint32_t *out, uint32_t *status, cudaStream_t s)
 {
-	k_stage_bases<<<1, 512, 0, s>>>(M, G, me, abits, gbits, cap_r, cap_s, child_r, child_s, out, status);
+	k_stage_bases<<<1, 512, 0, s>>>(M, G, me, abits, gbits, cap_r, cap_s, child_r, child_s, stage_base_r, stage_base_s, inplace, out, status);
 	return 1;
 }
 
 int launch_peer_copy(const uint32_t *sk, const uint32_t *sv, const PeerCols &peers, const uint32_t *desc, const uint32_t *abort_flag,
-                     int abits, int gbits, int me, cudaStream_t s, KernelTimer *t)
+                     int abits, int gbits, int me, int skip_me, cudaStream_t s, KernelTimer *t)
 {
 	KernelTimer off;
 	off.enabled = false;
 	off.n = 0;
 	if (!t) t = &off;
 	static const int ctas = [] {
-		const int v = getenv("HJB_COPY_CTAS") ? atoi(getenv("HJB_COPY_CTAS")) : 21;
-		return v < 1 ? 21 : v;
+		const int v = getenv("HJB_COPY_CTAS") ? atoi(getenv("HJB_COPY_CTAS")) : 30;
+		return v < 1 ? 30 : v;
 	}();
 	static std::atomic<unsigned long long> done_mask{0};         // the attribute is per device
 	int dev = 0;
@@ -301,7 +335,7 @@ int launch_peer_copy(const uint32_t *sk, const uint32_t *sv, const PeerCols &pee
 	const unsigned long long bit = 1ull << (dev & 63);
 	if (!(done_mask.fetch_or(bit) & bit)) cudaFuncSetAttribute(k_peer_copy, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCopySmem);
 	t->start(KK_PEER_COPY, s);
-	k_peer_copy<<<ctas, 32, kCopySmem, s>>>(sk, sv, peers, desc, abort_flag, abits, gbits, me);
+	k_peer_copy<<<ctas, 64, kCopySmem, s>>>(sk, sv, peers, desc, abort_flag, abits, gbits, me, skip_me);
 	t->stop(s);
 	return 1;
 }

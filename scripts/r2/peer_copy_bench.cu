@@ -46,7 +46,7 @@ __global__ void __launch_bounds__(32) k_copy_tma(const char *__restrict__ src, c
 		asm volatile("cp.async.bulk.commit_group;" ::: "memory");
 		if (issued < mine) {
 			// the stage that load `issued` refills was last read by the store of chunk issued - NS: at most NS - 2... stores may still be reading
-			asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(NS - 2) : "memory");
+			asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(1) : "memory");    // NS - (NS - 1) stores may still read
 			issue_load(issued);
 			++issued;
 		}
@@ -114,6 +114,45 @@ int main(int argc, char **argv)
 			snprintf(name, sizeof name, "tma %s ctas %3d chunk 8192 stages 4 (co-res)", tn, ctas);
 			timeit(name, [&] { k_copy_tma<4><<<ctas, 32, 4 * 8192>>>(src, d, bytes, 8192); });
 		}
+	}
+	// both directions at once (what the exchange does): device 1 copies into device 0 while device 0 copies into device 1
+	if (peer) {
+		char *src1, *dst0;
+		CK(cudaSetDevice(1));
+		CK(cudaDeviceEnablePeerAccess(0, 0));
+		CK(cudaMalloc(&src1, bytes));
+		CK(cudaMemset(src1, 2, bytes));
+		cudaStream_t s1;
+		CK(cudaStreamCreate(&s1));
+		CK(cudaSetDevice(0));
+		CK(cudaMalloc(&dst0, bytes));
+		cudaStream_t s0;
+		CK(cudaStreamCreate(&s0));
+		for (int ctas : {12, 16, 20, 24, 32, 48, 148}) {
+			for (uint32_t chunk : {8192u, 16384u, 32768u}) {
+				snprintf(name, sizeof name, "tma BIDIR ctas %3d chunk %5u stages 6", ctas, chunk);
+				timeit(name, [&] {
+					CK(cudaSetDevice(1));
+					CK(cudaFuncSetAttribute(k_copy_tma<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, 6 * 32768));
+					k_copy_tma<6><<<ctas, 32, 6 * chunk, s1>>>(src1, dst0, bytes, chunk);
+					CK(cudaSetDevice(0));
+					k_copy_tma<6><<<ctas, 32, 6 * chunk, 0>>>(src, dst, bytes, chunk);
+				});
+				CK(cudaSetDevice(1));
+				CK(cudaDeviceSynchronize());
+				CK(cudaSetDevice(0));
+			}
+		}
+		snprintf(name, sizeof name, "memcpyAsync BIDIR");
+		timeit(name, [&] {
+			CK(cudaSetDevice(1));
+			CK(cudaMemcpyAsync(dst0, src1, bytes, cudaMemcpyDeviceToDevice, s1));
+			CK(cudaSetDevice(0));
+			CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, 0));
+		});
+		CK(cudaSetDevice(1));
+		CK(cudaDeviceSynchronize());
+		CK(cudaSetDevice(0));
 	}
 	// check
 	CK(cudaMemset(dst, 0, bytes));

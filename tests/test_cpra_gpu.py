@@ -231,11 +231,16 @@ def test_fused_exchange_many_tiles_per_item(engines):
     assert tuple(fp) == e0.rows_fingerprint(sk, sv, inner.to(torch.int32))
 
 
-def run_staged_path(engines, G, rk, rv, sk, sv, r_cap, s_cap, plan=None):
+def run_staged_path(engines, G, rk, rv, sk, sv, r_cap, s_cap, plan=None, own_alloc=False):
     """the staged exchange (hjb_cpra_stage_*): stage A locally by owner and sub-partition, TMA copies of whole runs
     into the owners' buffers, one local pass, join; the all-gather is a torch.cat, the cross-GPU ordering a device
-    synchronise"""
-    bufs, peers = recv_buffers(G, r_cap, s_cap)
+    synchronise.  own_alloc: the receive buffers come from hjb_cpra_recv_alloc (as in the multi-process path) -- stage A
+    then writes every GPU's own runs straight to their final rows, the others into the staging region behind"""
+    if own_alloc:
+        owns = [engines[g].cpra_recv_alloc(r_cap, s_cap) for g in range(G)]
+        peers = [[owns[g]["ptrs"][c] for g in range(G)] for c in range(4)]
+    else:
+        bufs, peers = recv_buffers(G, r_cap, s_cap)
     plan = plan or engines[0].cpra_stage_plan(G, max(1, rk.size // G), max(1, sk.size // G))
     assert plan is not None
     abits, bbits, big = plan
@@ -276,12 +281,13 @@ def run_staged_path(engines, G, rk, rv, sk, sv, r_cap, s_cap, plan=None):
     return tuple(total), rows, recv, matrix.view(G, 2, 1 << abits).cpu().numpy()
 
 
+@pytest.mark.parametrize("own_alloc", [False, True])
 @pytest.mark.parametrize("G_", [2, 4, 8])
 @pytest.mark.parametrize("name,nr,ns,seed", CASES)
-def test_staged_exchange_with_virtual_owners_matches_oracle(engines, G_, name, nr, ns, seed):
+def test_staged_exchange_with_virtual_owners_matches_oracle(engines, G_, name, nr, ns, seed, own_alloc):
     rk, rv, sk, sv = skewed(nr, ns, seed) if name == "skewed" else oracle_generate(nr, ns, threads=2, seed=seed)[:4]
     want = oracle_join("cpra", rk, rv, sk, sv, threads=4)
-    got, rows, recv, matrix = run_staged_path(engines, G_, rk, rv, sk, sv, nr + 1024, ns + 1024)
+    got, rows, recv, matrix = run_staged_path(engines, G_, rk, rv, sk, sv, nr + 1024, ns + 1024, own_alloc=own_alloc)
     assert got == want.checks()
     assert (all_rows(rows) == want.sorted_rows()).all()
     per_owner = matrix.reshape(G_, 2, G_, -1).sum(axis=(0, 3))          # [rel][owner]
@@ -295,20 +301,21 @@ def test_staged_exchange_under_explicit_plans(engines, G_, plan):
     """512-way stage A, 12288-tuple join fills, no local pass at all, stage A with the owner bits only"""
     rk, rv, sk, sv = skewed(150000, 500000, 31)
     want = oracle_join("cpra", rk, rv, sk, sv, threads=4)
-    got, rows, _, _ = run_staged_path(engines, G_, rk, rv, sk, sv, rk.size, sk.size, plan=plan)
+    got, rows, _, _ = run_staged_path(engines, G_, rk, rv, sk, sv, rk.size, sk.size, plan=plan, own_alloc=G_ != 4)
     assert got == want.checks()
     assert (all_rows(rows) == want.sorted_rows()).all()
 
 
-def test_staged_exchange_reports_a_receive_buffer_that_is_too_small(engines):
+@pytest.mark.parametrize("own_alloc", [False, True])
+def test_staged_exchange_reports_a_receive_buffer_that_is_too_small(engines, own_alloc):
     rk, rv, sk, sv = skewed(150000, 500000, 23)
     want = oracle_join("cpra", rk, rv, sk, sv, threads=4)
     G_ = 4
     with pytest.raises(HjbCapacityError) as info:
-        run_staged_path(engines, G_, rk, rv, sk, sv, rk.size // G_ + 4096, sk.size // G_ + 4096)
+        run_staged_path(engines, G_, rk, rv, sk, sv, rk.size // G_ + 4096, sk.size // G_ + 4096, own_alloc=own_alloc)
     need_r, need_s = info.value.largest
     assert need_s > sk.size // 3 and need_r >= rk.size // G_ - 4096
-    got, rows, _, _ = run_staged_path(engines, G_, rk, rv, sk, sv, need_r, need_s)
+    got, rows, _, _ = run_staged_path(engines, G_, rk, rv, sk, sv, need_r, need_s, own_alloc=own_alloc)
     assert got == want.checks() and (all_rows(rows) == want.sorted_rows()).all()
 
 
@@ -325,7 +332,8 @@ def test_staged_exchange_many_pieces_per_run(engines, plan):
     plan = plan or e0.cpra_stage_plan(G_, per, per)
     abits, bbits, big = plan
     cap = per + per // 8
-    bufs, peers = recv_buffers(G_, cap, cap)
+    owns = [engines[g].cpra_recv_alloc(cap, cap) for g in range(G_)]
+    peers = [[owns[g]["ptrs"][c] for g in range(G_)] for c in range(4)]
     counts = [torch.zeros(2 << abits, dtype=torch.int64, device="cuda") for _ in range(G_)]
     for c in range(G_):
         engines[c].cpra_bind(c, G_, peers, cap, cap)
