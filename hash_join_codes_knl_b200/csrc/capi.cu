@@ -82,6 +82,8 @@ struct hjb_ctx {
 	uint32_t *stage_k[2], *stage_v[2];
 	int stage_abits, stage_state[2];   // per relation: 0 idle, 1 counted, 2 scattered, 3 copied
 	uint64_t recv_stage_off[2], recv_stage_cap[2];   // the staging region behind the receive region of recv_buf's columns (rows)
+	uint32_t *h_stage;        // pinned: the per-owner runs of both relations + the verdict, for the copy-engine form of the exchange
+	int stage_copy_engine;    // this step's copies are cudaMemcpyAsync calls (HJB_STAGE_COPY=ce) instead of k_peer_copy
 	int stage_inplace;        // stage A writes into recv_buf's columns: own runs at their final rows, the others into the staging region
 	uint32_t stage_base[2];
 	// heavy-hitter handling (hjb_cpra_split_hot ... hjb_cpra_hot_join)
@@ -179,6 +181,7 @@ extern "C" int hjb_destroy(hjb_ctx *ctx)
 	for (int i = 0; i < 4; ++i) cudaFree(ctx->recv_buf[i]);
 	cudaFree(ctx->cpra_dev);
 	cudaFree(ctx->stage_dev);
+	cudaFreeHost(ctx->h_stage);
 	cudaFree(ctx->skew_buf);
 	free(ctx->step_phj);
 	cudaFree(ctx->d_scalars);
@@ -481,7 +484,7 @@ static int make_plan(hjb_ctx *ctx, uint64_t nr, uint64_t ns, const hjb_opts *o, 
 	return HJB_OK;
 }
 
-static size_t phj_workspace(uint64_t nr, uint64_t ns, const Plan &p, size_t *radix_scratch, int pre_bits = 0)
+static size_t phj_workspace(uint64_t nr, uint64_t ns, const Plan &p, size_t *radix_scratch, int pre_bits = 0, uint32_t pre_segs = 1)
 {
 	size_t total = 0;
 	const int nb = p.npass >= 2 ? 2 : p.npass;
@@ -493,8 +496,9 @@ static size_t phj_workspace(uint64_t nr, uint64_t ns, const Plan &p, size_t *rad
 	uint32_t np = 1u << pre_bits;
 	for (int i = 0; i < p.npass; ++i) {
 		uint32_t chunk, mi, tiles;
-		size_t a = radix_scratch_bytes(nr, np, p.bits[i], &chunk, &mi, &tiles);
-		size_t b = radix_scratch_bytes(ns, np, p.bits[i], &chunk, &mi, &tiles);
+		const uint32_t np_eff = i == 0 ? np * pre_segs : np;          // every range of a pre-partitioned parent may end in a short item
+		size_t a = radix_scratch_bytes(nr, np_eff, p.bits[i], &chunk, &mi, &tiles);
+		size_t b = radix_scratch_bytes(ns, np_eff, p.bits[i], &chunk, &mi, &tiles);
 		if (a > rs) rs = a;
 		if (b > rs) rs = b;
 		np <<= p.bits[i];
@@ -511,12 +515,13 @@ struct Partitioned {
 // all passes over one relation; ping-pongs between two workspace buffers
 static int partition_relation(hjb_ctx *ctx, const hjb_rel *rel, const Plan &p, int consumed, uint32_t factor,
                               uint32_t *bufk[2], uint32_t *bufv[2], uint32_t *off[2], char *scratch,
-                              Partitioned *res, uint32_t *launches, const uint32_t *dev_range = nullptr, int pre_bits = 0)
+                              Partitioned *res, uint32_t *launches, const uint32_t *dev_range = nullptr, int pre_bits = 0,
+                              const uint32_t *seg = nullptr, uint32_t nseg = 0)
 {
 	// dev_range: {0, tuples} in DEVICE memory -- the relation's size is then only known there (CPRA's receive
 	// buffers in the stream-ordered path) and rel->tuples is an upper bound that sizes grids and scratch.
 	// pre_bits > 0: the relation arrives cut into 2^pre_bits partitions by the bits below `consumed` (the staged
-	// exchange); dev_range then holds their 2^pre_bits + 1 offsets.
+	// exchange); dev_range then holds their 2^pre_bits + 1 cumulative sizes and seg the nseg ranges each consists of.
 	const uint32_t *ink = rel->keys, *inv = rel->vals;
 	const uint32_t *parent = dev_range;
 	uint32_t np = 1u << pre_bits;
@@ -532,6 +537,10 @@ static int partition_relation(hjb_ctx *ctx, const hjb_rel *rel, const Plan &p, i
 		a.factor = factor;
 		a.bits = p.bits[i];
 		a.rshift = 32 - used - p.bits[i];
+		if (i == 0 && seg) {
+			a.seg = seg;
+			a.nseg = nseg;
+		}
 		radix_carve(a, scratch, true);
 		*launches += launch_radix_pass(a, ctx->stream, ctx->sms, &ctx->timer);
 		ink = a.keys_out; inv = a.vals_out;
@@ -551,6 +560,8 @@ struct PhjState {
 	Plan plan;
 	uint32_t P, owner, radix_factor;
 	int consumed, pre_bits, big_fill;
+	const uint32_t *seg[2];           // staged exchange: the ranges of the received sub-partitions, R and S
+	uint32_t nseg;
 	uint32_t *rbk[2], *rbv[2], *sbk[2], *sbv[2], *roff[2], *soff[2], *task_prefix, *task_counter;
 	char *scratch;
 	Partitioned pr, ps;
@@ -559,7 +570,7 @@ struct PhjState {
 
 static int phj_setup(hjb_ctx *ctx, uint64_t nr, uint64_t ns_slice, uint64_t ns_total, const hjb_opts *o, int consumed,
                      uint32_t owner, PhjState *st, uint64_t nr_plan = 0, uint64_t ns_plan = 0, const Plan *given = nullptr,
-                     int pre_bits = 0)
+                     int pre_bits = 0, uint32_t pre_segs = 1)
 {
 	// nr / ns_slice / ns_total size the buffers; the plan is made for nr_plan / ns_plan tuples when given (sizes
 	// that are only upper bounds here, the expected sizes there), or is `given` (the staged exchange: pre_bits of
@@ -571,7 +582,7 @@ static int phj_setup(hjb_ctx *ctx, uint64_t nr, uint64_t ns_slice, uint64_t ns_t
 	st->pre_bits = pre_bits;
 	const Plan &plan = st->plan;
 	size_t rscratch;
-	const size_t need = phj_workspace(nr, ns_slice, plan, &rscratch, pre_bits);
+	const size_t need = phj_workspace(nr, ns_slice, plan, &rscratch, pre_bits, pre_segs);
 	if ((rc = grow_device(ctx, &ctx->ws, &ctx->ws_bytes, need))) return rc;
 	if (o->materialize) {
 		const uint64_t cap = o->out_capacity ? o->out_capacity : (ns_total > nr ? ns_total : nr);
@@ -608,10 +619,6 @@ static int phj_partition_side(hjb_ctx *ctx, PhjState *st, const hjb_rel *rel, bo
 	cudaStream_t s = ctx->stream;
 	Partitioned *res = build_side ? &st->pr : &st->ps;
 	uint32_t **off = build_side ? st->roff : st->soff;
-	if (st->plan.npass == 0 && st->pre_bits) {       // the partitions the relation arrived in are the final ones
-		res->k = rel->keys; res->v = rel->vals; res->off = dev_range;
-		return HJB_OK;
-	}
 	if (st->plan.npass == 0) {
 		// by value in the kernel arguments: nothing on the host that a later call (or a graph replay) could find changed
 		k_set_pair<<<1, 1, 0, s>>>(off[0], 0u, (uint32_t)rel->tuples, dev_range);
@@ -619,7 +626,8 @@ static int phj_partition_side(hjb_ctx *ctx, PhjState *st, const hjb_rel *rel, bo
 		return HJB_OK;
 	}
 	return partition_relation(ctx, rel, st->plan, st->consumed, st->radix_factor, build_side ? st->rbk : st->sbk,
-	                          build_side ? st->rbv : st->sbv, off, st->scratch, res, launches, dev_range, st->pre_bits);
+	                          build_side ? st->rbv : st->sbv, off, st->scratch, res, launches, dev_range, st->pre_bits,
+	                          st->seg[build_side ? 0 : 1], st->nseg);
 }
 
 static int phj_launch_join(hjb_ctx *ctx, PhjState *st, const hjb_opts *o, uint32_t *launches)
@@ -1489,7 +1497,7 @@ extern "C" int hjb_cpra_stage_plan(hjb_ctx *ctx, int ngpus, uint64_t r_expect, u
 	if (a < gbits) a = gbits;
 	if (a < 2) a = 2;                              // the copy kernel's piece tables assume at least two sub-... owners x subs >= 4
 	*abits = a;
-	*bbits = total > a ? total - a : 0;
+	*bbits = total > a ? total - a : 1;            // always one local pass: it gathers a sub-partition's per-sender ranges
 	return HJB_OK;
 }
 
@@ -1585,6 +1593,20 @@ extern "C" int hjb_cpra_stage_scatter_async(hjb_ctx *ctx, const uint64_t *matrix
 		                                         ctx->bind_cap[0], ctx->bind_cap[1], ctx->pending[0].child_off, ctx->pending[1].child_off,
 		                                         ctx->stage_base[0], ctx->stage_base[1], ctx->stage_inplace, ctx->stage_dev,
 		                                         ctx->cpra_dev + CD_RANGE_R, s);
+	if (rel == 0) {
+		// HJB_STAGE_COPY=ce: the runs leave through the copy engines (cudaMemcpyAsync, the reference's memcpy gather
+		// cpra2.cpp:1896-1904 literally), which needs their rows on the HOST: one synchronisation per step, here, where the
+		// stream holds nothing but the counting kernels.  Default: k_peer_copy reads them on the device.
+		const int env_ce = getenv("HJB_STAGE_COPY") && !strcmp(getenv("HJB_STAGE_COPY"), "ce");       // read per step
+		ctx->stage_copy_engine = env_ce;
+		if (env_ce) {
+			if (!ctx->h_stage) CK(cudaMallocHost(&ctx->h_stage, 512 * 4));
+			for (int r = 0; r < 2; ++r)
+				CK(cudaMemcpyAsync(ctx->h_stage + 192 * r, ctx->stage_dev + (r ? SD_REL_S : SD_REL_R) + SD_OWN_SRC, 192 * 4, cudaMemcpyDeviceToHost, s));
+			CK(cudaMemcpyAsync(ctx->h_stage + 384, ctx->cpra_dev + CD_ABORT, 4, cudaMemcpyDeviceToHost, s));
+			CK(cudaStreamSynchronize(s));
+		}
+	}
 	RadixPassArgs &a = ctx->pending[rel];
 	if (a.n) ctx->step_launches += launch_radix_scatter(a, s, &ctx->timer, nullptr);
 	CK(cudaGetLastError());
@@ -1606,9 +1628,19 @@ extern "C" int hjb_cpra_stage_copy_async(hjb_ctx *ctx, int rel, void *cuda_strea
 		pc.k[g] = (uint32_t *)ctx->bind_peer[rel ? 2 : 0][g];
 		pc.v[g] = (uint32_t *)ctx->bind_peer[rel ? 3 : 1][g];
 	}
-	if (ctx->pending[rel].n)
+	if (ctx->stage_copy_engine) {
+		cudaStream_t cs = cuda_stream ? (cudaStream_t)cuda_stream : ctx->stream;
+		const uint32_t *src = ctx->h_stage + 192 * rel, *len = src + 64, *dst = src + 128;
+		if (!ctx->h_stage[384])
+			for (int i = 1; i <= G; ++i) {
+				const int g = (ctx->bind_gpu + i) % G;           // every sender starts with its right-hand neighbour
+				if ((g == ctx->bind_gpu && ctx->stage_inplace) || !len[g]) continue;
+				CK(cudaMemcpyAsync(pc.k[g] + dst[g], ctx->stage_k[rel] + src[g], (size_t)len[g] * 4, cudaMemcpyDeviceToDevice, cs));
+				CK(cudaMemcpyAsync(pc.v[g] + dst[g], ctx->stage_v[rel] + src[g], (size_t)len[g] * 4, cudaMemcpyDeviceToDevice, cs));
+			}
+	} else if (ctx->pending[rel].n)
 		ctx->step_launches += launch_peer_copy(ctx->stage_k[rel], ctx->stage_v[rel], pc, ctx->stage_dev + (rel ? SD_REL_S : SD_REL_R),
-		                                       ctx->cpra_dev + CD_ABORT, ctx->stage_abits, log2_exact(G), ctx->bind_gpu, ctx->stage_inplace,
+		                                       ctx->cpra_dev + CD_ABORT, log2_exact(G), ctx->bind_gpu, ctx->stage_inplace,
 		                                       cuda_stream ? (cudaStream_t)cuda_stream : ctx->stream, cuda_stream ? nullptr : &ctx->timer);
 	CK(cudaGetLastError());
 	ctx->stage_state[rel] = 3;
@@ -1622,7 +1654,7 @@ extern "C" int hjb_cpra_stage_local_async(hjb_ctx *ctx, const hjb_opts *opts, in
 	if (!ctx || rel < 0 || rel > 1) return HJB_E_INVALID;
 	if (ctx->step_state != (rel ? 11 : 10) || ctx->stage_state[rel] != 3)
 		return fail(ctx, HJB_E_INVALID, "hjb_cpra_stage_copy_async must precede; R's local pass comes before S's");
-	if (bbits < 0 || bbits > kStageMaxBits) return fail(ctx, HJB_E_INVALID, "the local pass takes at most 9 bits");
+	if (bbits < 1 || bbits > kStageMaxBits) return fail(ctx, HJB_E_INVALID, "the local pass takes between 1 and 9 bits");
 	const hjb_opts *o = opts ? opts : &kDefaultOpts;
 	CK(cudaSetDevice(ctx->device));
 	const int G = ctx->bind_gpus, me = ctx->bind_gpu, gbits = log2_exact(G), pre = ctx->stage_abits - gbits;
@@ -1635,26 +1667,27 @@ extern "C" int hjb_cpra_stage_local_async(hjb_ctx *ctx, const hjb_opts *opts, in
 		if (!oo.out_capacity) oo.out_capacity = sc_cap > rc_cap ? sc_cap : rc_cap;
 		Plan p;
 		memset(&p, 0, sizeof p);
-		if (bbits) {
-			p.npass = 1;
-			p.bits[0] = bbits;
-			p.total_bits = bbits;
-		}
+		p.npass = 1;
+		p.bits[0] = bbits;
+		p.total_bits = bbits;
 		if (32 - ctx->stage_abits - bbits > (big_fill ? 14 : 32)) return fail(ctx, HJB_E_INVALID, "12288-tuple fills need <= 14 hash bits below the partition id");
-		if ((rc = phj_setup(ctx, rc_cap, sc_cap, sc_cap, &oo, gbits, (uint32_t)me, ctx->step_phj, 0, 0, &p, pre))) return rc;
+		if ((rc = phj_setup(ctx, rc_cap, sc_cap, sc_cap, &oo, gbits, (uint32_t)me, ctx->step_phj, 0, 0, &p, pre, (uint32_t)G))) return rc;
 		ctx->step_phj->big_fill = big_fill;
+		ctx->step_phj->seg[0] = ctx->stage_dev + SD_REL_R + SD_SEG;
+		ctx->step_phj->seg[1] = ctx->stage_dev + SD_REL_S + SD_SEG;
+		ctx->step_phj->nseg = (uint32_t)G;
 		ctx->step_opts = oo;
 		CK(cudaEventRecord(ctx->ev[0], s));
 		CK(cudaMemsetAsync(ctx->d_scalars, 0, 16 * 8, s));
 		const hjb_rel Rr = {(const uint32_t *)ctx->bind_peer[0][me], (const uint32_t *)ctx->bind_peer[1][me], rc_cap};
-		if ((rc = phj_partition_side(ctx, ctx->step_phj, &Rr, true, &ctx->step_launches, ctx->stage_dev + SD_POFF_R))) return rc;
+		if ((rc = phj_partition_side(ctx, ctx->step_phj, &Rr, true, &ctx->step_launches, ctx->stage_dev + SD_REL_R + SD_POFF))) return rc;
 		CK(cudaGetLastError());
 		ctx->step_state = 11;
 		return HJB_OK;
 	}
 	PhjState &st = *ctx->step_phj;
 	const hjb_rel Sr = {(const uint32_t *)ctx->bind_peer[2][me], (const uint32_t *)ctx->bind_peer[3][me], sc_cap};
-	if ((rc = phj_partition_side(ctx, &st, &Sr, false, &ctx->step_launches, ctx->stage_dev + SD_POFF_S))) return rc;
+	if ((rc = phj_partition_side(ctx, &st, &Sr, false, &ctx->step_launches, ctx->stage_dev + SD_REL_S + SD_POFF))) return rc;
 	CK(cudaEventRecord(ctx->ev[2], s));
 	if ((rc = phj_launch_join(ctx, &st, &ctx->step_opts, &ctx->step_launches))) return rc;
 	CK(cudaEventRecord(ctx->ev[3], s));

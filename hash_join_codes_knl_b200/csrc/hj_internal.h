@@ -69,6 +69,8 @@ struct RadixPassArgs {
 	uint32_t *scan_counter;           // 1
 	uint16_t *tile_counts;            // max_items * tiles_per_item * 2^bits digit counts per scatter tile; nullptr: none
 	                                  // (fan-out > 512, or the pass feeds the peer scatter, which ranks its tiles itself)
+	const uint32_t *seg;              // device or nullptr: parent q is the union of nseg ranges, (first row, rows) at seg[(q * nseg + s) * 2]
+	uint32_t nseg;                    // (tile-count path only; parent_off then holds the parents' cumulative sizes)
 	const int32_t *shift;             // device, 2^bits entries or nullptr: added to every digit's output positions (staged CPRA
 	                                  // exchange, np == 1: each digit's run starts with the 16-byte phase of its destination row)
 };
@@ -96,11 +98,11 @@ int launch_histogram_only(const uint32_t *keys, uint64_t n, uint32_t *counts_dev
                           int rshift, int bits, cudaStream_t s, int sms);
 
 // ---- staged CPRA exchange (stage.cu)
-// device words written by k_stage_bases (uint32), per relation: tuples of this sender per digit, first row of the digit's run
-// in the staging columns, first row of the run in its owner's columns, and what stage A's scatter adds to the scan's positions
-enum { SD_N = 0, SD_S0 = 512, SD_T0 = 1024, SD_SHIFT = 1536, SD_REL_R = 0, SD_REL_S = 2048,
-       SD_POFF_R = 4096, SD_POFF_S = 4096 + 520,      // offsets of the sub-partitions this GPU receives (parents of the local pass)
-       SD_WORDS = 4096 + 1040 };
+// device words written by k_stage_bases (uint32), per relation: what stage A's scatter adds to the scan's positions per digit;
+// per owner this sender's run: first row in stage A's output columns, rows, first row in the owner's columns; the ranges
+// (first row, rows) every received sub-partition consists of, [sub-partition][sender]; the sub-partitions' cumulative sizes
+enum { SD_SHIFT = 0, SD_OWN_SRC = 512, SD_OWN_LEN = 576, SD_OWN_DST = 640, SD_SEG = 704, SD_POFF = 1728,
+       SD_REL_R = 0, SD_REL_S = 2048, SD_WORDS = 4096 };
 struct PeerCols {
 	uint32_t *k[64];
 	uint32_t *v[64];
@@ -110,7 +112,7 @@ int launch_stage_bases(const unsigned long long *M, int G, int me, int abits, in
                        const uint32_t *child_r, const uint32_t *child_s, uint32_t stage_base_r, uint32_t stage_base_s, int inplace,
                        uint32_t *out, uint32_t *status, cudaStream_t s);
 int launch_peer_copy(const uint32_t *sk, const uint32_t *sv, const PeerCols &peers, const uint32_t *desc, const uint32_t *abort_flag,
-                     int abits, int gbits, int me, int skip_me, cudaStream_t s, KernelTimer *t = nullptr);
+                     int gbits, int me, int skip_me, cudaStream_t s, KernelTimer *t = nullptr);
 
 struct JoinArgs {
 	const uint32_t *rk, *rv, *sk, *sv;       // partitioned columns

@@ -33,23 +33,31 @@ namespace hjb {
 
 __global__ void __launch_bounds__(1024)
 k_make_items(const uint32_t *__restrict__ parent_off, uint32_t np, uint64_t n, uint32_t chunk,
-             uint32_t *__restrict__ item_prefix, uint32_t *__restrict__ child_off, uint32_t child_total_idx)
+             uint32_t *__restrict__ item_prefix, uint32_t *__restrict__ child_off, uint32_t child_total_idx,
+             const uint32_t *__restrict__ seg, uint32_t nseg)
 {
 	__shared__ uint32_t warp_totals[34];
 	const uint32_t per = (np + blockDim.x - 1) / blockDim.x;
 	const uint32_t q0 = threadIdx.x * per;
+	// seg (may be null): parent q is the union of nseg ranges (first row, rows) at seg[(q * nseg + s) * 2] -- what a GPU
+	// received of one sub-partition, one piece per sender (staged CPRA exchange); every range is cut into its own items
+	auto items_of = [&](uint32_t q) -> uint32_t {
+		uint32_t items = 0;
+		if (seg) {
+			for (uint32_t sgm = 0; sgm < nseg; ++sgm) items += (seg[((size_t)q * nseg + sgm) * 2 + 1] + chunk - 1) / chunk;
+		} else {
+			const uint64_t size = parent_off ? (uint64_t)(parent_off[q + 1] - parent_off[q]) : n;
+			items = (uint32_t)((size + chunk - 1) / chunk);
+		}
+		return items ? items : 1u;                     // empty parents keep one (empty) item
+	};
 	uint32_t local = 0;
-	for (uint32_t q = q0; q < q0 + per && q < np; ++q) {
-		const uint64_t size = parent_off ? (uint64_t)(parent_off[q + 1] - parent_off[q]) : n;
-		const uint32_t items = size ? (uint32_t)((size + chunk - 1) / chunk) : 1u;   // empty parents keep one (empty) item
-		local += items;
-	}
+	for (uint32_t q = q0; q < q0 + per && q < np; ++q) local += items_of(q);
 	uint32_t total;
 	uint32_t run = block_exclusive_scan(local, warp_totals, &total);
 	for (uint32_t q = q0; q < q0 + per && q < np; ++q) {
-		const uint64_t size = parent_off ? (uint64_t)(parent_off[q + 1] - parent_off[q]) : n;
 		item_prefix[q] = run;
-		run += size ? (uint32_t)((size + chunk - 1) / chunk) : 1u;
+		run += items_of(q);
 	}
 	if (threadIdx.x == 0) {
 		item_prefix[np] = total;
@@ -62,11 +70,26 @@ struct ItemRange {
 };
 
 __device__ __forceinline__ bool locate_item(const uint32_t *item_prefix, uint32_t np, const uint32_t *parent_off,
-                                            uint64_t n, uint32_t chunk, uint32_t item, ItemRange *r)
+                                            uint64_t n, uint32_t chunk, uint32_t item, ItemRange *r,
+                                            const uint32_t *seg = nullptr, uint32_t nseg = 0)
 {
 	if (item >= item_prefix[np]) return false;
 	const uint32_t q = upper_parent(item_prefix, np, item);
-	const uint32_t j = item - item_prefix[q];
+	uint32_t j = item - item_prefix[q];
+	if (seg) {
+		const uint32_t *sq = seg + (size_t)q * nseg * 2;
+		for (uint32_t sgm = 0; sgm < nseg; ++sgm) {
+			const uint32_t first = sq[2 * sgm], len = sq[2 * sgm + 1], cnt = (len + chunk - 1) / chunk;
+			if (j < cnt) {
+				r->beg = (uint64_t)first + (uint64_t)j * chunk;
+				r->end = min(r->beg + chunk, (uint64_t)first + len);
+				return true;
+			}
+			j -= cnt;
+		}
+		r->beg = r->end = 0;                            // the one empty item of a parent without tuples
+		return true;
+	}
 	const uint64_t pbeg = parent_off ? parent_off[q] : 0, pend = parent_off ? parent_off[q + 1] : n;
 	uint64_t beg = pbeg + (uint64_t)j * chunk;
 	if (beg > pend) beg = pend;
@@ -331,7 +354,8 @@ template <uint32_t TILE>
 __global__ void __launch_bounds__(kHistThreads)
 k_hist_tiles(const uint32_t *__restrict__ keys, uint64_t n, uint32_t np, const uint32_t *__restrict__ parent_off,
              const uint32_t *__restrict__ item_prefix, uint32_t chunk, uint32_t factor, int rshift, int bits,
-             uint32_t *__restrict__ counts, uint16_t *__restrict__ tile_counts, uint32_t tiles_per_item)
+             uint32_t *__restrict__ counts, uint16_t *__restrict__ tile_counts, uint32_t tiles_per_item,
+             const uint32_t *__restrict__ seg, uint32_t nseg)
 {
 	__shared__ uint32_t s_hist[2][kTcMaxFanout];
 	constexpr uint32_t TILE_GROUPS = TILE / 4;
@@ -340,7 +364,7 @@ k_hist_tiles(const uint32_t *__restrict__ keys, uint64_t n, uint32_t np, const u
 	const uint32_t F = 1u << bits, mask = F - 1;
 	const bool aggregate = bits <= 4;
 	ItemRange r;
-	if (!locate_item(item_prefix, np, parent_off, n, chunk, blockIdx.x, &r)) return;
+	if (!locate_item(item_prefix, np, parent_off, n, chunk, blockIdx.x, &r, seg, nseg)) return;
 	if (threadIdx.x < kTcMaxFanout) {
 		s_hist[0][threadIdx.x] = 0;
 		s_hist[1][threadIdx.x] = 0;
@@ -447,7 +471,7 @@ k_scatter_tc(const uint32_t *__restrict__ keys, const uint32_t *__restrict__ val
              const uint32_t *__restrict__ parent_off, const uint32_t *__restrict__ item_prefix, uint32_t chunk,
              uint32_t factor, int rshift, int bits, const uint32_t *__restrict__ offsets,
              const uint16_t *__restrict__ tile_counts, uint32_t tiles_per_item, const int32_t *__restrict__ shift,
-             uint32_t *__restrict__ keys_out, uint32_t *__restrict__ vals_out)
+             const uint32_t *__restrict__ seg, uint32_t nseg, uint32_t *__restrict__ keys_out, uint32_t *__restrict__ vals_out)
 {
 	constexpr int IT = 4 * G;                                   // tuples per thread and tile
 	constexpr uint32_t TILE = THREADS * IT, TILE_GROUPS = TILE / 4;
@@ -462,7 +486,7 @@ k_scatter_tc(const uint32_t *__restrict__ keys, const uint32_t *__restrict__ val
 	const uint32_t F = 1u << bits, mask = F - 1;
 	const bool aggregate = bits <= 4;
 	ItemRange r;
-	if (!locate_item(item_prefix, np, parent_off, n, chunk, blockIdx.x, &r)) return;
+	if (!locate_item(item_prefix, np, parent_off, n, chunk, blockIdx.x, &r, seg, nseg)) return;
 	const uint64_t g_beg = r.beg >> 2, g_end = (r.end + 3) >> 2;
 	const uint32_t ntiles = (uint32_t)((g_end - g_beg + TILE_GROUPS - 1) / TILE_GROUPS);
 	if (ntiles == 0) return;
@@ -938,7 +962,7 @@ size_t radix_scratch_bytes(uint64_t n, uint32_t np, int bits, uint32_t *chunk, u
 void radix_carve(RadixPassArgs &a, char *scratch, bool tile_counts)
 {
 	uint32_t tiles;
-	radix_scratch_bytes(a.n, a.np, a.bits, &a.chunk, &a.max_items, &tiles, &a.tiles_per_item);
+	radix_scratch_bytes(a.n, a.np * (a.nseg ? a.nseg : 1u), a.bits, &a.chunk, &a.max_items, &tiles, &a.tiles_per_item);   // every range of a parent may end in a short item
 	size_t off = 0;
 	auto take = [&](size_t bytes) {
 		char *p = scratch + off;
@@ -984,12 +1008,12 @@ int launch_radix_count(const RadixPassArgs &a, cudaStream_t s, KernelTimer *t)
 	cudaMemsetAsync(a.scan_status, 0, (size_t)tiles * 8, s);
 	cudaMemsetAsync(a.scan_counter, 0, 4, s);
 	t->start(KK_MAKE_ITEMS, s);
-	k_make_items<<<1, 1024, 0, s>>>(a.parent_off, a.np, a.n, a.chunk, a.item_prefix, a.child_off, a.np << a.bits);
+	k_make_items<<<1, 1024, 0, s>>>(a.parent_off, a.np, a.n, a.chunk, a.item_prefix, a.child_off, a.np << a.bits, a.seg, a.nseg);
 	t->stop(s);
 	t->start(KK_HIST, s);
 	if (a.tile_counts)
 		k_hist_tiles<kTcTile><<<a.max_items, kHistThreads, 0, s>>>(a.keys, a.n, a.np, a.parent_off, a.item_prefix, a.chunk, a.factor,
-		                                                           a.rshift, a.bits, a.counts, a.tile_counts, a.tiles_per_item);
+		                                                           a.rshift, a.bits, a.counts, a.tile_counts, a.tiles_per_item, a.seg, a.nseg);
 	else if (a.bits <= 3)
 		k_hist_small<<<a.max_items, kHistThreads, 0, s>>>(a.keys, a.n, a.np, a.parent_off, a.item_prefix, a.chunk,
 		                                                  a.factor, a.rshift, a.bits, a.counts);
@@ -1028,11 +1052,11 @@ int launch_radix_scatter(const RadixPassArgs &a, cudaStream_t s, KernelTimer *t,
 	if (a.tile_counts && F > 256)
 		k_scatter_tc<1024, 4, 1, 512><<<grid, 1024, scatter_tc_smem(kTcTile, 512), s>>>(a.keys, a.vals, a.n, a.np, a.parent_off, a.item_prefix,
 		                                                                                a.chunk, a.factor, a.rshift, a.bits, a.counts, a.tile_counts,
-		                                                                                a.tiles_per_item, a.shift, a.keys_out, a.vals_out);
+		                                                                                a.tiles_per_item, a.shift, a.seg, a.nseg, a.keys_out, a.vals_out);
 	else if (a.tile_counts)
 		k_scatter_tc<1024, 4, 1, 256><<<grid, 1024, scatter_tc_smem(kTcTile, 256), s>>>(a.keys, a.vals, a.n, a.np, a.parent_off, a.item_prefix,
 		                                                                                a.chunk, a.factor, a.rshift, a.bits, a.counts, a.tile_counts,
-		                                                                                a.tiles_per_item, a.shift, a.keys_out, a.vals_out);
+		                                                                                a.tiles_per_item, a.shift, a.seg, a.nseg, a.keys_out, a.vals_out);
 	else
 		k_scatter<1024><<<grid, 1024, (size_t)F * 12 + (size_t)kTile * 8, s>>>(a.keys, a.vals, a.n, a.np, a.parent_off, a.item_prefix,
 		                                                                       a.chunk, a.factor, a.rshift, a.bits, a.counts, a.keys_out,

@@ -5,13 +5,14 @@
 // radix.cu (digit = owner << sub_bits | sub-partition), so that an owner's share is already cut into 2^sub_bits
 // sub-partitions when it leaves.  The exchange is then nothing but copies of whole digit runs:
 //   k_stage_counts : this sender's tuples per digit, R then S -- the all-gather's input
-//   k_stage_bases  : from the all-gathered G x 2 x 2^abits count matrix: for every digit the first row of its run in
-//                    the owner's columns (sub-partition-major, sender-minor -- the reference's interleave order,
-//                    cpra2.cpp:1426-1440), the offsets of the sub-partitions this GPU receives, whether every
-//                    owner's buffer is large enough, and where stage A must START each run in the staging columns
-//                    so that source and destination rows have the same 128-byte phase
+//   k_stage_bases  : from the all-gathered G x 2 x 2^abits count matrix: the first row of this sender's run in every
+//                    owner's columns (an owner receives sender-major: one run per sender, its sub-partitions in order
+//                    inside -- the pieces the reference's gather copies, cpra2.cpp:1896-1904), the ranges every
+//                    sub-partition this GPU receives consists of (one per sender: the parents of the local pass),
+//                    whether every owner's buffer is large enough, and where stage A must START each run in the
+//                    staging columns so that source and destination rows have the same 128-byte phase
 //   k_peer_copy    : a handful of two-warp CTAs drive the TMA unit: cp.async.bulk global -> shared (mbarrier) and
-//                    shared -> the owner's global memory over NVLink, 16 KB per column and piece, six stages.
+//                    shared -> the owner's global memory over NVLink, 16 KB per column and piece, two stages, three CTAs per SM.
 //                    Measured (scripts/r2/peer_copy_bench.cu, 2 GPUs): 16 such CTAs move 705 GB/s, the copy
 //                    engine 776 GB/s -- the SMs beside them stay free for stage A of the other relation and the
 //                    local pass of the relation that has arrived.
@@ -59,85 +60,110 @@ __device__ __forceinline__ unsigned long long block_exclusive_scan_u64(unsigned 
 }
 
 // Source and destination rows of a run agree modulo kCopyPhase rows = 128 bytes: the bulk copies then move whole,
-// identically aligned 128-byte lines on both sides (measured at 2 GPUs: with 16-byte agreement only, a 32 KB piece took
-// 5.4 us to leave shared memory and 23 CTAs moved 540 GB/s).
+// identically aligned 128-byte lines on both sides.
 constexpr uint32_t kCopyPhase = 32;
 
 // M[src][rel][digit] (uint64): the all-gathered counts.  One CTA of 512 threads, one digit per thread, R then S.
+// stage_base_*: first row of the staging region in stage A's output columns.  inplace: those columns ARE this GPU's
+// receive columns (staging region behind the receive region): the run this GPU owns itself is then scattered
+// straight to its final rows and never copied.
 __global__ void __launch_bounds__(512)
 k_stage_bases(const unsigned long long *__restrict__ M, int G, int me, int abits, int gbits, unsigned long long cap_r,
               unsigned long long cap_s, const uint32_t *__restrict__ child_r, const uint32_t *__restrict__ child_s,
               uint32_t stage_base_r, uint32_t stage_base_s, int inplace, uint32_t *__restrict__ out, uint32_t *__restrict__ status)
 {
-	// stage_base_*: first row of the staging region in stage A's output columns.  inplace: those columns ARE this GPU's
-	// receive columns (staging region behind the receive region): the runs this GPU owns itself are then scattered
-	// straight to their final rows and never copied.
 	__shared__ unsigned long long warp_tot[16];
-	__shared__ unsigned long long s_e[513];
+	__shared__ unsigned long long s_tot[2][64], s_bef[2][64], s_len[2][64];     // per owner: rows it receives, rows of the senders before me, my rows
 	__shared__ unsigned long long s_max[2];
+	__shared__ uint32_t s_src[64];
 	__shared__ int s_abort;
 	const uint32_t F = 1u << abits, nsub = F >> gbits, d = threadIdx.x;
+	if (d < 64) {
+		for (int rel = 0; rel < 2; ++rel) s_tot[rel][d] = s_bef[rel][d] = s_len[rel][d] = 0;
+	}
 	if (d == 0) {
 		s_abort = 0;
 		s_max[0] = s_max[1] = 0;
 	}
-	unsigned long long t0v[2] = {0, 0}, mine[2] = {0, 0};
+	__syncthreads();
 	for (int rel = 0; rel < 2; ++rel) {
-		unsigned long long col = 0, before = 0;
-		if (d < F)
+		unsigned long long col = 0, before = 0, mine = 0;
+		if (d < F) {
 			for (int src = 0; src < G; ++src) {
 				const unsigned long long c = M[((size_t)src * 2 + rel) * F + d];
 				col += c;
 				if (src < me) before += c;
-				if (src == me) mine[rel] = c;
+				if (src == me) mine = c;
 			}
-		unsigned long long total;
-		const unsigned long long e = block_exclusive_scan_u64(col, warp_tot, &total);
-		if (d < F) s_e[d] = e;
-		if (d == 0) s_e[F] = total;
-		__syncthreads();
-		if (d < F) {
 			const uint32_t o = d / nsub;
-			t0v[rel] = e - s_e[o * nsub] + before;
-			if (d % nsub == 0) {
-				const unsigned long long tot_o = s_e[(o + 1) * nsub] - s_e[o * nsub];
-				atomicMax(&s_max[rel], tot_o);
-				if (tot_o > (rel ? cap_s : cap_r)) s_abort = 1;
-			}
+			atomicAdd(&s_tot[rel][o], col);
+			atomicAdd(&s_bef[rel][o], before);
+			atomicAdd(&s_len[rel][o], mine);
 		}
-		__syncthreads();
-		// this GPU's sub-partition offsets (parents of the local pass); filled below once the verdict is known
-		if (d <= nsub) {
-			const unsigned long long p = s_e[(size_t)me * nsub + d] - s_e[(size_t)me * nsub];
-			out[(rel ? SD_POFF_S : SD_POFF_R) + d] = (uint32_t)p;       // provisional: zeroed below on abort
-		}
-		__syncthreads();
+		// the cumulative sizes of the sub-partitions this GPU receives (the parents of the local pass)
+		const bool my_sub = d < F && d / nsub == (uint32_t)me;
+		unsigned long long total;
+		const unsigned long long e = block_exclusive_scan_u64(my_sub ? col : 0ull, warp_tot, &total);
+		uint32_t *poff = out + (rel ? SD_REL_S : SD_REL_R) + SD_POFF;
+		if (my_sub) poff[d - me * nsub] = (uint32_t)e;
+		if (d == 0) poff[nsub] = (uint32_t)total;
 	}
+	__syncthreads();
+	if (d < (uint32_t)G)
+		for (int rel = 0; rel < 2; ++rel) {
+			atomicMax(&s_max[rel], s_tot[rel][d]);
+			if (s_tot[rel][d] > (rel ? cap_s : cap_r)) s_abort = 1;
+		}
+	__syncthreads();
 	const int abort = s_abort;
 	for (int rel = 0; rel < 2; ++rel) {
-		// the run of digit d starts in the staging columns at a row with the 16-byte phase of its destination row
-		const uint32_t a = (uint32_t)(t0v[rel] & (kCopyPhase - 1));
-		const bool home = inplace && !abort && d < F && d / nsub == (uint32_t)me;
-		const unsigned long long w = (d < F && mine[rel] && !home) ? ((a + mine[rel] + kCopyPhase - 1) & ~(unsigned long long)(kCopyPhase - 1)) : 0ull;
-		unsigned long long total;
-		const unsigned long long before = block_exclusive_scan_u64(w, warp_tot, &total);
-		const uint32_t *child = rel ? child_s : child_r;
 		uint32_t *o = out + (rel ? SD_REL_S : SD_REL_R);
-		if (d < F) {
-			const uint32_t s0 = home ? (uint32_t)t0v[rel] : (rel ? stage_base_s : stage_base_r) + (uint32_t)before + a;
-			o[SD_N + d] = (uint32_t)mine[rel];
-			o[SD_S0 + d] = s0;
-			o[SD_T0 + d] = (uint32_t)t0v[rel];
-			o[SD_SHIFT + d] = s0 - child[d];
+		// what this GPU receives: sender-major, and inside a sender's block its sub-partitions in order.  Range (q, src) of
+		// parent q: one exclusive scan over the sub-partitions per sender.
+		unsigned long long sender_base = 0;
+		const bool my_sub = d < F && d / nsub == (uint32_t)me;
+		for (int src = 0; src < G; ++src) {
+			const unsigned long long v = my_sub ? M[((size_t)src * 2 + rel) * F + d] : 0ull;
+			unsigned long long total;
+			const unsigned long long pre = block_exclusive_scan_u64(v, warp_tot, &total);
+			if (my_sub) {
+				const uint32_t q = d - me * nsub;
+				o[SD_SEG + ((size_t)q * G + src) * 2] = (uint32_t)(sender_base + pre);
+				o[SD_SEG + ((size_t)q * G + src) * 2 + 1] = abort ? 0u : (uint32_t)v;
+			}
+			sender_base += total;
 		}
-		if (abort && d <= nsub) out[(rel ? SD_POFF_S : SD_POFF_R) + d] = 0;
+		if (abort && d <= nsub) o[SD_POFF + d] = 0;
+		// my run for every owner: where stage A puts it (own run: its final rows; the others: the staging region, each
+		// starting with the 128-byte phase of its destination), its length, its first row in the owner's columns
+		if (d == 0) {
+			uint32_t next = rel ? stage_base_s : stage_base_r;
+			for (int g = 0; g < G; ++g) {
+				const uint32_t dst = (uint32_t)s_bef[rel][g], len = (uint32_t)s_len[rel][g];
+				const bool home = inplace && !abort && g == me;
+				uint32_t src;
+				if (home) src = dst;
+				else {
+					src = next + (dst & (kCopyPhase - 1));
+					next = (src + len + kCopyPhase - 1) & ~(kCopyPhase - 1);
+				}
+				s_src[g] = src;
+				o[SD_OWN_SRC + g] = src;
+				o[SD_OWN_LEN + g] = len;
+				o[SD_OWN_DST + g] = dst;
+			}
+		}
+		__syncthreads();
+		const uint32_t *child = rel ? child_s : child_r;
+		if (d < F) o[SD_SHIFT + d] = s_src[d / nsub] - child[(d / nsub) * nsub];     // a run keeps the scan's order of its sub-partitions
+		__syncthreads();
 	}
 	// what hjb_cpra_finish reports: rows received here, the verdict, the fullest owner's rows
 	if (d == 0) {
 		status[0] = 0;
-		status[1] = abort ? 0u : out[SD_POFF_R + nsub];
+		status[1] = abort ? 0u : (uint32_t)s_tot[0][me];
 		status[2] = 0;
-		status[3] = abort ? 0u : out[SD_POFF_S + nsub];
+		status[3] = abort ? 0u : (uint32_t)s_tot[1][me];
 		status[4] = abort ? 1u : 0u;
 		status[5] = (uint32_t)(s_max[0] > 0xFFFFFFFFull ? 0xFFFFFFFFull : s_max[0]);
 		status[6] = (uint32_t)(s_max[1] > 0xFFFFFFFFull ? 0xFFFFFFFFull : s_max[1]);
@@ -148,11 +174,13 @@ k_stage_bases(const unsigned long long *__restrict__ M, int G, int me, int abits
 
 #ifndef HJB_COPY_CHUNK
 #define HJB_COPY_CHUNK 4096
-#define HJB_COPY_STAGES 6
-#define HJB_COPY_DRAIN 2
+#define HJB_COPY_STAGES 2
+#define HJB_COPY_DRAIN 1
 #endif
 constexpr uint32_t kCopyChunk = HJB_COPY_CHUNK;     // tuples per piece and column: 16 KB
-constexpr int kCopyStages = HJB_COPY_STAGES;        // stages of 2 x 16 KB
+constexpr int kCopyStages = HJB_COPY_STAGES;        // stages of 2 x 16 KB: 64 KB + 10 KB of tables per CTA, so three CTAs share an SM.  Measured at 2
+                                                    // GPUs (bench.py --exchange staged-serial): one CTA with six stages per SM moves 23.5 GB/s,
+                                                    // two with three stages 38, three with two stages 48 -- a pipeline is a chain of waits
 constexpr int kCopyDrain = HJB_COPY_DRAIN;          // stores that may still be reading shared memory when a stage is handed back
 constexpr size_t kCopySmem = (size_t)kCopyStages * 2 * kCopyChunk * 4;
 constexpr uint32_t kCopyEnd = 0xFFFFFFFFu;
@@ -175,17 +203,18 @@ struct CopyPiece {
 // once its store has read shared memory.  Neither waits for the other's bookkeeping.
 __global__ void __launch_bounds__(64)
 k_peer_copy(const uint32_t *__restrict__ sk, const uint32_t *__restrict__ sv, const PeerCols peers,
-            const uint32_t *__restrict__ desc, const uint32_t *__restrict__ abort_flag, int abits, int gbits, int me, int skip_me)
+            const uint32_t *__restrict__ desc, const uint32_t *__restrict__ abort_flag, int gbits, int me, int skip_me)
 {
+	const int abits = gbits;                         // one run per owner (an owner's sub-partitions leave as one piece of the staging columns)
 	extern __shared__ __align__(128) unsigned char s_stage[];
 	__shared__ uint64_t full[kCopyStages], empty[kCopyStages];
-	__shared__ uint32_t s_n[512], s_s0[512], s_t0[512], s_end[512], s_total[64], s_cur[64];
+	__shared__ uint32_t s_n[64], s_s0[64], s_t0[64], s_end[64], s_total[64], s_cur[64];
 	__shared__ uint32_t *s_pk[64], *s_pv[64];
 	__shared__ CopyPiece ring[kCopyStages];
 	__shared__ uint32_t s_maxp;
 	if (*abort_flag) return;
 	const uint32_t F = 1u << abits, nsub = F >> gbits, G = 1u << gbits, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-	const uint32_t *dn = desc + SD_N, *ds0 = desc + SD_S0, *dt0 = desc + SD_T0;
+	const uint32_t *dn = desc + SD_OWN_LEN, *ds0 = desc + SD_OWN_SRC, *dt0 = desc + SD_OWN_DST;
 	for (uint32_t d = threadIdx.x; d < F; d += 64) {
 		s_n[d] = dn[d];
 		s_s0[d] = ds0[d];
@@ -319,15 +348,15 @@ int launch_stage_bases(const unsigned long long *M, int G, int me, int abits, in
 }
 
 int launch_peer_copy(const uint32_t *sk, const uint32_t *sv, const PeerCols &peers, const uint32_t *desc, const uint32_t *abort_flag,
-                     int abits, int gbits, int me, int skip_me, cudaStream_t s, KernelTimer *t)
+                     int gbits, int me, int skip_me, cudaStream_t s, KernelTimer *t)
 {
 	KernelTimer off;
 	off.enabled = false;
 	off.n = 0;
 	if (!t) t = &off;
 	static const int ctas = [] {
-		const int v = getenv("HJB_COPY_CTAS") ? atoi(getenv("HJB_COPY_CTAS")) : 30;
-		return v < 1 ? 30 : v;
+		const int v = getenv("HJB_COPY_CTAS") ? atoi(getenv("HJB_COPY_CTAS")) : 48;      // three per SM: 16 SMs
+		return v < 1 ? 48 : v;
 	}();
 	static std::atomic<unsigned long long> done_mask{0};         // the attribute is per device
 	int dev = 0;
@@ -335,7 +364,7 @@ int launch_peer_copy(const uint32_t *sk, const uint32_t *sv, const PeerCols &pee
 	const unsigned long long bit = 1ull << (dev & 63);
 	if (!(done_mask.fetch_or(bit) & bit)) cudaFuncSetAttribute(k_peer_copy, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCopySmem);
 	t->start(KK_PEER_COPY, s);
-	k_peer_copy<<<ctas, 64, kCopySmem, s>>>(sk, sv, peers, desc, abort_flag, abits, gbits, me, skip_me);
+	k_peer_copy<<<ctas, 64, kCopySmem, s>>>(sk, sv, peers, desc, abort_flag, gbits, me, skip_me);
 	t->stop(s);
 	return 1;
 }

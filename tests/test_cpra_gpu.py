@@ -281,10 +281,13 @@ def run_staged_path(engines, G, rk, rv, sk, sv, r_cap, s_cap, plan=None, own_all
     return tuple(total), rows, recv, matrix.view(G, 2, 1 << abits).cpu().numpy()
 
 
+@pytest.mark.parametrize("copy", ["tma", "ce"])
 @pytest.mark.parametrize("own_alloc", [False, True])
 @pytest.mark.parametrize("G_", [2, 4, 8])
 @pytest.mark.parametrize("name,nr,ns,seed", CASES)
-def test_staged_exchange_with_virtual_owners_matches_oracle(engines, G_, name, nr, ns, seed, own_alloc):
+def test_staged_exchange_with_virtual_owners_matches_oracle(engines, G_, name, nr, ns, seed, own_alloc, copy, monkeypatch):
+    """copy: the runs leave through k_peer_copy (TMA bulk copies) or through the copy engines (HJB_STAGE_COPY=ce)"""
+    monkeypatch.setenv("HJB_STAGE_COPY", copy)
     rk, rv, sk, sv = skewed(nr, ns, seed) if name == "skewed" else oracle_generate(nr, ns, threads=2, seed=seed)[:4]
     want = oracle_join("cpra", rk, rv, sk, sv, threads=4)
     got, rows, recv, matrix = run_staged_path(engines, G_, rk, rv, sk, sv, nr + 1024, ns + 1024, own_alloc=own_alloc)
@@ -295,10 +298,10 @@ def test_staged_exchange_with_virtual_owners_matches_oracle(engines, G_, name, n
     assert [r[1] for r in recv] == [int(x) for x in per_owner[1]]
 
 
-@pytest.mark.parametrize("G_,plan", [(2, (9, 9, 1)), (8, (9, 9, 1)), (4, (9, 0, 0)), (2, (2, 0, 0)), (4, (2, 9, 0)), (8, (3, 5, 0)),
+@pytest.mark.parametrize("G_,plan", [(2, (9, 9, 1)), (8, (9, 9, 1)), (4, (9, 1, 0)), (2, (2, 1, 0)), (4, (2, 9, 0)), (8, (3, 5, 0)),
                                      (2, (8, 8, 0)), (4, (5, 7, 0))])
 def test_staged_exchange_under_explicit_plans(engines, G_, plan):
-    """512-way stage A, 12288-tuple join fills, no local pass at all, stage A with the owner bits only"""
+    """512-way stage A, 12288-tuple join fills, a one-bit local pass, stage A with the owner bits only"""
     rk, rv, sk, sv = skewed(150000, 500000, 31)
     want = oracle_join("cpra", rk, rv, sk, sv, threads=4)
     got, rows, _, _ = run_staged_path(engines, G_, rk, rv, sk, sv, rk.size, sk.size, plan=plan, own_alloc=G_ != 4)
