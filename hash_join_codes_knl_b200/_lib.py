@@ -78,10 +78,10 @@ SYMBOLS = {
     "hjb_cpra_finish": (C.c_int, [C.c_void_p, C.POINTER(Result), u64p, u64p]),
     "hjb_cpra_stage_plan": (C.c_int, [C.c_void_p, C.c_int, C.c_uint64, C.c_uint64, C.POINTER(Opts), C.POINTER(C.c_int),
                                       C.POINTER(C.c_int), C.POINTER(C.c_int)]),
-    "hjb_cpra_stage_count_async": (C.c_int, [C.c_void_p, C.POINTER(Rel), C.POINTER(Rel), C.POINTER(Opts), C.c_int, C.c_void_p]),
+    "hjb_cpra_stage_count_async": (C.c_int, [C.c_void_p, C.POINTER(Rel), C.POINTER(Rel), C.POINTER(Opts), C.c_int, C.c_int, C.c_void_p]),
     "hjb_cpra_stage_scatter_async": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
-    "hjb_cpra_stage_copy_async": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
-    "hjb_cpra_stage_local_async": (C.c_int, [C.c_void_p, C.POINTER(Opts), C.c_int, C.c_int, C.c_int]),
+    "hjb_cpra_stage_copy_async": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    "hjb_cpra_stage_local_async": (C.c_int, [C.c_void_p, C.POINTER(Opts), C.c_int, C.c_int, C.c_int, C.c_int]),
     "hjb_cpra_split_hot": (C.c_int, [C.c_void_p, C.POINTER(Rel), C.c_void_p, C.c_uint32, C.POINTER(Rel), C.POINTER(Rel)]),
     "hjb_cpra_select_hot": (C.c_int, [C.c_void_p, C.POINTER(Rel), C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint32, u64p]),
     "hjb_cpra_hot_join": (C.c_int, [C.c_void_p, C.POINTER(Rel), C.POINTER(Rel)]),

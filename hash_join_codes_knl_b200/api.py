@@ -324,13 +324,14 @@ class Engine:
                                            C.byref(f))
         return None if rc != 0 else (int(a.value), int(b.value), int(f.value))
 
-    def cpra_stage_count_async(self, inner_chunk, outer_chunk, abits, counts_dev, **opts):
-        """counts_dev: int64 CUDA tensor of 2 * 2^abits elements (the all-gather's input)"""
+    def cpra_stage_count_async(self, inner_chunk, outer_chunk, abits, counts_dev, nparts=1, **opts):
+        """counts_dev: int64 CUDA tensor of 2 * 2^abits elements (the all-gather's input); nparts: the runs leave, and are
+        processed by their owners, in this many parts (ranges of sub-partitions)"""
         R, S, on_dev, keep = self._rels(inner_chunk, outer_chunk)
         if not on_dev:
             raise HjbError("cpra_stage_count_async takes device columns")
         o = self._opts(**opts)
-        self._check(self._lib.hjb_cpra_stage_count_async(self._ctx, C.byref(R), C.byref(S), C.byref(o), int(abits),
+        self._check(self._lib.hjb_cpra_stage_count_async(self._ctx, C.byref(R), C.byref(S), C.byref(o), int(abits), int(nparts),
                                                          C.c_void_p(counts_dev.data_ptr())), "hjb_cpra_stage_count_async")
         self._pending_keep = keep
         self._step_from_host = False
@@ -339,14 +340,14 @@ class Engine:
         self._check(self._lib.hjb_cpra_stage_scatter_async(self._ctx, C.c_void_p(matrix_dev.data_ptr()), int(rel)),
                     "hjb_cpra_stage_scatter_async")
 
-    def cpra_stage_copy_async(self, rel, cuda_stream=None):
+    def cpra_stage_copy_async(self, rel, cuda_stream=None, part=0):
         """cuda_stream: raw cudaStream_t of a side stream that already waits for the scatter (None: the engine's stream)"""
-        self._check(self._lib.hjb_cpra_stage_copy_async(self._ctx, int(rel), C.c_void_p(int(cuda_stream) if cuda_stream else None)),
+        self._check(self._lib.hjb_cpra_stage_copy_async(self._ctx, int(rel), int(part), C.c_void_p(int(cuda_stream) if cuda_stream else None)),
                     "hjb_cpra_stage_copy_async")
 
-    def cpra_stage_local_async(self, bbits, big_fill, rel, **opts):
+    def cpra_stage_local_async(self, bbits, big_fill, rel, part=0, **opts):
         o = self._opts(**opts)
-        self._check(self._lib.hjb_cpra_stage_local_async(self._ctx, C.byref(o), int(bbits), int(big_fill), int(rel)),
+        self._check(self._lib.hjb_cpra_stage_local_async(self._ctx, C.byref(o), int(bbits), int(big_fill), int(rel), int(part)),
                     "hjb_cpra_stage_local_async")
 
     # ---- heavy-hitter handling (include/hjb200.h: hjb_cpra_split_hot / _select_hot / _hot_join)

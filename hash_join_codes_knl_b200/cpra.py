@@ -252,13 +252,14 @@ def cpra_join_fused(engine, inner_chunk, outer_chunk, state, group=None, skew=Fa
             "hot_outer_tuples": int(hot_parts[1][0].numel()) if hot_parts is not None else 0}
 
 
-def cpra_join_staged(engine, inner_chunk, outer_chunk, state, group=None, overlap=True, **opts):
+def cpra_join_staged(engine, inner_chunk, outer_chunk, state, group=None, overlap=True, parts=None, **opts):
     """CPRA with the STAGED exchange (csrc/stage.cu; the reference's own order -- chunk-local passes, then the gather of
     whole partition pieces, cpra2.cpp:1783-1827,1861-1905): stage A partitions the chunk locally by owner and
-    sub-partition, TMA copies on a high-priority side stream push the runs into the owners' columns while the SMs
-    work on the other relation, one local pass and the join follow.  Two radix passes over the data where the fused
-    path needs three.  The plan (how the radix bits are split) is made once per `state` from the first step's sizes;
-    inputs that need more than two 9-bit passes take cpra_join_fused.  Same result dict as cpra_join_fused.
+    sub-partition; the runs then leave in `parts` pieces (ranges of sub-partitions, R's piece before S's) as copies on a
+    high-priority side stream, and while piece k + 1 crosses NVLink the owners already run the local pass over piece
+    k and join its partitions.  Two radix passes over the data where the fused path needs three.  The plan (how the
+    radix bits are split, how many parts) is made once per `state` from the first step's sizes; inputs that need more
+    than two 9-bit passes take cpra_join_fused.  Same result dict as cpra_join_fused.
 
     overlap=False runs the copies on the main stream (no side stream): for A/B runs."""
     world = state.world
@@ -275,17 +276,31 @@ def cpra_join_staged(engine, inner_chunk, outer_chunk, state, group=None, overla
             f = 1 << plan[0]
             state.stage_counts = torch.zeros(2 * f, dtype=torch.int64, device=dev)
             state.stage_matrix = torch.zeros(2 * f * world, dtype=torch.int64, device=dev)
+            # pieces worth pipelining: a few hundred microseconds of copying each
+            import os
+            auto = int(os.environ.get("HJB_STAGE_PARTS", "0")) or (4 if (tr + ts) // world >= (1 << 26) else 1)
+            state.stage_parts = max(1, min(parts or auto, f // world, 8))
+            state.stage_tokens = torch.zeros(2 * state.stage_parts, dtype=torch.int32, device=dev)
         if state.own is None:
             state.ensure(tr // world + tr // (4 * world) + 1024, ts // world + ts // (4 * world) + 1024)
     if state.stage_plan == "fused":
         return cpra_join_fused(engine, inner_chunk, outer_chunk, state, group, **opts)
     abits, bbits, big_fill = state.stage_plan
+    K = state.stage_parts
     main = torch.cuda.current_stream(dev)
     side = state.side if overlap else main
+    # the order the pieces leave in: R's piece one ahead of S's, so that S's stage A has finished when its first piece is due
+    order = [(0, 0)]
+    for k in range(K):
+        if k + 1 < K:
+            order.append((0, k + 1))
+        order.append((1, k))
     while True:
-        ev = [torch.cuda.Event(enable_timing=True) for _ in range(6)]
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+        arrived = {piece: torch.cuda.Event(enable_timing=True) for piece in order}
+        through = {}
         ev[0].record()
-        engine.cpra_stage_count_async(inner_chunk, outer_chunk, abits, state.stage_counts, **opts)
+        engine.cpra_stage_count_async(inner_chunk, outer_chunk, abits, state.stage_counts, nparts=K, **opts)
         dist.all_gather_into_tensor(state.stage_matrix, state.stage_counts, group=group)
         engine.cpra_stage_scatter_async(state.stage_matrix, 0)
         ev[1].record()                                       # R is staged
@@ -293,20 +308,24 @@ def cpra_join_staged(engine, inner_chunk, outer_chunk, state, group=None, overla
         ev[2].record()                                       # S is staged
         with torch.cuda.stream(side):
             side.wait_event(ev[1])
-            engine.cpra_stage_copy_async(0, side.cuda_stream)
-            dist.all_reduce(state.token, group=group)        # completes once every rank's copies of R are through
-            ev[3].record()
-            side.wait_event(ev[2])
-            engine.cpra_stage_copy_async(1, side.cuda_stream)
-            dist.all_reduce(state.token2, group=group)
-            ev[4].record()
-        main.wait_event(ev[3])
-        engine.cpra_stage_local_async(bbits, big_fill, 0, **opts)
-        main.wait_event(ev[4])
-        engine.cpra_stage_local_async(bbits, big_fill, 1, **opts)
+            s_waited = False
+            for i, (rel, k) in enumerate(order):
+                if rel == 1 and not s_waited:
+                    side.wait_event(ev[2])
+                    s_waited = True
+                engine.cpra_stage_copy_async(rel, side.cuda_stream, part=k)
+                arrived[(rel, k)].record()                   # this rank's copies of the piece are through
+                # completes once EVERY rank's copies of the piece are through; asynchronous: the side stream goes straight on to
+                # the next piece, only the main stream will wait for it
+                through[(rel, k)] = dist.all_reduce(state.stage_tokens[i:i + 1], group=group, async_op=True)
+        for k in range(K):
+            through[(0, k)].wait()                           # orders the main stream behind the collective, not the host
+            engine.cpra_stage_local_async(bbits, big_fill, 0, part=k, **opts)
+            through[(1, k)].wait()
+            engine.cpra_stage_local_async(bbits, big_fill, 1, part=k, **opts)
         state.sums.copy_(engine.cpra_sums_dev())
         dist.all_reduce(state.sums, group=group)
-        ev[5].record()
+        ev[3].record()
         try:
             local, received, largest = engine.cpra_finish()
         except HjbCapacityError as e:
@@ -315,9 +334,10 @@ def cpra_join_staged(engine, inner_chunk, outer_chunk, state, group=None, overla
         break
     state.expect = received
     count, sum_key, sum_outer, sum_inner = (int(x) & ((1 << 64) - 1) for x in state.sums.tolist())
+    last = arrived[order[-1]]
     return {"count": count, "sum_key": sum_key, "sum_outer": sum_outer, "sum_inner": sum_inner, "local": local,
-            "split_ms": ev[0].elapsed_time(ev[2]), "exchange_ms": ev[1].elapsed_time(ev[4]),
-            "join_ms": float(local.seconds) * 1e3, "step_ms": ev[0].elapsed_time(ev[5]),
+            "split_ms": ev[0].elapsed_time(ev[2]), "exchange_ms": ev[1].elapsed_time(last),
+            "join_ms": float(local.seconds) * 1e3, "step_ms": ev[0].elapsed_time(ev[3]),
+            "copy_r_done_ms": ev[0].elapsed_time(arrived[(0, K - 1)]), "copy_s_done_ms": ev[0].elapsed_time(last),
             "recv_tuples": received, "largest_recv": largest, "hot_keys": 0, "hot_outer_tuples": 0,
-            "stage_plan": {"stage_a_bits": abits, "local_bits": bbits, "big_fill": big_fill},
-            "copy_r_done_ms": ev[0].elapsed_time(ev[3]), "copy_s_done_ms": ev[0].elapsed_time(ev[4])}
+            "stage_plan": {"stage_a_bits": abits, "local_bits": bbits, "big_fill": big_fill, "parts": K}}

@@ -80,7 +80,9 @@ struct hjb_ctx {
 	// staged exchange (hjb_cpra_stage_*): stage A's output columns live in split_buf
 	uint32_t *stage_dev;      // device words of k_stage_bases (enum SD_*)
 	uint32_t *stage_k[2], *stage_v[2];
-	int stage_abits, stage_state[2];   // per relation: 0 idle, 1 counted, 2 scattered, 3 copied
+	int stage_abits, stage_state[2];   // per relation: 0 idle, 1 counted, 2 scattered
+	int stage_parts;          // the runs leave, and are processed by their owners, in this many parts (ranges of sub-partitions)
+	uint32_t stage_copied[2], stage_done[2];   // bit k: part k of the relation has been copied / passed (and, for S, joined)
 	uint64_t recv_stage_off[2], recv_stage_cap[2];   // the staging region behind the receive region of recv_buf's columns (rows)
 	uint32_t *h_stage;        // pinned: the per-owner runs of both relations + the verdict, for the copy-engine form of the exchange
 	int stage_copy_engine;    // this step's copies are cudaMemcpyAsync calls (HJB_STAGE_COPY=ce) instead of k_peer_copy
@@ -484,7 +486,8 @@ static int make_plan(hjb_ctx *ctx, uint64_t nr, uint64_t ns, const hjb_opts *o, 
 	return HJB_OK;
 }
 
-static size_t phj_workspace(uint64_t nr, uint64_t ns, const Plan &p, size_t *radix_scratch, int pre_bits = 0, uint32_t pre_segs = 1)
+static size_t phj_workspace(uint64_t nr, uint64_t ns, const Plan &p, size_t *radix_scratch, int pre_bits = 0, uint32_t pre_segs = 1,
+                            uint32_t chunk_div = 1)
 {
 	size_t total = 0;
 	const int nb = p.npass >= 2 ? 2 : p.npass;
@@ -497,8 +500,8 @@ static size_t phj_workspace(uint64_t nr, uint64_t ns, const Plan &p, size_t *rad
 	for (int i = 0; i < p.npass; ++i) {
 		uint32_t chunk, mi, tiles;
 		const uint32_t np_eff = i == 0 ? np * pre_segs : np;          // every range of a pre-partitioned parent may end in a short item
-		size_t a = radix_scratch_bytes(nr, np_eff, p.bits[i], &chunk, &mi, &tiles);
-		size_t b = radix_scratch_bytes(ns, np_eff, p.bits[i], &chunk, &mi, &tiles);
+		size_t a = radix_scratch_bytes(nr, np_eff, p.bits[i], &chunk, &mi, &tiles, nullptr, i == 0 ? chunk_div : 1u);
+		size_t b = radix_scratch_bytes(ns, np_eff, p.bits[i], &chunk, &mi, &tiles, nullptr, i == 0 ? chunk_div : 1u);
 		if (a > rs) rs = a;
 		if (b > rs) rs = b;
 		np <<= p.bits[i];
@@ -570,7 +573,7 @@ struct PhjState {
 
 static int phj_setup(hjb_ctx *ctx, uint64_t nr, uint64_t ns_slice, uint64_t ns_total, const hjb_opts *o, int consumed,
                      uint32_t owner, PhjState *st, uint64_t nr_plan = 0, uint64_t ns_plan = 0, const Plan *given = nullptr,
-                     int pre_bits = 0, uint32_t pre_segs = 1)
+                     int pre_bits = 0, uint32_t pre_segs = 1, uint32_t chunk_div = 1)
 {
 	// nr / ns_slice / ns_total size the buffers; the plan is made for nr_plan / ns_plan tuples when given (sizes
 	// that are only upper bounds here, the expected sizes there), or is `given` (the staged exchange: pre_bits of
@@ -582,7 +585,7 @@ static int phj_setup(hjb_ctx *ctx, uint64_t nr, uint64_t ns_slice, uint64_t ns_t
 	st->pre_bits = pre_bits;
 	const Plan &plan = st->plan;
 	size_t rscratch;
-	const size_t need = phj_workspace(nr, ns_slice, plan, &rscratch, pre_bits, pre_segs);
+	const size_t need = phj_workspace(nr, ns_slice, plan, &rscratch, pre_bits, pre_segs, chunk_div);
 	if ((rc = grow_device(ctx, &ctx->ws, &ctx->ws_bytes, need))) return rc;
 	if (o->materialize) {
 		const uint64_t cap = o->out_capacity ? o->out_capacity : (ns_total > nr ? ns_total : nr);
@@ -630,12 +633,14 @@ static int phj_partition_side(hjb_ctx *ctx, PhjState *st, const hjb_rel *rel, bo
 	                          st->seg[build_side ? 0 : 1], st->nseg);
 }
 
-static int phj_launch_join(hjb_ctx *ctx, PhjState *st, const hjb_opts *o, uint32_t *launches)
+static int phj_launch_join(hjb_ctx *ctx, PhjState *st, const hjb_opts *o, uint32_t *launches, uint32_t p0 = 0, uint32_t p1 = 0)
 {
+	// [p0, p1): the partitions to join (default: all)
+	if (p1 == 0) p1 = st->P;
 	JoinArgs &j = st->j;
 	j.rk = st->pr.k; j.rv = st->pr.v; j.sk = st->ps.k; j.sv = st->ps.v;
-	j.r_off = st->pr.off; j.s_off = st->ps.off;
-	j.P = st->P;
+	j.r_off = st->pr.off + p0; j.s_off = st->ps.off + p0;
+	j.P = p1 - p0;
 	j.radix_factor = st->radix_factor;
 	j.rem_bits = 32 - st->consumed - st->pre_bits - st->plan.total_bits;
 	j.big_fill = st->big_fill;
@@ -1511,13 +1516,15 @@ static int stage_dev_alloc(hjb_ctx *ctx)
 
 // stage A's histogram + scan of both chunks; counts_dev[rel * 2^abits + digit] = this sender's tuples (uint64)
 extern "C" int hjb_cpra_stage_count_async(hjb_ctx *ctx, const hjb_rel *R, const hjb_rel *S, const hjb_opts *opts, int abits,
-                                          uint64_t *counts_dev)
+                                          int nparts, uint64_t *counts_dev)
 {
 	if (!ctx || !counts_dev) return HJB_E_INVALID;
 	if (!ctx->bind_gpus) return fail(ctx, HJB_E_INVALID, "hjb_cpra_bind must precede");
 	const hjb_opts *o = opts ? opts : &kDefaultOpts;
 	const int gbits = log2_exact(ctx->bind_gpus);
 	if (abits < gbits || abits < 2 || abits > kStageMaxBits) return fail(ctx, HJB_E_INVALID, "stage A takes between max(2, owner bits) and 9 bits");
+	if (nparts < 1 || nparts > kStageMaxParts || (nparts & (nparts - 1)) || nparts > (1 << (abits - gbits)))
+		return fail(ctx, HJB_E_INVALID, "parts: a power of two, at most 8 and at most the sub-partitions per owner");
 	int rc;
 	if ((rc = check_rel(ctx, R, true)) || (rc = check_rel(ctx, S, true))) return rc;
 	CK(cudaSetDevice(ctx->device));
@@ -1575,6 +1582,8 @@ extern "C" int hjb_cpra_stage_count_async(hjb_ctx *ctx, const hjb_rel *R, const 
 	                                          (unsigned long long *)counts_dev, s);
 	CK(cudaGetLastError());
 	ctx->stage_abits = abits;
+	ctx->stage_parts = nparts;
+	ctx->stage_copied[0] = ctx->stage_copied[1] = ctx->stage_done[0] = ctx->stage_done[1] = 0;
 	ctx->step_state = 10;
 	return HJB_OK;
 }
@@ -1591,7 +1600,7 @@ extern "C" int hjb_cpra_stage_scatter_async(hjb_ctx *ctx, const uint64_t *matrix
 	if (rel == 0)
 		ctx->step_launches += launch_stage_bases((const unsigned long long *)matrix_dev, G, ctx->bind_gpu, ctx->stage_abits, log2_exact(G),
 		                                         ctx->bind_cap[0], ctx->bind_cap[1], ctx->pending[0].child_off, ctx->pending[1].child_off,
-		                                         ctx->stage_base[0], ctx->stage_base[1], ctx->stage_inplace, ctx->stage_dev,
+		                                         ctx->stage_base[0], ctx->stage_base[1], ctx->stage_inplace, ctx->stage_parts, ctx->stage_dev,
 		                                         ctx->cpra_dev + CD_RANGE_R, s);
 	if (rel == 0) {
 		// HJB_STAGE_COPY=ce: the runs leave through the copy engines (cudaMemcpyAsync, the reference's memcpy gather
@@ -1600,10 +1609,10 @@ extern "C" int hjb_cpra_stage_scatter_async(hjb_ctx *ctx, const uint64_t *matrix
 		const int env_ce = getenv("HJB_STAGE_COPY") && !strcmp(getenv("HJB_STAGE_COPY"), "ce");       // read per step
 		ctx->stage_copy_engine = env_ce;
 		if (env_ce) {
-			if (!ctx->h_stage) CK(cudaMallocHost(&ctx->h_stage, 512 * 4));
-			for (int r = 0; r < 2; ++r)
-				CK(cudaMemcpyAsync(ctx->h_stage + 192 * r, ctx->stage_dev + (r ? SD_REL_S : SD_REL_R) + SD_OWN_SRC, 192 * 4, cudaMemcpyDeviceToHost, s));
-			CK(cudaMemcpyAsync(ctx->h_stage + 384, ctx->cpra_dev + CD_ABORT, 4, cudaMemcpyDeviceToHost, s));
+			if (!ctx->h_stage) CK(cudaMallocHost(&ctx->h_stage, (2 * 1536 + 8) * 4));
+			for (int r = 0; r < 2; ++r)           // SD_OWN_SRC, _LEN, _DST: 3 x [8 parts][64 owners]
+				CK(cudaMemcpyAsync(ctx->h_stage + 1536 * r, ctx->stage_dev + (r ? SD_REL_S : SD_REL_R) + SD_OWN_SRC, 1536 * 4, cudaMemcpyDeviceToHost, s));
+			CK(cudaMemcpyAsync(ctx->h_stage + 3072, ctx->cpra_dev + CD_ABORT, 4, cudaMemcpyDeviceToHost, s));
 			CK(cudaStreamSynchronize(s));
 		}
 	}
@@ -1614,12 +1623,13 @@ extern "C" int hjb_cpra_stage_scatter_async(hjb_ctx *ctx, const uint64_t *matrix
 	return HJB_OK;
 }
 
-// the copies of one relation's runs into the owners' columns, on `cuda_stream` (null: the context's stream) -- a side
-// stream that waits for the scatter lets them cross NVLink beside the passes: the copies need 16 SMs, not the GPU
-extern "C" int hjb_cpra_stage_copy_async(hjb_ctx *ctx, int rel, void *cuda_stream)
+// the copies of part `part` of one relation's runs into the owners' columns, on `cuda_stream` (null: the context's stream)
+// -- a side stream that waits for the scatter lets them cross NVLink beside the passes
+extern "C" int hjb_cpra_stage_copy_async(hjb_ctx *ctx, int rel, int part, void *cuda_stream)
 {
 	if (!ctx || rel < 0 || rel > 1) return HJB_E_INVALID;
-	if (ctx->step_state != 10 || ctx->stage_state[rel] != 2) return fail(ctx, HJB_E_INVALID, "hjb_cpra_stage_scatter_async must precede");
+	if (ctx->step_state < 10 || ctx->step_state > 11 || ctx->stage_state[rel] != 2) return fail(ctx, HJB_E_INVALID, "hjb_cpra_stage_scatter_async must precede");
+	if (part < 0 || part >= ctx->stage_parts || (ctx->stage_copied[rel] >> part & 1)) return fail(ctx, HJB_E_INVALID, "no such part, or copied already");
 	CK(cudaSetDevice(ctx->device));
 	const int G = ctx->bind_gpus;
 	PeerCols pc;
@@ -1630,8 +1640,8 @@ extern "C" int hjb_cpra_stage_copy_async(hjb_ctx *ctx, int rel, void *cuda_strea
 	}
 	if (ctx->stage_copy_engine) {
 		cudaStream_t cs = cuda_stream ? (cudaStream_t)cuda_stream : ctx->stream;
-		const uint32_t *src = ctx->h_stage + 192 * rel, *len = src + 64, *dst = src + 128;
-		if (!ctx->h_stage[384])
+		const uint32_t *src = ctx->h_stage + 1536 * rel + 64 * part, *len = src + 512, *dst = src + 1024;
+		if (!ctx->h_stage[3072])
 			for (int i = 1; i <= G; ++i) {
 				const int g = (ctx->bind_gpu + i) % G;           // every sender starts with its right-hand neighbour
 				if ((g == ctx->bind_gpu && ctx->stage_inplace) || !len[g]) continue;
@@ -1639,21 +1649,51 @@ extern "C" int hjb_cpra_stage_copy_async(hjb_ctx *ctx, int rel, void *cuda_strea
 				CK(cudaMemcpyAsync(pc.v[g] + dst[g], ctx->stage_v[rel] + src[g], (size_t)len[g] * 4, cudaMemcpyDeviceToDevice, cs));
 			}
 	} else if (ctx->pending[rel].n)
-		ctx->step_launches += launch_peer_copy(ctx->stage_k[rel], ctx->stage_v[rel], pc, ctx->stage_dev + (rel ? SD_REL_S : SD_REL_R),
+		ctx->step_launches += launch_peer_copy(ctx->stage_k[rel], ctx->stage_v[rel], pc, ctx->stage_dev + (rel ? SD_REL_S : SD_REL_R) + 64 * part,
 		                                       ctx->cpra_dev + CD_ABORT, log2_exact(G), ctx->bind_gpu, ctx->stage_inplace,
 		                                       cuda_stream ? (cudaStream_t)cuda_stream : ctx->stream, cuda_stream ? nullptr : &ctx->timer);
 	CK(cudaGetLastError());
-	ctx->stage_state[rel] = 3;
+	ctx->stage_copied[rel] |= 1u << part;
 	return HJB_OK;
 }
 
-// rel 0: the local pass over what this GPU received of R (call once every sender's copies of R have landed); rel 1: the
-// same for S, then the join.  hjb_cpra_finish follows.
-extern "C" int hjb_cpra_stage_local_async(hjb_ctx *ctx, const hjb_opts *opts, int bbits, int big_fill, int rel)
+// One local pass over the sub-partitions [q0, q1) of what this GPU received of a relation (stage.cu: every sub-partition is
+// the union of one range per sender) into the work columns, continuing at the rows where the range begins.
+static int stage_local_pass(hjb_ctx *ctx, PhjState *st, int rel, uint32_t q0, uint32_t q1, int bbits)
+{
+	const int G = ctx->bind_gpus, me = ctx->bind_gpu;
+	const uint32_t *desc = ctx->stage_dev + (rel ? SD_REL_S : SD_REL_R);
+	RadixPassArgs a = {};
+	a.keys = (const uint32_t *)ctx->bind_peer[rel ? 2 : 0][me];
+	a.vals = (const uint32_t *)ctx->bind_peer[rel ? 3 : 1][me];
+	a.keys_out = rel ? st->sbk[0] : st->rbk[0];
+	a.vals_out = rel ? st->sbv[0] : st->rbv[0];
+	a.n = ctx->bind_cap[rel];
+	a.np = q1 - q0;
+	a.parent_off = desc + SD_POFF + q0;
+	a.seg = desc + SD_SEG + (size_t)q0 * G * 2;
+	a.nseg = (uint32_t)G;
+	a.out_base = desc + SD_POFF + q0;
+	a.chunk_div = (uint32_t)ctx->stage_parts;
+	a.child_off = (rel ? st->soff[0] : st->roff[0]) + ((size_t)q0 << bbits);
+	a.factor = st->radix_factor;
+	a.bits = bbits;
+	a.rshift = 32 - ctx->stage_abits - bbits;
+	radix_carve(a, st->scratch, true);
+	ctx->step_launches += launch_radix_pass(a, ctx->stream, ctx->sms, &ctx->timer);
+	return HJB_OK;
+}
+
+// rel 0: the local pass over part `part` of what this GPU received of R (call once every sender's copies of that part have
+// landed); rel 1: the same for S, then the join of the part's partitions (R's part must have been passed).  After the last
+// part of S hjb_cpra_finish follows.
+extern "C" int hjb_cpra_stage_local_async(hjb_ctx *ctx, const hjb_opts *opts, int bbits, int big_fill, int rel, int part)
 {
 	if (!ctx || rel < 0 || rel > 1) return HJB_E_INVALID;
-	if (ctx->step_state != (rel ? 11 : 10) || ctx->stage_state[rel] != 3)
-		return fail(ctx, HJB_E_INVALID, "hjb_cpra_stage_copy_async must precede; R's local pass comes before S's");
+	if (ctx->step_state < 10 || ctx->step_state > 11) return fail(ctx, HJB_E_INVALID, "hjb_cpra_stage_copy_async must precede");
+	if (part < 0 || part >= ctx->stage_parts || !(ctx->stage_copied[rel] >> part & 1) || (ctx->stage_done[rel] >> part & 1))
+		return fail(ctx, HJB_E_INVALID, "that part has not been copied, or has been passed already");
+	if (rel == 1 && !(ctx->stage_done[0] >> part & 1)) return fail(ctx, HJB_E_INVALID, "R's part is passed before S's");
 	if (bbits < 1 || bbits > kStageMaxBits) return fail(ctx, HJB_E_INVALID, "the local pass takes between 1 and 9 bits");
 	const hjb_opts *o = opts ? opts : &kDefaultOpts;
 	CK(cudaSetDevice(ctx->device));
@@ -1661,7 +1701,8 @@ extern "C" int hjb_cpra_stage_local_async(hjb_ctx *ctx, const hjb_opts *opts, in
 	int rc;
 	cudaStream_t s = ctx->stream;
 	const uint64_t rc_cap = ctx->bind_cap[0], sc_cap = ctx->bind_cap[1];
-	if (rel == 0) {
+	if (ctx->step_state == 10) {                   // the first part: plan, workspace, scalars
+		if (rel != 0) return fail(ctx, HJB_E_INVALID, "R's part is passed before S's");
 		if (!ctx->step_phj && !(ctx->step_phj = (PhjState *)calloc(1, sizeof(PhjState)))) return HJB_E_NOMEM;
 		hjb_opts oo = *o;
 		if (!oo.out_capacity) oo.out_capacity = sc_cap > rc_cap ? sc_cap : rc_cap;
@@ -1671,30 +1712,34 @@ extern "C" int hjb_cpra_stage_local_async(hjb_ctx *ctx, const hjb_opts *opts, in
 		p.bits[0] = bbits;
 		p.total_bits = bbits;
 		if (32 - ctx->stage_abits - bbits > (big_fill ? 14 : 32)) return fail(ctx, HJB_E_INVALID, "12288-tuple fills need <= 14 hash bits below the partition id");
-		if ((rc = phj_setup(ctx, rc_cap, sc_cap, sc_cap, &oo, gbits, (uint32_t)me, ctx->step_phj, 0, 0, &p, pre, (uint32_t)G))) return rc;
+		if ((rc = phj_setup(ctx, rc_cap, sc_cap, sc_cap, &oo, gbits, (uint32_t)me, ctx->step_phj, 0, 0, &p, pre, (uint32_t)G,
+		                    (uint32_t)ctx->stage_parts))) return rc;
 		ctx->step_phj->big_fill = big_fill;
-		ctx->step_phj->seg[0] = ctx->stage_dev + SD_REL_R + SD_SEG;
-		ctx->step_phj->seg[1] = ctx->stage_dev + SD_REL_S + SD_SEG;
-		ctx->step_phj->nseg = (uint32_t)G;
 		ctx->step_opts = oo;
 		CK(cudaEventRecord(ctx->ev[0], s));
+		CK(cudaEventRecord(ctx->ev[2], s));
 		CK(cudaMemsetAsync(ctx->d_scalars, 0, 16 * 8, s));
-		const hjb_rel Rr = {(const uint32_t *)ctx->bind_peer[0][me], (const uint32_t *)ctx->bind_peer[1][me], rc_cap};
-		if ((rc = phj_partition_side(ctx, ctx->step_phj, &Rr, true, &ctx->step_launches, ctx->stage_dev + SD_REL_R + SD_POFF))) return rc;
-		CK(cudaGetLastError());
 		ctx->step_state = 11;
-		return HJB_OK;
 	}
 	PhjState &st = *ctx->step_phj;
-	const hjb_rel Sr = {(const uint32_t *)ctx->bind_peer[2][me], (const uint32_t *)ctx->bind_peer[3][me], sc_cap};
-	if ((rc = phj_partition_side(ctx, &st, &Sr, false, &ctx->step_launches, ctx->stage_dev + SD_REL_S + SD_POFF))) return rc;
-	CK(cudaEventRecord(ctx->ev[2], s));
-	if ((rc = phj_launch_join(ctx, &st, &ctx->step_opts, &ctx->step_launches))) return rc;
-	CK(cudaEventRecord(ctx->ev[3], s));
+	if (st.plan.bits[0] != bbits || st.big_fill != big_fill) return fail(ctx, HJB_E_INVALID, "every part of a step takes the same plan");
+	const uint32_t nsub = 1u << pre, q0 = (uint32_t)part * nsub / ctx->stage_parts, q1 = (uint32_t)(part + 1) * nsub / ctx->stage_parts;
+	if ((rc = stage_local_pass(ctx, &st, rel, q0, q1, bbits))) return rc;
+	ctx->stage_done[rel] |= 1u << part;
+	if (rel == 1) {
+		// the part's partitions: both sides are in place
+		st.pr.k = st.rbk[0]; st.pr.v = st.rbv[0]; st.pr.off = st.roff[0];
+		st.ps.k = st.sbk[0]; st.ps.v = st.sbv[0]; st.ps.off = st.soff[0];
+		if ((rc = phj_launch_join(ctx, &st, &ctx->step_opts, &ctx->step_launches, q0 << bbits, q1 << bbits))) return rc;
+		CK(cudaEventRecord(ctx->ev[3], s));
+	}
 	CK(cudaGetLastError());
-	ctx->stage_state[0] = ctx->stage_state[1] = 0;
-	ctx->pending_gpus = 0;
-	ctx->step_state = 3;
+	const uint32_t all = (1u << ctx->stage_parts) - 1;
+	if (ctx->stage_done[0] == all && ctx->stage_done[1] == all) {
+		ctx->stage_state[0] = ctx->stage_state[1] = 0;
+		ctx->pending_gpus = 0;
+		ctx->step_state = 3;
+	}
 	return HJB_OK;
 }
 

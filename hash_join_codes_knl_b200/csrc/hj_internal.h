@@ -71,6 +71,8 @@ struct RadixPassArgs {
 	                                  // (fan-out > 512, or the pass feeds the peer scatter, which ranks its tiles itself)
 	const uint32_t *seg;              // device or nullptr: parent q is the union of nseg ranges, (first row, rows) at seg[(q * nseg + s) * 2]
 	uint32_t nseg;                    // (tile-count path only; parent_off then holds the parents' cumulative sizes)
+	const uint32_t *out_base;         // device or nullptr: output position of the first parent's first tuple (a pass over a range of parents)
+	uint32_t chunk_div;               // 0 / 1, or: the pass sees about n / chunk_div tuples (sizes the work items)
 	const int32_t *shift;             // device, 2^bits entries or nullptr: added to every digit's output positions (staged CPRA
 	                                  // exchange, np == 1: each digit's run starts with the 16-byte phase of its destination row)
 };
@@ -86,7 +88,7 @@ struct PeerTable {
 };
 constexpr uint32_t kPeerCarry = 32;       // peer stores are combined to whole 128-byte lines (fan-out <= 64)
 size_t radix_scratch_bytes(uint64_t n, uint32_t np, int bits, uint32_t *chunk, uint32_t *max_items, uint32_t *tiles,
-                           uint32_t *tiles_per_item = nullptr);
+                           uint32_t *tiles_per_item = nullptr, uint32_t chunk_div = 1);
 // fills a.chunk / max_items / tiles_per_item and carves a's scratch arrays out of `scratch` (radix_scratch_bytes of
 // a.n, a.np, a.bits); tile_counts = false leaves a.tile_counts null
 void radix_carve(RadixPassArgs &a, char *scratch, bool tile_counts);
@@ -101,8 +103,10 @@ int launch_histogram_only(const uint32_t *keys, uint64_t n, uint32_t *counts_dev
 // device words written by k_stage_bases (uint32), per relation: what stage A's scatter adds to the scan's positions per digit;
 // per owner this sender's run: first row in stage A's output columns, rows, first row in the owner's columns; the ranges
 // (first row, rows) every received sub-partition consists of, [sub-partition][sender]; the sub-partitions' cumulative sizes
-enum { SD_SHIFT = 0, SD_OWN_SRC = 512, SD_OWN_LEN = 576, SD_OWN_DST = 640, SD_SEG = 704, SD_POFF = 1728,
-       SD_REL_R = 0, SD_REL_S = 2048, SD_WORDS = 4096 };
+// The runs leave in up to kStageMaxParts parts (ranges of sub-partitions): [part][owner].
+constexpr int kStageMaxParts = 8;
+enum { SD_SHIFT = 0, SD_OWN_SRC = 512, SD_OWN_LEN = 1024, SD_OWN_DST = 1536, SD_SEG = 2048, SD_POFF = 3072,
+       SD_REL_R = 0, SD_REL_S = 4096, SD_WORDS = 8192 };
 struct PeerCols {
 	uint32_t *k[64];
 	uint32_t *v[64];
@@ -110,7 +114,7 @@ struct PeerCols {
 int launch_stage_counts(const uint32_t *r_off, const uint32_t *s_off, int abits, unsigned long long *counts, cudaStream_t s);
 int launch_stage_bases(const unsigned long long *M, int G, int me, int abits, int gbits, uint64_t cap_r, uint64_t cap_s,
                        const uint32_t *child_r, const uint32_t *child_s, uint32_t stage_base_r, uint32_t stage_base_s, int inplace,
-                       uint32_t *out, uint32_t *status, cudaStream_t s);
+                       int nparts, uint32_t *out, uint32_t *status, cudaStream_t s);
 int launch_peer_copy(const uint32_t *sk, const uint32_t *sv, const PeerCols &peers, const uint32_t *desc, const uint32_t *abort_flag,
                      int gbits, int me, int skip_me, cudaStream_t s, KernelTimer *t = nullptr);
 

@@ -232,8 +232,11 @@ constexpr uint64_t kFlagAggregate = 1ull << 62, kFlagInclusive = 2ull << 62, kFl
 // predecessors' status words until it meets an inclusive prefix (Merrill & Garland).
 __global__ void __launch_bounds__(kScanThreads)
 k_scan(const uint32_t *__restrict__ item_prefix, uint32_t np, int bits, uint32_t *__restrict__ counts,
-       uint32_t *__restrict__ child_off, uint64_t *__restrict__ status, uint32_t *__restrict__ tile_counter)
+       uint32_t *__restrict__ child_off, uint64_t *__restrict__ status, uint32_t *__restrict__ tile_counter,
+       const uint32_t *__restrict__ out_base)
 {
+	// out_base (may be null): *out_base is the output position of the first parent's first tuple -- a pass over a RANGE of
+	// the parents (the staged CPRA exchange handles the received sub-partitions in parts) continues where the range begins
 	__shared__ uint32_t warp_totals[34];
 	__shared__ uint32_t s_tile;
 	__shared__ uint32_t s_excl;
@@ -314,7 +317,7 @@ k_scan(const uint32_t *__restrict__ item_prefix, uint32_t np, int bits, uint32_t
 		}
 	}
 	__syncthreads();
-	uint32_t run = s_excl + thread_excl;
+	uint32_t run = s_excl + thread_excl + (out_base ? *out_base : 0u);
 #pragma unroll
 	for (uint32_t k = 0; k < kScanItems; ++k) {
 		if (addr[k] != 0xFFFFFFFFu) {
@@ -933,14 +936,16 @@ static int radix_items()
 }
 
 size_t radix_scratch_bytes(uint64_t n, uint32_t np, int bits, uint32_t *chunk, uint32_t *max_items, uint32_t *tiles,
-                           uint32_t *tiles_per_item)
+                           uint32_t *tiles_per_item, uint32_t chunk_div)
 {
+	// chunk_div > 1: the pass will see about n / chunk_div of the n tuples the array can hold (one part of a relation that
+	// is processed in parts); items are sized for that, the bound on their number still covers all n
 	// ~1.2K items (eight per SM of a B200): enough to balance the SMs over a pass, few enough that the
 	// counts matrix and its scan stay small (measured: 1024-1184 items 4.23 ms per config-2 step, 2048
 	// 4.27, 4096 4.35); chunk is a multiple of the scatter tile
 	const int target = radix_items();
 	const uint32_t tile = kTcTile;
-	uint64_t c = (n + target - 1) / target;
+	uint64_t c = (n / (chunk_div ? chunk_div : 1u) + target - 1) / target;
 	c = (c + kTcTile - 1) / kTcTile * kTcTile;                 // a multiple of every tile size in use
 	if (c < kTcTile) c = kTcTile;
 	if (c > (1u << 24)) c = 1u << 24;
@@ -962,7 +967,8 @@ size_t radix_scratch_bytes(uint64_t n, uint32_t np, int bits, uint32_t *chunk, u
 void radix_carve(RadixPassArgs &a, char *scratch, bool tile_counts)
 {
 	uint32_t tiles;
-	radix_scratch_bytes(a.n, a.np * (a.nseg ? a.nseg : 1u), a.bits, &a.chunk, &a.max_items, &tiles, &a.tiles_per_item);   // every range of a parent may end in a short item
+	radix_scratch_bytes(a.n, a.np * (a.nseg ? a.nseg : 1u), a.bits, &a.chunk, &a.max_items, &tiles, &a.tiles_per_item,
+	                    a.chunk_div);                       // every range of a parent may end in a short item
 	size_t off = 0;
 	auto take = [&](size_t bytes) {
 		char *p = scratch + off;
@@ -1023,7 +1029,7 @@ int launch_radix_count(const RadixPassArgs &a, cudaStream_t s, KernelTimer *t)
 	t->stop(s);
 	t->start(KK_SCAN, s);
 	k_scan<<<tiles, kScanThreads, 0, s>>>(a.item_prefix, a.np, a.bits, a.counts, a.child_off, a.scan_status,
-	                                      a.scan_counter);
+	                                      a.scan_counter, a.out_base);
 	t->stop(s);
 	return 3;
 }

@@ -70,8 +70,10 @@ constexpr uint32_t kCopyPhase = 32;
 __global__ void __launch_bounds__(512)
 k_stage_bases(const unsigned long long *__restrict__ M, int G, int me, int abits, int gbits, unsigned long long cap_r,
               unsigned long long cap_s, const uint32_t *__restrict__ child_r, const uint32_t *__restrict__ child_s,
-              uint32_t stage_base_r, uint32_t stage_base_s, int inplace, uint32_t *__restrict__ out, uint32_t *__restrict__ status)
+              uint32_t stage_base_r, uint32_t stage_base_s, int inplace, int nparts, uint32_t *__restrict__ out,
+              uint32_t *__restrict__ status)
 {
+	// nparts: the runs leave in nparts pieces, piece k = the sub-partitions [k nsub / nparts, (k + 1) nsub / nparts)
 	__shared__ unsigned long long warp_tot[16];
 	__shared__ unsigned long long s_tot[2][64], s_bef[2][64], s_len[2][64];     // per owner: rows it receives, rows of the senders before me, my rows
 	__shared__ unsigned long long s_max[2];
@@ -148,13 +150,19 @@ k_stage_bases(const unsigned long long *__restrict__ M, int G, int me, int abits
 					next = (src + len + kCopyPhase - 1) & ~(kCopyPhase - 1);
 				}
 				s_src[g] = src;
-				o[SD_OWN_SRC + g] = src;
-				o[SD_OWN_LEN + g] = len;
-				o[SD_OWN_DST + g] = dst;
 			}
 		}
 		__syncthreads();
 		const uint32_t *child = rel ? child_s : child_r;
+		if (d < (uint32_t)(nparts * G)) {
+			// piece (k, g): the scan's offsets of this sender's chunk say where the sub-partitions begin inside the run
+			const uint32_t k = d / G, g = d % G;
+			const uint32_t first = child[g * nsub], lo = child[g * nsub + k * nsub / nparts] - first,
+			               hi = child[g * nsub + (k + 1) * nsub / nparts] - first;
+			o[SD_OWN_SRC + k * 64 + g] = s_src[g] + lo;
+			o[SD_OWN_LEN + k * 64 + g] = hi - lo;
+			o[SD_OWN_DST + k * 64 + g] = (uint32_t)s_bef[rel][g] + lo;
+		}
 		if (d < F) o[SD_SHIFT + d] = s_src[d / nsub] - child[(d / nsub) * nsub];     // a run keeps the scan's order of its sub-partitions
 		__syncthreads();
 	}
@@ -341,9 +349,10 @@ int launch_stage_counts(const uint32_t *r_off, const uint32_t *s_off, int abits,
 
 int launch_stage_bases(const unsigned long long *M, int G, int me, int abits, int gbits, uint64_t cap_r, uint64_t cap_s,
                        const uint32_t *child_r, const uint32_t *child_s, uint32_t stage_base_r, uint32_t stage_base_s, int inplace,
-                       uint32_t *out, uint32_t *status, cudaStream_t s)
+                       int nparts, uint32_t *out, uint32_t *status, cudaStream_t s)
 {
-	k_stage_bases<<<1, 512, 0, s>>>(M, G, me, abits, gbits, cap_r, cap_s, child_r, child_s, stage_base_r, stage_base_s, inplace, out, status);
+	k_stage_bases<<<1, 512, 0, s>>>(M, G, me, abits, gbits, cap_r, cap_s, child_r, child_s, stage_base_r, stage_base_s, inplace, nparts, out,
+	                                status);
 	return 1;
 }
 

@@ -203,10 +203,10 @@ int hjb_cpra_finish(hjb_ctx *ctx, hjb_result *out, uint64_t received[2], uint64_
 int hjb_cpra_stage_plan(hjb_ctx *ctx, int ngpus, uint64_t r_expect, uint64_t s_expect, const hjb_opts *opts, int *abits,
                         int *bbits, int *big_fill);
 int hjb_cpra_stage_count_async(hjb_ctx *ctx, const hjb_rel *R_chunk, const hjb_rel *S_chunk, const hjb_opts *opts, int abits,
-                               uint64_t *counts_dev);
+                               int nparts, uint64_t *counts_dev);
 int hjb_cpra_stage_scatter_async(hjb_ctx *ctx, const uint64_t *matrix_dev, int rel);
-int hjb_cpra_stage_copy_async(hjb_ctx *ctx, int rel, void *cuda_stream);
-int hjb_cpra_stage_local_async(hjb_ctx *ctx, const hjb_opts *opts, int bbits, int big_fill, int rel);
+int hjb_cpra_stage_copy_async(hjb_ctx *ctx, int rel, int part, void *cuda_stream);
+int hjb_cpra_stage_local_async(hjb_ctx *ctx, const hjb_opts *opts, int bbits, int big_fill, int rel, int part);
 
 /* Skew (write.cpp's `zipf` knob, write.cpp:1685-1689; the reference's static ownership par_start / par_end,
  * cpra2.cpp:1868-1872, sends every tuple of a frequent key to one thread).  The probe tuples of a small set of

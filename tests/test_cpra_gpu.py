@@ -231,7 +231,7 @@ def test_fused_exchange_many_tiles_per_item(engines):
     assert tuple(fp) == e0.rows_fingerprint(sk, sv, inner.to(torch.int32))
 
 
-def run_staged_path(engines, G, rk, rv, sk, sv, r_cap, s_cap, plan=None, own_alloc=False):
+def run_staged_path(engines, G, rk, rv, sk, sv, r_cap, s_cap, plan=None, own_alloc=False, parts=1):
     """the staged exchange (hjb_cpra_stage_*): stage A locally by owner and sub-partition, TMA copies of whole runs
     into the owners' buffers, one local pass, join; the all-gather is a torch.cat, the cross-GPU ordering a device
     synchronise.  own_alloc: the receive buffers come from hjb_cpra_recv_alloc (as in the multi-process path) -- stage A
@@ -250,8 +250,9 @@ def run_staged_path(engines, G, rk, rv, sk, sv, r_cap, s_cap, plan=None, own_all
         engines[c].cpra_bind(c, G, peers, r_cap, s_cap)
         keep.append(((dev(chunk(rk, c, G)), dev(chunk(rv, c, G))), (dev(chunk(sk, c, G)), dev(chunk(sv, c, G)))))
     torch.cuda.synchronize()
+    parts = min(parts, 1 << abits >> (G.bit_length() - 1))
     for c in range(G):
-        engines[c].cpra_stage_count_async(keep[c][0], keep[c][1], abits, counts[c])
+        engines[c].cpra_stage_count_async(keep[c][0], keep[c][1], abits, counts[c], nparts=parts)
     torch.cuda.synchronize()
     matrix = torch.cat(counts).contiguous()
     torch.cuda.synchronize()
@@ -259,15 +260,20 @@ def run_staged_path(engines, G, rk, rv, sk, sv, r_cap, s_cap, plan=None, own_all
         engines[c].cpra_stage_scatter_async(matrix, 0)
         engines[c].cpra_stage_scatter_async(matrix, 1)
     torch.cuda.synchronize()
-    for c in range(G):
-        engines[c].cpra_stage_copy_async(0)
-        engines[c].cpra_stage_copy_async(1)
+    # the pieces in the order cpra_join_staged sends them; the owners pass and join piece k while later pieces are still due
+    order = [(0, 0)] + [p for k in range(parts) for p in ([(0, k + 1)] if k + 1 < parts else []) + [(1, k)]]
+    for i, (rel, k) in enumerate(order):
+        for c in range(G):
+            engines[c].cpra_stage_copy_async(rel, part=k)
+        torch.cuda.synchronize()
+        if rel == 1:
+            for g in range(G):
+                engines[g].cpra_stage_local_async(bbits, big, 0, part=k)
+                engines[g].cpra_stage_local_async(bbits, big, 1, part=k)
     torch.cuda.synchronize()
     total, rows, recv = [0, 0, 0, 0], [], []
     err = None
     for g in range(G):
-        engines[g].cpra_stage_local_async(bbits, big, 0)
-        engines[g].cpra_stage_local_async(bbits, big, 1)
         try:
             res, got, largest = engines[g].cpra_finish()
         except HjbCapacityError as e:
@@ -290,7 +296,7 @@ def test_staged_exchange_with_virtual_owners_matches_oracle(engines, G_, name, n
     monkeypatch.setenv("HJB_STAGE_COPY", copy)
     rk, rv, sk, sv = skewed(nr, ns, seed) if name == "skewed" else oracle_generate(nr, ns, threads=2, seed=seed)[:4]
     want = oracle_join("cpra", rk, rv, sk, sv, threads=4)
-    got, rows, recv, matrix = run_staged_path(engines, G_, rk, rv, sk, sv, nr + 1024, ns + 1024, own_alloc=own_alloc)
+    got, rows, recv, matrix = run_staged_path(engines, G_, rk, rv, sk, sv, nr + 1024, ns + 1024, own_alloc=own_alloc, parts=4 if copy == "ce" else 1)
     assert got == want.checks()
     assert (all_rows(rows) == want.sorted_rows()).all()
     per_owner = matrix.reshape(G_, 2, G_, -1).sum(axis=(0, 3))          # [rel][owner]
@@ -298,13 +304,14 @@ def test_staged_exchange_with_virtual_owners_matches_oracle(engines, G_, name, n
     assert [r[1] for r in recv] == [int(x) for x in per_owner[1]]
 
 
+@pytest.mark.parametrize("parts", [1, 2, 8])
 @pytest.mark.parametrize("G_,plan", [(2, (9, 9, 1)), (8, (9, 9, 1)), (4, (9, 1, 0)), (2, (2, 1, 0)), (4, (2, 9, 0)), (8, (3, 5, 0)),
                                      (2, (8, 8, 0)), (4, (5, 7, 0))])
-def test_staged_exchange_under_explicit_plans(engines, G_, plan):
+def test_staged_exchange_under_explicit_plans(engines, G_, plan, parts):
     """512-way stage A, 12288-tuple join fills, a one-bit local pass, stage A with the owner bits only"""
     rk, rv, sk, sv = skewed(150000, 500000, 31)
     want = oracle_join("cpra", rk, rv, sk, sv, threads=4)
-    got, rows, _, _ = run_staged_path(engines, G_, rk, rv, sk, sv, rk.size, sk.size, plan=plan, own_alloc=G_ != 4)
+    got, rows, _, _ = run_staged_path(engines, G_, rk, rv, sk, sv, rk.size, sk.size, plan=plan, own_alloc=G_ != 4, parts=parts)
     assert got == want.checks()
     assert (all_rows(rows) == want.sorted_rows()).all()
 
@@ -322,8 +329,8 @@ def test_staged_exchange_reports_a_receive_buffer_that_is_too_small(engines, own
     assert got == want.checks() and (all_rows(rows) == want.sorted_rows()).all()
 
 
-@pytest.mark.parametrize("plan", [None, (9, 9, 1)])
-def test_staged_exchange_many_pieces_per_run(engines, plan):
+@pytest.mark.parametrize("plan,parts", [(None, 1), ((9, 9, 1), 4), (None, 4)])
+def test_staged_exchange_many_pieces_per_run(engines, plan, parts):
     """2^25 x 2^25 over 4 virtual owners: runs of many 16 KB pieces, every copy stage in use; checked by count,
     checksums and the device fingerprint of the rows against the rows rebuilt from S"""
     G_, n = 4, 1 << 25
@@ -341,7 +348,7 @@ def test_staged_exchange_many_pieces_per_run(engines, plan):
     for c in range(G_):
         engines[c].cpra_bind(c, G_, peers, cap, cap)
         engines[c].cpra_stage_count_async((rk[c * per:(c + 1) * per], rv[c * per:(c + 1) * per]),
-                                          (sk[c * per:(c + 1) * per], sv[c * per:(c + 1) * per]), abits, counts[c])
+                                          (sk[c * per:(c + 1) * per], sv[c * per:(c + 1) * per]), abits, counts[c], nparts=parts)
     torch.cuda.synchronize()
     matrix = torch.cat(counts).contiguous()
     torch.cuda.synchronize()
@@ -349,14 +356,17 @@ def test_staged_exchange_many_pieces_per_run(engines, plan):
         for c in range(G_):
             engines[c].cpra_stage_scatter_async(matrix, rel)
     torch.cuda.synchronize()
-    for c in range(G_):
-        engines[c].cpra_stage_copy_async(0)
-        engines[c].cpra_stage_copy_async(1)
+    for k in range(parts):
+        for c in range(G_):
+            engines[c].cpra_stage_copy_async(0, part=k)
+            engines[c].cpra_stage_copy_async(1, part=k)
+        torch.cuda.synchronize()
+        for g in range(G_):
+            engines[g].cpra_stage_local_async(bbits, big, 0, part=k)
+            engines[g].cpra_stage_local_async(bbits, big, 1, part=k)
     torch.cuda.synchronize()
     total, fp = [0, 0, 0, 0], [0, 0]
     for g in range(G_):
-        engines[g].cpra_stage_local_async(bbits, big, 0)
-        engines[g].cpra_stage_local_async(bbits, big, 1)
         res, _, _ = engines[g].cpra_finish()
         total = add_checks(total, res)
         f = engines[g].rows_fingerprint(*res.rows_torch())

@@ -43,12 +43,14 @@ def main():
         cs = slice(rank * ns // world, (rank + 1) * ns // world)
         dev = lambda a: torch.from_numpy(np.ascontiguousarray(a).view(np.int32)).cuda()
         fused.stage_plan = None                                  # the staged plan is made per input shape
-        for mode in ("nccl", "fused", "fused", "fused+skew", "staged", "staged", "staged-serial"):    # twice: the second step reuses plans / buffers
+        for mode in ("nccl", "fused", "fused", "fused+skew", "staged", "staged", "staged-serial", "staged-parts", "staged-parts"):    # twice: the second step reuses plans / buffers
             if mode == "nccl":
                 res = cpra.cpra_join(eng, (dev(rk[cr]), dev(rv[cr])), (dev(sk[cs]), dev(sv[cs])))
             elif mode.startswith("staged"):
+                if mode.endswith("parts") and getattr(fused, "stage_parts", 0) != 4:
+                    fused.stage_plan = None                      # re-plan: the runs leave in four pieces
                 res = cpra.cpra_join_staged(eng, (dev(rk[cr]), dev(rv[cr])), (dev(sk[cs]), dev(sv[cs])), fused,
-                                            overlap=not mode.endswith("serial"))
+                                            overlap=not mode.endswith("serial"), parts=4 if mode.endswith("parts") else None)
             else:
                 res = cpra.cpra_join_fused(eng, (dev(rk[cr]), dev(rv[cr])), (dev(sk[cs]), dev(sv[cs])), fused,
                                            skew=mode.endswith("skew"))
