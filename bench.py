@@ -626,7 +626,7 @@ def main():
     sb = step_bytes("npj" if algo == "npj" else "phj", nr_g, ns_g, ns_g, passes)
     staged = algo == "cpra" and world > 1 and args.exchange.startswith("staged")
     if staged:
-        sb += 16 * n_in                                      # the copies: every run read from the staging columns, written into an owner's columns
+        sb += 16 * n_in * (world - 1) / world                # the copies: a run for another owner is read from the staging columns and written into that owner's columns
     elif algo == "cpra" and world > 1:
         sb += 20 * n_in + 16 * n_in * (world - 1) / world    # GPU-assign pass (hist + scatter) and the receive-side writes / send-side reads
     line = {
@@ -659,8 +659,8 @@ def main():
             line["nvlink"] = {"bytes_out_per_gpu": sent, "scatter_kernel_ms": round(bulk_ms, 4),
                               "achieved_gbs_per_direction": sent / (bulk_ms * 1e-3) / 1e9 if bulk_ms else None,
                               "reference_gbs": NVLINK_REF_GBS,
-                              "note": ("k_peer_copy on the side stream: span from the first relation staged to the last copy through on every rank "
-                                       "(includes stage A of S running beside it)" if staged else "k_scatter_bulk's event-timed launches (R and S)")
+                              "note": ("copies (copy engines, or k_peer_copy with HJB_STAGE_COPY=tma) on the side stream: span from the first relation staged to the last copy through on every rank "
+                                       "(stage A of S, the local passes and the joins of the pieces that have arrived run beside it)" if staged else "k_scatter_bulk's event-timed launches (R and S)")
                                       + "; measured peer-copy bandwidth per direction 770 GB/s (B200_PROFILING.md), nominal 900"}
             # SURVEY 8d's serial model for CPRA at G GPUs: HBM bytes / HBM bandwidth + NVLink bytes / NVLink bandwidth.
             # `as_built`: the bytes this code moves (GPU-assign + `passes` local passes + join); `survey`: the survey's
