@@ -601,6 +601,11 @@ def main():
     peak, peak_src = measured_peak_gbs()
     n_in = nr_g + ns_g                              # tuples this GPU partitions per pass / joins
     alg = kernel_bytes(nr_g, ns_g, ns_g)
+    staged = algo == "cpra" and world > 1 and args.exchange.startswith("staged")
+    if staged:
+        # two passes over this GPU's tuples whatever the number of launches (the local pass and the join run once per part)
+        alg["k_hist"] = lambda L: 4 * n_in * 2
+        alg["k_scatter"] = lambda L: 16 * n_in * 2
     per_step = {k: (v[0] / args.steps, v[1] / args.steps) for k, v in ktimes.items() if v[1]}
     dom = max(per_step.items(), key=lambda kv: kv[1][0])[0] if per_step else None
     ncu_traffic = {}
@@ -622,9 +627,8 @@ def main():
                 "launches_per_step": launches_k, "share_of_step": ms_k / (ms_instrumented / args.steps),
                 "traffic_source": "profiles/ncu_traffic.json (dram__bytes_read.sum + dram__bytes_write.sum per launch, "
                                   "ncu --set full)" if tr else None}
-    passes = max(1, round(per_step.get("k_scatter", (0, 4))[1] / 2))     # local scatter launches come in (R, S) pairs
+    passes = 2 if staged else max(1, round(per_step.get("k_scatter", (0, 4))[1] / 2))     # local scatter launches come in (R, S) pairs
     sb = step_bytes("npj" if algo == "npj" else "phj", nr_g, ns_g, ns_g, passes)
-    staged = algo == "cpra" and world > 1 and args.exchange.startswith("staged")
     if staged:
         sb += 16 * n_in * (world - 1) / world                # the copies: a run for another owner is read from the staging columns and written into that owner's columns
     elif algo == "cpra" and world > 1:

@@ -152,6 +152,7 @@ struct NpjArgs {
 int launch_npj_build(const NpjArgs &a, cudaStream_t s, int sms, KernelTimer *t = nullptr);
 int launch_npj_probe(const NpjArgs &a, cudaStream_t s, int sms, KernelTimer *t = nullptr);
 
+
 // heavy-hitter handling of the multi-GPU join (skew.cu)
 constexpr uint32_t kMaxHotKeys = 256;        // keys that may be declared hot
 constexpr uint32_t kMaxHotBuild = 4096;      // build tuples with hot keys, all GPUs together
