@@ -181,24 +181,35 @@ int hjb_cpra_join_async(hjb_ctx *ctx, const hjb_opts *opts, uint64_t r_expect, u
 void *hjb_cpra_sums_dev(hjb_ctx *ctx);
 int hjb_cpra_finish(hjb_ctx *ctx, hjb_result *out, uint64_t received[2], uint64_t largest[2]);
 
-/* ---- the STAGED exchange: two radix passes over the data instead of the fused path's three, and an exchange that
- * leaves the SMs alone.  The reference's own order -- chunk-local passes first (cpra2.cpp:1783-1827), then the
- * per-owner gather of whole partition pieces with memcpy (cpra2.cpp:1861-1905,1940-1959):
+/* ---- the STAGED exchange (the default for N > 1 in cpra.py / bench.py): two radix passes over the data instead of the
+ * fused path's three, and an exchange that leaves the SMs alone.  It is the reference's own order -- chunk-local passes
+ * first (cpra2.cpp:1783-1827), then the per-owner gather of whole partition pieces with memcpy
+ * (cpra2.cpp:1861-1905,1940-1959):
  *   hjb_cpra_stage_plan          how one step's radix bits are split (same arguments on every rank): stage A takes
- *                                abits = owner bits + sub-partition bits, the local pass bbits
- *   hjb_cpra_stage_count_async   stage A's histogram + scan of both chunks; this sender's 2 * 2^abits counts
- *                                (R per digit, then S) -> counts_dev
+ *                                abits = owner bits + sub-partition bits (<= 9), the local pass bbits (1..9); big_fill: the
+ *                                partitions average 8192 build tuples and the join takes 12288-tuple fills (2^31 tuples
+ *                                on 8 GPUs).  HJB_E_INVALID: two passes do not suffice, use the fused path
+ *   hjb_cpra_stage_count_async   stage A's histogram + scan of both chunks; this sender's 2 * 2^abits counts (R per digit,
+ *                                then S) -> counts_dev.  nparts (a power of two <= 8): the runs will leave, and be
+ *                                processed by their owners, in that many parts (ranges of sub-partitions)
  *   (caller)                     all-gather into matrix_dev[ngpus][2][2^abits] (uint64, device)
- *   hjb_cpra_stage_scatter_async rel 0: every run's row in its owner's columns from the matrix (sub-partition-major,
- *                                sender-minor -- the reference's interleave), then stage A's scatter of R into staging
- *                                columns where each run starts with the 16-byte phase of its destination; rel 1: S
- *   hjb_cpra_stage_copy_async    the runs of one relation -> the owners' columns: a few one-warp CTAs driving TMA bulk
- *                                copies (k_peer_copy), on `cuda_stream` (null: the context's stream): on a side stream
- *                                that waits for the scatter, the copies of R cross NVLink while stage A works on S,
- *                                those of S while R's local pass runs
- *   (caller)                     per relation, a collective after the copy: when it completes every sender's runs are in
- *   hjb_cpra_stage_local_async   rel 0: the local pass over R's received sub-partitions; rel 1: S's, then the join
- *   hjb_cpra_finish              as above
+ *   hjb_cpra_stage_scatter_async rel 0: from the matrix, this sender's run in every owner's columns (an owner receives
+ *                                sender-major: one run per sender with its sub-partitions in order -- the pieces of the
+ *                                reference's gather, cpra2.cpp:1896-1904) and the per-sender ranges every received
+ *                                sub-partition consists of; then stage A's scatter of R -- the run this GPU owns itself
+ *                                straight to its final rows (receive buffers from hjb_cpra_recv_alloc), the others into
+ *                                the staging region behind them, each starting with the 128-byte phase of its destination.
+ *                                rel 1: S.  One host synchronisation (rel 0, the stream holds the counting kernels only)
+ *                                unless HJB_STAGE_COPY=tma
+ *   hjb_cpra_stage_copy_async    part `part` of one relation's runs -> the owners' columns, on `cuda_stream` (null: the
+ *                                context's stream): cudaMemcpyAsync per owner and column (copy engines, no SM), or with
+ *                                HJB_STAGE_COPY=tma the kernel k_peer_copy (TMA bulk copies global -> shared -> peer).  On a
+ *                                side stream that waits for the scatter the copies cross NVLink beside the passes
+ *   (caller)                     per piece, a collective after the copy: when it completes every sender's piece is in
+ *   hjb_cpra_stage_local_async   rel 0: the local pass over part `part` of what arrived of R (every sub-partition is the
+ *                                union of one range per sender); rel 1: the same for S, then the join of the part's
+ *                                partitions.  R's part before S's; any order of parts
+ *   hjb_cpra_finish              after the last part: as above
  * hjb_cpra_bind precedes as for the fused path; capacity failures are reported the same way. */
 int hjb_cpra_stage_plan(hjb_ctx *ctx, int ngpus, uint64_t r_expect, uint64_t s_expect, const hjb_opts *opts, int *abits,
                         int *bbits, int *big_fill);

@@ -24,8 +24,9 @@ for r in rows[2:]:
             print(f"  {w:70s} {r[i]:>16s} {units[i]}")
     try:
         rd = float(r[hdr.index("dram__bytes_read.sum")]); wr = float(r[hdr.index("dram__bytes_write.sum")])
-        u = units[hdr.index("dram__bytes_read.sum")]
-        print(f"  {'traffic = dram read + write':70s} {rd + wr:16.6f} {u}")
+        scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}      # ncu picks a unit per column
+        tot = rd * scale[units[hdr.index("dram__bytes_read.sum")]] + wr * scale[units[hdr.index("dram__bytes_write.sum")]]
+        print(f"  {'traffic = dram read + write':70s} {tot / 1e9:16.6f} Gbyte")
     except Exception:
         pass
     top = sorted(((float(r[hdr.index(h)] or 0), h) for h in stalls), reverse=True)[:6]

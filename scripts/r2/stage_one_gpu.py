@@ -4,7 +4,8 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspa
 import torch
 import hash_join_codes_knl_b200 as hj
 from hash_join_codes_knl_b200 import datagen
-G, n = 2, 1 << 27
+G, n = int(os.environ.get("STAGE_G", "2")), 1 << int(os.environ.get("STAGE_LOG2", "27"))
+PLAN = tuple(int(x) for x in os.environ["STAGE_PLAN"].split(",")) if os.environ.get("STAGE_PLAN") else None
 es = [hj.Engine(0) for _ in range(G)]
 tot = n * G
 cols = []
@@ -20,7 +21,7 @@ for own_alloc in (True, False):
     else:
         bufs = [[torch.empty(cap + 64, dtype=torch.int32, device="cuda") for _ in range(4)] for _ in range(G)]
         peers = [[bufs[g][c].data_ptr() for g in range(G)] for c in range(4)]
-    plan = es[0].cpra_stage_plan(G, n, n)
+    plan = PLAN or es[0].cpra_stage_plan(G, n, n)
     abits, bbits, big = plan
     counts = [torch.zeros(2 << abits, dtype=torch.int64, device="cuda") for _ in range(G)]
     for c in range(G):
