@@ -329,6 +329,19 @@ def test_staged_exchange_reports_a_receive_buffer_that_is_too_small(engines, own
     assert got == want.checks() and (all_rows(rows) == want.sorted_rows()).all()
 
 
+def test_staged_exchange_regrows_the_result_when_equal_build_keys_multiply_the_rows(engines):
+    """the heavy-hitter probe key occurs eight times on the build side: more rows than the result columns were sized for;
+    hjb_cpra_finish grows them and runs the join phase again over all parts' partitions"""
+    rk, rv, sk, sv = skewed(150000, 500000, 27)
+    rk, rv = rk.copy(), rv.copy()
+    rk[20:27] = rk[7]
+    rv[20:27] = np.arange(7, dtype=np.uint32) + np.uint32(1000)
+    want = numpy_join(rk, rv, sk, sv)
+    assert want.count > 2 * sk.size
+    got, rows, _, _ = run_staged_path(engines, 4, rk, rv, sk, sv, rk.size, sk.size, own_alloc=True, parts=2)
+    assert got == want.checks() and (all_rows(rows) == want.sorted_rows()).all()
+
+
 @pytest.mark.parametrize("plan,parts", [(None, 1), ((9, 9, 1), 4), (None, 4)])
 def test_staged_exchange_many_pieces_per_run(engines, plan, parts):
     """2^25 x 2^25 over 4 virtual owners: runs of many 16 KB pieces, every copy stage in use; checked by count,
