@@ -1724,7 +1724,8 @@ extern "C" int hjb_cpra_stage_local_async(hjb_ctx *ctx, const hjb_opts *opts, in
 	}
 	PhjState &st = *ctx->step_phj;
 	if (st.plan.bits[0] != bbits || st.big_fill != big_fill) return fail(ctx, HJB_E_INVALID, "every part of a step takes the same plan");
-	const uint32_t nsub = 1u << pre, q0 = (uint32_t)part * nsub / ctx->stage_parts, q1 = (uint32_t)(part + 1) * nsub / ctx->stage_parts;
+	const uint32_t nsub = 1u << pre, q0 = stage_part_lo((uint32_t)part, (uint32_t)ctx->stage_parts, nsub),
+	               q1 = stage_part_lo((uint32_t)part + 1, (uint32_t)ctx->stage_parts, nsub);
 	if ((rc = stage_local_pass(ctx, &st, rel, q0, q1, bbits))) return rc;
 	ctx->stage_done[rel] |= 1u << part;
 	if (rel == 1) {

@@ -73,7 +73,7 @@ k_stage_bases(const unsigned long long *__restrict__ M, int G, int me, int abits
               uint32_t stage_base_r, uint32_t stage_base_s, int inplace, int nparts, uint32_t *__restrict__ out,
               uint32_t *__restrict__ status)
 {
-	// nparts: the runs leave in nparts pieces, piece k = the sub-partitions [k nsub / nparts, (k + 1) nsub / nparts)
+	// nparts: the runs leave in nparts pieces, piece k = the sub-partitions [stage_part_lo(k), stage_part_lo(k + 1))
 	__shared__ unsigned long long warp_tot[16];
 	__shared__ unsigned long long s_tot[2][64], s_bef[2][64], s_len[2][64];     // per owner: rows it receives, rows of the senders before me, my rows
 	__shared__ unsigned long long s_max[2];
@@ -157,8 +157,8 @@ k_stage_bases(const unsigned long long *__restrict__ M, int G, int me, int abits
 		if (d < (uint32_t)(nparts * G)) {
 			// piece (k, g): the scan's offsets of this sender's chunk say where the sub-partitions begin inside the run
 			const uint32_t k = d / G, g = d % G;
-			const uint32_t first = child[g * nsub], lo = child[g * nsub + k * nsub / nparts] - first,
-			               hi = child[g * nsub + (k + 1) * nsub / nparts] - first;
+			const uint32_t first = child[g * nsub], lo = child[g * nsub + stage_part_lo(k, nparts, nsub)] - first,
+			               hi = child[g * nsub + stage_part_lo(k + 1, nparts, nsub)] - first;
 			o[SD_OWN_SRC + k * 64 + g] = s_src[g] + lo;
 			o[SD_OWN_LEN + k * 64 + g] = hi - lo;
 			o[SD_OWN_DST + k * 64 + g] = (uint32_t)s_bef[rel][g] + lo;
