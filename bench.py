@@ -469,6 +469,7 @@ def main():
     phases = np.zeros(8)
     extra = {"split_ms": 0.0, "exchange_ms": 0.0, "join_ms": 0.0, "step_ms": 0.0, "copy_r_done_ms": 0.0, "copy_s_done_ms": 0.0}
     recv_stats = []
+    stage_plan = {}
 
     def timed_region(instrumented):
         eng.set_profiling(instrumented)
@@ -488,6 +489,8 @@ def main():
                     for key in extra:
                         extra[key] += r.get(key, 0.0)
                     recv_stats.append(r["recv_tuples"])
+                    if r.get("stage_plan"):
+                        stage_plan.update(r["stage_plan"])
                 continue
             for name, (ms, n) in eng.kernel_times().items():
                 a = ktimes.setdefault(name, [0.0, 0])
@@ -640,6 +643,8 @@ def main():
         "config": {"workload": workload_label(workload, world, nr_g.bit_length() - 1),
                    "inner_tuples": nr_tot, "outer_tuples": ns_tot, "materialize": True, "algorithm": algo,
                    "exchange": (args.exchange if world > 1 else None),
+                   "exchange_plan": (dict(stage_plan, copies="k_peer_copy (TMA)" if os.environ.get("HJB_STAGE_COPY") == "tma" else "copy engines")
+                                     if stage_plan else None),
                    "l2_policy": "inputs (%.1f GiB per GPU) and every intermediate exceed the 126 MB L2; no flush needed"
                                 % (8 * (nr_g + ns_g) / 2**30),
                    "result_check": "count and 3 checksums verified every step; all rows verified once as a multiset (device fingerprint)"},
