@@ -1,7 +1,7 @@
 // radix.cu -- one radix-partitioning pass = four kernels on one stream:
 //   k_make_items  : cut every parent partition into work items of <= chunk tuples
 //   k_hist_tiles  : per-item digit histogram in shared memory, and the digit   (reference: histogram, cpra2.cpp:801-880)
-//                   counts of every 8192-tuple TILE of the item as a by-product
+//                   counts of every 16384-tuple TILE of the item as a by-product
 //   k_scan        : single-pass decoupled-look-back prefix sum over the         (reference: interleave, phj.cpp:1263-1291)
 //                   (parent, digit, item) ordered counts
 //   k_scatter_tc  : tile-wise shared-memory reorder + run-wise coalesced stores (reference: partition / partition_shared +
@@ -16,7 +16,9 @@
 // chain), and the plan of tile t+1 is computed by eight warps while the others already stream tile t.
 //
 // Also here:
-//   k_hist / k_scatter : the same pass for fan-outs of 512..2048 (no tile counts, no write-combining)
+//   k_hist / k_scatter : the same pass for fan-outs of 1024..2048 (no tile counts, no write-combining)
+// A pass may run over a RANGE of the parents whose members are unions of several row ranges (RadixPassArgs::seg / out_base):
+// the local pass of the staged CPRA exchange (stage.cu), where a received sub-partition is one range per sender.
 //   k_hist_small   : histogram for <= 8 digits (CPRA's GPU-assign pass), register counters
 //   k_scatter_bulk : the scatter whose output columns live in other GPUs' memory; digit runs leave the SM as
 //                    TMA bulk copies (cp.async.bulk) -- the fused exchange of CPRA (product path for N > 1)
@@ -349,7 +351,7 @@ __device__ __forceinline__ void hist_add(uint32_t *h, uint32_t d, bool valid, bo
 	if (valid && (int)lane_id() == __ffs(m) - 1) atomicAdd(&h[d], (uint32_t)__popc(m));
 }
 
-// k_hist for fan-outs <= 256.  The item is walked in the scatter's tiles (TILE tuples from the item's
+// k_hist for fan-outs <= 512.  The item is walked in the scatter's tiles (TILE tuples from the item's
 // first aligned group on); besides the item's counts row, the digit counts of every tile go to
 // tile_counts[item][tile][digit] (uint16: a tile holds at most 16384 tuples).  Two shared-memory histograms
 // take turns so that one barrier per tile suffices.
@@ -414,9 +416,9 @@ k_hist_tiles(const uint32_t *__restrict__ keys, uint64_t n, uint32_t np, const u
 	if (threadIdx.x < F) counts[(size_t)blockIdx.x * F + threadIdx.x] = total;
 }
 
-// ------------------------------------------------------------------ scatter (fan-out <= 256, tile counts known)
+// ------------------------------------------------------------------ scatter (fan-out <= 512, tile counts known)
 //
-// Per tile of 8192 tuples:
+// Per tile of 16384 tuples:
 //   place   every tuple takes its slot in the digit-grouped shared-memory tile with ONE shared-memory atomicAdd
 //           on its digit's cursor (the cursors start at the digits' tile offsets, known from k_hist_tiles'
 //           counts), and goes there with one 8-byte store; the tuples a digit carried over from the previous
@@ -624,7 +626,7 @@ k_scatter_tc(const uint32_t *__restrict__ keys, const uint32_t *__restrict__ val
 	}
 }
 
-// ------------------------------------------------------------------ scatter (fan-out 512 .. 2048)
+// ------------------------------------------------------------------ scatter (fan-out 1024 .. 2048)
 //
 // Per tile: (1) every tuple takes a rank inside its digit with a shared-memory atomicAdd, (2) the digit
 // counts become tile offsets, (3) tuples are placed into shared memory grouped by digit, (4) the tile is
